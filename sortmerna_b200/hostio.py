@@ -1,0 +1,260 @@
+"""Host-side I/O helpers around the alignment hot path (numpy only; no GPU, no oracle).
+
+They restate the small pieces of the reference that sit immediately on either side of the
+drop-in boundary so that tests and bench.py can feed the C-ABI the same bytes the reference's
+`align()` sees:
+
+  * `encode_nt`      -- `nt_table` (include/common.hpp:68-77): ACGTU -> 0..3, anything else -> 4
+  * `load_references`-- `References::load` + `convert_fix` (src/sortmerna/references.cpp:55-164)
+  * `read_fastx`     -- single-line-record FASTA/FASTQ reader (the reference's Readfeed is out of scope)
+  * `parse_stats`    -- the `.stats` index file (`Refstats::load`, src/sortmerna/refstats.cpp:103-190)
+  * `minimal_score`  -- the E-value -> minimal SW score formula (refstats.cpp:236-265) given lambda, K
+  * `format_sam_rows`-- the SAM row layout of `ReportSam::append` (src/sortmerna/report_sam.cpp:64-152)
+"""
+from __future__ import annotations
+
+import glob
+import gzip
+import math
+import os
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_NT = np.full(256, 4, dtype=np.uint8)
+for _c, _v in (("A", 0), ("C", 1), ("G", 2), ("T", 3), ("U", 3)):
+    _NT[ord(_c)] = _v
+    _NT[ord(_c.lower())] = _v
+NT_MAP = "ACGTN"
+
+
+def encode_nt(seq: bytes | str) -> np.ndarray:
+    """ASCII -> 0..4 (4 = ambiguous), include/common.hpp:68-77."""
+    if isinstance(seq, str):
+        seq = seq.encode()
+    return _NT[np.frombuffer(seq, dtype=np.uint8)]
+
+
+def _open(path: str):
+    return gzip.open(path, "rb") if path.endswith(".gz") else open(path, "rb")
+
+
+def read_fastx(path: str, limit: int | None = None):
+    """Return (headers, seqs, quals) of a FASTA/FASTQ file (multi-line FASTA is concatenated)."""
+    headers, seqs, quals = [], [], []
+    with _open(path) as fh:
+        data = fh.read()
+    lines = data.split(b"\n")
+    i, n = 0, len(lines)
+    while i < n:
+        ln = lines[i].rstrip(b"\r")
+        if not ln:
+            i += 1
+            continue
+        if ln[:1] == b"@":
+            headers.append(ln.decode())
+            seqs.append(lines[i + 1].rstrip(b"\r"))
+            quals.append(lines[i + 3].rstrip(b"\r"))
+            i += 4
+        elif ln[:1] == b">":
+            headers.append(ln.decode())
+            i += 1
+            parts = []
+            while i < n and lines[i][:1] != b">":
+                if lines[i].strip():
+                    parts.append(lines[i].strip())
+                i += 1
+            seqs.append(b"".join(parts))
+            quals.append(b"")
+        else:
+            raise ValueError(f"{path}: unexpected line {i}: {ln[:40]!r}")
+        if limit is not None and len(seqs) >= limit:
+            break
+    return headers, seqs, quals
+
+
+def seq_id(header: str) -> str:
+    """Read::getSeqId (read.cpp:365-371): header up to the first space, leading '>'/'@' removed."""
+    h = header.split(" ")[0]
+    return h.lstrip(">@")
+
+
+@dataclass
+class ReadBatch:
+    headers: list
+    seqs: list            # raw bytes
+    quals: list
+    cat: np.ndarray       # uint8, 0..4
+    off: np.ndarray       # uint64, nreads+1
+
+    @property
+    def n(self):
+        return len(self.seqs)
+
+
+def pack_reads(headers, seqs, quals=None) -> ReadBatch:
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.uint64, count=len(seqs))
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    cat = encode_nt(b"".join(seqs)) if seqs else np.zeros(0, np.uint8)
+    return ReadBatch(list(headers), list(seqs), list(quals) if quals else [b""] * len(seqs), cat, off)
+
+
+def load_reads(path: str, limit: int | None = None) -> ReadBatch:
+    h, s, q = read_fastx(path, limit)
+    return pack_reads(h, s, q)
+
+
+@dataclass
+class References:
+    path: str
+    ids: list             # BaseRecord::getId -- header up to first space without '>'
+    cat: np.ndarray       # uint8 0..4, all sequences concatenated
+    off: np.ndarray       # uint64, nref+1
+
+    @property
+    def n(self):
+        return len(self.ids)
+
+
+def load_references(path: str) -> References:
+    """References::load for a single-part index (references.cpp:55-154)."""
+    h, s, _ = read_fastx(path)
+    lens = np.fromiter((len(x) for x in s), dtype=np.uint64, count=len(s))
+    off = np.zeros(len(s) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    return References(path, [seq_id(x) for x in h], encode_nt(b"".join(s)), off)
+
+
+@dataclass
+class IndexStats:
+    """Contents of <prefix>.stats (refstats.cpp:129-190; writer indexdb.cpp:2020-2080)."""
+    prefix: str
+    fasta_size: int = 0
+    fasta_name: str = ""
+    background_freq: tuple = (0.25, 0.25, 0.25, 0.25)
+    full_ref: int = 0
+    lnwin: int = 18
+    numseq: int = 0
+    num_parts: int = 1
+    parts: list = field(default_factory=list)  # (start_part, seq_part_size, numseq_part)
+
+
+def parse_stats(prefix: str) -> IndexStats:
+    with open(prefix + ".stats", "rb") as fh:
+        b = fh.read()
+    o = 0
+    (fsize,) = struct.unpack_from("<Q", b, o); o += 8
+    (nlen,) = struct.unpack_from("<I", b, o); o += 4
+    name = b[o:o + nlen].split(b"\0")[0].decode(); o += nlen
+    freq = struct.unpack_from("<4d", b, o); o += 32
+    (full_ref,) = struct.unpack_from("<Q", b, o); o += 8
+    (lnwin,) = struct.unpack_from("<I", b, o); o += 4
+    (numseq,) = struct.unpack_from("<Q", b, o); o += 8
+    (nparts,) = struct.unpack_from("<H", b, o); o += 2
+    parts = []
+    for _ in range(nparts):
+        sp, sz, ns = struct.unpack_from("<QQI", b, o); o += 24  # struct index_parts_stats, 8+8+4(+4 pad)
+        parts.append((sp, sz, ns))
+    return IndexStats(prefix, fsize, name, freq, full_ref, lnwin, numseq, nparts, parts)
+
+
+def find_index_prefixes(idx_dir: str) -> dict:
+    """Map reference FASTA basename -> index prefix for every *.stats in idx_dir."""
+    out = {}
+    for st in glob.glob(os.path.join(idx_dir, "*.stats")):
+        s = parse_stats(st[: -len(".stats")])
+        out[os.path.basename(s.fasta_name)] = s.prefix
+    return out
+
+
+def minimal_score(stats: IndexStats, lam: float, K: float, all_reads_len: int, all_reads_count: int,
+                  evalue: float = 1.0) -> int:
+    """refstats.cpp:236-265 (is_score_split = false)."""
+    f = stats.background_freq
+    entropy = -sum(p * math.log2(p) for p in f)
+    full_ref = stats.full_ref
+    full_read = all_reads_len
+    expect_L = int(math.log(K * full_ref * full_read) / entropy)
+    if full_ref > expect_L * stats.numseq:
+        full_ref -= expect_L * stats.numseq
+    full_read -= expect_L * all_reads_count
+    return int(math.log(evalue / (K * full_ref * full_read)) / -lam) & 0xFFFFFFFF
+
+
+_OPS = "MID"
+
+
+def cigar_string(cig) -> str:
+    return "".join(f"{int(c) >> 4}{_OPS[int(c) & 0xF] if (int(c) & 0xF) < 3 else 'D'}" for c in cig)
+
+
+def revcomp_str(s: str) -> str:
+    return s.translate(str.maketrans("ACGTN", "TGCAN"))[::-1]
+
+
+def calc_miss_gap_match(ref: np.ndarray, read04: np.ndarray, aln, cigar) -> tuple:
+    """Read::calc_miss_gap_match (read.cpp:547-589): (mismatches, gaps, matches)."""
+    qb, pb = int(aln["ref_begin1"]), int(aln["read_begin1"])
+    miss = gap = match = 0
+    for c in cigar:
+        op, ln = int(c) & 0xF, int(c) >> 4
+        if op == 0:
+            a = ref[qb:qb + ln]
+            b = read04[pb:pb + ln]
+            eq = int(np.count_nonzero(a == b))
+            match += eq
+            miss += ln - eq
+            qb += ln
+            pb += ln
+        elif op == 1:
+            pb += ln
+            gap += ln
+        else:
+            qb += ln
+            gap += ln
+    return miss, gap, match
+
+
+def format_sam_rows(batch: ReadBatch, refs_by_index: list, results, alns, cigar_pool, slots: int,
+                    with_seq: bool = True) -> list:
+    """SAM alignment rows as `ReportSam::append` prints them (report_sam.cpp:64-152), one list entry
+    per stored alignment, in read order.  `results`/`alns` are the structured numpy arrays returned
+    by the C-ABI (or the oracle); refs_by_index[index_num] is a `References`."""
+    rows = []
+    for r in range(batch.n):
+        na = int(results["n_align"][r])
+        if na == 0:
+            continue
+        seq = batch.seqs[r].decode().upper()
+        enc = batch.cat[int(batch.off[r]):int(batch.off[r + 1])]
+        name = seq_id(batch.headers[r])
+        for a in range(na):
+            al = alns[r * slots + a]
+            refs = refs_by_index[int(al["index_num"])]
+            cig = cigar_pool[int(al["cigar_off"]):int(al["cigar_off"]) + int(al["cigar_len"])]
+            strand = bool(al["strand"])
+            cs = ""
+            if int(al["read_begin1"]) != 0:
+                cs += f"{int(al['read_begin1'])}S"
+            cs += cigar_string(cig)
+            end_mask = len(seq) - int(al["read_end1"]) - 1
+            if end_mask > 0:
+                cs += f"{end_mask}S"
+            # the read as aligned (04 alphabet, reverse-complemented for the minus strand)
+            s04 = "".join(NT_MAP[v] for v in enc)
+            e04 = enc
+            if not strand:
+                s04 = revcomp_str(s04)
+                e04 = np.where(enc < 4, 3 - enc, 4)[::-1]
+            rseq = refs.cat[int(refs.off[int(al["ref_num"])]):int(refs.off[int(al["ref_num"]) + 1])]
+            miss, gap, _ = calc_miss_gap_match(rseq, e04, al, cig)
+            q = batch.quals[r].decode() if batch.quals[r] else "*"
+            if batch.quals[r] and not strand:
+                q = q[::-1]
+            row = [name, "16" if not strand else "0", refs.ids[int(al["ref_num"])], str(int(al["ref_begin1"]) + 1),
+                   "255", cs, "*", "0", "0", s04 if with_seq else "*", q if with_seq else "*",
+                   f"AS:i:{int(al['score1'])}", f"NM:i:{miss + gap}"]
+            rows.append("\t".join(row))
+    return rows
