@@ -1,0 +1,153 @@
+/*
+ * include/smr_b200.h -- C ABI of the B200-native alignment hot path (libsmr_b200.so).
+ *
+ * The reference (sortmerna v5.0.0) has no FFI; the seam this library replaces is the C++ call
+ *     void align(Readfeed&, Readstats&, Index&, KeyValueDatabase&, Runopts&)
+ *         (src/sortmerna/processor.cpp:173, called from src/sortmerna/main.cpp:88,99,105)
+ * whose unit of work is
+ *     void traverse(Runopts&, Index&, References&, Readstats&, Refstats&, Read&, bool)
+ *         (src/sortmerna/paralleltraversal.cpp:81-90).
+ * Each entry point below names the reference code it stands in for.  All functions return 0 on
+ * success and a non-zero smr_status otherwise (the reference prints and exit()s; a host wrapper
+ * maps non-zero to that).  Plain pointers and sizes only; no C++ or torch types.  Every compute
+ * entry point requires a CUDA device: there is no CPU fallback.
+ */
+#ifndef SMR_B200_H
+#define SMR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smr_ctx smr_ctx; /* opaque; one per GPU, driven by one host thread */
+
+enum smr_status {
+  SMR_OK = 0,
+  SMR_ERR_CUDA = 1,        /* a CUDA call failed (smr_last_error has the text) */
+  SMR_ERR_ARG = 2,         /* invalid argument */
+  SMR_ERR_INDEX = 3,       /* malformed index file (index.cpp:282-286 is fatal in the reference too) */
+  SMR_ERR_UNSUPPORTED = 4, /* option combination outside this build */
+  SMR_ERR_CAPACITY = 5,    /* caller-provided output buffer too small */
+  SMR_ERR_NO_DEVICE = 6    /* no CUDA device / extension cannot run: fail loudly, never fall back */
+};
+
+/* The opts.* fields that cross the seam; defaults are those of
+ * Runopts::validate (src/sortmerna/options.cpp:1684-1738). */
+typedef struct {
+  int32_t match, mismatch, score_N, gap_open, gap_ext; /* --match --mismatch -N --gap_open --gap_ext */
+  int32_t num_seeds, min_lis, edges, edges_is_percent; /* --num_seeds --min_lis --edges */
+  int32_t num_alignments, is_best;                     /* --num_alignments / --best / --no-best */
+  int32_t is_forward, is_reverse, is_full_search;      /* -F -R --full_search */
+  int32_t minoccur;                                    /* include/options.hpp:572 (no CLI option) */
+} smr_params;
+
+/* Per-read result = the fields Read::toBinString persists (src/sortmerna/read.cpp:429-462), i.e.
+ * what the unchanged report stage reads back through Read::load_db. */
+typedef struct {
+  uint32_t lastIndex, lastPart;
+  uint32_t hit_seeds;
+  uint32_t min_index, max_index; /* alignment_struct2 (include/ssw.hpp:157-159) */
+  uint32_t n_align;              /* alignv.size() */
+  uint16_t max_SW_count;
+  uint8_t is_done, is_hit;
+} smr_read_result;
+
+/* One stored alignment = s_align2 (include/ssw.hpp:44-56); slot (read * max(1,num_alignments) + k) */
+typedef struct {
+  uint32_t cigar_off, cigar_len; /* into the cigar pool; BAM style len<<4|op, op 0=M 1=I 2=D (ssw.c:750-758) */
+  uint32_t ref_num;
+  int32_t ref_begin1, ref_end1, read_begin1, read_end1;
+  uint32_t readlen;
+  uint16_t score1, part, index_num;
+  uint8_t strand, pad;
+} smr_aln;
+
+/* Counters.  The first block is Readstats (include/readstats.hpp:77-84) as mutated by this path;
+ * it is what the single NCCL all-reduce sums across GPUs.  The second block is instrumentation
+ * used for the roofline arithmetic. */
+enum {
+  SMR_CNT_NUM_ALIGNED = 0,   /* readstats.num_aligned (alignment.cpp:414) */
+  SMR_CNT_NUM_SHORT = 1,     /* readstats.num_short of the LAST index pass (processor.cpp:109-114,228) */
+  SMR_CNT_SW_CALLS = 2,      /* ssw_align-equivalent calls */
+  SMR_CNT_SW_CELLS = 3,      /* sum refLen*readLen over those calls (forward pass only) */
+  SMR_CNT_WINDOWS = 4,       /* seed windows searched (speculative windows included) */
+  SMR_CNT_TRIE_NODES = 5,    /* trie nodes visited */
+  SMR_CNT_BUCKETS = 6,       /* buckets visited */
+  SMR_CNT_BUCKET_ENTRIES = 7,/* bucket entries visited */
+  SMR_CNT_POS_ENTRIES = 8,   /* position entries touched by candidate voting */
+  SMR_CNT_LIS_CALLS = 9,     /* compute_lis_alignment-equivalent calls */
+  SMR_CNT_FIXED = 16         /* reads_matched_per_db[i] lives at counters[SMR_CNT_FIXED + i] */
+};
+
+/* -- lifetime ------------------------------------------------------------------------------- */
+int smr_init(int device, smr_ctx** out);
+void smr_destroy(smr_ctx*);
+const char* smr_last_error(const smr_ctx*); /* text of the last failure on this context */
+int smr_device_count(void);                 /* number of visible CUDA devices (0 if none) */
+
+/* -- index + references: Index::load (src/sortmerna/index.cpp:143-357) and References::load
+ *    (src/sortmerna/references.cpp:55-164) for one (index_num, part), in --ref order.  Takes the
+ *    raw bytes of <idx>.kmer_<p>.dat / .bursttrie_<p>.dat / .pos_<p>.dat, flattens them to
+ *    contiguous HBM arrays and keeps them resident (all indexes stay loaded; the reference loads
+ *    and unloads one at a time, processor.cpp:225-266).
+ *    refseq_cat: reference sequences in the 0..4 alphabet (nt_table, common.hpp:68-77), concatenated;
+ *    ref_off[nref+1] offsets.  minimal_score / lnwin / skiplengths come from Refstats
+ *    (src/sortmerna/refstats.cpp:147-166,259-265). */
+int smr_load_index_part(smr_ctx*, uint32_t index_num, uint32_t part,
+                        const void* kmer_file, size_t kmer_bytes,
+                        const void* bursttrie_file, size_t bursttrie_bytes,
+                        const void* pos_file, size_t pos_bytes,
+                        const uint8_t* refseq_cat, const uint64_t* ref_off, uint32_t nref,
+                        uint32_t lnwin, uint32_t minimal_score, const uint32_t skiplengths[3]);
+/* refstats.minimal_score depends on the read set (refstats.cpp:247-265): update without reloading */
+int smr_set_minimal_score(smr_ctx*, uint32_t index_num, uint32_t minimal_score);
+int smr_set_params(smr_ctx*, const smr_params*);
+/* out[0]=#parts loaded [1]=bytes resident in HBM [2]=trie nodes [3]=bucket entries [4]=ids [5]=positions */
+int smr_index_info(const smr_ctx*, uint64_t out[6]);
+
+/* -- the hot path: align() (processor.cpp:173-285) over one batch of reads, read-major.
+ *    For each read: for each loaded (index,part) in order: forward then reverse strand through
+ *    traverse() with KVDB-equivalent carry-over (read.cpp:429-539).
+ *    seq_cat: reads in 0..4 (4 = ambiguous, as nt_table yields), concatenated; seq_off[nreads+1].
+ *    Host buffers; the call copies host->device, runs, and copies the results back.
+ *    results[nreads]; alns[nreads * max(1,num_alignments)]; cigar_pool[cigar_cap] u32 words;
+ *    counters[SMR_CNT_FIXED + n_index_files] are ADDED to (caller zeroes them). */
+int smr_align_batch(smr_ctx*, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads,
+                    smr_read_result* results, smr_aln* alns,
+                    uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used,
+                    uint64_t* counters, uint32_t n_counters);
+
+/* Same work with the batch already resident: upload once, run many times (bench `value` leg). */
+int smr_upload_batch(smr_ctx*, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads);
+int smr_run_resident(smr_ctx*);                       /* all kernels of one pass over the resident batch */
+int smr_download_results(smr_ctx*, smr_read_result* results, smr_aln* alns, uint32_t* cigar_pool,
+                         uint64_t cigar_cap, uint64_t* cigar_used, uint64_t* counters, uint32_t n_counters);
+
+/* Device-side timings of the last smr_run_resident / smr_align_batch, CUDA events on the
+ * library's stream, milliseconds: out[0]=total [1]=seed kernels [2]=candidate/SW kernels
+ * [3]=finalize (reverse SW + traceback) [4]=h2d [5]=d2h; out[6]=number of kernel launches */
+int smr_last_timings(const smr_ctx*, double out[8]);
+
+/* -- multi-GPU: the only cross-read state is the counter vector.  The library
+ *    shards nothing itself: each rank calls smr_align_batch on its own reads and the host sums
+ *    `counters` with one all-reduce (torch.distributed / NCCL). */
+
+/* -- unit-test entry points (run the same device functions the hot path uses) ------------------ */
+/* seed search of explicit windows: for window k, sequence seq03 (0..3, length >= win_pos+lnwin) of
+ * read read_of[k]; returns ids per window into ids[k*cap .. ), counts[k] (may exceed cap),
+ * zero[k] = accept_zero_kmer. */
+int smr_debug_seed_windows(smr_ctx*, uint32_t part_slot, const uint8_t* seq_cat, const uint64_t* seq_off,
+                           uint32_t nreads, const uint32_t* win_read, const uint32_t* win_pos, uint32_t nwin,
+                           uint32_t* ids, uint32_t cap, uint32_t* counts, uint8_t* zero);
+/* ssw_align(flag=2) equivalents on explicit (query, target) pairs:
+ * out[k*6..] = score1, ref_begin1, ref_end1, read_begin1, read_end1, cigar_len; cigars at k*cigar_cap */
+int smr_debug_ssw(smr_ctx*, const uint8_t* q_cat, const uint64_t* q_off, const uint8_t* t_cat,
+                  const uint64_t* t_off, uint32_t npairs, uint32_t filters, int32_t* out, uint32_t* cigars,
+                  uint32_t cigar_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

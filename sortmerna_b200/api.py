@@ -1,0 +1,231 @@
+"""ctypes binding of libsmr_b200.so (include/smr_b200.h) and a host-side driver that mirrors the
+reference's `align()` call (src/sortmerna/processor.cpp:173-285): load every (index, part) given
+with --ref, then push batches of reads through the GPU hot path.
+
+There is NO CPU fallback: importing this module without the built extension, or creating an
+`Aligner` without a CUDA device, raises.  (The CPU oracle lives under oracle/ and is test
+infrastructure; nothing here imports it.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import hostio
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsmr_b200.so")
+
+STATUS = {0: "SMR_OK", 1: "SMR_ERR_CUDA", 2: "SMR_ERR_ARG", 3: "SMR_ERR_INDEX", 4: "SMR_ERR_UNSUPPORTED",
+          5: "SMR_ERR_CAPACITY", 6: "SMR_ERR_NO_DEVICE"}
+
+# every symbol include/smr_b200.h declares
+SYMBOLS = ["smr_init", "smr_destroy", "smr_last_error", "smr_device_count", "smr_load_index_part",
+           "smr_set_minimal_score", "smr_set_params", "smr_index_info", "smr_align_batch", "smr_upload_batch",
+           "smr_run_resident", "smr_download_results", "smr_last_timings", "smr_debug_seed_windows", "smr_debug_ssw"]
+
+CNT_NAMES = ("num_aligned", "num_short", "sw_calls", "sw_cells", "windows", "trie_nodes", "buckets",
+             "bucket_entries", "pos_entries", "lis_calls")
+CNT_FIXED = 16
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "match", "mismatch", "score_N", "gap_open", "gap_ext", "num_seeds", "min_lis", "edges",
+        "edges_is_percent", "num_alignments", "is_best", "is_forward", "is_reverse", "is_full_search",
+        "minoccur")]
+
+
+def default_params(**kw) -> Params:
+    """Runopts::validate defaults (src/sortmerna/options.cpp:1684-1738)."""
+    p = Params(match=2, mismatch=-3, score_N=-3, gap_open=5, gap_ext=2, num_seeds=2, min_lis=2, edges=4,
+               edges_is_percent=0, num_alignments=1, is_best=1, is_forward=1, is_reverse=1, is_full_search=0,
+               minoccur=0)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+RESULT_DTYPE = np.dtype([("lastIndex", "<u4"), ("lastPart", "<u4"), ("hit_seeds", "<u4"), ("min_index", "<u4"),
+                         ("max_index", "<u4"), ("n_align", "<u4"), ("max_SW_count", "<u2"), ("is_done", "u1"),
+                         ("is_hit", "u1")])
+ALN_DTYPE = np.dtype([("cigar_off", "<u4"), ("cigar_len", "<u4"), ("ref_num", "<u4"), ("ref_begin1", "<i4"),
+                      ("ref_end1", "<i4"), ("read_begin1", "<i4"), ("read_end1", "<i4"), ("readlen", "<u4"),
+                      ("score1", "<u2"), ("part", "<u2"), ("index_num", "<u2"), ("strand", "u1"), ("pad", "u1")])
+
+_lib = None
+
+
+def load_library():
+    """Load the extension; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(nvcc, sm_100a). There is no CPU fallback for the alignment hot path.")
+        L = C.CDLL(LIB_PATH)
+        L.smr_last_error.restype = C.c_char_p
+        L.smr_last_error.argtypes = [C.c_void_p]
+        L.smr_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.smr_destroy.argtypes = [C.c_void_p]
+        L.smr_destroy.restype = None
+        for name in SYMBOLS:
+            getattr(L, name)  # AttributeError if the build is stale
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class SmrError(RuntimeError):
+    pass
+
+
+class Aligner:
+    """One GPU context.  Mirrors the objects `align()` receives: Index (+References, Refstats) via
+    load_index_part, Runopts via set_params, Readfeed batches via align()."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rc = self.L.smr_init(device, C.byref(self.h))
+        if rc != 0:
+            raise SmrError(f"smr_init(device={device}) failed: {STATUS.get(rc, rc)} -- a CUDA device is required; "
+                           "there is no CPU fallback")
+        self.params = None
+        self.n_index_files = 0
+        self.refs_by_index = {}
+        self._keep = []
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise SmrError(f"{what}: {STATUS.get(rc, rc)}: {self.L.smr_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.L.smr_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params: Params):
+        self.params = params
+        self._check(self.L.smr_set_params(self.h, C.byref(params)), "smr_set_params")
+
+    def load_index_part(self, index_num: int, part: int, prefix: str, refs: hostio.References, minimal_score: int,
+                        skiplengths=(18, 9, 3), lnwin: int = 18):
+        sfx = f"_{part}.dat"
+        bufs = [np.fromfile(prefix + ext + sfx, dtype=np.uint8) for ext in (".kmer", ".bursttrie", ".pos")]
+        sk = (C.c_uint32 * 3)(*skiplengths)
+        cat = np.ascontiguousarray(refs.cat, np.uint8)
+        off = np.ascontiguousarray(refs.off, np.uint64)
+        rc = self.L.smr_load_index_part(self.h, C.c_uint32(index_num), C.c_uint32(part),
+                                        _ptr(bufs[0]), C.c_size_t(bufs[0].size), _ptr(bufs[1]), C.c_size_t(bufs[1].size),
+                                        _ptr(bufs[2]), C.c_size_t(bufs[2].size), _ptr(cat), _ptr(off), C.c_uint32(refs.n),
+                                        C.c_uint32(lnwin), C.c_uint32(minimal_score), sk)
+        self._check(rc, f"smr_load_index_part({prefix})")
+        self.n_index_files = max(self.n_index_files, index_num + 1)
+        self.refs_by_index[index_num] = refs
+
+    def set_minimal_score(self, index_num: int, score: int):
+        self._check(self.L.smr_set_minimal_score(self.h, C.c_uint32(index_num), C.c_uint32(score)), "smr_set_minimal_score")
+
+    def index_info(self):
+        out = np.zeros(6, np.uint64)
+        self._check(self.L.smr_index_info(self.h, _ptr(out)), "smr_index_info")
+        return dict(zip(("parts", "hbm_bytes", "nodes", "entries", "ids", "positions"), map(int, out)))
+
+    def _outputs(self, n):
+        slots = max(1, self.params.num_alignments)
+        res = np.zeros(n, RESULT_DTYPE)
+        alns = np.zeros(n * slots, ALN_DTYPE)
+        cap = 48 * n * slots + 4096
+        pool = np.zeros(cap, np.uint32)
+        counters = np.zeros(CNT_FIXED + max(1, self.n_index_files), np.uint64)
+        return slots, res, alns, pool, cap, counters
+
+    def _pack(self, res, alns, pool, used, counters, slots):
+        cnt = {k: int(counters[i]) for i, k in enumerate(CNT_NAMES)}
+        return dict(res=res, alns=alns, cigar=pool[: used], matched=counters[CNT_FIXED:].copy(), counters=cnt,
+                    slots=slots, timings=self.timings())
+
+    def align(self, cat: np.ndarray, off: np.ndarray):
+        """smr_align_batch: host buffers in, host results out (H2D and D2H inside the call)."""
+        cat = np.ascontiguousarray(cat, np.uint8)
+        off = np.ascontiguousarray(off, np.uint64)
+        n = off.size - 1
+        slots, res, alns, pool, cap, counters = self._outputs(n)
+        used = C.c_uint64(0)
+        rc = self.L.smr_align_batch(self.h, _ptr(cat), _ptr(off), C.c_uint32(n), _ptr(res), _ptr(alns), _ptr(pool),
+                                    C.c_uint64(cap), C.byref(used), _ptr(counters), C.c_uint32(counters.size))
+        self._check(rc, "smr_align_batch")
+        return self._pack(res, alns, pool, used.value, counters, slots)
+
+    def upload(self, cat: np.ndarray, off: np.ndarray):
+        cat = np.ascontiguousarray(cat, np.uint8)
+        off = np.ascontiguousarray(off, np.uint64)
+        self._n_resident = off.size - 1
+        self._check(self.L.smr_upload_batch(self.h, _ptr(cat), _ptr(off), C.c_uint32(off.size - 1)), "smr_upload_batch")
+
+    def run_resident(self):
+        self._check(self.L.smr_run_resident(self.h), "smr_run_resident")
+
+    def download(self):
+        n = self._n_resident
+        slots, res, alns, pool, cap, counters = self._outputs(n)
+        used = C.c_uint64(0)
+        rc = self.L.smr_download_results(self.h, _ptr(res), _ptr(alns), _ptr(pool), C.c_uint64(cap), C.byref(used),
+                                         _ptr(counters), C.c_uint32(counters.size))
+        self._check(rc, "smr_download_results")
+        return self._pack(res, alns, pool, used.value, counters, slots)
+
+    def timings(self):
+        out = np.zeros(8, np.float64)
+        self.L.smr_last_timings(self.h, _ptr(out))
+        return dict(total_ms=out[0], seed_ms=out[1], lis_ms=out[2], final_ms=out[3], h2d_ms=out[4], d2h_ms=out[5],
+                    launches=int(out[6]))
+
+    # ---- unit-test entry points ----
+    def debug_seed_windows(self, part_slot, cat03, off, win_read, win_pos, cap=64):
+        cat03 = np.ascontiguousarray(cat03, np.uint8)
+        off = np.ascontiguousarray(off, np.uint64)
+        win_read = np.ascontiguousarray(win_read, np.uint32)
+        win_pos = np.ascontiguousarray(win_pos, np.uint32)
+        nwin = win_read.size
+        ids = np.zeros(nwin * cap, np.uint32)
+        counts = np.zeros(nwin, np.uint32)
+        zero = np.zeros(nwin, np.uint8)
+        rc = self.L.smr_debug_seed_windows(self.h, C.c_uint32(part_slot), _ptr(cat03), _ptr(off), C.c_uint32(off.size - 1),
+                                           _ptr(win_read), _ptr(win_pos), C.c_uint32(nwin), _ptr(ids), C.c_uint32(cap),
+                                           _ptr(counts), _ptr(zero))
+        self._check(rc, "smr_debug_seed_windows")
+        return ids.reshape(nwin, cap), counts, zero
+
+    def debug_ssw(self, q_cat, q_off, t_cat, t_off, filters=0, cigar_cap=256):
+        q_cat = np.ascontiguousarray(q_cat, np.uint8)
+        t_cat = np.ascontiguousarray(t_cat, np.uint8)
+        q_off = np.ascontiguousarray(q_off, np.uint64)
+        t_off = np.ascontiguousarray(t_off, np.uint64)
+        n = q_off.size - 1
+        out = np.zeros(n * 6, np.int32)
+        cig = np.zeros(n * cigar_cap, np.uint32)
+        rc = self.L.smr_debug_ssw(self.h, _ptr(q_cat), _ptr(q_off), _ptr(t_cat), _ptr(t_off), C.c_uint32(n),
+                                  C.c_uint32(filters), _ptr(out), _ptr(cig), C.c_uint32(cigar_cap))
+        self._check(rc, "smr_debug_ssw")
+        return out.reshape(n, 6), cig.reshape(n, cigar_cap)
+
+
+def align_files(aligner: Aligner, batch: hostio.ReadBatch):
+    """Convenience: align a parsed read batch and return results + SAM rows."""
+    out = aligner.align(batch.cat, batch.off)
+    refs = [aligner.refs_by_index[i] for i in range(aligner.n_index_files)]
+    out["sam"] = hostio.format_sam_rows(batch, refs, out["res"], out["alns"], out["cigar"], out["slots"])
+    return out

@@ -1,0 +1,635 @@
+// C ABI of libsmr_b200.so (include/smr_b200.h): context, index residency, batch driver.
+// Host side of the seam that replaces align() (src/sortmerna/processor.cpp:173-285).
+#include "../../include/smr_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "smr_final.cuh"
+#include "smr_index.h"
+
+using namespace smr;
+
+namespace {
+
+struct Part {
+  DevIndex d{};
+  std::vector<void*> owned;   // device allocations
+  size_t bytes = 0, n_nodes = 0, n_entries = 0, n_ids = 0, n_pos = 0;
+};
+
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+};
+
+}  // namespace
+
+struct smr_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  smr_params prm{};
+  bool have_params = false;
+  std::vector<Part> parts;
+  uint32_t n_index_files = 0;
+  int sm_count = 148;
+  uint32_t chunk_reads = 1u << 20;
+
+  // resident batch
+  uint32_t nreads = 0; uint64_t total_nt = 0; uint32_t max_len = 0;
+  std::vector<uint8_t> h_seq; std::vector<uint64_t> h_off;    // host copy (scratch-overflow retries)
+  std::vector<uint32_t> off32;                                // 32-bit read offsets of the resident batch
+  DevBuf seq04, seq_off, pk03, pk03alt, pk_off, has_n, hit_cnt, flags, state, hit_db, aln_work, out_aln;
+  DevBuf hits, worklist, scalars, counters, cigar_pool, parts_dev;
+  DevBuf lis_arena, lis_epochs, final_arena, lane_hits;
+  uint32_t lis_warps = 0, final_warps = 0;
+  size_t lis_stride = 0, final_stride = 0;
+  uint32_t hist_cap = 0, cand_cap = 0, pair_cap = 0, row_cap = 0, cap_w = 0, cap_cig = 0; size_t cap_dir = 0;
+  uint32_t lane_hits_cap = 0, lane_hits_warps = 0;
+  uint64_t cigar_cap_dev = 0;
+  uint32_t scale = 1;         // scratch scale of the current run (1 = fast path)
+  bool instr = true;          // count windows/nodes/entries in the seed kernel
+  // timings
+  std::vector<cudaEvent_t> ev;
+  double t_total = 0, t_seed = 0, t_lis = 0, t_final = 0, t_h2d = 0, t_d2h = 0; uint64_t n_launch = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+      return SMR_ERR_CUDA;                                                                         \
+    }                                                                                              \
+  } while (0)
+
+int ensure(smr_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return SMR_OK;
+  if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  size_t want = bytes + bytes / 8 + 256;
+  CK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return SMR_OK;
+}
+void release(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+template <class T>
+int upload_vec(smr_ctx* ctx, Part& pt, const std::vector<T>& v, const T** out) {
+  void* d = nullptr;
+  size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+  CK(cudaMalloc(&d, bytes));
+  if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  pt.owned.push_back(d); pt.bytes += bytes;
+  *out = (const T*)d;
+  return SMR_OK;
+}
+
+DevParams to_dev(const smr_params& p) {
+  DevParams d;
+  d.match = p.match; d.mismatch = p.mismatch; d.score_N = p.score_N; d.gap_open = p.gap_open; d.gap_ext = p.gap_ext;
+  d.num_seeds = p.num_seeds; d.min_lis = p.min_lis; d.edges = p.edges; d.edges_is_percent = p.edges_is_percent;
+  d.num_alignments = p.num_alignments; d.is_best = p.is_best; d.is_forward = p.is_forward; d.is_reverse = p.is_reverse;
+  d.is_full_search = p.is_full_search;
+  return d;
+}
+
+uint32_t pow2_ge(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+cudaEvent_t get_event(smr_ctx* ctx, size_t i) {
+  while (ctx->ev.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev.push_back(e); }
+  return ctx->ev[i];
+}
+
+// scalars block layout (u32): [0]=work_n [1]=lis work_next [2]=final work_next ; cigar_used (u64) at byte 16
+struct Scalars { uint32_t* work_n; uint32_t* lis_next; uint32_t* fin_next; unsigned long long* cigar_used; };
+Scalars scalars_of(smr_ctx* ctx) {
+  uint8_t* p = (uint8_t*)ctx->scalars.p;
+  return Scalars{(uint32_t*)p, (uint32_t*)(p + 4), (uint32_t*)(p + 8), (unsigned long long*)(p + 16)};
+}
+
+int setup_arenas(smr_ctx* ctx) {
+  uint32_t max_nref = 1;
+  for (auto& pt : ctx->parts) max_nref = std::max(max_nref, pt.d.nref);
+  ctx->hist_cap = max_nref;
+  ctx->cand_cap = pow2_ge(max_nref);
+  ctx->pair_cap = pow2_ge(4096u * ctx->scale);
+  ctx->row_cap = ctx->max_len + 2 * 64 + 64;
+  ctx->lis_warps = (uint32_t)ctx->sm_count * 4 * kLisWarpsPerCta;
+  ctx->lis_stride = lis_arena_bytes(ctx->hist_cap, ctx->cand_cap, ctx->pair_cap, ctx->row_cap);
+  // keep the arena total under ~8 GB: fewer persistent warps for huge reference sets
+  const size_t budget = (size_t)8 << 30;
+  while (ctx->lis_warps > 64 && ctx->lis_stride * ctx->lis_warps > budget) ctx->lis_warps /= 2;
+  if (int rc = ensure(ctx, ctx->lis_arena, ctx->lis_stride * ctx->lis_warps)) return rc;
+  const size_t old_cap = ctx->lis_epochs.cap;
+  if (int rc = ensure(ctx, ctx->lis_epochs, (size_t)ctx->lis_warps * 4)) return rc;
+  // histogram epochs start at 0 over a zeroed histogram
+  if (ctx->lis_epochs.cap != old_cap || true) {
+    CK(cudaMemsetAsync(ctx->lis_arena.p, 0, ctx->lis_stride * ctx->lis_warps, ctx->stream));
+    CK(cudaMemsetAsync(ctx->lis_epochs.p, 0, (size_t)ctx->lis_warps * 4, ctx->stream));
+  }
+  ctx->cap_w = 2 * 256 * ctx->scale + 8;          // band widths up to 256*scale
+  ctx->cap_cig = 2 * (ctx->max_len + 64) + 16;
+  ctx->cap_dir = (size_t)65536 * ctx->scale + (size_t)ctx->max_len * 9 * 3 + 64;
+  ctx->final_warps = (uint32_t)ctx->sm_count * 4 * kFinalWarpsPerCta;
+  ctx->final_stride = final_arena_bytes(ctx->cap_w, ctx->cap_cig, ctx->row_cap, ctx->cap_dir);
+  while (ctx->final_warps > 64 && ctx->final_stride * ctx->final_warps > budget) ctx->final_warps /= 2;
+  if (int rc = ensure(ctx, ctx->final_arena, ctx->final_stride * ctx->final_warps)) return rc;
+  if (ctx->scale > 1) {
+    ctx->lane_hits_cap = kLaneHitCap * ctx->scale * 4;
+    ctx->lane_hits_warps = 1024;
+    if (int rc = ensure(ctx, ctx->lane_hits, (size_t)ctx->lane_hits_warps * ctx->lane_hits_cap * 32 * 4)) return rc;
+  }
+  return SMR_OK;
+}
+
+int upload_batch_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads, bool keep_host) {
+  if (nreads == 0) { ctx->nreads = 0; return SMR_OK; }
+  const uint64_t total = seq_off[nreads] - seq_off[0];
+  if (total >= 0xF0000000ull) { ctx->err = "batch larger than 2^32 nucleotides: split it"; return SMR_ERR_ARG; }
+  cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1);
+  CK(cudaEventRecord(e0, ctx->stream));
+  std::vector<uint32_t>& off32 = ctx->off32; off32.resize(nreads + 1);
+  std::vector<uint32_t> pkoff(nreads + 1);
+  uint32_t max_len = 0; uint64_t w = 0;
+  for (uint32_t r = 0; r <= nreads; ++r) {
+    off32[r] = (uint32_t)(seq_off[r] - seq_off[0]);
+    pkoff[r] = (uint32_t)w;
+    if (r < nreads) {
+      const uint64_t len = seq_off[r + 1] - seq_off[r];
+      max_len = std::max<uint32_t>(max_len, (uint32_t)len);
+      w += (len + 15) / 16 + 2;     // +2 padding words: window_fwd reads three consecutive words
+    }
+  }
+  if (w >= 0xFFFFFFFFull) { ctx->err = "batch too large"; return SMR_ERR_ARG; }
+  ctx->nreads = nreads; ctx->total_nt = total; ctx->max_len = max_len;
+  if (keep_host) {
+    ctx->h_seq.assign(seq_cat + seq_off[0], seq_cat + seq_off[nreads]);
+    ctx->h_off.resize(nreads + 1);
+    for (uint32_t r = 0; r <= nreads; ++r) ctx->h_off[r] = seq_off[r] - seq_off[0];
+  }
+  const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
+  int rc;
+  if ((rc = ensure(ctx, ctx->seq04, total + 64))) return rc;
+  if ((rc = ensure(ctx, ctx->seq_off, (size_t)(nreads + 1) * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->pk_off, (size_t)(nreads + 1) * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->pk03, (size_t)(w + 4) * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->pk03alt, (size_t)(w + 4) * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->has_n, nreads))) return rc;
+  if ((rc = ensure(ctx, ctx->hit_cnt, (size_t)nreads * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->flags, (size_t)nreads * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->state, (size_t)nreads * sizeof(ReadState)))) return rc;
+  if ((rc = ensure(ctx, ctx->hit_db, (size_t)nreads * 2))) return rc;
+  if ((rc = ensure(ctx, ctx->aln_work, (size_t)nreads * slots * sizeof(AlnWork)))) return rc;
+  if ((rc = ensure(ctx, ctx->out_aln, (size_t)nreads * slots * sizeof(OutAln)))) return rc;
+  if ((rc = ensure(ctx, ctx->worklist, (size_t)std::min(nreads, ctx->chunk_reads) * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->scalars, 64))) return rc;
+  if ((rc = ensure(ctx, ctx->counters, (size_t)(dcCount + 64) * 8))) return rc;
+  CK(cudaMemcpyAsync(ctx->seq04.p, seq_cat + seq_off[0], total, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->seq_off.p, off32.data(), (size_t)(nreads + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->pk_off.p, pkoff.data(), (size_t)(nreads + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->pk03.p, 0, (size_t)(w + 4) * 4, ctx->stream));
+  CK(cudaMemsetAsync(ctx->pk03alt.p, 0, (size_t)(w + 4) * 4, ctx->stream));
+  // hit regions are per chunk
+  uint64_t max_chunk_nt = 0;
+  for (uint32_t c0 = 0; c0 < nreads; c0 += ctx->chunk_reads) {
+    const uint32_t c1 = std::min(nreads, c0 + ctx->chunk_reads);
+    max_chunk_nt = std::max<uint64_t>(max_chunk_nt, off32[c1] - off32[c0]);
+  }
+  const uint64_t hit_entries = (uint64_t)ctx->scale * (2 * max_chunk_nt + 32ull * std::min(nreads, ctx->chunk_reads)) + 64;
+  if ((rc = ensure(ctx, ctx->hits, hit_entries * 8))) return rc;
+  // 2-bit packing + N detection
+  DevBatch b{};
+  b.nreads = nreads; b.r0 = 0; b.seq04 = (const uint8_t*)ctx->seq04.p; b.seq_off = (const uint32_t*)ctx->seq_off.p;
+  b.pk_off = (const uint32_t*)ctx->pk_off.p;
+  pack_reads_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(b, (uint32_t*)ctx->pk03.p, (uint32_t*)ctx->pk03alt.p, (uint8_t*)ctx->has_n.p);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // off32/pkoff are stack-owned
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->t_h2d = ms;
+  return SMR_OK;
+}
+
+DevBatch make_batch(smr_ctx* ctx, uint32_t c0, uint32_t n, const std::vector<uint32_t>& /*unused*/) {
+  DevBatch b{};
+  b.nreads = n; b.r0 = c0;
+  b.seq04 = (const uint8_t*)ctx->seq04.p; b.seq_off = (const uint32_t*)ctx->seq_off.p;
+  b.pk03 = (const uint32_t*)ctx->pk03.p; b.pk03alt = (const uint32_t*)ctx->pk03alt.p; b.pk_off = (const uint32_t*)ctx->pk_off.p;
+  b.has_n = (const uint8_t*)ctx->has_n.p; b.hit_scale = ctx->scale; b.hits = (uint2*)ctx->hits.p;
+  b.hit_cnt = (uint32_t*)ctx->hit_cnt.p; b.flags = (uint32_t*)ctx->flags.p; b.state = (ReadState*)ctx->state.p;
+  b.hit_db = (uint16_t*)ctx->hit_db.p; b.worklist = (uint32_t*)ctx->worklist.p;
+  b.work_n = scalars_of(ctx).work_n; b.counters = (unsigned long long*)ctx->counters.p;
+  return b;
+}
+
+// all kernels of one pass over the resident batch
+int run_impl(smr_ctx* ctx) {
+  if (!ctx->have_params) { ctx->err = "smr_set_params not called"; return SMR_ERR_ARG; }
+  if (ctx->parts.empty()) { ctx->err = "no index loaded"; return SMR_ERR_ARG; }
+  if (ctx->prm.num_alignments <= 0) { ctx->err = "num_alignments == 0 (report all alignments) is not supported"; return SMR_ERR_UNSUPPORTED; }
+  if (ctx->prm.minoccur != 0) { ctx->err = "minoccur != 0 is not supported"; return SMR_ERR_UNSUPPORTED; }
+  ctx->t_seed = ctx->t_lis = ctx->t_final = ctx->t_total = 0; ctx->n_launch = 0;
+  const uint32_t nreads = ctx->nreads;
+  if (nreads == 0) return SMR_OK;
+  const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
+  int rc;
+  if ((rc = setup_arenas(ctx))) return rc;
+  // device copy of the part table (finalize looks parts up by slot)
+  std::vector<DevIndex> hp;
+  for (size_t i = 0; i < ctx->parts.size(); ++i) {
+    DevIndex d = ctx->parts[i].d; d.slot = (uint32_t)i; d.is_last = (i + 1 == ctx->parts.size()) ? 1u : 0u;
+    hp.push_back(d);
+  }
+  if ((rc = ensure(ctx, ctx->parts_dev, hp.size() * sizeof(DevIndex)))) return rc;
+  CK(cudaMemcpyAsync(ctx->parts_dev.p, hp.data(), hp.size() * sizeof(DevIndex), cudaMemcpyHostToDevice, ctx->stream));
+  // cigar pool on the device: generous fixed share per alignment slot
+  ctx->cigar_cap_dev = (uint64_t)nreads * slots * 24 * ctx->scale + 4096;
+  if ((rc = ensure(ctx, ctx->cigar_pool, ctx->cigar_cap_dev * 4))) return rc;
+  const Scalars sc = scalars_of(ctx);
+  CK(cudaMemsetAsync(ctx->scalars.p, 0, 64, ctx->stream));
+  CK(cudaMemsetAsync(ctx->counters.p, 0, (size_t)(dcCount + 64) * 8, ctx->stream));
+  CK(cudaMemsetAsync(ctx->state.p, 0, (size_t)nreads * sizeof(ReadState), ctx->stream));
+  CK(cudaMemsetAsync(ctx->flags.p, 0, (size_t)nreads * 4, ctx->stream));
+  CK(cudaMemsetAsync(ctx->hit_db.p, 0xFF, (size_t)nreads * 2, ctx->stream));
+  const DevParams dp = to_dev(ctx->prm);
+  size_t evi = 2;
+  std::vector<std::pair<size_t, int>> spans;   // (event index of start, kind) ; end = start+1
+  cudaEvent_t eb = get_event(ctx, evi++); CK(cudaEventRecord(eb, ctx->stream));
+  for (uint32_t c0 = 0; c0 < nreads; c0 += ctx->chunk_reads) {
+    const uint32_t n = std::min(ctx->chunk_reads, nreads - c0);
+    DevBatch b = make_batch(ctx, c0, n, {});
+    b.seq_base0 = ctx->off32[c0];
+    for (size_t pi = 0; pi < hp.size(); ++pi) {
+      CK(cudaMemsetAsync(sc.work_n, 0, 8, ctx->stream));   // work_n + lis_next
+      cudaEvent_t s0 = get_event(ctx, evi), s1 = get_event(ctx, evi + 1), s2 = get_event(ctx, evi + 2); evi += 3;
+      CK(cudaEventRecord(s0, ctx->stream));
+      const int seed_ctas = ctx->sm_count * 8;
+      if (ctx->scale == 1) {
+        if (ctx->instr) seed_kernel<true><<<seed_ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, nullptr, 0);
+        else seed_kernel<false><<<seed_ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, nullptr, 0);
+      } else {
+        const int ctas = (int)(ctx->lane_hits_warps / kSeedWarpsPerCta);
+        seed_kernel<true><<<ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, (uint32_t*)ctx->lane_hits.p, ctx->lane_hits_cap);
+      }
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(s1, ctx->stream));
+      LisGlobals lg{};
+      lg.arena_base = (uint8_t*)ctx->lis_arena.p; lg.arena_stride = ctx->lis_stride;
+      lg.hist_cap = ctx->hist_cap; lg.cand_cap = ctx->cand_cap; lg.pair_cap = ctx->pair_cap; lg.row_cap = ctx->row_cap;
+      lg.epochs = (uint32_t*)ctx->lis_epochs.p; lg.aln_work = (AlnWork*)ctx->aln_work.p; lg.slots = slots; lg.work_next = sc.lis_next;
+      lis_kernel<<<ctx->lis_warps / kLisWarpsPerCta, kLisWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, lg);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(s2, ctx->stream));
+      spans.push_back({evi - 3, 0});
+      ctx->n_launch += 2;
+    }
+    // finalize this chunk
+    CK(cudaMemsetAsync(sc.fin_next, 0, 4, ctx->stream));
+    cudaEvent_t f0 = get_event(ctx, evi), f1 = get_event(ctx, evi + 1); evi += 2;
+    CK(cudaEventRecord(f0, ctx->stream));
+    FinalGlobals fg{};
+    fg.arena_base = (uint8_t*)ctx->final_arena.p; fg.arena_stride = ctx->final_stride;
+    fg.cap_w = ctx->cap_w; fg.cap_cig = ctx->cap_cig; fg.row_cap = ctx->row_cap; fg.cap_dir = ctx->cap_dir;
+    fg.parts = (const DevIndex*)ctx->parts_dev.p; fg.aln_work = (const AlnWork*)ctx->aln_work.p; fg.out = (OutAln*)ctx->out_aln.p;
+    fg.slots = slots; fg.cigar_pool = (uint32_t*)ctx->cigar_pool.p; fg.cigar_cap = ctx->cigar_cap_dev; fg.cigar_used = sc.cigar_used;
+    fg.work_next = sc.fin_next;
+    finalize_kernel<<<ctx->final_warps / kFinalWarpsPerCta, kFinalWarpsPerCta * 32, 0, ctx->stream>>>(b, dp, fg);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(f1, ctx->stream));
+    spans.push_back({evi - 2, 1});
+    ctx->n_launch += 1;
+  }
+  cudaEvent_t ee = get_event(ctx, evi++); CK(cudaEventRecord(ee, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, eb, ee); ctx->t_total = ms;
+  for (auto& s : spans) {
+    if (s.second == 0) {
+      cudaEventElapsedTime(&ms, ctx->ev[s.first], ctx->ev[s.first + 1]); ctx->t_seed += ms;
+      cudaEventElapsedTime(&ms, ctx->ev[s.first + 1], ctx->ev[s.first + 2]); ctx->t_lis += ms;
+    } else { cudaEventElapsedTime(&ms, ctx->ev[s.first], ctx->ev[s.first + 1]); ctx->t_final += ms; }
+  }
+  return SMR_OK;
+}
+
+struct HostOut {
+  smr_read_result* results; smr_aln* alns; uint32_t* cigar_pool; uint64_t cigar_cap; uint64_t cigar_used;
+  uint64_t* counters; uint32_t n_counters;
+};
+
+// copies results of the resident batch to the host; returns the indices of reads whose scratch overflowed
+int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, const uint32_t* map /*local->caller index or null*/) {
+  const uint32_t n = ctx->nreads;
+  flagged.clear();
+  if (n == 0) return SMR_OK;
+  const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
+  cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1);
+  CK(cudaEventRecord(e0, ctx->stream));
+  std::vector<ReadState> st(n); std::vector<uint32_t> fl(n); std::vector<uint16_t> hdb(n);
+  std::vector<OutAln> oa((size_t)n * slots);
+  unsigned long long used = 0;
+  std::vector<unsigned long long> cnt(dcCount + 64);
+  CK(cudaMemcpyAsync(st.data(), ctx->state.p, (size_t)n * sizeof(ReadState), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(fl.data(), ctx->flags.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(hdb.data(), ctx->hit_db.p, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(oa.data(), ctx->out_aln.p, (size_t)n * slots * sizeof(OutAln), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&used, scalars_of(ctx).cigar_used, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(cnt.data(), ctx->counters.p, cnt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  used = std::min<unsigned long long>(used, ctx->cigar_cap_dev);
+  std::vector<uint32_t> cig(used);
+  if (used) CK(cudaMemcpy(cig.data(), ctx->cigar_pool.p, used * 4, cudaMemcpyDeviceToHost));
+  CK(cudaEventRecord(e1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->t_d2h = ms;
+  int rc = SMR_OK;
+  for (uint32_t r = 0; r < n; ++r) {
+    const uint32_t dst = map ? map[r] : r;
+    if (fl[r] & kErrTrace) { ctx->err = "trace back error (ssw.c:707 is fatal in the reference too)"; rc = SMR_ERR_INDEX; }
+    if (fl[r]) { flagged.push_back(r); continue; }
+    smr_read_result& o = out.results[dst];
+    const ReadState& s = st[r];
+    o.lastIndex = s.lastIndex; o.lastPart = s.lastPart; o.hit_seeds = s.hit_seeds; o.min_index = s.min_index; o.max_index = s.max_index;
+    o.n_align = s.n_align; o.max_SW_count = s.max_SW_count; o.is_done = s.is_done; o.is_hit = s.is_hit;
+    for (uint32_t k = 0; k < slots; ++k) {
+      smr_aln& a = out.alns[(size_t)dst * slots + k];
+      memset(&a, 0, sizeof(a));
+      if (k >= s.n_align) continue;
+      const OutAln& d = oa[(size_t)r * slots + k];
+      if (out.cigar_used + d.cigar_len > out.cigar_cap) { ctx->err = "cigar pool too small"; return SMR_ERR_CAPACITY; }
+      memcpy(out.cigar_pool + out.cigar_used, cig.data() + d.cigar_off, (size_t)d.cigar_len * 4);
+      a.cigar_off = (uint32_t)out.cigar_used; a.cigar_len = d.cigar_len; out.cigar_used += d.cigar_len;
+      a.ref_num = d.ref_num; a.ref_begin1 = d.ref_begin1; a.ref_end1 = d.ref_end1; a.read_begin1 = d.read_begin1; a.read_end1 = d.read_end1;
+      a.readlen = d.readlen; a.score1 = d.score1; a.part = d.part; a.index_num = d.index_num; a.strand = d.strand;
+    }
+    if (s.is_hit && out.counters) {
+      if (out.n_counters > SMR_CNT_NUM_ALIGNED) out.counters[SMR_CNT_NUM_ALIGNED]++;
+      const uint32_t ci = SMR_CNT_FIXED + hdb[r];
+      if (hdb[r] != 0xFFFF && ci < out.n_counters) out.counters[ci]++;
+    }
+  }
+  if (out.counters) {
+    static const int mapc[][2] = {{SMR_CNT_NUM_SHORT, dcNumShort}, {SMR_CNT_SW_CALLS, dcSwCalls}, {SMR_CNT_SW_CELLS, dcSwCells},
+                                  {SMR_CNT_WINDOWS, dcWindows}, {SMR_CNT_TRIE_NODES, dcNodes}, {SMR_CNT_BUCKETS, dcBuckets},
+                                  {SMR_CNT_BUCKET_ENTRIES, dcEntries}, {SMR_CNT_POS_ENTRIES, dcPosEntries}, {SMR_CNT_LIS_CALLS, dcLisCalls}};
+    for (auto& m : mapc) if ((uint32_t)m[0] < out.n_counters) out.counters[m[0]] += cnt[m[1]];
+  }
+  return rc;
+}
+
+// align a host batch, retrying reads whose scratch overflowed with a larger scale
+int align_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads, HostOut& out, const uint32_t* map, int depth) {
+  int rc = upload_batch_impl(ctx, seq_cat, seq_off, nreads, false);
+  if (rc) return rc;
+  const double h2d = ctx->t_h2d;
+  if ((rc = run_impl(ctx))) return rc;
+  std::vector<uint32_t> flagged;
+  if ((rc = download_impl(ctx, out, flagged, map))) return rc;
+  ctx->t_h2d = h2d;
+  if (flagged.empty()) return SMR_OK;
+  if (depth >= 3) { ctx->err = "scratch overflow persists after 3 retries (" + std::to_string(flagged.size()) + " reads)"; return SMR_ERR_CAPACITY; }
+  // sub-batch of the flagged reads, 8x the scratch
+  std::vector<uint8_t> sseq; std::vector<uint64_t> soff(1, 0); std::vector<uint32_t> smap;
+  for (uint32_t r : flagged) {
+    sseq.insert(sseq.end(), seq_cat + seq_off[r], seq_cat + seq_off[r + 1]);
+    soff.push_back(sseq.size());
+    smap.push_back(map ? map[r] : r);
+  }
+  const uint32_t old_scale = ctx->scale;
+  const double tt = ctx->t_total, ts = ctx->t_seed, tl = ctx->t_lis, tf = ctx->t_final, td = ctx->t_d2h; const uint64_t nl = ctx->n_launch;
+  ctx->scale = old_scale * 8;
+  rc = align_impl(ctx, sseq.data(), soff.data(), (uint32_t)flagged.size(), out, smap.data(), depth + 1);
+  ctx->scale = old_scale;
+  ctx->t_total += tt; ctx->t_seed += ts; ctx->t_lis += tl; ctx->t_final += tf; ctx->t_d2h += td; ctx->t_h2d += h2d; ctx->n_launch += nl;
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int smr_init(int device, smr_ctx** out) {
+  if (!out) return SMR_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return SMR_ERR_NO_DEVICE;
+  smr_ctx* ctx = new smr_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return SMR_ERR_NO_DEVICE; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return SMR_ERR_NO_DEVICE; }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SMR_ERR_CUDA; }
+  *out = ctx;
+  return SMR_OK;
+}
+
+void smr_destroy(smr_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto& pt : ctx->parts) for (void* p : pt.owned) cudaFree(p);
+  DevBuf* bufs[] = {&ctx->seq04, &ctx->seq_off, &ctx->pk03, &ctx->pk03alt, &ctx->pk_off, &ctx->has_n, &ctx->hit_cnt, &ctx->flags, &ctx->state,
+                    &ctx->hit_db, &ctx->aln_work, &ctx->out_aln, &ctx->hits, &ctx->worklist, &ctx->scalars, &ctx->counters, &ctx->cigar_pool,
+                    &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->final_arena, &ctx->lane_hits};
+  for (DevBuf* b : bufs) release(*b);
+  for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* smr_last_error(const smr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int smr_load_index_part(smr_ctx* ctx, uint32_t index_num, uint32_t part, const void* kmer_file, size_t kmer_bytes,
+                        const void* bursttrie_file, size_t bursttrie_bytes, const void* pos_file, size_t pos_bytes,
+                        const uint8_t* refseq_cat, const uint64_t* ref_off, uint32_t nref, uint32_t lnwin, uint32_t minimal_score,
+                        const uint32_t skiplengths[3]) {
+  if (!ctx || !kmer_file || !bursttrie_file || !pos_file || !refseq_cat || !ref_off || !skiplengths) return SMR_ERR_ARG;
+  if (skiplengths[0] == 0 || skiplengths[1] == 0 || skiplengths[2] == 0) { ctx->err = "skiplengths must be positive"; return SMR_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  FlatIndex fx;
+  std::string e = flatten_index(kmer_file, kmer_bytes, bursttrie_file, bursttrie_bytes, pos_file, pos_bytes, lnwin, fx);
+  if (!e.empty()) { ctx->err = e; return SMR_ERR_INDEX; }
+  const uint64_t ref_total = ref_off[nref] - ref_off[0];
+  if (ref_total >= 0xFFFFFFFFull) { ctx->err = "reference part larger than 4 GB"; return SMR_ERR_UNSUPPORTED; }
+  for (const auto& sp : fx.pos) if (sp.seq >= nref) { ctx->err = "position table names a sequence beyond the references"; return SMR_ERR_INDEX; }
+  Part pt;
+  pt.d.index_num = index_num; pt.d.part = part; pt.d.lnwin = lnwin; pt.d.partialwin = lnwin / 2; pt.d.minimal_score = minimal_score;
+  for (int i = 0; i < 3; ++i) pt.d.skip[i] = skiplengths[i];
+  pt.d.nref = nref; pt.d.nids = (uint32_t)(fx.pos_off.size() - 1);
+  std::vector<uint32_t> roff(nref + 1);
+  for (uint32_t i = 0; i <= nref; ++i) roff[i] = (uint32_t)(ref_off[i] - ref_off[0]);
+  std::vector<uint8_t> rseq(refseq_cat + ref_off[0], refseq_cat + ref_off[nref]);
+  rseq.resize(rseq.size() + 64, 4);
+  int rc;
+  const uint32_t* lk = nullptr; const FlatNode* nd = nullptr; const Entry* en = nullptr; const uint32_t* po = nullptr; const SeqPos* ps = nullptr;
+  const uint8_t* rs = nullptr; const uint32_t* ro = nullptr;
+  if ((rc = upload_vec(ctx, pt, fx.lookup, &lk))) return rc;
+  if ((rc = upload_vec(ctx, pt, fx.nodes, &nd))) return rc;
+  if ((rc = upload_vec(ctx, pt, fx.entries, &en))) return rc;
+  if ((rc = upload_vec(ctx, pt, fx.pos_off, &po))) return rc;
+  if ((rc = upload_vec(ctx, pt, fx.pos, &ps))) return rc;
+  if ((rc = upload_vec(ctx, pt, rseq, &rs))) return rc;
+  if ((rc = upload_vec(ctx, pt, roff, &ro))) return rc;
+  pt.d.lookup = (const uint2*)lk; pt.d.nodes = (const uint4*)nd; pt.d.entries = (const uint2*)en; pt.d.pos_off = po; pt.d.pos = (const uint2*)ps;
+  pt.d.refseq = rs; pt.d.ref_off = ro;
+  pt.n_nodes = fx.nodes.size(); pt.n_entries = fx.entries.size(); pt.n_ids = pt.d.nids; pt.n_pos = fx.pos.size();
+  ctx->parts.push_back(std::move(pt));
+  ctx->n_index_files = std::max(ctx->n_index_files, index_num + 1);
+  return SMR_OK;
+}
+
+int smr_set_minimal_score(smr_ctx* ctx, uint32_t index_num, uint32_t minimal_score) {
+  if (!ctx) return SMR_ERR_ARG;
+  bool any = false;
+  for (auto& pt : ctx->parts) if (pt.d.index_num == index_num) { pt.d.minimal_score = minimal_score; any = true; }
+  if (!any) { ctx->err = "no such index"; return SMR_ERR_ARG; }
+  return SMR_OK;
+}
+
+int smr_set_params(smr_ctx* ctx, const smr_params* p) {
+  if (!ctx || !p) return SMR_ERR_ARG;
+  if (p->match < -128 || p->match > 127 || p->gap_open < 0 || p->gap_ext < 0) { ctx->err = "scores out of range"; return SMR_ERR_ARG; }
+  ctx->prm = *p; ctx->have_params = true;
+  return SMR_OK;
+}
+
+int smr_index_info(const smr_ctx* ctx, uint64_t out[6]) {
+  if (!ctx || !out) return SMR_ERR_ARG;
+  memset(out, 0, 6 * sizeof(uint64_t));
+  out[0] = ctx->parts.size();
+  for (auto& pt : ctx->parts) { out[1] += pt.bytes; out[2] += pt.n_nodes; out[3] += pt.n_entries; out[4] += pt.n_ids; out[5] += pt.n_pos; }
+  return SMR_OK;
+}
+
+int smr_align_batch(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads, smr_read_result* results, smr_aln* alns,
+                    uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used, uint64_t* counters, uint32_t n_counters) {
+  if (!ctx || !seq_cat || !seq_off || !results || !alns || (!cigar_pool && cigar_cap)) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
+  memset(results, 0, (size_t)nreads * sizeof(smr_read_result));
+  memset(alns, 0, (size_t)nreads * slots * sizeof(smr_aln));
+  HostOut out{results, alns, cigar_pool, cigar_cap, 0, counters, n_counters};
+  ctx->scale = 1;
+  int rc = align_impl(ctx, seq_cat, seq_off, nreads, out, nullptr, 0);
+  if (cigar_used) *cigar_used = out.cigar_used;
+  return rc;
+}
+
+int smr_upload_batch(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads) {
+  if (!ctx || !seq_cat || !seq_off) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ctx->scale = 1;
+  return upload_batch_impl(ctx, seq_cat, seq_off, nreads, true);
+}
+
+int smr_run_resident(smr_ctx* ctx) {
+  if (!ctx) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  return run_impl(ctx);
+}
+
+int smr_download_results(smr_ctx* ctx, smr_read_result* results, smr_aln* alns, uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used,
+                         uint64_t* counters, uint32_t n_counters) {
+  if (!ctx || !results || !alns) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
+  const uint32_t n = ctx->nreads;
+  memset(results, 0, (size_t)n * sizeof(smr_read_result));
+  memset(alns, 0, (size_t)n * slots * sizeof(smr_aln));
+  HostOut out{results, alns, cigar_pool, cigar_cap, 0, counters, n_counters};
+  std::vector<uint32_t> flagged;
+  int rc = download_impl(ctx, out, flagged, nullptr);
+  if (rc == SMR_OK && !flagged.empty()) {
+    // redo the overflowed reads from the retained host copy with larger scratch
+    std::vector<uint8_t> hs; std::vector<uint64_t> ho;
+    hs.swap(ctx->h_seq); ho.swap(ctx->h_off);
+    std::vector<uint8_t> sseq; std::vector<uint64_t> soff(1, 0);
+    for (uint32_t r : flagged) { sseq.insert(sseq.end(), hs.begin() + ho[r], hs.begin() + ho[r + 1]); soff.push_back(sseq.size()); }
+    const uint32_t keep_n = ctx->nreads;
+    ctx->scale = 8;
+    rc = align_impl(ctx, sseq.data(), soff.data(), (uint32_t)flagged.size(), out, flagged.data(), 1);
+    ctx->scale = 1;
+    (void)keep_n;   // the resident batch was replaced by the retry batch: upload again before the next smr_run_resident
+    ctx->nreads = 0;
+  }
+  if (cigar_used) *cigar_used = out.cigar_used;
+  return rc;
+}
+
+int smr_last_timings(const smr_ctx* ctx, double out[8]) {
+  if (!ctx || !out) return SMR_ERR_ARG;
+  out[0] = ctx->t_total; out[1] = ctx->t_seed; out[2] = ctx->t_lis; out[3] = ctx->t_final; out[4] = ctx->t_h2d; out[5] = ctx->t_d2h;
+  out[6] = (double)ctx->n_launch; out[7] = 0;
+  return SMR_OK;
+}
+
+int smr_debug_seed_windows(smr_ctx* ctx, uint32_t part_slot, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads,
+                           const uint32_t* win_read, const uint32_t* win_pos, uint32_t nwin, uint32_t* ids, uint32_t cap, uint32_t* counts,
+                           uint8_t* zero) {
+  if (!ctx || part_slot >= ctx->parts.size() || !seq_cat || !seq_off || !win_read || !win_pos || !ids || !counts || !zero) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t total = seq_off[nreads] - seq_off[0];
+  std::vector<uint32_t> off32(nreads + 1);
+  for (uint32_t r = 0; r <= nreads; ++r) off32[r] = (uint32_t)(seq_off[r] - seq_off[0]);
+  uint8_t *d_seq = nullptr, *d_zero = nullptr; uint32_t *d_off = nullptr, *d_wr = nullptr, *d_wp = nullptr, *d_ids = nullptr, *d_cnt = nullptr;
+  CK(cudaMalloc(&d_seq, total + 64)); CK(cudaMalloc(&d_off, (size_t)(nreads + 1) * 4)); CK(cudaMalloc(&d_wr, (size_t)nwin * 4 + 4));
+  CK(cudaMalloc(&d_wp, (size_t)nwin * 4 + 4)); CK(cudaMalloc(&d_ids, (size_t)nwin * cap * 4 + 4)); CK(cudaMalloc(&d_cnt, (size_t)nwin * 4 + 4));
+  CK(cudaMalloc(&d_zero, nwin + 4));
+  CK(cudaMemcpy(d_seq, seq_cat + seq_off[0], total, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_off, off32.data(), (size_t)(nreads + 1) * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_wr, win_read, (size_t)nwin * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_wp, win_pos, (size_t)nwin * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(d_ids, 0, (size_t)nwin * cap * 4));
+  DevIndex d = ctx->parts[part_slot].d;
+  seed_debug_kernel<<<(nwin + 127) / 128, 128, 0, ctx->stream>>>(d, d_seq, d_off, d_wr, d_wp, nwin, d_ids, cap, d_cnt, d_zero,
+                                                                 ctx->have_params ? ctx->prm.is_full_search : 0);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(ids, d_ids, (size_t)nwin * cap * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(counts, d_cnt, (size_t)nwin * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(zero, d_zero, nwin, cudaMemcpyDeviceToHost));
+  cudaFree(d_seq); cudaFree(d_off); cudaFree(d_wr); cudaFree(d_wp); cudaFree(d_ids); cudaFree(d_cnt); cudaFree(d_zero);
+  return SMR_OK;
+}
+
+int smr_debug_ssw(smr_ctx* ctx, const uint8_t* q_cat, const uint64_t* q_off, const uint8_t* t_cat, const uint64_t* t_off, uint32_t npairs,
+                  uint32_t filters, int32_t* out, uint32_t* cigars, uint32_t cigar_cap) {
+  if (!ctx || !q_cat || !q_off || !t_cat || !t_off || !out || !cigars || !ctx->have_params) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t qt = q_off[npairs] - q_off[0], tt = t_off[npairs] - t_off[0];
+  std::vector<uint32_t> qo(npairs + 1), to(npairs + 1);
+  uint32_t maxlen = 0;
+  for (uint32_t i = 0; i <= npairs; ++i) { qo[i] = (uint32_t)(q_off[i] - q_off[0]); to[i] = (uint32_t)(t_off[i] - t_off[0]); }
+  for (uint32_t i = 0; i < npairs; ++i) maxlen = std::max(maxlen, std::max(qo[i + 1] - qo[i], to[i + 1] - to[i]));
+  uint8_t *dq = nullptr, *dt = nullptr, *arena = nullptr; uint32_t *dqo = nullptr, *dto = nullptr, *dc = nullptr; int32_t* dout = nullptr;
+  FinalGlobals g{};
+  g.cap_w = 2 * 2048 + 8; g.cap_cig = 2 * (maxlen + 64) + 16; g.row_cap = maxlen + 128; g.cap_dir = (size_t)(2 * 64 + 1) * (maxlen + 8) * 3 + 65536;
+  const uint32_t nwarps = 512;
+  g.arena_stride = final_arena_bytes(g.cap_w, g.cap_cig, g.row_cap, g.cap_dir);
+  CK(cudaMalloc(&arena, g.arena_stride * nwarps)); g.arena_base = arena;
+  CK(cudaMalloc(&dq, qt + 64)); CK(cudaMalloc(&dt, tt + 64)); CK(cudaMalloc(&dqo, (size_t)(npairs + 1) * 4)); CK(cudaMalloc(&dto, (size_t)(npairs + 1) * 4));
+  CK(cudaMalloc(&dc, (size_t)npairs * cigar_cap * 4 + 4)); CK(cudaMalloc(&dout, (size_t)npairs * 6 * 4 + 4));
+  CK(cudaMemcpy(dq, q_cat + q_off[0], qt, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dt, t_cat + t_off[0], tt, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dqo, qo.data(), (size_t)(npairs + 1) * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dto, to.data(), (size_t)(npairs + 1) * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dc, 0, (size_t)npairs * cigar_cap * 4));
+  ssw_debug_kernel<<<nwarps / kFinalWarpsPerCta, kFinalWarpsPerCta * 32, 0, ctx->stream>>>(dq, dqo, dt, dto, npairs, filters, to_dev(ctx->prm), dout, dc,
+                                                                                           cigar_cap, g);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, dout, (size_t)npairs * 6 * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cigars, dc, (size_t)npairs * cigar_cap * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dq); cudaFree(dt); cudaFree(dqo); cudaFree(dto); cudaFree(dc); cudaFree(dout); cudaFree(arena);
+  return SMR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+// Finalize: for every STORED alignment, the reverse Smith-Waterman pass (begin coordinates,
+// src/sortmerna/ssw.c:899-915) and the banded traceback (CIGAR, ssw.c:917-935 -> banded_sw :577-773),
+// then the coordinate shift of compute_lis_alignment (src/sortmerna/alignment.cpp:394-405).
+// The reference computes both for every ssw_align call that reaches the score filter (on average
+// 7-14 calls per read); they are pure functions of (query segment, reference window, score), so
+// computing them once per alignment that survives is equivalent.
+#pragma once
+#include "smr_lis.cuh"
+
+namespace smr {
+
+// layout-compatible with smr_aln (include/smr_b200.h)
+struct OutAln {
+  uint32_t cigar_off, cigar_len, ref_num;
+  int32_t ref_begin1, ref_end1, read_begin1, read_end1;
+  uint32_t readlen;
+  uint16_t score1, part, index_num;
+  uint8_t strand, pad;
+};
+
+struct FinalGlobals {
+  uint8_t* arena_base; size_t arena_stride;
+  uint32_t cap_w, cap_cig, row_cap; size_t cap_dir;
+  const DevIndex* parts;             // [nparts] device copy
+  const AlnWork* aln_work; OutAln* out; uint32_t slots;
+  uint32_t* cigar_pool; unsigned long long cigar_cap; unsigned long long* cigar_used;
+  uint32_t* work_next;
+};
+__host__ __device__ inline size_t final_arena_bytes(uint32_t cap_w, uint32_t cap_cig, uint32_t row_cap, size_t cap_dir) {
+  size_t b = (size_t)cap_w * 12 + (size_t)cap_cig * 4 + (size_t)row_cap * 8 + cap_dir;
+  return (b + 255) & ~(size_t)255;
+}
+
+constexpr int kFinalWarpsPerCta = 4;
+
+__global__ void __launch_bounds__(kFinalWarpsPerCta * 32)
+finalize_kernel(DevBatch b, DevParams prm, FinalGlobals g) {
+  const unsigned lane = lane_id();
+  const uint32_t warp = blockIdx.x * kFinalWarpsPerCta + (threadIdx.x >> 5);
+  uint8_t* p = g.arena_base + (size_t)warp * g.arena_stride;
+  TraceArena A;
+  A.cap_w = g.cap_w; A.cap_cig = g.cap_cig; A.cap_dir = g.cap_dir;
+  A.hb = (int32_t*)p; p += (size_t)g.cap_w * 4;
+  A.eb = (int32_t*)p; p += (size_t)g.cap_w * 4;
+  A.hc = (int32_t*)p; p += (size_t)g.cap_w * 4;
+  A.cig = (uint32_t*)p; p += (size_t)g.cap_cig * 4;
+  int32_t* rowH = (int32_t*)p; p += (size_t)g.row_cap * 4;
+  int32_t* rowF = (int32_t*)p; p += (size_t)g.row_cap * 4;
+  A.dir = (int8_t*)p;
+  const SwScore sc{prm.match, prm.mismatch, prm.score_N, prm.gap_open, prm.gap_ext};
+  const uint32_t total = b.nreads * g.slots;
+  for (;;) {
+    uint32_t wi = 0;
+    if (lane == 0) wi = atomicAdd(g.work_next, 1u);
+    wi = __shfl_sync(kFull, wi, 0);
+    if (wi >= total) break;
+    const uint32_t r = b.r0 + wi / g.slots, k = wi % g.slots;
+    if (k >= b.state[r].n_align || b.flags[r]) continue;
+    const AlnWork a = g.aln_work[(size_t)r * g.slots + k];
+    const DevIndex& ix = g.parts[a.idx_slot];
+    const uint32_t seq_base = b.seq_off[r], len = b.seq_off[r + 1] - seq_base;
+    SeqView q = a.strand ? SeqView{b.seq04 + seq_base, (int32_t)a.q_start, 1, false}
+                         : SeqView{b.seq04 + seq_base, (int32_t)(len - 1 - a.q_start), -1, true};
+    const SeqView t{ix.refseq + ix.ref_off[a.ref_num], (int32_t)a.win_ref_start, 1, false};
+    // reverse pass over the prefixes that end at the forward optimum (ssw.c:899-915)
+    const SwEnd rev = sw_forward(q.reversed_prefix(a.read_end), a.read_end + 1, t.reversed_prefix(a.ref_end), a.ref_end + 1, sc, rowH, rowF);
+    const int32_t ref_begin = a.ref_end - rev.ref, read_begin = a.read_end - rev.read;
+    const int32_t rl = a.ref_end - ref_begin + 1, ql = a.read_end - read_begin + 1;
+    const int32_t band = (rl > ql ? rl - ql : ql - rl) + 1;                                  // ssw.c:924
+    for (uint32_t i = lane; i < g.cap_w; i += 32) { A.hb[i] = 0; A.eb[i] = 0; A.hc[i] = 0; }
+    __syncwarp();
+    int32_t nc = 0;
+    if (lane == 0) nc = banded_traceback_lane(t.sub(ref_begin), q.sub(read_begin), rl, ql, (int32_t)a.score1, sc, band, A);
+    nc = __shfl_sync(kFull, nc, 0);
+    __syncwarp();
+    if (nc < 0) { if (lane == 0) atomicOr(&b.flags[r], nc == -1 ? kOvfTrace : kErrTrace); continue; }
+    unsigned long long off = 0;
+    if (lane == 0) off = atomicAdd(g.cigar_used, (unsigned long long)nc);
+    off = __shfl_sync(kFull, off, 0);
+    if (off + (unsigned long long)nc > g.cigar_cap) { if (lane == 0) atomicOr(&b.flags[r], kOvfCigar); continue; }
+    for (int32_t i = lane; i < nc; i += 32) g.cigar_pool[off + i] = A.cig[nc - 1 - i];        // ssw.c:750-758 (reverse)
+    if (lane == 0) {
+      OutAln o;
+      o.cigar_off = (uint32_t)off; o.cigar_len = (uint32_t)nc; o.ref_num = a.ref_num;
+      o.ref_begin1 = ref_begin + (int32_t)a.win_ref_start; o.ref_end1 = a.ref_end + (int32_t)a.win_ref_start;   // alignment.cpp:396-399
+      o.read_begin1 = read_begin + (int32_t)a.q_start; o.read_end1 = a.read_end + (int32_t)a.q_start;
+      o.readlen = len; o.score1 = a.score1; o.part = a.part; o.index_num = a.index_num; o.strand = a.strand; o.pad = 0;
+      g.out[(size_t)r * g.slots + k] = o;
+    }
+    __syncwarp();
+  }
+}
+
+// unit-test kernel: full ssw_align(flag=2) equivalent on explicit pairs, one warp per pair (smr_debug_ssw)
+__global__ void __launch_bounds__(kFinalWarpsPerCta * 32)
+ssw_debug_kernel(const uint8_t* qcat, const uint32_t* qoff, const uint8_t* tcat, const uint32_t* toff, uint32_t npairs, uint32_t filters,
+                 DevParams prm, int32_t* out, uint32_t* cigars, uint32_t cigar_cap, FinalGlobals g) {
+  const unsigned lane = lane_id();
+  const uint32_t warp = blockIdx.x * kFinalWarpsPerCta + (threadIdx.x >> 5), nwarps = gridDim.x * kFinalWarpsPerCta;
+  uint8_t* p = g.arena_base + (size_t)warp * g.arena_stride;
+  TraceArena A;
+  A.cap_w = g.cap_w; A.cap_cig = g.cap_cig; A.cap_dir = g.cap_dir;
+  A.hb = (int32_t*)p; p += (size_t)g.cap_w * 4;
+  A.eb = (int32_t*)p; p += (size_t)g.cap_w * 4;
+  A.hc = (int32_t*)p; p += (size_t)g.cap_w * 4;
+  A.cig = (uint32_t*)p; p += (size_t)g.cap_cig * 4;
+  int32_t* rowH = (int32_t*)p; p += (size_t)g.row_cap * 4;
+  int32_t* rowF = (int32_t*)p; p += (size_t)g.row_cap * 4;
+  A.dir = (int8_t*)p;
+  const SwScore sc{prm.match, prm.mismatch, prm.score_N, prm.gap_open, prm.gap_ext};
+  for (uint32_t k = warp; k < npairs; k += nwarps) {
+    const int32_t m = (int32_t)(qoff[k + 1] - qoff[k]), n = (int32_t)(toff[k + 1] - toff[k]);
+    const SeqView q{qcat + qoff[k], 0, 1, false}, t{tcat + toff[k], 0, 1, false};
+    int32_t* o = out + (size_t)k * 6;
+    const SwEnd f = sw_forward(q, m, t, n, sc, rowH, rowF);
+    int32_t rb = -1, qb = -1, nc = 0;
+    if ((uint32_t)(f.score & 0xFFFF) >= filters && f.score > 0) {
+      const SwEnd rev = sw_forward(q.reversed_prefix(f.read), f.read + 1, t.reversed_prefix(f.ref), f.ref + 1, sc, rowH, rowF);
+      rb = f.ref - rev.ref; qb = f.read - rev.read;
+      const int32_t rl = f.ref - rb + 1, ql = f.read - qb + 1;
+      for (uint32_t i = lane; i < g.cap_w; i += 32) { A.hb[i] = 0; A.eb[i] = 0; A.hc[i] = 0; }
+      __syncwarp();
+      if (lane == 0) nc = banded_traceback_lane(t.sub(rb), q.sub(qb), rl, ql, f.score, sc, (rl > ql ? rl - ql : ql - rl) + 1, A);
+      nc = __shfl_sync(kFull, nc, 0);
+      __syncwarp();
+      for (int32_t i = lane; i < nc && i < (int32_t)cigar_cap; i += 32) cigars[(size_t)k * cigar_cap + i] = A.cig[nc - 1 - i];
+    }
+    if (lane == 0) { o[0] = f.score; o[1] = rb; o[2] = f.ref; o[3] = qb; o[4] = f.read; o[5] = nc; }
+    __syncwarp();
+  }
+}
+
+}  // namespace smr

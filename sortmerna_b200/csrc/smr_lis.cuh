@@ -1,0 +1,438 @@
+// Candidate voting, LIS, region selection, Smith-Waterman and the accept / replace / stop state
+// machine: one warp per read, executing the reference's SEQUENTIAL decision order for that read.
+//
+// Stands in for the pass loop of traverse() (src/sortmerna/paralleltraversal.cpp:114-297),
+// compute_lis_alignment() + find_lis() (src/sortmerna/alignment.cpp:58-509) and the per-read body of
+// align2() (src/sortmerna/processor.cpp:104-162) for one (index, part).
+//
+// The seed kernel has already produced, per read, the id hits of every window of every pass; this
+// kernel replays pass 1 / 2 / 3 on them.  Differences in mechanism (not in results):
+//   * votes per reference are counted in a warp-private histogram in HBM (epoch-tagged, so it is never
+//     cleared) instead of a std::map (alignment.cpp:118-130); the candidate list is sorted by
+//     (count desc, ref asc) with a warp bitonic sort (:143-148);
+//   * a candidate's (refpos, readpos) pairs are gathered by binary search in the per-id position
+//     lists, which the flattener keeps sorted by (seq,pos), instead of rescanning every list (:181-194);
+//   * the deque `match_set` is a [front, next) index range over the sorted pairs (:205-238, 486-506);
+//   * ssw_align's reverse pass and CIGAR are deferred to the finalize kernel: accept / replace / stop
+//     decisions only need score1 (:388-469).
+#pragma once
+#include "smr_seed.cuh"
+#include "smr_sw.cuh"
+
+namespace smr {
+
+constexpr int kLisWarpsPerCta = 4;
+constexpr int kPairsShared = 128;  // pairs / LIS arrays kept in shared memory up to this many
+
+struct LisArena {            // per-warp scratch in HBM
+  uint32_t* hist;            // [hist_cap] epoch<<20 | count, indexed by reference number
+  unsigned long long* cand;  // [cand_cap] (power of two)
+  unsigned long long* pairs; // [pair_cap] (power of two) refpos<<32 | readpos
+  uint32_t* lis_b; uint32_t* lis_p;  // [pair_cap]
+  int32_t* rowH; int32_t* rowF;      // [row_cap]
+  uint32_t hist_cap, cand_cap, pair_cap, row_cap;
+};
+
+struct LisGlobals {
+  uint8_t* arena_base; size_t arena_stride;   // per-warp arena
+  uint32_t hist_cap, cand_cap, pair_cap, row_cap;
+  uint32_t* epochs;                            // [total warps]
+  AlnWork* aln_work;                           // [nreads * slots]
+  uint32_t slots;
+  uint32_t* work_next;                         // [1] persistent-loop cursor
+};
+
+__device__ __forceinline__ LisArena carve_arena(const LisGlobals& g, uint32_t warp) {
+  LisArena a;
+  uint8_t* p = g.arena_base + (size_t)warp * g.arena_stride;
+  a.hist_cap = g.hist_cap; a.cand_cap = g.cand_cap; a.pair_cap = g.pair_cap; a.row_cap = g.row_cap;
+  a.cand = (unsigned long long*)p; p += (size_t)g.cand_cap * 8;
+  a.pairs = (unsigned long long*)p; p += (size_t)g.pair_cap * 8;
+  a.hist = (uint32_t*)p; p += (size_t)g.hist_cap * 4;
+  a.lis_b = (uint32_t*)p; p += (size_t)g.pair_cap * 4;
+  a.lis_p = (uint32_t*)p; p += (size_t)g.pair_cap * 4;
+  a.rowH = (int32_t*)p; p += (size_t)g.row_cap * 4;
+  a.rowF = (int32_t*)p;
+  return a;
+}
+__host__ __device__ inline size_t lis_arena_bytes(uint32_t hist_cap, uint32_t cand_cap, uint32_t pair_cap, uint32_t row_cap) {
+  size_t b = (size_t)cand_cap * 8 + (size_t)pair_cap * 8 + (size_t)hist_cap * 4 + (size_t)pair_cap * 8 + (size_t)row_cap * 8;
+  return (b + 255) & ~(size_t)255;
+}
+
+// ---- warp bitonic sort of 64-bit keys, ascending; n_pow2 = power of two >= n, tail padded by the caller ----
+__device__ void warp_sort_u64(unsigned long long* a, uint32_t n_pow2) {
+  const unsigned lane = lane_id();
+  for (uint32_t k = 2; k <= n_pow2; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = lane; i < n_pow2; i += 32) {
+        const uint32_t l = i ^ j;
+        if (l > i) {
+          const unsigned long long x = a[i], y = a[l];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { a[i] = y; a[l] = x; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+__device__ __forceinline__ uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+// class of a window position = the first pass whose grid contains it (paralleltraversal.cpp:118-131)
+__device__ __forceinline__ uint32_t pass_class(uint32_t p, uint32_t s0, uint32_t s1, uint32_t s2) {
+  if (p % s0 == 0) return 0;
+  if (p % s1 == 0) return 1;
+  if (p % s2 == 0) return 2;
+  return 3;
+}
+
+struct ReadCtx {           // per-read working state (uniform across the warp)
+  uint32_t r, len, seq_base;
+  bool reversed, hasn;
+  uint32_t vcls[3];        // variant in effect when pass class c was searched on the current strand
+  uint32_t pass_n;         // passes with class <= pass_n are in id_win_hits
+  // Read fields
+  uint32_t hit_seeds, min_index, max_index, n_align;
+  int32_t best;
+  uint32_t max_SW_count;
+  bool is_done, is_hit, is_new_hit;
+  bool form04;             // read currently in the 0-4 alphabet (read.is04); only meaningful when hasn
+  uint32_t flags;
+};
+
+__device__ __forceinline__ bool hit_selected(const uint2 h, const ReadCtx& rc, uint32_t s0, uint32_t s1, uint32_t s2) {
+  const uint32_t var = h.y >> 24, p = h.y & kWinMask;
+  const uint32_t c = pass_class(p, s0, s1, s2);
+  if (c > rc.pass_n) return false;
+  return var == rc.vcls[c];
+}
+
+// find_lis (alignment.cpp:58-98) over pairs[f .. f+n): returns |LIS| and the index (relative to f) of its first element
+__device__ uint32_t find_lis_dev(const unsigned long long* __restrict__ P, uint32_t n, uint32_t* b, uint32_t* p, uint32_t& first) {
+  if (n == 0) { first = 0; return 0; }
+  uint32_t nb = 1; b[0] = 0;
+  for (uint32_t i = 1; i < n; ++i) {
+    const uint32_t ai = (uint32_t)P[i];
+    if ((uint32_t)P[b[nb - 1]] < ai) { p[i] = b[nb - 1]; b[nb++] = i; continue; }
+    uint32_t u = 0, v = nb - 1;
+    while (u < v) { const uint32_t c = (u + v) >> 1; if ((uint32_t)P[b[c]] < ai) u = c + 1; else v = c; }
+    if (ai < (uint32_t)P[b[u]]) { if (u > 0) p[i] = b[u - 1]; b[u] = i; }
+  }
+  uint32_t v = b[nb - 1];
+  for (uint32_t u = nb; u-- > 1;) v = p[v];
+  first = v;
+  return nb;
+}
+
+struct PassEnv {
+  const DevIndex* ix; const DevBatch* b; const DevParams* prm; const LisGlobals* g;
+  LisArena ar; uint32_t* epoch_ptr; uint32_t epoch;
+  unsigned long long* s_pairs; uint32_t* s_b; uint32_t* s_p;   // shared-memory fast buffers (kPairsShared)
+  unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls;
+};
+
+// compute_lis_alignment (alignment.cpp:100-509).  Uniform control flow; warp-parallel inner scans.
+__device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score) {
+  const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
+  const unsigned lane = lane_id();
+  const uint32_t s0 = ix.skip[0], s1 = ix.skip[1], s2 = ix.skip[2];
+  const uint2* hits = B.hits + hit_base(B, rc.r);
+  const uint32_t nh = B.hit_cnt[rc.r];
+  const uint32_t ns = (uint32_t)max(o.num_seeds, 1);
+  E.n_lis_calls++;
+
+  // ---- 1. votes per reference (alignment.cpp:118-138) ----
+  if (++E.epoch >= 4096u) {   // epoch tag wrapped: clear the histogram once
+    for (uint32_t i = lane; i < E.ar.hist_cap; i += 32) E.ar.hist[i] = 0;
+    E.epoch = 1; __syncwarp();
+  }
+  const uint32_t ep = E.epoch;
+  uint32_t ncand = 0;
+  for (uint32_t h0 = 0; h0 < nh; h0 += 32) {
+    const uint32_t h = h0 + lane;
+    uint32_t o_l = 0, s_l = 0;
+    if (h < nh) {
+      const uint2 hv = hits[h];
+      if (hit_selected(hv, rc, s0, s1, s2)) { o_l = __ldg(ix.pos_off + hv.x); s_l = __ldg(ix.pos_off + hv.x + 1) - o_l; }
+    }
+    const uint32_t incl = warp_incl_scan_u32(s_l), tot = __shfl_sync(kFull, incl, 31), excl = incl - s_l;
+    E.n_pos_entries += tot;
+    for (uint32_t e0 = 0; e0 < tot; e0 += 32) {
+      const uint32_t e = e0 + lane;
+      const bool act = e < tot;
+      uint32_t lo = 0;                       // owner = first lane whose inclusive sum exceeds e
+#pragma unroll
+      for (int stp = 16; stp > 0; stp >>= 1) { const uint32_t v = __shfl_sync(kFull, incl, lo + stp - 1); if (v <= e) lo += stp; }
+      lo = min(lo, 31u);
+      const uint32_t o_own = __shfl_sync(kFull, o_l, lo), ex_own = __shfl_sync(kFull, excl, lo);
+      const uint32_t seq = act ? __ldg(&ix.pos[o_own + (e - ex_own)]).y : 0xFFFFFFFFu;
+      const unsigned grp = __match_any_sync(kFull, seq);
+      bool trans = false;
+      if (act && (unsigned)(__ffs(grp) - 1) == lane && seq < E.ar.hist_cap) {
+        const uint32_t old = E.ar.hist[seq];
+        const uint32_t c = (old >> 20) == ep ? (old & 0xFFFFFu) : 0u;
+        const uint32_t nn = min(c + (uint32_t)__popc(grp), 0xFFFFFu);
+        E.ar.hist[seq] = (ep << 20) | nn;
+        trans = c < ns && nn >= ns;
+      }
+      const unsigned tb = __ballot_sync(kFull, trans);
+      if (trans) { const uint32_t slot = ncand + __popc(tb & ((1u << lane) - 1)); if (slot < E.ar.cand_cap) E.ar.cand[slot] = seq; }
+      ncand += __popc(tb);
+      __syncwarp();
+    }
+  }
+  if (ncand == 0) return;
+  if (ncand > E.ar.cand_cap) { rc.flags |= kOvfPairs; return; }
+  // ---- 2. order candidates: count desc, reference number asc (alignment.cpp:143-148) ----
+  const uint32_t nc2 = next_pow2(ncand);
+  for (uint32_t i = lane; i < nc2; i += 32) {
+    unsigned long long key = ~0ull;
+    if (i < ncand) { const uint32_t seq = (uint32_t)E.ar.cand[i]; const uint32_t c = E.ar.hist[seq] & 0xFFFFFu; key = ((unsigned long long)(0xFFFFFu - c) << 32) | seq; }
+    E.ar.cand[i] = key;
+  }
+  __syncwarp();
+  warp_sort_u64(E.ar.cand, nc2);
+
+  // ---- 3. candidates in order (alignment.cpp:150-508) ----
+  bool is_aligned = false, is_search_candidates = true;
+  uint32_t prev_occur = 0;
+  const uint64_t rlen = rc.len, lnwin = ix.lnwin;
+  const uint32_t N = (uint32_t)o.num_alignments;
+  AlnWork* slots = E.g->aln_work + (size_t)rc.r * E.g->slots;
+  const SwScore sc{o.match, o.mismatch, o.score_N, o.gap_open, o.gap_ext};
+
+  for (uint32_t k = 0; k < ncand && is_search_candidates; ++k) {
+    const unsigned long long ck = E.ar.cand[k];
+    const uint32_t max_ref = (uint32_t)ck, max_occur = 0xFFFFFu - (uint32_t)(ck >> 32);
+    if (max_occur < (uint32_t)o.num_seeds) break;                                            // :158
+    if (is_aligned && o.min_lis > 0 && k > 0 && max_occur < prev_occur) { --rc.best; if (rc.best < 1) break; }  // :165-169
+    prev_occur = max_occur;
+
+    // gather (refpos, readpos) pairs of this reference (:181-201)
+    const uint32_t np = max_occur;
+    unsigned long long* P; uint32_t* lb; uint32_t* lp;
+    if (np <= (uint32_t)kPairsShared) { P = E.s_pairs; lb = E.s_b; lp = E.s_p; }
+    else if (np <= E.ar.pair_cap) { P = E.ar.pairs; lb = E.ar.lis_b; lp = E.ar.lis_p; }
+    else { rc.flags |= kOvfPairs; return; }
+    uint32_t filled = 0;
+    for (uint32_t h0 = 0; h0 < nh; h0 += 32) {
+      const uint32_t h = h0 + lane;
+      uint32_t first = 0, cnt = 0, win = 0;
+      if (h < nh) {
+        const uint2 hv = hits[h];
+        if (hit_selected(hv, rc, s0, s1, s2)) {
+          win = hv.y & kWinMask;
+          uint32_t lo = __ldg(ix.pos_off + hv.x), hi = __ldg(ix.pos_off + hv.x + 1);
+          const uint32_t end = hi;
+          while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&ix.pos[mid]).y < max_ref) lo = mid + 1; else hi = mid; }
+          first = lo;
+          while (first + cnt < end && __ldg(&ix.pos[first + cnt]).y == max_ref) ++cnt;
+        }
+      }
+      const uint32_t incl = warp_incl_scan_u32(cnt), tot = __shfl_sync(kFull, incl, 31);
+      uint32_t w = filled + incl - cnt;
+      for (uint32_t c = 0; c < cnt; ++c, ++w) if (w < np) P[w] = ((unsigned long long)__ldg(&ix.pos[first + c]).x << 32) | win;
+      filled += tot;
+    }
+    __syncwarp();
+    if (filled != np) { rc.flags |= kErrTrace; return; }   // internal consistency: votes == gathered pairs
+    const uint32_t np2 = next_pow2(np);
+    for (uint32_t i = np + lane; i < np2; i += 32) P[i] = ~0ull;
+    __syncwarp();
+    warp_sort_u64(P, np2);
+
+    // sliding window over the sorted pairs (:205-507)
+    uint32_t it = 0, f = 0;
+    uint32_t begin_ref = (uint32_t)(P[0] >> 32), begin_read = (uint32_t)P[0];
+    while (it != np && is_search_candidates) {
+      const uint64_t end_ref_max = (uint64_t)begin_ref + rlen - begin_read - lnwin + 1;     // :231
+      bool push = false;
+      while (it != np && (uint64_t)(uint32_t)(P[it] >> 32) <= end_ref_max) { ++it; push = true; }
+      bool skip = false;
+      if (!push && is_aligned) skip = true; else is_aligned = false;                        // heuristic 1 (:244-245)
+      if (!skip && (it - f) >= (uint32_t)o.num_seeds) {
+        // find_lis is sequential: lane 0 runs it, the result is broadcast
+        uint32_t lis_first = 0, lis_len = 0;
+        if (lane == 0) lis_len = find_lis_dev(P + f, it - f, lb, lp, lis_first);
+        lis_len = __shfl_sync(kFull, lis_len, 0); lis_first = __shfl_sync(kFull, lis_first, 0);
+        if (lis_len >= (uint32_t)o.min_lis) {                                               // :261
+          const uint32_t lcs_ref_start = (uint32_t)(P[f + lis_first] >> 32), lcs_que_start = (uint32_t)P[f + lis_first];
+          uint64_t head = 0, tail = 0, ars = 0, aqs = 0, alen = 0;
+          const uint64_t reflen = __ldg(ix.ref_off + max_ref + 1) - __ldg(ix.ref_off + max_ref);
+          const uint32_t edges = o.edges_is_percent ? (uint32_t)((o.edges / 100.0) * (double)rlen) : (uint32_t)o.edges;  // :278-282
+          const uint64_t em1 = (uint64_t)(uint32_t)(edges - 1u);
+          if (lcs_ref_start < lcs_que_start) {                                              // :288-330
+            aqs = lcs_que_start - lcs_ref_start;
+            if (reflen < rlen) {
+              if (aqs > (rlen - reflen)) alen = reflen - (aqs - (rlen - reflen)); else alen = reflen;
+            } else {
+              tail = reflen - ars - rlen; if (tail > em1) tail = edges;
+              alen = rlen + head + tail - aqs;
+            }
+          } else {                                                                          // :331-357
+            ars = lcs_ref_start - lcs_que_start;
+            if (ars > em1) head = edges;
+            if (ars + rlen > reflen) { tail = 0; alen = reflen - ars - head; }
+            else { tail = reflen - ars - rlen; if (tail > em1) tail = edges; alen = rlen + head + tail; }
+          }
+          if (rc.hasn) rc.form04 = true;                                                    // flip34 before SSW (:360-361)
+          const int32_t qlen = (int32_t)(alen - head - tail);
+          const uint32_t win_start = (uint32_t)(ars - head);
+          // query = current strand in the 0-4 alphabet, starting at aqs
+          SeqView q;
+          if (!rc.reversed) q = SeqView{B.seq04 + rc.seq_base, (int32_t)aqs, 1, false};
+          else q = SeqView{B.seq04 + rc.seq_base, (int32_t)(rc.len - 1 - aqs), -1, true};
+          const SeqView t{ix.refseq + __ldg(ix.ref_off + max_ref), (int32_t)win_start, 1, false};
+          SwEnd res{0, -1, 0};
+          if (qlen > 0 && alen > 0 && (uint32_t)alen <= E.ar.row_cap) res = sw_forward(q, qlen, t, (int32_t)alen, sc, E.ar.rowH, E.ar.rowF);
+          E.n_sw_calls++; E.n_sw_cells += (unsigned long long)alen * (unsigned long long)(qlen > 0 ? qlen : 0);
+          const uint32_t score1 = (uint32_t)res.score & 0xFFFFu;                            // s_align.score1 is uint16
+          is_aligned = score1 > ix.minimal_score;                                           // :388
+          if (is_aligned) {
+            if (score1 == max_SW_score) ++rc.max_SW_count;                                  // :391
+            AlnWork a;
+            a.ref_num = max_ref; a.win_ref_start = win_start; a.win_len = (uint32_t)alen; a.q_start = (uint32_t)aqs; a.q_len = (uint32_t)qlen;
+            a.ref_end = res.ref; a.read_end = res.read; a.score1 = (uint16_t)score1; a.part = (uint16_t)ix.part; a.index_num = (uint16_t)ix.index_num;
+            a.strand = rc.reversed ? 0 : 1; a.idx_slot = (uint16_t)ix.slot;
+            if (!rc.is_hit) {                                                               // :411-416
+              rc.is_hit = true;   // readstats.num_aligned / reads_matched_per_db are summed from hit_db at download time
+              if (lane == 0) B.hit_db[rc.r] = (uint16_t)ix.index_num;
+            }
+            if (N == 0 || !o.is_best || (o.is_best && rc.n_align < N)) {                    // :420-424
+              if (rc.n_align < E.g->slots) { if (lane == 0) slots[rc.n_align] = a; rc.n_align++; rc.is_new_hit = true; }
+            } else if (o.is_best && rc.n_align == N && slots[rc.min_index].score1 < score1) {  // :425-459
+              if (N > 1 && rc.max_index == 0 && rc.min_index == 0) {
+                uint32_t mn = 0, mx = 0, mns = slots[0].score1, mxs = slots[0].score1;      // findMinIndex / findMaxIndex (:533-561)
+                for (uint32_t i2 = 0; i2 < rc.n_align; ++i2) { const uint32_t s = slots[i2].score1; if (s < mns) { mns = s; mn = i2; } if (s > mxs) { mxs = s; mx = i2; } }
+                rc.min_index = mn; rc.max_index = mx;
+              }
+              const uint32_t mn = rc.min_index, mx = rc.max_index;
+              __syncwarp();
+              if (lane == 0) slots[mn] = a;
+              __syncwarp();
+              rc.is_new_hit = true;
+              if (score1 > slots[mx].score1 && rc.n_align > 1) {
+                rc.max_index = mn;
+                uint32_t m2 = 0, ms = slots[0].score1;
+                for (uint32_t i2 = 0; i2 < rc.n_align; ++i2) { const uint32_t s = slots[i2].score1; if (s < ms) { ms = s; m2 = i2; } }
+                rc.min_index = m2;
+              }
+            }
+            __syncwarp();
+            if (N > 0) {                                                                    // :462-469
+              if (o.is_best) { if (N == rc.max_SW_count) is_search_candidates = false; }
+              else if (N == rc.n_align) is_search_candidates = false;
+            }
+            search = false;                                                                 // :472
+          }
+        }
+      }
+      // pop (:486-506)
+      if (it > f) ++f;
+      if (it == f) {
+        if (it != np) { begin_ref = (uint32_t)(P[it] >> 32); begin_read = (uint32_t)P[it]; } else break;
+      } else { begin_ref = (uint32_t)(P[f] >> 32); begin_read = (uint32_t)P[f]; }
+    }
+    __syncwarp();
+  }
+}
+
+// traverse() pass loop for one strand (paralleltraversal.cpp:92-297)
+__device__ void traverse_dev(PassEnv& E, ReadCtx& rc, const bool is_last_strand) {
+  const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
+  const unsigned lane = lane_id();
+  const uint32_t s0 = ix.skip[0], s1 = ix.skip[1], s2 = ix.skip[2];
+  const uint2* hits = B.hits + hit_base(B, rc.r);
+  const uint32_t nh = B.hit_cnt[rc.r];
+  const uint32_t max_SW_score = rc.len * (uint32_t)o.match;                                 // :101
+  // which seed variant the windows of this strand see
+  uint32_t var = rc.reversed ? kVarRevT : kVarFwd;
+  uint32_t pass_n = 0;
+  bool search = true;
+  while (search) {
+    // first window of the pass: `if (read.is04) read.flip34()` (:126) -> back to 0-3 with N positions = 0 (A)
+    if (rc.hasn && rc.form04) { rc.form04 = false; if (rc.reversed) var = kVarRevA; }
+    rc.vcls[pass_n] = var;
+    rc.pass_n = pass_n;
+    // windows searched for the first time in this pass that produced hits (:242-249)
+    uint32_t newly = 0;
+    for (uint32_t h0 = 0; h0 < nh; h0 += 32) {
+      const uint32_t h = h0 + lane;
+      bool cnt = false;
+      if (h < nh) {
+        const uint2 hv = hits[h];
+        const uint32_t p = hv.y & kWinMask;
+        if ((hv.y >> 24) == var && pass_class(p, s0, s1, s2) == pass_n) cnt = (h == 0) || (hits[h - 1].y != hv.y);
+      }
+      newly += __popc(__ballot_sync(kFull, cnt));
+    }
+    rc.hit_seeds += newly;
+    if (rc.hit_seeds >= (uint32_t)o.num_seeds) compute_lis_dev(E, rc, search, max_SW_score);  // :256-258
+    if (rc.flags) return;
+    if (search) {                                                                              // :262-277
+      if (pass_n == 2) search = false;
+      else {
+        while (pass_n < 2 && ix.skip[pass_n] == ix.skip[pass_n + 1]) { ++pass_n; rc.vcls[pass_n] = var; }
+        if (++pass_n > 2) search = false;
+      }
+    }
+  }
+  const uint32_t N = (uint32_t)o.num_alignments;                                              // :286-297
+  if (N > 0) {
+    if ((o.is_best && N == rc.max_SW_count) || (!o.is_best && rc.n_align == N)) rc.is_done = true;
+  } else if (ix.is_last && is_last_strand && rc.n_align > 0) rc.is_done = true;
+}
+
+// The candidate kernel: persistent warps pull reads from the worklist of this (index, part).
+__global__ void __launch_bounds__(kLisWarpsPerCta * 32)
+lis_kernel(DevIndex ix, DevBatch b, DevParams prm, LisGlobals g) {
+  __shared__ unsigned long long s_pairs[kLisWarpsPerCta][kPairsShared];
+  __shared__ uint32_t s_b[kLisWarpsPerCta][kPairsShared];
+  __shared__ uint32_t s_p[kLisWarpsPerCta][kPairsShared];
+  const unsigned lane = lane_id();
+  const uint32_t wic = threadIdx.x >> 5, warp = blockIdx.x * kLisWarpsPerCta + wic;
+  PassEnv E;
+  E.ix = &ix; E.b = &b; E.prm = &prm; E.g = &g;
+  E.ar = carve_arena(g, warp);
+  E.epoch_ptr = g.epochs + warp; E.epoch = *E.epoch_ptr;
+  E.s_pairs = s_pairs[wic]; E.s_b = s_b[wic]; E.s_p = s_p[wic];
+  E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = 0;
+  const uint32_t nwork = *b.work_n;
+  const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);
+  for (;;) {
+    uint32_t wi = 0;
+    if (lane == 0) wi = atomicAdd(g.work_next, 1u);
+    wi = __shfl_sync(kFull, wi, 0);
+    if (wi >= nwork) break;
+    const uint32_t r = b.worklist[wi];
+    const ReadState st = b.state[r];
+    ReadCtx rc;
+    rc.r = r; rc.seq_base = b.seq_off[r]; rc.len = b.seq_off[r + 1] - rc.seq_base;
+    rc.hasn = b.has_n[r] != 0; rc.reversed = false; rc.form04 = false; rc.flags = 0;
+    rc.vcls[0] = rc.vcls[1] = rc.vcls[2] = kVarFwd; rc.pass_n = 0;
+    rc.hit_seeds = st.hit_seeds; rc.min_index = st.min_index; rc.max_index = st.max_index; rc.n_align = st.n_align;  // load_db (read.cpp:467-539)
+    rc.max_SW_count = st.max_SW_count; rc.is_done = st.is_done != 0; rc.is_hit = st.is_hit != 0; rc.is_new_hit = false;
+    rc.best = prm.min_lis > 0 ? prm.min_lis : 0;                                              // Read::init (read.cpp:264-271)
+    const int num_strands = single ? 1 : 2;                                                   // processor.cpp:130-146
+    for (int count = 0; count < num_strands && !rc.is_done && !rc.flags; ++count) {
+      if ((single && prm.is_reverse) || count == 1) rc.reversed = true;
+      traverse_dev(E, rc, single || count == 1);
+    }
+    if (rc.flags) { if (lane == 0) atomicOr(&b.flags[r], rc.flags); continue; }
+    if (rc.is_new_hit && rc.n_align > 0 && lane == 0) {                                       // kvdb.put (processor.cpp:150-155)
+      ReadState ns;
+      ns.lastIndex = ix.index_num; ns.lastPart = ix.part; ns.hit_seeds = rc.hit_seeds; ns.min_index = rc.min_index; ns.max_index = rc.max_index;
+      ns.n_align = rc.n_align; ns.max_SW_count = (uint16_t)rc.max_SW_count; ns.is_done = rc.is_done ? 1 : 0; ns.is_hit = rc.is_hit ? 1 : 0;
+      b.state[r] = ns;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    *E.epoch_ptr = E.epoch;
+    atomicAdd(&b.counters[dcSwCalls], E.n_sw_calls); atomicAdd(&b.counters[dcSwCells], E.n_sw_cells);
+    atomicAdd(&b.counters[dcPosEntries], E.n_pos_entries); atomicAdd(&b.counters[dcLisCalls], E.n_lis_calls);
+  }
+}
+
+}  // namespace smr

@@ -1,0 +1,210 @@
+// Smith-Waterman for one (query segment, reference window) pair, cooperatively by one warp.
+//
+// Stands in for ssw_init / ssw_align (src/sortmerna/ssw.c:788-941): the striped SSE2 kernels
+// sw_sse2_byte / sw_sse2_word (:150-575) become a warp-wide anti-diagonal wavefront -- lane l owns R
+// consecutive query rows, reference columns stream through the lanes one column per step, the
+// H/F values of a lane's last row travel to the next lane by shuffle -- and banded_sw (:577-773)
+// keeps its scalar band arithmetic (CIGARs must match bit for bit, so the band coordinates,
+// direction codes and band doubling are the reference's).
+//
+// Cell arithmetic uses the DPX instructions (__vimax3_s32_relu, __viaddmax_s32); the problem is an
+// integer recurrence, not a contraction, so tensor cores do not apply.  Outputs are defined by true
+// affine-gap local scores plus the reference's tie-breaks:
+//   end   = among cells holding the global maximum: smallest reference column, then smallest read row
+//   begin = same rule on the reversed prefixes (ssw.c:899-915).
+#pragma once
+#include "smr_dev.cuh"
+
+namespace smr {
+
+// strided byte view: element i = f(base[start + i*step]); comp => 3-x for x<4 (complement[], common.hpp:93)
+struct SeqView {
+  const uint8_t* base; int32_t start, step; bool comp;
+  __device__ __forceinline__ uint32_t at(int32_t i) const {
+    const uint32_t c = __ldg(base + start + (int64_t)i * step);
+    return (comp && c < 4u) ? 3u - c : c;
+  }
+  __device__ __forceinline__ SeqView sub(int32_t off) const { return SeqView{base, start + off * step, step, comp}; }
+  // the prefix [0..end] reversed (seq_reverse, ssw.c:775-786)
+  __device__ __forceinline__ SeqView reversed_prefix(int32_t end) const { return SeqView{base, start + end * step, -step, comp}; }
+};
+
+struct SwScore { int32_t match, mismatch, sN, go, ge; };
+struct SwEnd { int32_t score, ref, read; };
+
+// Forward score pass.  q: query (m rows), t: target (n columns).  rowH/rowF: scratch of >= n ints each,
+// used only when m > 32*R (the query is then processed in row blocks of 32*R rows).
+template <int R>
+__device__ SwEnd sw_warp(const SeqView q, const int32_t m, const SeqView t, const int32_t n, const SwScore sc,
+                         int32_t* __restrict__ rowH, int32_t* __restrict__ rowF) {
+  const int lane = (int)lane_id();
+  int32_t best = 0, best_j = 0x7FFFFFFF, best_i = 0x7FFFFFFF;
+  const bool multi = m > 32 * R;
+  for (int32_t blk0 = 0; blk0 < m; blk0 += 32 * R) {
+    const int32_t i0 = blk0 + lane * R;
+    int32_t qc[R], qmis[R], Hp[R], E[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int32_t i = i0 + r;
+      uint32_t c = i < m ? q.at(i) : 7u;
+      qmis[r] = c == 7u ? -(1 << 20) : (c >= 4u ? sc.sN : sc.mismatch);  // mat[ref*5+read] (read.cpp:274-288)
+      qc[r] = c >= 4u ? (c == 7u ? 7 : 5) : (int32_t)c;                   // N never compares equal
+      Hp[r] = 0; E[r] = 0;
+    }
+    int32_t diagH = 0, outH = 0, outF = 0;
+    uint32_t chunk_cur = lane < n ? t.at(lane) : 0u, chunk_prev = 0u;
+    const int32_t nsteps = n + 31;
+    for (int32_t ts = 0; ts < nsteps; ++ts) {
+      if ((ts & 31) == 0 && ts > 0) { chunk_prev = chunk_cur; chunk_cur = (ts + lane) < n ? t.at(ts + lane) : 0u; }
+      // reference character of column j = ts - lane: source lane s supplies position ts - ((ts - s) & 31)
+      const int32_t pos_s = ts - ((ts - lane) & 31);
+      const uint32_t supply = pos_s >= (ts & ~31) ? chunk_cur : chunk_prev;
+      const int32_t rc = (int32_t)__shfl_sync(kFull, supply, (ts - lane) & 31);
+      int32_t upH = __shfl_up_sync(kFull, outH, 1), upF = __shfl_up_sync(kFull, outF, 1);
+      const int32_t j = ts - lane;
+      const bool active = (j >= 0) && (j < n);
+      if (lane == 0) {
+        if (multi && blk0 > 0 && active) { upH = rowH[j]; upF = rowF[j]; } else { upH = 0; upF = 0; }
+      }
+      if (active) {
+        int32_t diag = diagH, F = upF, colmax = 0;
+        diagH = upH;
+        const int32_t misN = rc == 4 ? 1 : 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int32_t miss = misN ? sc.sN : qmis[r];
+          const int32_t s = (rc == qc[r]) ? sc.match : miss;
+          const int32_t h = __vimax3_s32_relu(diag + s, E[r], F);
+          diag = Hp[r]; Hp[r] = h;
+          const int32_t open = h - sc.go;
+          E[r] = __viaddmax_s32(E[r], -sc.ge, open);
+          F = __viaddmax_s32(F, -sc.ge, open);
+          colmax = max(colmax, h);
+        }
+        outH = Hp[R - 1]; outF = max(F, 0);
+        if (multi && lane == 31) { rowH[j] = outH; rowF[j] = outF; }
+        if (colmax > best || (colmax == best && colmax > 0 && j < best_j)) {
+          best = colmax; best_j = j;
+          int rr = 0;
+#pragma unroll
+          for (int r = R - 1; r >= 0; --r) if (Hp[r] == colmax) rr = r;
+          best_i = i0 + rr;
+        }
+      }
+    }
+    if (multi) __syncwarp();
+  }
+  // warp arg-max: score desc, column asc, row asc
+  unsigned long long key = ((unsigned long long)(uint32_t)best << 42) | ((unsigned long long)(0x1FFFFF - min(best_j, 0x1FFFFF)) << 21) |
+                           (unsigned long long)(0x1FFFFF - min(best_i, 0x1FFFFF));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long k2 = __shfl_xor_sync(kFull, key, o); key = k2 > key ? k2 : key; }
+  SwEnd e;
+  e.score = (int32_t)(key >> 42);
+  e.ref = 0x1FFFFF - (int32_t)((key >> 21) & 0x1FFFFF);
+  e.read = 0x1FFFFF - (int32_t)(key & 0x1FFFFF);
+  if (e.score == 0) { e.ref = -1; e.read = 0; }  // ssw.c:179 (byte kernel, no overflow): end_ref stays -1
+  return e;
+}
+
+// dispatch on the query length: the smallest R with 32*R >= m (R = 8 and row blocks beyond 256 rows)
+__device__ __noinline__ SwEnd sw_forward(const SeqView q, const int32_t m, const SeqView t, const int32_t n, const SwScore sc,
+                                         int32_t* rowH, int32_t* rowF) {
+  if (m <= 32) return sw_warp<1>(q, m, t, n, sc, rowH, rowF);
+  if (m <= 64) return sw_warp<2>(q, m, t, n, sc, rowH, rowF);
+  if (m <= 96) return sw_warp<3>(q, m, t, n, sc, rowH, rowF);
+  if (m <= 128) return sw_warp<4>(q, m, t, n, sc, rowH, rowF);
+  if (m <= 160) return sw_warp<5>(q, m, t, n, sc, rowH, rowF);
+  if (m <= 192) return sw_warp<6>(q, m, t, n, sc, rowH, rowF);
+  return sw_warp<8>(q, m, t, n, sc, rowH, rowF);
+}
+
+// ---------------------------------------------------------------------------------------------
+// banded_sw (ssw.c:577-773) -- executed by ONE lane; band coordinates as set_u / set_d (:70,:73)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int32_t band_u(int32_t w, int32_t i, int32_t j) { int32_t x = i - w; x = x > 0 ? x : 0; return j - x + 1; }
+__device__ __forceinline__ int32_t band_d(int32_t w, int32_t i, int32_t j, int32_t p) { int32_t x = i - w; x = x > 0 ? x : 0; return (j - x) * 3 + p; }
+
+struct TraceArena {
+  int32_t* hb; int32_t* eb; int32_t* hc;  // band rows, cap_w ints each
+  int8_t* dir; size_t cap_dir;            // direction matrix
+  uint32_t* cig; uint32_t cap_cig;        // cigar scratch (reverse order)
+  uint32_t cap_w;
+};
+
+// returns: >=0 cigar length (cig holds the ops in REVERSE order), -1 arena too small, -2 trace back error
+__device__ int32_t banded_traceback_lane(const SeqView t, const SeqView q, const int32_t refLen, const int32_t readLen, const int32_t score,
+                                         const SwScore sc, int32_t band_width, TraceArena& A) {
+  // the caller zeroes hb/eb/hc[0..cap_w) (the reference's band rows keep their contents across the
+  // band-doubling iterations, ssw.c:601-606; only the cells named below are reset per iteration)
+  int32_t maxv = 0, width = 0, width_d = 0;
+  do {
+    width = band_width * 2 + 3; width_d = band_width * 2 + 1;
+    if ((uint32_t)(width + 1) > A.cap_w) return -1;
+    if ((size_t)width_d * readLen * 3 + 8 > A.cap_dir) return -1;
+    for (int32_t j = 1; j < width - 1; ++j) A.hb[j] = 0;
+    for (int32_t i = 0; i < readLen; ++i) {
+      const int32_t beg = max(0, i - band_width), end = min(refLen - 1, i + band_width);
+      const int32_t edge = end + 1 < width - 1 ? end + 1 : width - 1;
+      int32_t f = 0, u = 0;
+      A.hb[0] = 0; A.eb[0] = 0; A.hb[edge] = 0; A.eb[edge] = 0; A.hc[0] = 0;
+      int8_t* dl = A.dir + (size_t)width_d * i * 3;
+      const uint32_t qi = q.at(i);
+      for (int32_t j = beg; j <= end; ++j) {
+        u = band_u(band_width, i, j);
+        const int32_t up = band_u(band_width, i - 1, j), lf = band_u(band_width, i, j - 1), dg = band_u(band_width, i - 1, j - 1);
+        const int32_t de = band_d(band_width, i, j, 0), df = de + 1, dh = de + 2;
+        int32_t t1 = i == 0 ? -sc.go : A.hb[up] - sc.go;
+        int32_t t2 = i == 0 ? -sc.ge : A.eb[up] - sc.ge;
+        const int32_t ev = t1 > t2 ? t1 : t2;
+        A.eb[u] = ev;
+        const int8_t cde = t1 > t2 ? 3 : 2;
+        dl[de] = cde;
+        t1 = A.hc[lf] - sc.go; t2 = f - sc.ge;
+        f = t1 > t2 ? t1 : t2;
+        const int8_t cdf = t1 > t2 ? 5 : 4;
+        dl[df] = cdf;
+        const int32_t e1 = ev > 0 ? ev : 0, f1 = f > 0 ? f : 0;
+        t1 = e1 > f1 ? e1 : f1;
+        const uint32_t tj = t.at(j);
+        const int32_t s = (tj >= 4u || qi >= 4u) ? sc.sN : (tj == qi ? sc.match : sc.mismatch);
+        t2 = A.hb[dg] + s;
+        const int32_t hv = t1 > t2 ? t1 : t2;
+        A.hc[u] = hv;
+        if (hv > maxv) maxv = hv;
+        dl[dh] = (t1 <= t2) ? (int8_t)1 : (e1 > f1 ? cde : cdf);
+      }
+      for (int32_t j = 1; j <= u; ++j) A.hb[j] = A.hc[j];
+    }
+    band_width *= 2;
+  } while (maxv < score);
+  band_width /= 2;
+  // trace back (ssw.c:674-747)
+  int32_t i = readLen - 1, j = refLen - 1, run = 0, cur_op = 0, op = 0, which = 2;
+  uint32_t l = 0;
+  const int8_t* dl = A.dir + (size_t)width_d * (readLen - 1) * 3;
+  while (i > 0) {
+    const int32_t tt = band_d(band_width, i, j, which);
+    const int64_t abs_off = (dl - A.dir) + tt;        // same linear layout as the reference's direction array
+    if (abs_off < 0 || abs_off >= (int64_t)width_d * readLen * 3) return -2;
+    switch (dl[tt]) {
+      case 1: --i; --j; which = 2; dl -= width_d * 3; op = 0; break;
+      case 2: --i; which = 0; dl -= width_d * 3; op = 1; break;
+      case 3: --i; which = 2; dl -= width_d * 3; op = 1; break;
+      case 4: --j; which = 1; op = 2; break;
+      case 5: --j; which = 2; op = 2; break;
+      default: return -2;
+    }
+    if (op == cur_op) ++run;
+    else {
+      if (l >= A.cap_cig) return -1;
+      A.cig[l++] = (uint32_t)run << 4 | (uint32_t)cur_op; cur_op = op; run = 1;
+    }
+  }
+  if (l + 2 > A.cap_cig) return -1;
+  if (op == 0) A.cig[l++] = (uint32_t)(run + 1) << 4;
+  else { A.cig[l++] = (uint32_t)run << 4 | (uint32_t)op; A.cig[l++] = 16u; }
+  return (int32_t)l;
+}
+
+}  // namespace smr

@@ -1,0 +1,53 @@
+import gzip
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_idx_dir():
+    """The reference-built index of the two golden database slices, gunzipped into a temp dir."""
+    d = tempfile.mkdtemp(prefix="smr_idx_")
+    src = os.path.join(GOLDEN, "idx")
+    for fn in os.listdir(src):
+        if fn.endswith(".gz"):
+            with gzip.open(os.path.join(src, fn), "rb") as fi, open(os.path.join(d, fn[:-3]), "wb") as fo:
+                shutil.copyfileobj(fi, fo)
+        else:
+            shutil.copy(os.path.join(src, fn), d)
+    yield d
+    shutil.rmtree(d, ignore_errors=True)
+
+
+@pytest.fixture(scope="session")
+def golden(golden_idx_dir):
+    """Inputs of the golden cases: references, reads, index prefixes (in --ref order: arc, bac)."""
+    from sortmerna_b200 import hostio
+    refs = [hostio.load_references(os.path.join(GOLDEN, "db_arc.fasta")), hostio.load_references(os.path.join(GOLDEN, "db_bac.fasta"))]
+    pre = hostio.find_index_prefixes(golden_idx_dir)
+    prefixes = [pre["db_arc.fasta"], pre["db_bac.fasta"]]
+    stats = [hostio.parse_stats(p) for p in prefixes]
+    batch = hostio.load_reads(os.path.join(GOLDEN, "reads_mix.fq"))
+    return dict(refs=refs, prefixes=prefixes, stats=stats, batch=batch)
+
+
+def load_case(name):
+    with open(os.path.join(GOLDEN, "case_" + name, "expected.json")) as f:
+        return json.load(f)
+
+
+def case_names():
+    return sorted(d[5:] for d in os.listdir(GOLDEN) if d.startswith("case_"))

@@ -1,0 +1,160 @@
+"""Parity tests proper (need a B200): the CUDA hot path, called through the C ABI, against the
+oracle on the same inputs, and against the committed golden output of the reference binary."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import case_names, load_case
+from helpers import assert_same_results, params_kwargs_from_args, strip_seq
+from sortmerna_b200 import api, hostio
+
+pytestmark = pytest.mark.gpu
+
+
+def _ora():
+    from oracle import ora  # the checker; never imported by the product
+    return ora
+
+
+@pytest.fixture(scope="module")
+def aligner(golden):
+    a = api.Aligner(0)
+    a.set_params(api.default_params())
+    exp = load_case("default")
+    for k in range(2):
+        a.load_index_part(k, 0, golden["prefixes"][k], golden["refs"][k], exp["log"]["minimal_score"][k], (18, 9, 3), golden["stats"][k].lnwin)
+    yield a
+    a.close()
+
+
+@pytest.fixture(scope="module")
+def oracle_indexes(golden):
+    ora = _ora()
+    return [ora.OracleIndex(p, 0, s.lnwin) for p, s in zip(golden["prefixes"], golden["stats"])]
+
+
+def test_index_resident(aligner, oracle_indexes):
+    info = aligner.index_info()
+    st = [ix.stats() for ix in oracle_indexes]
+    assert info["parts"] == 2
+    assert info["nodes"] == sum(s["nodes"] for s in st) and info["entries"] == sum(s["entries"] for s in st)
+    assert info["ids"] == sum(s["ids"] for s in st) and info["positions"] == sum(s["positions"] for s in st)
+
+
+def test_seed_windows_match_oracle(aligner, golden, oracle_indexes):
+    """traversetrie_align: per-window id hits (order included) and the accept_zero_kmer flag."""
+    b = golden["batch"]
+    rng = np.random.default_rng(7)
+    cat03 = np.where(b.cat > 3, 0, b.cat).astype(np.uint8)
+    wr, wp = [], []
+    for r in range(b.n):
+        ln = int(b.off[r + 1] - b.off[r])
+        if ln < 18:
+            continue
+        for p in range(0, ln - 18 + 1, 3):
+            wr.append(r); wp.append(p)
+    wr, wp = np.array(wr, np.uint32), np.array(wp, np.uint32)
+    for slot, ix in enumerate(oracle_indexes):
+        ids, counts, zero = aligner.debug_seed_windows(slot, cat03, b.off, wr, wp, cap=64)
+        nz = 0
+        for k in range(wr.size):
+            seq = cat03[int(b.off[wr[k]]):int(b.off[wr[k] + 1])]
+            eids, ez = ix.seed_window(seq, int(wp[k]))
+            assert counts[k] == eids.size, (slot, k, counts[k], eids)
+            assert ids[k, :eids.size].tolist() == eids.tolist(), (slot, k)
+            assert bool(zero[k]) == ez
+            nz += eids.size > 0
+        assert nz > 500
+
+
+@pytest.mark.parametrize("scores", [(2, -3, -3, 5, 2), (2, -4, -2, 6, 3), (2, -7, -7, 3, 1)])
+def test_ssw_matches_oracle(aligner, scores):
+    """ssw_align equivalents (score, end, begin, CIGAR) on random pairs, incl. long queries (row blocks) and N."""
+    ora = _ora()
+    match, mis, sn, go, ge = scores
+    aligner.set_params(api.default_params(match=match, mismatch=mis, score_N=sn, gap_open=go, gap_ext=ge))
+    mat = ora.score_matrix(match, mis, sn)
+    rng = np.random.default_rng(99)
+    qs, ts = [], []
+    for it in range(600):
+        qlen = int(rng.integers(18, 200)) if it % 12 else int(rng.integers(257, 700))
+        t = rng.integers(0, 4, qlen + int(rng.integers(0, 30))).astype(np.uint8)
+        p = int(rng.integers(0, t.size - qlen + 1))
+        q = t[p:p + qlen].copy()
+        err = float(rng.choice([0.0, 0.02, 0.1]))
+        m = rng.random(q.size) < err
+        q[m] = rng.integers(0, 4, int(m.sum()))
+        if it % 5 == 0 and q.size > 40:  # an indel
+            k = int(rng.integers(10, q.size - 10))
+            q = np.concatenate([q[:k], q[k + int(rng.integers(1, 4)):]]) if it % 10 else np.concatenate([q[:k], rng.integers(0, 4, 2).astype(np.uint8), q[k:]])
+        if it % 9 == 0:
+            q[int(rng.integers(0, q.size))] = 4
+            t[int(rng.integers(0, t.size))] = 4
+        qs.append(q); ts.append(t)
+    q_off = np.zeros(len(qs) + 1, np.uint64); np.cumsum([x.size for x in qs], out=q_off[1:])
+    t_off = np.zeros(len(ts) + 1, np.uint64); np.cumsum([x.size for x in ts], out=t_off[1:])
+    out, cig = aligner.debug_ssw(np.concatenate(qs), q_off, np.concatenate(ts), t_off, filters=30, cigar_cap=512)
+    for k, (q, t) in enumerate(zip(qs, ts)):
+        rc, eo, ec = ora.ssw_align(q.astype(np.int8), t.astype(np.int8), mat, go, ge, 30)
+        assert rc == 0
+        assert out[k, 0] == eo[0] and out[k, 2] == eo[2] and out[k, 4] == eo[4], (k, out[k], eo)
+        if eo[0] >= 30:
+            assert out[k, 1] == eo[1] and out[k, 3] == eo[3] and out[k, 5] == eo[5], (k, out[k], eo)
+            assert cig[k, :eo[5]].tolist() == ec.tolist(), k
+    aligner.set_params(api.default_params())
+
+
+@pytest.mark.parametrize("case", case_names())
+def test_align_matches_oracle_and_reference(aligner, golden, oracle_indexes, case):
+    """End to end through smr_align_batch: identical per-read state, alignments and CIGARs to the oracle,
+    and identical SAM rows / totals to what the reference binary printed."""
+    ora = _ora()
+    exp = load_case(case)
+    kw = params_kwargs_from_args(exp["args"])
+    aligner.set_params(api.default_params(**kw))
+    for k in range(2):
+        aligner.set_minimal_score(k, exp["log"]["minimal_score"][k])
+    b = golden["batch"]
+    got = aligner.align(b.cat, b.off)
+    want = ora.align(oracle_indexes, [0, 1], [0, 0], 2, golden["refs"], exp["log"]["minimal_score"], [18, 9, 3, 18, 9, 3],
+                     ora.default_params(**kw), b, nthreads=4)
+    assert_same_results(got, want, case)
+    assert got["matched"].tolist() == want["matched"].tolist()
+    assert got["counters"]["num_aligned"] == want["counters"]["num_aligned"] == exp["log"]["passing"]
+    assert got["counters"]["num_short"] == want["counters"]["num_short_last"]
+    rows = hostio.format_sam_rows(b, golden["refs"], got["res"], got["alns"], got["cigar"], got["slots"])
+    if case != "default":
+        rows = strip_seq(rows)
+    assert sorted(rows) == sorted(exp["sam"])
+    aligner.set_params(api.default_params())
+
+
+def test_resident_path_equals_host_path(aligner, golden):
+    exp = load_case("default")
+    for k in range(2):
+        aligner.set_minimal_score(k, exp["log"]["minimal_score"][k])
+    b = golden["batch"]
+    a = aligner.align(b.cat, b.off)
+    aligner.upload(b.cat, b.off)
+    aligner.run_resident()
+    aligner.run_resident()  # idempotent: a second pass over the resident batch gives the same answer
+    c = aligner.download()
+    assert_same_results(a, c, "resident")
+    t = aligner.timings()
+    assert t["launches"] > 0 and t["total_ms"] > 0
+
+
+def test_edge_batches(aligner, golden, oracle_indexes):
+    """empty read, reads shorter than the seed, single read, all-N read, duplicate reads"""
+    ora = _ora()
+    seqs = [b"", b"ACGT", b"ACGTACGTACGTACGTAC", b"N" * 60, golden["batch"].seqs[0], golden["batch"].seqs[0], b"ACGTTGCA" * 40]
+    batch = hostio.pack_reads([f"@r{i}" for i in range(len(seqs))], seqs)
+    got = aligner.align(batch.cat, batch.off)
+    want = ora.align(oracle_indexes, [0, 1], [0, 0], 2, golden["refs"], [37, 36], [18, 9, 3, 18, 9, 3], ora.default_params(), batch)
+    assert_same_results(got, want, "edge")
+    assert got["counters"]["num_short"] == want["counters"]["num_short_last"] == 2
+    one = hostio.pack_reads(["@x"], [golden["batch"].seqs[3]])
+    g1 = aligner.align(one.cat, one.off)
+    w1 = ora.align(oracle_indexes, [0, 1], [0, 0], 2, golden["refs"], [37, 36], [18, 9, 3, 18, 9, 3], ora.default_params(), one)
+    assert_same_results(g1, w1, "single")

@@ -1,0 +1,64 @@
+"""The oracle (oracle/smr_oracle.cpp) against what the unmodified reference binary printed
+(tests/golden/case_*/expected.json, made by tests/golden/make_golden.py): every SAM row
+(read, strand flag, reference, position, CIGAR with soft clips, AS:i score, NM:i) must be identical,
+and so must the pass/fail totals and the per-database coverage of aligned.log."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import case_names, load_case
+from helpers import params_kwargs_from_args, strip_seq
+from oracle import ora
+from sortmerna_b200 import hostio
+
+
+@pytest.fixture(scope="module")
+def oracle_indexes(golden):
+    return [ora.OracleIndex(p, 0, s.lnwin) for p, s in zip(golden["prefixes"], golden["stats"])]
+
+
+def run_oracle(golden, oracle_indexes, case, nthreads=2):
+    exp = load_case(case)
+    prm = ora.default_params(**params_kwargs_from_args(exp["args"]))
+    out = ora.align(oracle_indexes, [0, 1], [0, 0], 2, golden["refs"], exp["log"]["minimal_score"], [18, 9, 3, 18, 9, 3], prm,
+                    golden["batch"], nthreads=nthreads)
+    return exp, prm, out
+
+
+@pytest.mark.parametrize("case", case_names())
+def test_oracle_matches_reference_sam(golden, oracle_indexes, case):
+    exp, prm, out = run_oracle(golden, oracle_indexes, case)
+    rows = hostio.format_sam_rows(golden["batch"], golden["refs"], out["res"], out["alns"], out["cigar"], out["slots"])
+    if case != "default":
+        rows = strip_seq(rows)
+    # with several references the reference writes rows index-major; compare as multisets
+    assert sorted(rows) == sorted(exp["sam"])
+    assert int(out["res"]["is_hit"].sum()) == exp["log"]["passing"]
+    assert golden["batch"].n - int(out["res"]["is_hit"].sum()) == exp["log"]["failing"]
+    # aligned.log "Coverage by database" (summary.cpp:160-170), %.2f of matched/total
+    cov = [round(100.0 * int(m) / golden["batch"].n, 2) for m in out["matched"]]
+    assert cov == pytest.approx(exp["log"]["coverage"], abs=0.011)
+
+
+def test_oracle_thread_invariance(golden, oracle_indexes):
+    _, _, a = run_oracle(golden, oracle_indexes, "default", nthreads=1)
+    _, _, b = run_oracle(golden, oracle_indexes, "default", nthreads=4)
+    assert np.array_equal(a["res"], b["res"]) and np.array_equal(a["alns"], b["alns"]) and np.array_equal(a["cigar"], b["cigar"])
+
+
+def test_minimal_score_formula(golden):
+    """refstats.cpp:236-265 restated in hostio.minimal_score reproduces the reference's log."""
+    exp = load_case("default")
+    b = golden["batch"]
+    lens = np.diff(b.off.astype(np.int64))
+    for k, st in enumerate(golden["stats"]):
+        ms = hostio.minimal_score(st, exp["log"]["lambda_"][k], exp["log"]["K"][k], int(lens.sum()), b.n)
+        assert ms == exp["log"]["minimal_score"][k]
+
+
+def test_empty_and_short_batches(golden, oracle_indexes):
+    prm = ora.default_params()
+    batch = hostio.pack_reads(["@e", "@s", "@x"], [b"", b"ACGTACGTAC", b"ACGTNNNN"])
+    out = ora.align(oracle_indexes, [0, 1], [0, 0], 2, golden["refs"], [37, 36], [18, 9, 3, 18, 9, 3], prm, batch)
+    assert int(out["res"]["is_hit"].sum()) == 0 and out["counters"]["num_short_last"] == 3
