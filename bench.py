@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- reads/sec of the alignment hot path (150 bp reads vs the 8 bundled rRNA databases).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of R synthetic reads per GPU (default: BASELINE.json
+config "10 M synthetic 150 bp Illumina reads vs all 8 data/rRNA_databases refs, 1xB200").
+  value  : whole-job reads/s, kernels only, batch resident in HBM (CUDA events inside the C ABI)
+  e2e    : reads/s through smr_align_batch with pinned HOST buffers (H2D + kernels + D2H inside the timed region)
+  roofline: the seed-search kernel (dominant) against the measured HBM peak
+  cpu_baseline: the reference CPU build (oracle/_ref/sortmerna_ref), all host threads, bounded sample
+--impl reference times that same reference build only (rank 0), one bounded sample per step.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from sortmerna_b200 import hostio  # noqa: E402
+from tools import stage_data  # noqa: E402
+
+READ_LEN = 150
+GEN_SEED = 20260924
+METRIC = "reads/sec (150 bp vs SILVA-8)"
+
+
+# ------------------------------------------------------------------------------------------------
+# workload: synthetic Illumina-like reads: 1/3 at 1 % substitutions + 0.1 % indels,
+# 1/3 at 10 % + 1 %, 1/3 i.i.d. uniform ACGT; sources sampled uniformly over the nucleotides of the 8
+# databases (sequences >= 150 nt), random strand.  Returned in the 0..3 alphabet the C ABI takes.
+# ------------------------------------------------------------------------------------------------
+class DbPool:
+    def __init__(self, refs_list):
+        self.cat = np.concatenate([r.cat for r in refs_list])
+        starts = []
+        base = 0
+        for r in refs_list:
+            off = r.off.astype(np.int64)
+            for i in range(r.n):
+                n = int(off[i + 1] - off[i])
+                if n >= READ_LEN:
+                    starts.append((base + int(off[i]), n - READ_LEN + 1))
+            base += int(off[-1])
+        s = np.array(starts, dtype=np.int64)
+        self.seq_start, self.seq_nwin = s[:, 0], s[:, 1]
+        self.cum = np.cumsum(self.seq_nwin)
+
+    def sample_starts(self, rng, n):
+        u = rng.integers(0, int(self.cum[-1]), n)
+        k = np.searchsorted(self.cum, u, side="right")
+        prev = np.where(k > 0, self.cum[k - 1], 0)
+        return self.seq_start[k] + (u - prev)
+
+
+def gen_reads(pool, n, seed):
+    """Returns an (n, 150) uint8 array in the 0..3 alphabet.  Generated with torch on the GPU when one is
+    visible (10 M reads in about a second), else on the CPU (only ever used for small samples there)."""
+    import torch
+    if not torch.cuda.is_available():
+        return _gen_reads_numpy(pool, n, seed)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    if not hasattr(pool, "_t") or pool._t.device != dev:
+        pool._t = torch.from_numpy(pool.cat).to(dev)
+        pool._start = torch.from_numpy(pool.seq_start).to(dev)
+        pool._cum = torch.from_numpy(pool.cum).to(dev)
+    out = np.empty((n, READ_LEN), dtype=np.uint8)
+    W = READ_LEN + 2
+    col = torch.arange(READ_LEN, device=dev)[None, :]
+    colw = torch.arange(W, device=dev)[None, :]
+    CH = 1 << 20
+    for c0 in range(0, n, CH):
+        m = min(CH, n - c0)
+        cls = torch.randint(0, 3, (m,), generator=g, device=dev)
+        u = torch.randint(0, int(pool.cum[-1]), (m,), generator=g, device=dev)
+        k = torch.searchsorted(pool._cum, u, right=True)
+        prev = torch.where(k > 0, pool._cum[(k - 1).clamp(min=0)], torch.zeros_like(u))
+        st = pool._start[k] + (u - prev)
+        idx = (st[:, None] + colw).clamp(max=pool._t.numel() - 1)
+        src = pool._t[idx]                                         # 152 columns: room for one deletion
+        rnd_w = torch.randint(0, 4, (m, W), generator=g, device=dev, dtype=torch.uint8)
+        src = torch.where(src > 3, rnd_w, src)
+        sub_p = torch.where(cls == 0, 0.01, 0.10)[:, None]
+        sub = torch.rand((m, W), generator=g, device=dev) < sub_p
+        src = torch.where(sub, torch.randint(0, 4, (m, W), generator=g, device=dev, dtype=torch.uint8), src)
+        # one indel event per read with probability 150 * rate (0.1 % / 1 %)
+        ind_p = torch.where(cls == 0, 0.001, 0.01) * READ_LEN
+        has = torch.rand((m,), generator=g, device=dev) < ind_p
+        pos = torch.randint(5, READ_LEN - 5, (m,), generator=g, device=dev)[:, None]
+        is_del = (torch.rand((m,), generator=g, device=dev) < 0.5)
+        hd, hi = (has & is_del)[:, None], (has & ~is_del)[:, None]
+        take = torch.where(hd, col + (col >= pos).long(), torch.where(hi, col - (col > pos).long(), col.expand(m, -1)))
+        r = torch.gather(src, 1, take)
+        rnd = torch.randint(0, 4, (m, READ_LEN), generator=g, device=dev, dtype=torch.uint8)
+        r = torch.where(hi & (col == pos), rnd, r)                 # the inserted base
+        r = torch.where((cls == 2)[:, None], torch.randint(0, 4, (m, READ_LEN), generator=g, device=dev, dtype=torch.uint8), r)
+        flip = (torch.rand((m,), generator=g, device=dev) < 0.5)[:, None]
+        r = torch.where(flip, (3 - r).flip(1), r)
+        out[c0:c0 + m] = r.cpu().numpy()
+    return out
+
+
+def _gen_reads_numpy(pool, n, seed):
+    """CPU twin of gen_reads (same mixture, numpy generator)."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, READ_LEN), dtype=np.uint8)
+    W = READ_LEN + 2
+    CH = 1 << 18
+    col = np.arange(READ_LEN)[None, :]
+    for c0 in range(0, n, CH):
+        m = min(CH, n - c0)
+        cls = rng.integers(0, 3, m)
+        st = pool.sample_starts(rng, m)
+        idx = np.minimum(st[:, None] + np.arange(W)[None, :], pool.cat.size - 1)
+        src = pool.cat[idx]
+        src = np.where(src > 3, rng.integers(0, 4, src.shape, dtype=np.uint8), src)
+        sub = rng.random((m, W), dtype=np.float32) < np.where(cls == 0, 0.01, 0.10)[:, None]
+        src = np.where(sub, rng.integers(0, 4, src.shape, dtype=np.uint8), src)
+        has = rng.random(m) < np.where(cls == 0, 0.001, 0.01) * READ_LEN
+        pos = rng.integers(5, READ_LEN - 5, m)[:, None]
+        is_del = rng.random(m) < 0.5
+        hd, hi = (has & is_del)[:, None], (has & ~is_del)[:, None]
+        take = np.where(hd, col + (col >= pos), np.where(hi, col - (col > pos), col))
+        r = np.take_along_axis(src, take, axis=1)
+        r = np.where(hi & (col == pos), rng.integers(0, 4, r.shape, dtype=np.uint8), r)
+        r = np.where((cls == 2)[:, None], rng.integers(0, 4, (m, READ_LEN), dtype=np.uint8), r)
+        flip = (rng.random(m) < 0.5)[:, None]
+        out[c0:c0 + m] = np.where(flip, (3 - r)[:, ::-1], r)
+    return out
+
+
+def write_fastq(path, reads):
+    lut = np.frombuffer(b"ACGT", dtype=np.uint8)
+    qual = b"I" * READ_LEN
+    with open(path, "wb") as f:
+        for i in range(reads.shape[0]):
+            f.write(b"@s%d\n" % i + lut[reads[i]].tobytes() + b"\n+\n" + qual + b"\n")
+
+
+# ------------------------------------------------------------------------------------------------
+def load_databases():
+    stage_data.stage_inputs() if os.path.isdir(stage_data.REF_DATA) else None
+    fastas = [stage_data.db_path(n) for n in stage_data.DBS]
+    missing = [f for f in fastas if not os.path.exists(f)]
+    if missing:
+        raise SystemExit(f"missing database FASTA files {missing}: run tools/stage_data.py where /root/reference exists")
+    idx_dir, built = stage_data.ensure_indexes(fastas)
+    pre = hostio.find_index_prefixes(idx_dir)
+    refs = [hostio.load_references(f) for f in fastas]
+    stats = [hostio.parse_stats(pre[os.path.basename(f)]) for f in fastas]
+    return fastas, idx_dir, [pre[os.path.basename(f)] for f in fastas], refs, stats, built
+
+
+def minimal_scores(stats, fastas, nreads_total):
+    g = json.load(open(os.path.join(ROOT, "sortmerna_b200", "gumbel_defaults.json")))["gumbel"]
+    return [hostio.minimal_score(st, g[os.path.basename(f)]["lambda_"], g[os.path.basename(f)]["K"], nreads_total * READ_LEN, nreads_total)
+            for st, f in zip(stats, fastas)]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, dev):
+        super().__init__(daemon=True)
+        self.dev, self.rows, self.stop_flag = dev, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   stdout=subprocess.PIPE, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = []
+        for i, n in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(n)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(self.rows))
+
+
+def run_reference_sample(fastas, idx_dir, reads, threads):
+    """The reference's own align() on a bounded sample: returns (reads/s over the per-index alignment loops,
+    seconds, 'Done alignment' seconds incl. index loading)."""
+    from oracle import ora
+    with tempfile.TemporaryDirectory(prefix="smr_ref_") as d:
+        fq = os.path.join(d, "sample.fq")
+        write_fastq(fq, reads)
+        r = ora.run_reference(fastas, fq, os.path.join(d, "w"), extra=["-fastx"], threads=threads, idx_dir=idx_dir)
+        per_idx = [float(x) for x in re.findall(r"done index: \d+ part: \d+ in ([0-9.eE+-]+) sec", r["stdout"])]
+        m = re.search(r"Done alignment in ([0-9.eE+-]+) sec", r["stdout"])
+        total = float(m.group(1)) if m else float("nan")
+        t = sum(per_idx) if per_idx else total
+        log = ora.parse_log(r["log"])
+    return reads.shape[0] / t, t, total, log
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        fastas, idx_dir, prefixes, refs, stats, built = load_databases()
+        pool = DbPool(refs)
+        sample = args.cpu_sample or int(min(200_000, max(5_000, 1_500 * cores)))
+        vals, secs = [], []
+        for s in range(args.warmup + args.steps):
+            if s < args.warmup and s > 0:
+                continue  # one warm-up run is enough to page the index files in; each run is tens of seconds
+            reads = gen_reads(pool, sample, GEN_SEED + 1000 + s)
+            v, t, total, _ = run_reference_sample(fastas, idx_dir, reads, cores)
+            if s >= args.warmup:
+                vals.append(v); secs.append(t)
+        v = float(np.mean(vals))
+        desc = f"{sample} synthetic 150 bp reads per step vs the 8 databases, alignment loops only (index loading excluded), -threads {cores}"
+        print(json.dumps({
+            "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16/u8 (SSE2)", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "10 M synthetic 150 bp Illumina reads vs all 8 data/rRNA_databases refs (bounded sample per step)",
+                       "reads_per_step": sample, "read_len": READ_LEN, "databases": 8},
+            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": desc},
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    import torch
+    from sortmerna_b200 import api
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    t_setup = time.time()
+    fastas, idx_dir, prefixes, refs, stats, built = load_databases()
+    n = args.reads
+    ms = minimal_scores(stats, fastas, n * world)   # refstats totals stay GLOBAL across shards
+    al = api.Aligner(local_rank)
+    prm = api.default_params()
+    al.set_params(prm)
+    for k in range(len(fastas)):
+        al.load_index_part(k, 0, prefixes[k], refs[k], ms[k], (18, 9, 3), stats[k].lnwin)
+    info = al.index_info()
+    pool = DbPool(refs)
+    reads = gen_reads(pool, n, GEN_SEED + rank)      # reads are sharded by record: each rank owns its own reads
+    pin = torch.empty(n * READ_LEN, dtype=torch.uint8, pin_memory=True)
+    cat = pin.numpy(); cat[:] = reads.reshape(-1)
+    pin_off = torch.empty(n + 1, dtype=torch.int64, pin_memory=True)
+    off = pin_off.numpy().view(np.uint64); off[:] = np.arange(n + 1, dtype=np.uint64) * READ_LEN
+    setup_s = time.time() - t_setup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- kernels only, batch resident ----
+    al.upload(cat, off)
+    for _ in range(args.warmup):
+        al.run_resident()
+    sampler = ClockSampler(local_rank); sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms, seed_ms, lis_ms, fin_ms, launches = [], [], [], [], 0
+    for _ in range(args.steps):
+        al.run_resident()
+        t = al.timings()
+        dev_ms.append(t["total_ms"]); seed_ms.append(t["seed_ms"]); lis_ms.append(t["lis_ms"]); fin_ms.append(t["final_ms"]); launches += t["launches"]
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1000.0
+    sampler.stop_flag = True; sampler.join(timeout=2)
+    res = al.download()
+    step_ms = float(np.sum(dev_ms))          # CUDA events on the library's stream, summed over the K steps
+    # ---- end to end through the public call, host buffers ----
+    al.align(cat[: min(n, 1 << 18) * READ_LEN], off[: min(n, 1 << 18) + 1])  # warm the host path
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        res_e = al.align(cat, off)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = int(cat.nbytes + off.nbytes)
+    slots = res_e["slots"]
+    d2h = int(n * (28 + 4 + 2) + n * slots * 40 + res_e["cigar"].nbytes + 8 * 80)
+    # ---- reductions over ranks (the path's only collective: one all-reduce of the counter vector) ----
+    cnt_names = list(api.CNT_NAMES)
+    vec = np.array([res["counters"][k] for k in cnt_names] + [int(x) for x in res["matched"]], dtype=np.int64)
+    tm = np.array([step_ms, e2e_s * 1000.0, wall_ms], dtype=np.float64)
+    if world > 1:
+        tv = torch.from_numpy(vec).cuda(); dist.all_reduce(tv); vec = tv.cpu().numpy()
+        tt = torch.from_numpy(tm).cuda(); dist.all_reduce(tt, op=dist.ReduceOp.MAX); tm = tt.cpu().numpy()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    counters = dict(zip(cnt_names, (int(x) for x in vec[: len(cnt_names)])))
+    total_reads_step = n * world
+    value = total_reads_step * args.steps / (tm[0] / 1000.0)
+    e2e_value = total_reads_step * e2e_steps / (tm[1] / 1000.0)
+    # roofline of the dominant kernel (seed search): algorithmic bytes per SURVEY 8(d), counters are per step per rank-sum
+    alg_bytes = counters["windows"] * 8 + counters["trie_nodes"] * 4 + counters["buckets"] * 4 + counters["bucket_entries"] * 8 + total_reads_step * READ_LEN * 16
+    peak, peak_src = peaks()
+    seed_s = float(np.mean(seed_ms)) / 1000.0
+    ach = alg_bytes / world / seed_s / 1e9 if seed_s > 0 else 0.0
+    sw_cells_s = counters["sw_cells"] / world / (float(np.mean(lis_ms)) / 1000.0) if np.mean(lis_ms) > 0 else 0.0
+    out = {
+        "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tm[0] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32 (DPX) / u8", "data": "synthetic",
+        "config": {"workload": "10 M synthetic 150 bp Illumina reads vs all 8 data/rRNA_databases refs, 1xB200" if n == 10_000_000 else
+                   f"{n} synthetic 150 bp Illumina reads per GPU vs all 8 data/rRNA_databases refs",
+                   "reads_per_gpu_per_step": n, "read_len": READ_LEN, "databases": 8, "index_hbm_bytes": info["hbm_bytes"],
+                   "l2": "inputs larger than L2 (index 1.3 GB + reads 1.5 GB per pass)", "parallelism": f"reads sharded by record x{world}",
+                   "hit_rate": counters["num_aligned"] / total_reads_step},
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "seed_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_step": int(alg_bytes / world),
+                     "kernel_ms_per_step": {"seed": float(np.mean(seed_ms)), "candidates_sw": float(np.mean(lis_ms)), "finalize": float(np.mean(fin_ms))},
+                     "sw_cell_updates_per_s_in_candidate_kernel": sw_cells_s},
+        "clocks": sampler.summary(),
+        "counters": counters,
+        "setup_s": setup_s, "index_build_s": built,
+    }
+    if not args.no_cpu_baseline:
+        sample = args.cpu_sample or int(min(100_000, max(5_000, 1_000 * cores)))
+        v, t, total, _ = run_reference_sample(fastas, idx_dir, reads[:sample], cores)
+        out["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference",
+                               "sample": f"first {sample} reads of the same synthetic workload vs the 8 databases, reference CPU build "
+                                         f"(oracle/_ref/sortmerna_ref -threads {cores}), alignment loops {t:.1f} s (index loading excluded; "
+                                         f"'Done alignment' incl. loading {total:.1f} s)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
