@@ -43,7 +43,8 @@ struct smr_ctx {
   std::vector<uint8_t> h_seq; std::vector<uint64_t> h_off;    // host copy (scratch-overflow retries)
   std::vector<uint32_t> off32;                                // 32-bit read offsets of the resident batch
   DevBuf seq04, seq_off, pk03, pk03alt, pk_off, has_n, hit_cnt, flags, state, hit_db, aln_work, out_aln;
-  DevBuf hits, worklist, scalars, counters, cigar_pool, parts_dev;
+  DevBuf hits, cost, bins, scalars, counters, cigar_pool, parts_dev;
+  size_t hits_stride = 0; uint32_t cnt_stride = 0;
   DevBuf lis_arena, lis_epochs, final_arena, lane_hits;
   uint32_t lis_warps = 0, final_warps = 0;
   size_t lis_stride = 0, final_stride = 0;
@@ -180,13 +181,11 @@ int upload_batch_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_
   if ((rc = ensure(ctx, ctx->pk03, (size_t)(w + 4) * 4))) return rc;
   if ((rc = ensure(ctx, ctx->pk03alt, (size_t)(w + 4) * 4))) return rc;
   if ((rc = ensure(ctx, ctx->has_n, nreads))) return rc;
-  if ((rc = ensure(ctx, ctx->hit_cnt, (size_t)nreads * 4))) return rc;
   if ((rc = ensure(ctx, ctx->flags, (size_t)nreads * 4))) return rc;
   if ((rc = ensure(ctx, ctx->state, (size_t)nreads * sizeof(ReadState)))) return rc;
   if ((rc = ensure(ctx, ctx->hit_db, (size_t)nreads * 2))) return rc;
   if ((rc = ensure(ctx, ctx->aln_work, (size_t)nreads * slots * sizeof(AlnWork)))) return rc;
   if ((rc = ensure(ctx, ctx->out_aln, (size_t)nreads * slots * sizeof(OutAln)))) return rc;
-  if ((rc = ensure(ctx, ctx->worklist, (size_t)std::min(nreads, ctx->chunk_reads) * 4))) return rc;
   if ((rc = ensure(ctx, ctx->scalars, 64))) return rc;
   if ((rc = ensure(ctx, ctx->counters, (size_t)(dcCount + 64) * 8))) return rc;
   CK(cudaMemcpyAsync(ctx->seq04.p, seq_cat + seq_off[0], total, cudaMemcpyHostToDevice, ctx->stream));
@@ -200,8 +199,14 @@ int upload_batch_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_
     const uint32_t c1 = std::min(nreads, c0 + ctx->chunk_reads);
     max_chunk_nt = std::max<uint64_t>(max_chunk_nt, off32[c1] - off32[c0]);
   }
-  const uint64_t hit_entries = (uint64_t)ctx->scale * (2 * max_chunk_nt + 32ull * std::min(nreads, ctx->chunk_reads)) + 64;
-  if ((rc = ensure(ctx, ctx->hits, hit_entries * 8))) return rc;
+  // one hit-region set per loaded (index,part): all parts are seeded before the candidate kernel runs read-major
+  const uint32_t nparts = (uint32_t)std::max<size_t>(1, ctx->parts.size());
+  ctx->cnt_stride = std::min(nreads, ctx->chunk_reads);
+  ctx->hits_stride = (size_t)((uint64_t)ctx->scale * (2 * max_chunk_nt + 32ull * ctx->cnt_stride) + 64);
+  if ((rc = ensure(ctx, ctx->hits, ctx->hits_stride * nparts * 8))) return rc;
+  if ((rc = ensure(ctx, ctx->hit_cnt, (size_t)ctx->cnt_stride * nparts * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->cost, (size_t)ctx->cnt_stride * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->bins, (size_t)ctx->cnt_stride * kCostBins * 4 + (size_t)kCostBins * 4))) return rc;
   // 2-bit packing + N detection
   DevBatch b{};
   b.nreads = nreads; b.r0 = 0; b.seq04 = (const uint8_t*)ctx->seq04.p; b.seq_off = (const uint32_t*)ctx->seq_off.p;
@@ -221,8 +226,9 @@ DevBatch make_batch(smr_ctx* ctx, uint32_t c0, uint32_t n, const std::vector<uin
   b.pk03 = (const uint32_t*)ctx->pk03.p; b.pk03alt = (const uint32_t*)ctx->pk03alt.p; b.pk_off = (const uint32_t*)ctx->pk_off.p;
   b.has_n = (const uint8_t*)ctx->has_n.p; b.hit_scale = ctx->scale; b.hits = (uint2*)ctx->hits.p;
   b.hit_cnt = (uint32_t*)ctx->hit_cnt.p; b.flags = (uint32_t*)ctx->flags.p; b.state = (ReadState*)ctx->state.p;
-  b.hit_db = (uint16_t*)ctx->hit_db.p; b.worklist = (uint32_t*)ctx->worklist.p;
-  b.work_n = scalars_of(ctx).work_n; b.counters = (unsigned long long*)ctx->counters.p;
+  b.hit_db = (uint16_t*)ctx->hit_db.p; b.counters = (unsigned long long*)ctx->counters.p;
+  b.hits_stride = ctx->hits_stride; b.cnt_stride = ctx->cnt_stride; b.cost = (uint32_t*)ctx->cost.p;
+  b.bins = (uint32_t*)ctx->bins.p; b.bin_count = (uint32_t*)ctx->bins.p + (size_t)ctx->cnt_stride * kCostBins;
   return b;
 }
 
@@ -263,10 +269,12 @@ int run_impl(smr_ctx* ctx) {
     const uint32_t n = std::min(ctx->chunk_reads, nreads - c0);
     DevBatch b = make_batch(ctx, c0, n, {});
     b.seq_base0 = ctx->off32[c0];
+    CK(cudaMemsetAsync(sc.work_n, 0, 8, ctx->stream));   // (unused word) + lis_next
+    CK(cudaMemsetAsync(b.cost, 0, (size_t)n * 4, ctx->stream));
+    CK(cudaMemsetAsync(b.bin_count, 0, (size_t)kCostBins * 4, ctx->stream));
+    cudaEvent_t s0 = get_event(ctx, evi), s1 = get_event(ctx, evi + 1), s2 = get_event(ctx, evi + 2); evi += 3;
+    CK(cudaEventRecord(s0, ctx->stream));
     for (size_t pi = 0; pi < hp.size(); ++pi) {
-      CK(cudaMemsetAsync(sc.work_n, 0, 8, ctx->stream));   // work_n + lis_next
-      cudaEvent_t s0 = get_event(ctx, evi), s1 = get_event(ctx, evi + 1), s2 = get_event(ctx, evi + 2); evi += 3;
-      CK(cudaEventRecord(s0, ctx->stream));
       const int seed_ctas = ctx->sm_count * 8;
       if (ctx->scale == 1) {
         if (ctx->instr) seed_kernel<true><<<seed_ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, nullptr, 0);
@@ -276,12 +284,18 @@ int run_impl(smr_ctx* ctx) {
         seed_kernel<true><<<ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, (uint32_t*)ctx->lane_hits.p, ctx->lane_hits_cap);
       }
       CK(cudaGetLastError());
-      CK(cudaEventRecord(s1, ctx->stream));
+      ctx->n_launch += 1;
+    }
+    bin_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(b);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(s1, ctx->stream));
+    {
       LisGlobals lg{};
       lg.arena_base = (uint8_t*)ctx->lis_arena.p; lg.arena_stride = ctx->lis_stride;
       lg.hist_cap = ctx->hist_cap; lg.cand_cap = ctx->cand_cap; lg.pair_cap = ctx->pair_cap; lg.row_cap = ctx->row_cap;
       lg.epochs = (uint32_t*)ctx->lis_epochs.p; lg.aln_work = (AlnWork*)ctx->aln_work.p; lg.slots = slots; lg.work_next = sc.lis_next;
-      lis_kernel<<<ctx->lis_warps / kLisWarpsPerCta, kLisWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, lg);
+      lg.parts = (const DevIndex*)ctx->parts_dev.p; lg.nparts = (uint32_t)hp.size();
+      lis_kernel<<<ctx->lis_warps / kLisWarpsPerCta, kLisWarpsPerCta * 32, 0, ctx->stream>>>(b, dp, lg);
       CK(cudaGetLastError());
       CK(cudaEventRecord(s2, ctx->stream));
       spans.push_back({evi - 3, 0});
@@ -439,7 +453,7 @@ void smr_destroy(smr_ctx* ctx) {
   cudaSetDevice(ctx->device);
   for (auto& pt : ctx->parts) for (void* p : pt.owned) cudaFree(p);
   DevBuf* bufs[] = {&ctx->seq04, &ctx->seq_off, &ctx->pk03, &ctx->pk03alt, &ctx->pk_off, &ctx->has_n, &ctx->hit_cnt, &ctx->flags, &ctx->state,
-                    &ctx->hit_db, &ctx->aln_work, &ctx->out_aln, &ctx->hits, &ctx->worklist, &ctx->scalars, &ctx->counters, &ctx->cigar_pool,
+                    &ctx->hit_db, &ctx->aln_work, &ctx->out_aln, &ctx->hits, &ctx->cost, &ctx->bins, &ctx->scalars, &ctx->counters, &ctx->cigar_pool,
                     &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->final_arena, &ctx->lane_hits};
   for (DevBuf* b : bufs) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);

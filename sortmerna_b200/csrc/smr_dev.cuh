@@ -50,7 +50,6 @@ struct AlnWork {
   uint32_t win_ref_start;   // align_ref_start - head (alignment.cpp:373)
   uint32_t win_len;         // align_length
   uint32_t q_start, q_len;  // align_que_start, align_length - head - tail (alignment.cpp:365-366)
-  int32_t ref_end, read_end;// ssw ends, local to the window / query segment
   uint16_t score1, part, index_num;
   uint16_t idx_slot;        // ordinal of the loaded (index,part) in the context
   uint8_t strand, pad0;

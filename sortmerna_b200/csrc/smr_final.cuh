@@ -62,10 +62,14 @@ finalize_kernel(DevBatch b, DevParams prm, FinalGlobals g) {
     SeqView q = a.strand ? SeqView{b.seq04 + seq_base, (int32_t)a.q_start, 1, false}
                          : SeqView{b.seq04 + seq_base, (int32_t)(len - 1 - a.q_start), -1, true};
     const SeqView t{ix.refseq + ix.ref_off[a.ref_num], (int32_t)a.win_ref_start, 1, false};
-    // reverse pass over the prefixes that end at the forward optimum (ssw.c:899-915)
-    const SwEnd rev = sw_forward(q.reversed_prefix(a.read_end), a.read_end + 1, t.reversed_prefix(a.ref_end), a.ref_end + 1, sc, rowH, rowF);
-    const int32_t ref_begin = a.ref_end - rev.ref, read_begin = a.read_end - rev.read;
-    const int32_t rl = a.ref_end - ref_begin + 1, ql = a.read_end - read_begin + 1;
+    // forward pass again, now with the end-point tie-breaks (ssw.c:310-336), then the reverse pass over
+    // the prefixes that end at the forward optimum (ssw.c:899-915)
+    const SwEnd fwd = sw_forward(q, (int32_t)a.q_len, t, (int32_t)a.win_len, sc, rowH, rowF);
+    if ((uint32_t)(fwd.score & 0xFFFF) != a.score1) { if (lane == 0) atomicOr(&b.flags[r], kErrTrace); continue; }
+    const int32_t a_ref_end = fwd.ref, a_read_end = fwd.read;
+    const SwEnd rev = sw_forward(q.reversed_prefix(a_read_end), a_read_end + 1, t.reversed_prefix(a_ref_end), a_ref_end + 1, sc, rowH, rowF);
+    const int32_t ref_begin = a_ref_end - rev.ref, read_begin = a_read_end - rev.read;
+    const int32_t rl = a_ref_end - ref_begin + 1, ql = a_read_end - read_begin + 1;
     const int32_t band = (rl > ql ? rl - ql : ql - rl) + 1;                                  // ssw.c:924
     for (uint32_t i = lane; i < g.cap_w; i += 32) { A.hb[i] = 0; A.eb[i] = 0; A.hc[i] = 0; }
     __syncwarp();
@@ -82,8 +86,8 @@ finalize_kernel(DevBatch b, DevParams prm, FinalGlobals g) {
     if (lane == 0) {
       OutAln o;
       o.cigar_off = (uint32_t)off; o.cigar_len = (uint32_t)nc; o.ref_num = a.ref_num;
-      o.ref_begin1 = ref_begin + (int32_t)a.win_ref_start; o.ref_end1 = a.ref_end + (int32_t)a.win_ref_start;   // alignment.cpp:396-399
-      o.read_begin1 = read_begin + (int32_t)a.q_start; o.read_end1 = a.read_end + (int32_t)a.q_start;
+      o.ref_begin1 = ref_begin + (int32_t)a.win_ref_start; o.ref_end1 = a_ref_end + (int32_t)a.win_ref_start;   // alignment.cpp:396-399
+      o.read_begin1 = read_begin + (int32_t)a.q_start; o.read_end1 = a_read_end + (int32_t)a.q_start;
       o.readlen = len; o.score1 = a.score1; o.part = a.part; o.index_num = a.index_num; o.strand = a.strand; o.pad = 0;
       g.out[(size_t)r * g.slots + k] = o;
     }
@@ -95,6 +99,7 @@ finalize_kernel(DevBatch b, DevParams prm, FinalGlobals g) {
 __global__ void __launch_bounds__(kFinalWarpsPerCta * 32)
 ssw_debug_kernel(const uint8_t* qcat, const uint32_t* qoff, const uint8_t* tcat, const uint32_t* toff, uint32_t npairs, uint32_t filters,
                  DevParams prm, int32_t* out, uint32_t* cigars, uint32_t cigar_cap, FinalGlobals g) {
+  __shared__ __align__(16) uint8_t s_ref[kFinalWarpsPerCta][kRefStage + 64];
   const unsigned lane = lane_id();
   const uint32_t warp = blockIdx.x * kFinalWarpsPerCta + (threadIdx.x >> 5), nwarps = gridDim.x * kFinalWarpsPerCta;
   uint8_t* p = g.arena_base + (size_t)warp * g.arena_stride;
@@ -112,7 +117,9 @@ ssw_debug_kernel(const uint8_t* qcat, const uint32_t* qoff, const uint8_t* tcat,
     const int32_t m = (int32_t)(qoff[k + 1] - qoff[k]), n = (int32_t)(toff[k + 1] - toff[k]);
     const SeqView q{qcat + qoff[k], 0, 1, false}, t{tcat + toff[k], 0, 1, false};
     int32_t* o = out + (size_t)k * 6;
-    const SwEnd f = sw_forward(q, m, t, n, sc, rowH, rowF);
+    SwEnd f = sw_forward(q, m, t, n, sc, rowH, rowF);
+    // the score-only kernel of the candidate loop must agree with the arg-max kernel
+    if (sw_score(q, m, t, n, sc, s_ref[threadIdx.x >> 5], rowH, rowF) != f.score) f.score = -12345;
     int32_t rb = -1, qb = -1, nc = 0;
     if ((uint32_t)(f.score & 0xFFFF) >= filters && f.score > 0) {
       const SwEnd rev = sw_forward(q.reversed_prefix(f.read), f.read + 1, t.reversed_prefix(f.ref), f.ref + 1, sc, rowH, rowF);

@@ -40,6 +40,7 @@ struct LisGlobals {
   AlnWork* aln_work;                           // [nreads * slots]
   uint32_t slots;
   uint32_t* work_next;                         // [1] persistent-loop cursor
+  const DevIndex* parts; uint32_t nparts;      // every loaded (index,part) in --ref order
 };
 
 __device__ __forceinline__ LisArena carve_arena(const LisGlobals& g, uint32_t warp) {
@@ -129,6 +130,8 @@ struct PassEnv {
   const DevIndex* ix; const DevBatch* b; const DevParams* prm; const LisGlobals* g;
   LisArena ar; uint32_t* epoch_ptr; uint32_t epoch;
   unsigned long long* s_pairs; uint32_t* s_b; uint32_t* s_p;   // shared-memory fast buffers (kPairsShared)
+  uint8_t* s_ref;                                               // staged reference window (kRefStage + 64)
+  const uint2* hits; uint32_t nh;                               // hit region of (current part, current read)
   unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls;
 };
 
@@ -137,8 +140,8 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
   const unsigned lane = lane_id();
   const uint32_t s0 = ix.skip[0], s1 = ix.skip[1], s2 = ix.skip[2];
-  const uint2* hits = B.hits + hit_base(B, rc.r);
-  const uint32_t nh = B.hit_cnt[rc.r];
+  const uint2* hits = E.hits;
+  const uint32_t nh = E.nh;
   const uint32_t ns = (uint32_t)max(o.num_seeds, 1);
   E.n_lis_calls++;
 
@@ -284,16 +287,16 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
           if (!rc.reversed) q = SeqView{B.seq04 + rc.seq_base, (int32_t)aqs, 1, false};
           else q = SeqView{B.seq04 + rc.seq_base, (int32_t)(rc.len - 1 - aqs), -1, true};
           const SeqView t{ix.refseq + __ldg(ix.ref_off + max_ref), (int32_t)win_start, 1, false};
-          SwEnd res{0, -1, 0};
-          if (qlen > 0 && alen > 0 && (uint32_t)alen <= E.ar.row_cap) res = sw_forward(q, qlen, t, (int32_t)alen, sc, E.ar.rowH, E.ar.rowF);
+          int32_t sw = 0;
+          if (qlen > 0 && alen > 0 && (uint32_t)alen <= E.ar.row_cap) sw = sw_score(q, qlen, t, (int32_t)alen, sc, E.s_ref, E.ar.rowH, E.ar.rowF);
           E.n_sw_calls++; E.n_sw_cells += (unsigned long long)alen * (unsigned long long)(qlen > 0 ? qlen : 0);
-          const uint32_t score1 = (uint32_t)res.score & 0xFFFFu;                            // s_align.score1 is uint16
+          const uint32_t score1 = (uint32_t)sw & 0xFFFFu;                                   // s_align.score1 is uint16
           is_aligned = score1 > ix.minimal_score;                                           // :388
           if (is_aligned) {
             if (score1 == max_SW_score) ++rc.max_SW_count;                                  // :391
             AlnWork a;
             a.ref_num = max_ref; a.win_ref_start = win_start; a.win_len = (uint32_t)alen; a.q_start = (uint32_t)aqs; a.q_len = (uint32_t)qlen;
-            a.ref_end = res.ref; a.read_end = res.read; a.score1 = (uint16_t)score1; a.part = (uint16_t)ix.part; a.index_num = (uint16_t)ix.index_num;
+            a.score1 = (uint16_t)score1; a.part = (uint16_t)ix.part; a.index_num = (uint16_t)ix.index_num;
             a.strand = rc.reversed ? 0 : 1; a.idx_slot = (uint16_t)ix.slot;
             if (!rc.is_hit) {                                                               // :411-416
               rc.is_hit = true;   // readstats.num_aligned / reads_matched_per_db are summed from hit_db at download time
@@ -343,8 +346,8 @@ __device__ void traverse_dev(PassEnv& E, ReadCtx& rc, const bool is_last_strand)
   const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
   const unsigned lane = lane_id();
   const uint32_t s0 = ix.skip[0], s1 = ix.skip[1], s2 = ix.skip[2];
-  const uint2* hits = B.hits + hit_base(B, rc.r);
-  const uint32_t nh = B.hit_cnt[rc.r];
+  const uint2* hits = E.hits;
+  const uint32_t nh = E.nh;
   const uint32_t max_SW_score = rc.len * (uint32_t)o.match;                                 // :101
   // which seed variant the windows of this strand see
   uint32_t var = rc.reversed ? kVarRevT : kVarFwd;
@@ -384,48 +387,73 @@ __device__ void traverse_dev(PassEnv& E, ReadCtx& rc, const bool is_last_strand)
   } else if (ix.is_last && is_last_strand && rc.n_align > 0) rc.is_done = true;
 }
 
-// The candidate kernel: persistent warps pull reads from the worklist of this (index, part).
-__global__ void __launch_bounds__(kLisWarpsPerCta * 32)
-lis_kernel(DevIndex ix, DevBatch b, DevParams prm, LisGlobals g) {
+// The candidate kernel: persistent warps drain the chunk's reads heaviest-first; each read is taken
+// through every loaded (index, part) in --ref order -- the reference's index-major loop
+// (processor.cpp:219-277) run read-major, with the KVDB carry-over of read.cpp:429-539 kept in
+// DevBatch::state between parts (equivalent because reads are independent).
+__global__ void __launch_bounds__(kLisWarpsPerCta * 32, 4)
+lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   __shared__ unsigned long long s_pairs[kLisWarpsPerCta][kPairsShared];
   __shared__ uint32_t s_b[kLisWarpsPerCta][kPairsShared];
   __shared__ uint32_t s_p[kLisWarpsPerCta][kPairsShared];
+  __shared__ __align__(16) uint8_t s_ref[kLisWarpsPerCta][kRefStage + 64];
+  __shared__ uint32_t s_bin_start[kCostBins + 1];
   const unsigned lane = lane_id();
   const uint32_t wic = threadIdx.x >> 5, warp = blockIdx.x * kLisWarpsPerCta + wic;
+  if (threadIdx.x == 0) {   // bins are drained from the heaviest (highest log2 cost) down
+    uint32_t acc = 0;
+    for (int k = 0; k < kCostBins; ++k) { s_bin_start[k] = acc; acc += b.bin_count[kCostBins - 1 - k]; }
+    s_bin_start[kCostBins] = acc;
+  }
+  __syncthreads();
   PassEnv E;
-  E.ix = &ix; E.b = &b; E.prm = &prm; E.g = &g;
+  E.b = &b; E.prm = &prm; E.g = &g;
   E.ar = carve_arena(g, warp);
   E.epoch_ptr = g.epochs + warp; E.epoch = *E.epoch_ptr;
-  E.s_pairs = s_pairs[wic]; E.s_b = s_b[wic]; E.s_p = s_p[wic];
+  E.s_pairs = s_pairs[wic]; E.s_b = s_b[wic]; E.s_p = s_p[wic]; E.s_ref = s_ref[wic];
   E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = 0;
-  const uint32_t nwork = *b.work_n;
+  const uint32_t nwork = s_bin_start[kCostBins];
   const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);
   for (;;) {
     uint32_t wi = 0;
     if (lane == 0) wi = atomicAdd(g.work_next, 1u);
     wi = __shfl_sync(kFull, wi, 0);
     if (wi >= nwork) break;
-    const uint32_t r = b.worklist[wi];
-    const ReadState st = b.state[r];
+    uint32_t k = 0;
+    while (wi >= s_bin_start[k + 1]) ++k;
+    const uint32_t r = b.bins[(size_t)(kCostBins - 1 - k) * b.cnt_stride + (wi - s_bin_start[k])];
     ReadCtx rc;
     rc.r = r; rc.seq_base = b.seq_off[r]; rc.len = b.seq_off[r + 1] - rc.seq_base;
-    rc.hasn = b.has_n[r] != 0; rc.reversed = false; rc.form04 = false; rc.flags = 0;
-    rc.vcls[0] = rc.vcls[1] = rc.vcls[2] = kVarFwd; rc.pass_n = 0;
-    rc.hit_seeds = st.hit_seeds; rc.min_index = st.min_index; rc.max_index = st.max_index; rc.n_align = st.n_align;  // load_db (read.cpp:467-539)
-    rc.max_SW_count = st.max_SW_count; rc.is_done = st.is_done != 0; rc.is_hit = st.is_hit != 0; rc.is_new_hit = false;
-    rc.best = prm.min_lis > 0 ? prm.min_lis : 0;                                              // Read::init (read.cpp:264-271)
-    const int num_strands = single ? 1 : 2;                                                   // processor.cpp:130-146
-    for (int count = 0; count < num_strands && !rc.is_done && !rc.flags; ++count) {
-      if ((single && prm.is_reverse) || count == 1) rc.reversed = true;
-      traverse_dev(E, rc, single || count == 1);
+    rc.hasn = b.has_n[r] != 0; rc.flags = 0;
+    for (uint32_t p = 0; p < g.nparts && !rc.flags; ++p) {
+      const DevIndex& ix = g.parts[p];
+      const ReadState st = b.state[r];
+      if (st.is_done) break;                                                                  // processor.cpp:120-126
+      if (rc.len < ix.lnwin) continue;                                                        // processor.cpp:109-114
+      E.nh = b.hit_cnt[(size_t)p * b.cnt_stride + (r - b.r0)];
+      if (E.nh == 0) continue;   // no window hit in this part: traverse() changes nothing that is persisted
+      E.hits = b.hits + hit_base(b, p, r);
+      E.ix = &ix;
+      rc.reversed = false; rc.form04 = false;                                                 // a fresh Read per index pass (processor.cpp:107)
+      rc.vcls[0] = rc.vcls[1] = rc.vcls[2] = kVarFwd; rc.pass_n = 0;
+      rc.hit_seeds = st.hit_seeds; rc.min_index = st.min_index; rc.max_index = st.max_index; rc.n_align = st.n_align;  // load_db (read.cpp:467-539)
+      rc.max_SW_count = st.max_SW_count; rc.is_done = false; rc.is_hit = st.is_hit != 0; rc.is_new_hit = false;
+      rc.best = prm.min_lis > 0 ? prm.min_lis : 0;                                            // Read::init (read.cpp:264-271)
+      const int num_strands = single ? 1 : 2;                                                 // processor.cpp:130-146
+      for (int count = 0; count < num_strands && !rc.is_done && !rc.flags; ++count) {
+        if ((single && prm.is_reverse) || count == 1) rc.reversed = true;
+        traverse_dev(E, rc, single || count == 1);
+      }
+      if (rc.flags) break;
+      if (rc.is_new_hit && rc.n_align > 0 && lane == 0) {                                     // kvdb.put (processor.cpp:150-155)
+        ReadState ns;
+        ns.lastIndex = ix.index_num; ns.lastPart = ix.part; ns.hit_seeds = rc.hit_seeds; ns.min_index = rc.min_index; ns.max_index = rc.max_index;
+        ns.n_align = rc.n_align; ns.max_SW_count = (uint16_t)rc.max_SW_count; ns.is_done = rc.is_done ? 1 : 0; ns.is_hit = rc.is_hit ? 1 : 0;
+        b.state[r] = ns;
+      }
+      __syncwarp();
     }
-    if (rc.flags) { if (lane == 0) atomicOr(&b.flags[r], rc.flags); continue; }
-    if (rc.is_new_hit && rc.n_align > 0 && lane == 0) {                                       // kvdb.put (processor.cpp:150-155)
-      ReadState ns;
-      ns.lastIndex = ix.index_num; ns.lastPart = ix.part; ns.hit_seeds = rc.hit_seeds; ns.min_index = rc.min_index; ns.max_index = rc.max_index;
-      ns.n_align = rc.n_align; ns.max_SW_count = (uint16_t)rc.max_SW_count; ns.is_done = rc.is_done ? 1 : 0; ns.is_hit = rc.is_hit ? 1 : 0;
-      b.state[r] = ns;
-    }
+    if (rc.flags && lane == 0) atomicOr(&b.flags[r], rc.flags);
     __syncwarp();
   }
   if (lane == 0) {

@@ -188,22 +188,26 @@ struct DevBatch {
   uint32_t hit_scale;        // read r owns hits[hit_base(r) .. +hit_cap(r)): see hit_base()/hit_cap()
   uint32_t seq_base0;        // seq_off of the first read of the chunk, r0 = first read of the chunk
   uint32_t r0;
-  uint2* hits;               // {id, win_pos | variant<<24}
+  uint2* hits;               // {id, win_pos | variant<<24}; one region set per (index,part): part p starts at p*hits_stride
+  size_t hits_stride;        // entries per part
+  uint32_t cnt_stride;       // hit_cnt of (part p, read r) lives at hit_cnt[p*cnt_stride + (r - r0)]
+  uint32_t* cost;            // [chunk] estimated candidate work of a read (sum of position-list lengths of its hits, all parts)
+  uint32_t* bins;            // [kCostBins * cnt_stride] reads of this chunk binned by log2(cost): heaviest-first schedule
+  uint32_t* bin_count;       // [kCostBins]
   uint16_t* hit_db;          // [nreads] index_num of the first accepted alignment (reads_matched_per_db)
   uint32_t* hit_cnt;         // [nreads]
   uint32_t* flags;           // [nreads] overflow flags
   ReadState* state;          // [nreads]
-  uint32_t* worklist;        // reads that need the candidate kernel in this pass
-  uint32_t* work_n;          // [1]
   unsigned long long* counters;  // [dcCount + n_index_files]
 };
 
 // per-read hit region: capacity proportional to the read length (2 hits per nucleotide covers the
 // ~1 window per 3 nt x 2-3 strand variants with ~2-3 ids per window), scaled up on a retry
 __device__ __forceinline__ uint32_t hit_cap(const DevBatch& b, uint32_t r) { return b.hit_scale * (2u * (b.seq_off[r + 1] - b.seq_off[r]) + 32u); }
-__device__ __forceinline__ size_t hit_base(const DevBatch& b, uint32_t r) {
-  return (size_t)b.hit_scale * (2ull * (b.seq_off[r] - b.seq_base0) + 32ull * (r - b.r0));
+__device__ __forceinline__ size_t hit_base(const DevBatch& b, uint32_t part, uint32_t r) {
+  return (size_t)part * b.hits_stride + (size_t)b.hit_scale * (2ull * (b.seq_off[r] - b.seq_base0) + 32ull * (r - b.r0));
 }
+constexpr int kCostBins = 24;
 
 // 2-bit packing of a batch: one warp per read
 __global__ void pack_reads_kernel(DevBatch b, uint32_t* pk03, uint32_t* pk03alt, uint8_t* has_n) {
@@ -261,17 +265,18 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
 
   for (uint32_t r = b.r0 + warp; r < b.r0 + b.nreads; r += nwarps) {
     const uint32_t len = b.seq_off[r + 1] - b.seq_off[r];
-    if (lane == 0) b.hit_cnt[r] = 0;
+    const uint32_t cnt_idx = ix.slot * b.cnt_stride + (r - b.r0);
+    if (lane == 0) b.hit_cnt[cnt_idx] = 0;
     if (len < L) { n_short += (lane == 0 && ix.is_last); continue; }           // processor.cpp:109-114 (reset per pass, :228)
-    const ReadState rs = b.state[r];
-    if (rs.is_done) continue;                                                   // processor.cpp:120-126
+    // (reads that become is_done in an earlier part are still searched here: parts are seeded before the
+    //  candidate kernel replays them read-major; the candidate kernel skips them, processor.cpp:120-126)
     if (b.flags[r]) continue;                                                   // scratch overflow earlier: the read is redone by the retry
     const bool hasn = b.has_n[r] != 0;
     const uint32_t* pk = b.pk03 + b.pk_off[r];
     const uint32_t* pka = hasn ? b.pk03alt + b.pk_off[r] : pk;
     const uint32_t npos = (len - L) / step + 1;          // positions q*step, q < npos
-    const size_t region = hit_base(b, r); const uint32_t region_cap = hit_cap(b, r);
-    uint32_t total = 0, win_with_hits = 0, flags = 0;
+    const size_t region = hit_base(b, ix.slot, r); const uint32_t region_cap = hit_cap(b, r);
+    uint32_t total = 0, flags = 0, cost = 0;
     const uint32_t nvar = hasn ? 3u : 2u;
     for (uint32_t var = 0; var < nvar; ++var) {
       if (var == kVarFwd && !do_fwd) continue;
@@ -291,26 +296,25 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
         if (lh.overflow) flags |= kOvfSeedLane;
         const uint32_t n = lh.overflow ? 0u : lh.n;
         const uint32_t incl = warp_incl_scan_u32(n), tot = __shfl_sync(kFull, incl, 31);
-        win_with_hits += __popc(__ballot_sync(kFull, lh.n > 0));
         if (total + tot > region_cap) { flags |= kOvfSeedRegion; }
         else {
           const size_t base = region + total + incl - n;
-          for (uint32_t k = 0; k < n; ++k) b.hits[base + k] = make_uint2(lh.buf[k * lh.stride], p | (var << 24));
+          for (uint32_t k = 0; k < n; ++k) {
+            const uint32_t id = lh.buf[k * lh.stride];
+            b.hits[base + k] = make_uint2(id, p | (var << 24));
+            cost += __ldg(ix.pos_off + id + 1) - __ldg(ix.pos_off + id);
+          }
         }
         total += tot;
         __syncwarp();
       }
     }
     flags = __reduce_or_sync(kFull, flags);
+    cost = warp_sum_u32(min(cost, 1u << 24));
     if (lane == 0) {
-      b.hit_cnt[r] = (flags & kOvfSeedRegion) ? 0u : total;
+      b.hit_cnt[cnt_idx] = (flags & kOvfSeedRegion) ? 0u : total;
       if (flags) atomicOr(&b.flags[r], flags);
-      // hit_seeds only grows (paralleltraversal.cpp:242-249): the candidate kernel can matter only if the
-      // carried count plus every window with hits reaches num_seeds (:256)
-      if (rs.hit_seeds + win_with_hits >= (uint32_t)max(prm.num_seeds, 0) && win_with_hits > 0 && !flags) {
-        const uint32_t slot = atomicAdd(b.work_n, 1u);
-        b.worklist[slot] = r;
-      }
+      if (total) atomicAdd(&b.cost[r - b.r0], max(cost, 1u));
     }
   }
   // instrumentation + num_short (processor.cpp:113)
@@ -323,6 +327,19 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
       atomicAdd(&b.counters[dcBuckets], (unsigned long long)nb); atomicAdd(&b.counters[dcEntries], (unsigned long long)ne);
     }
   }
+}
+
+// heaviest-first schedule for the candidate kernel: a few reads carry thousands of Smith-Waterman calls
+// (16S/23S conserved regions vote for thousands of references), so reads are binned by log2 of their
+// estimated work and the persistent warps drain the bins from the heaviest down.
+__global__ void bin_kernel(DevBatch b) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b.nreads) return;
+  const uint32_t c = b.cost[i];
+  if (c == 0 || b.flags[b.r0 + i]) return;
+  const uint32_t bin = min((uint32_t)(kCostBins - 1), 31u - (uint32_t)__clz(c));
+  const uint32_t slot = atomicAdd(&b.bin_count[bin], 1u);
+  b.bins[(size_t)bin * b.cnt_stride + slot] = b.r0 + i;
 }
 
 // unit-test kernel: explicit windows, one lane per window (smr_debug_seed_windows)
