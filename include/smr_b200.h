@@ -137,7 +137,7 @@ int smr_last_timings(const smr_ctx*, double out[8]);
 /* -- unit-test entry points (run the same device functions the hot path uses) ------------------ */
 /* seed search of explicit windows: for window k, sequence seq03 (0..3, length >= win_pos+lnwin) of
  * read read_of[k]; returns ids per window into ids[k*cap .. ), counts[k] (may exceed cap),
- * zero[k] = accept_zero_kmer. */
+ * zero[k] = accept_zero_kmer.  Bit 31 of cap selects the per-lane fallback search instead of the cooperative one. */
 int smr_debug_seed_windows(smr_ctx*, uint32_t part_slot, const uint8_t* seq_cat, const uint64_t* seq_off,
                            uint32_t nreads, const uint32_t* win_read, const uint32_t* win_pos, uint32_t nwin,
                            uint32_t* ids, uint32_t cap, uint32_t* counts, uint8_t* zero);

@@ -194,7 +194,7 @@ class Aligner:
                     launches=int(out[6]))
 
     # ---- unit-test entry points ----
-    def debug_seed_windows(self, part_slot, cat03, off, win_read, win_pos, cap=64):
+    def debug_seed_windows(self, part_slot, cat03, off, win_read, win_pos, cap=64, fallback_path=False):
         cat03 = np.ascontiguousarray(cat03, np.uint8)
         off = np.ascontiguousarray(off, np.uint64)
         win_read = np.ascontiguousarray(win_read, np.uint32)
@@ -204,8 +204,8 @@ class Aligner:
         counts = np.zeros(nwin, np.uint32)
         zero = np.zeros(nwin, np.uint8)
         rc = self.L.smr_debug_seed_windows(self.h, C.c_uint32(part_slot), _ptr(cat03), _ptr(off), C.c_uint32(off.size - 1),
-                                           _ptr(win_read), _ptr(win_pos), C.c_uint32(nwin), _ptr(ids), C.c_uint32(cap),
-                                           _ptr(counts), _ptr(zero))
+                                           _ptr(win_read), _ptr(win_pos), C.c_uint32(nwin), _ptr(ids),
+                                           C.c_uint32(cap | (0x80000000 if fallback_path else 0)), _ptr(counts), _ptr(zero))
         self._check(rc, "smr_debug_seed_windows")
         return ids.reshape(nwin, cap), counts, zero
 

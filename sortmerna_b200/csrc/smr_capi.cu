@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -53,6 +54,7 @@ struct smr_ctx {
   uint64_t cigar_cap_dev = 0;
   uint32_t scale = 1;         // scratch scale of the current run (1 = fast path)
   bool instr = true;          // count windows/nodes/entries in the seed kernel
+  uint64_t flag_hist[6] = {0, 0, 0, 0, 0, 0};  // overflow causes seen so far (seed lane / seed region / pairs / trace / cigar / error)
   // timings
   std::vector<cudaEvent_t> ev;
   double t_total = 0, t_seed = 0, t_lis = 0, t_final = 0, t_h2d = 0, t_d2h = 0; uint64_t n_launch = 0;
@@ -140,11 +142,9 @@ int setup_arenas(smr_ctx* ctx) {
   ctx->final_stride = final_arena_bytes(ctx->cap_w, ctx->cap_cig, ctx->row_cap, ctx->cap_dir);
   while (ctx->final_warps > 64 && ctx->final_stride * ctx->final_warps > budget) ctx->final_warps /= 2;
   if (int rc = ensure(ctx, ctx->final_arena, ctx->final_stride * ctx->final_warps)) return rc;
-  if (ctx->scale > 1) {
-    ctx->lane_hits_cap = kLaneHitCap * ctx->scale * 4;
-    ctx->lane_hits_warps = 1024;
-    if (int rc = ensure(ctx, ctx->lane_hits, (size_t)ctx->lane_hits_warps * ctx->lane_hits_cap * 32 * 4)) return rc;
-  }
+  ctx->lane_hits_cap = kLaneHitCap * ctx->scale;
+  ctx->lane_hits_warps = ctx->scale == 1 ? (uint32_t)ctx->sm_count * 8 * kSeedWarpsPerCta : 1024u;
+  if (int rc = ensure(ctx, ctx->lane_hits, (size_t)ctx->lane_hits_warps * ctx->lane_hits_cap * 32 * 4)) return rc;
   return SMR_OK;
 }
 
@@ -275,14 +275,9 @@ int run_impl(smr_ctx* ctx) {
     cudaEvent_t s0 = get_event(ctx, evi), s1 = get_event(ctx, evi + 1), s2 = get_event(ctx, evi + 2); evi += 3;
     CK(cudaEventRecord(s0, ctx->stream));
     for (size_t pi = 0; pi < hp.size(); ++pi) {
-      const int seed_ctas = ctx->sm_count * 8;
-      if (ctx->scale == 1) {
-        if (ctx->instr) seed_kernel<true><<<seed_ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, nullptr, 0);
-        else seed_kernel<false><<<seed_ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, nullptr, 0);
-      } else {
-        const int ctas = (int)(ctx->lane_hits_warps / kSeedWarpsPerCta);
-        seed_kernel<true><<<ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, (uint32_t*)ctx->lane_hits.p, ctx->lane_hits_cap);
-      }
+      const int ctas = (int)(ctx->lane_hits_warps / kSeedWarpsPerCta);
+      if (ctx->instr) seed_kernel<true><<<ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, (uint32_t*)ctx->lane_hits.p, ctx->lane_hits_cap);
+      else seed_kernel<false><<<ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, (uint32_t*)ctx->lane_hits.p, ctx->lane_hits_cap);
       CK(cudaGetLastError());
       ctx->n_launch += 1;
     }
@@ -364,7 +359,7 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
   for (uint32_t r = 0; r < n; ++r) {
     const uint32_t dst = map ? map[r] : r;
     if (fl[r] & kErrTrace) { ctx->err = "trace back error (ssw.c:707 is fatal in the reference too)"; rc = SMR_ERR_INDEX; }
-    if (fl[r]) { flagged.push_back(r); continue; }
+    if (fl[r]) { flagged.push_back(r); for (int bit = 0; bit < 6; ++bit) if (fl[r] & (1u << bit)) ctx->flag_hist[bit]++; continue; }
     smr_read_result& o = out.results[dst];
     const ReadState& s = st[r];
     o.lastIndex = s.lastIndex; o.lastPart = s.lastPart; o.hit_seeds = s.hit_seeds; o.min_index = s.min_index; o.max_index = s.max_index;
@@ -405,6 +400,8 @@ int align_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_off, ui
   if ((rc = download_impl(ctx, out, flagged, map))) return rc;
   ctx->t_h2d = h2d;
   if (flagged.empty()) return SMR_OK;
+  if (getenv("SMR_VERBOSE")) fprintf(stderr, "[smr] %zu reads overflowed their scratch at scale %u: retrying with scale %u (causes so far: lane %llu region %llu pairs %llu trace %llu cigar %llu err %llu)\n", flagged.size(), ctx->scale, ctx->scale * 8,
+      (unsigned long long)ctx->flag_hist[0], (unsigned long long)ctx->flag_hist[1], (unsigned long long)ctx->flag_hist[2], (unsigned long long)ctx->flag_hist[3], (unsigned long long)ctx->flag_hist[4], (unsigned long long)ctx->flag_hist[5]);
   if (depth >= 3) { ctx->err = "scratch overflow persists after 3 retries (" + std::to_string(flagged.size()) + " reads)"; return SMR_ERR_CAPACITY; }
   // sub-batch of the flagged reads, 8x the scratch
   std::vector<uint8_t> sseq; std::vector<uint64_t> soff(1, 0); std::vector<uint32_t> smap;
@@ -564,6 +561,8 @@ int smr_download_results(smr_ctx* ctx, smr_read_result* results, smr_aln* alns, 
   std::vector<uint32_t> flagged;
   int rc = download_impl(ctx, out, flagged, nullptr);
   if (rc == SMR_OK && !flagged.empty()) {
+    if (getenv("SMR_VERBOSE")) fprintf(stderr, "[smr] %zu reads overflowed their scratch (resident batch): retrying with scale 8 (causes so far: lane %llu region %llu pairs %llu trace %llu cigar %llu err %llu)\n", flagged.size(),
+      (unsigned long long)ctx->flag_hist[0], (unsigned long long)ctx->flag_hist[1], (unsigned long long)ctx->flag_hist[2], (unsigned long long)ctx->flag_hist[3], (unsigned long long)ctx->flag_hist[4], (unsigned long long)ctx->flag_hist[5]);
     // redo the overflowed reads from the retained host copy with larger scratch
     std::vector<uint8_t> hs; std::vector<uint64_t> ho;
     hs.swap(ctx->h_seq); ho.swap(ctx->h_off);
@@ -592,6 +591,8 @@ int smr_debug_seed_windows(smr_ctx* ctx, uint32_t part_slot, const uint8_t* seq_
                            uint8_t* zero) {
   if (!ctx || part_slot >= ctx->parts.size() || !seq_cat || !seq_off || !win_read || !win_pos || !ids || !counts || !zero) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
+  const uint32_t cap_arg = cap;
+  cap &= 0x7FFFFFFFu;
   const uint64_t total = seq_off[nreads] - seq_off[0];
   std::vector<uint32_t> off32(nreads + 1);
   for (uint32_t r = 0; r <= nreads; ++r) off32[r] = (uint32_t)(seq_off[r] - seq_off[0]);
@@ -605,8 +606,9 @@ int smr_debug_seed_windows(smr_ctx* ctx, uint32_t part_slot, const uint8_t* seq_
   CK(cudaMemcpy(d_wp, win_pos, (size_t)nwin * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(d_ids, 0, (size_t)nwin * cap * 4));
   DevIndex d = ctx->parts[part_slot].d;
-  seed_debug_kernel<<<(nwin + 127) / 128, 128, 0, ctx->stream>>>(d, d_seq, d_off, d_wr, d_wp, nwin, d_ids, cap, d_cnt, d_zero,
-                                                                 ctx->have_params ? ctx->prm.is_full_search : 0);
+  const int mode = cap_arg >= 0x80000000u ? 1 : 0;   // high bit of cap selects the per-lane fallback path (tests exercise both)
+  seed_debug_kernel<<<(nwin + kSeedWarpsPerCta * 32 - 1) / (kSeedWarpsPerCta * 32), kSeedWarpsPerCta * 32, 0, ctx->stream>>>(
+      d, d_seq, d_off, d_wr, d_wp, nwin, d_ids, cap, d_cnt, d_zero, ctx->have_params ? ctx->prm.is_full_search : 0, mode);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(ids, d_ids, (size_t)nwin * cap * 4, cudaMemcpyDeviceToHost));

@@ -13,33 +13,27 @@
 // position, index)); the candidate kernel later replays the reference's pass order on them.
 #pragma once
 #include "smr_dev.cuh"
+#include "smr_levbits.h"
 
 namespace smr {
 
-// Universal Levenshtein automaton d=1 as used by the reference (traverse_bursttrie.cpp:68-98):
-// 15 states (14 = dead); table t, row bv, column state at kLevOff[t] + bv*14 + state.
-__constant__ uint8_t c_lev[420] = {
-    // t = 0 : 16 rows
-    3,14,14,14,14,14,14,14,14,14,14,14,14,14,  3,14,14,14,14,14,14,14,14,14,14,14,14,14,
-    7,14,14,14,4,4,4,4,14,14,14,14,14,14,      7,14,14,14,4,4,4,4,14,14,14,14,14,14,
-    0,14,2,2,14,14,2,2,14,14,14,14,14,14,      0,14,2,2,14,14,2,2,14,14,14,14,14,14,
-    0,14,2,2,4,4,6,6,14,14,14,14,14,14,        0,14,2,2,4,4,6,6,14,14,14,14,14,14,
-    3,1,14,1,14,1,14,1,14,14,14,14,14,14,      3,1,14,1,14,1,14,1,14,14,14,14,14,14,
-    7,1,14,1,4,5,4,5,14,14,14,14,14,14,        7,1,14,1,4,5,4,5,14,14,14,14,14,14,
-    0,1,2,3,14,1,2,3,14,14,14,14,14,14,        0,1,2,3,14,1,2,3,14,14,14,14,14,14,
-    0,1,2,3,4,5,6,7,14,14,14,14,14,14,         0,1,2,3,4,5,6,7,14,14,14,14,14,14,
-    // t = 1 : 8 rows
-    3,14,14,14,14,14,14,14,14,14,14,14,14,14,  13,14,14,14,10,10,10,10,14,14,14,14,14,14,
-    8,14,2,2,14,14,2,2,14,14,14,14,14,14,      8,14,2,2,10,10,12,12,14,14,14,14,14,14,
-    3,1,14,1,14,1,14,1,14,14,14,14,14,14,      13,1,14,1,10,11,10,11,14,14,14,14,14,14,
-    8,1,2,3,14,1,2,3,14,14,14,14,14,14,        8,1,2,3,10,11,12,13,14,14,14,14,14,14,
-    // t = 2 : 4 rows
-    12,14,14,14,14,14,14,14,12,14,14,14,14,14, 9,14,10,10,14,14,10,10,9,14,14,14,10,10,
-    12,1,14,1,14,1,14,1,12,14,14,1,14,1,       9,1,10,12,14,1,10,12,9,14,14,1,10,12,
-    // t = 3 : 2 rows
-    10,14,14,14,14,14,14,14,14,10,14,14,14,14, 10,10,14,10,14,10,14,10,14,10,14,14,10,14};
-
-__device__ __forceinline__ uint32_t lev_off(uint32_t t) { return t == 0 ? 0u : (t == 1 ? 224u : (t == 2 ? 336u : 392u)); }
+// ---------------------------------------------------------------------------------------------
+// The reference drives the trie DFS with a table-driven universal Levenshtein automaton for d=1
+// (traverse_bursttrie.cpp:68-98, bit-vectors from bitvector.cpp:56-132).  That automaton accepts at
+// depth d (d+1 text characters consumed) exactly when the edit distance between those d+1 characters
+// and the 9-nt half window is <= 1, is "alive" exactly when some prefix of the half window is within
+// distance 1 of the text so far, and reaches state 9 at depth 8 exactly on an exact match (checked
+// exhaustively against the table: tests/test_lev_equivalence.py, and by the GPU-vs-oracle window tests;
+// the oracle keeps the table).  The kernels therefore evaluate those three predicates with a few
+// bit-parallel operations on 2-bit packed strings instead of walking a table:
+//   P = the half window (pw chars), T = the text (trie path letters + bucket tail, pw+1 chars),
+//   both packed first character in the LOWEST two bits (the bucket tails' own layout).
+// ---------------------------------------------------------------------------------------------
+// reverse the order of the pw 2-bit characters of v
+__device__ __forceinline__ uint32_t rev_chars(uint32_t v, uint32_t pw) {
+  uint32_t x = __brev(v) >> (32 - 2 * pw);
+  return ((x & 0x55555555u) << 1) | ((x >> 1) & 0x55555555u);
+}
 
 // 2-bit packed reads, first base most significant: base i of a read lives in word i>>4 at bit 30-2*(i&15).
 // Returns the L-mer starting at forward position p as a 2L-bit integer (first base most significant).
@@ -65,42 +59,36 @@ struct LaneHits {
 
 struct SeedStats { uint32_t nodes, buckets, entries; };
 
-// characteristic bit masks of a 9-nt half window: for letter c, bit (pw+1-k) of field c is set iff
-// p[k]==c, so that the reference's bit-vector row d (bitvector.cpp:56-132) is (M_c >> (pw-1-d)) & 15.
-__device__ __forceinline__ uint64_t build_masks(uint32_t half, uint32_t pw, bool ascending) {
-  // ascending: p[k] = base k of `half` (first base most significant); else p[k] = base pw-1-k
-  uint64_t M = 0;
-  for (uint32_t k = 0; k < pw; ++k) {
-    const uint32_t c = ascending ? (half >> (2 * (pw - 1 - k))) & 3u : (half >> (2 * k)) & 3u;
-    M |= 1ull << (16 * c + pw + 1 - k);
-  }
-  return M;
+// the reference's per-entry side effects (traverse_bursttrie.cpp:249-281) applied to a classification code;
+// returns true when the window search ends on a 0-error match
+__device__ __forceinline__ bool apply_entry(uint32_t code, uint32_t id, bool full_search, LaneHits& lh) {
+  const uint32_t d1 = code & 3u;
+  if (d1 == 0) return false;
+  const bool z = (code & 4u) && !full_search;
+  if (d1 == 2 && z) { lh.n = 1; lh.buf[0] = id; lh.overflow = false; return true; }                  // :256-262
+  for (uint32_t f = 0; f < lh.n && f < lh.cap; ++f) if (lh.buf[f * lh.stride] == id) return false;   // duplicate: :265-277
+  if (lh.n < lh.cap) lh.buf[lh.n * lh.stride] = id; else lh.overflow = true;
+  lh.n++;
+  if (d1 == 1 && z) { lh.n = 1; lh.buf[0] = id; lh.overflow = false; return true; }                  // 0-error one step after the push
+  return false;
 }
 
-__device__ __forceinline__ uint32_t lev_next(const uint8_t* __restrict__ s_lev, uint64_t M, uint32_t pw, uint32_t depth,
-                                             uint32_t c, uint32_t lev) {
-  const uint32_t mc = (uint32_t)(M >> (16 * c)) & 0xFFFFu;
-  if (depth < pw - 2) return s_lev[((mc >> (pw - 1 - depth)) & 15u) * 14u + lev];            // traverse_bursttrie.cpp:131-135
-  const uint32_t t = 3 - pw + depth;                                                            // :136-139
-  return s_lev[lev_off(t) + ((mc >> 2) & ((2u << (pw - depth)) - 1u)) * 14u + lev];
-}
-
-// DFS of one mini burst trie in lock step with the automaton (traverse_bursttrie.cpp:100-298).
-// Returns true when a 0-error match ended the search of this window (accept_zero_kmer).
+// Sequential DFS of one mini burst trie for one window (traverse_bursttrie.cpp:100-298): used for the few
+// windows that overflow the cooperative buffers, and by the unit-test entry point.
 template <bool INSTR>
-__device__ bool walk_trie(const DevIndex& ix, const uint8_t* __restrict__ s_lev, uint32_t root, uint64_t M, bool full_search,
-                          LaneHits& hits, SeedStats& st) {
+__device__ bool walk_trie(const DevIndex& ix, uint32_t root, uint32_t P, bool full_search, LaneHits& hits, SeedStats& st) {
   const uint32_t pw = ix.partialwin;
   uint32_t stk_node[16];
-  uint8_t stk_meta[16];
-  uint32_t depth = 0, node = root, lev_in = 0, letter = 0;
+  uint8_t stk_letter[16];
+  uint32_t depth = 0, node = root, letter = 0, path = 0;
   uint4 na = __ldg(ix.nodes + 2 * (size_t)node), nb = __ldg(ix.nodes + 2 * (size_t)node + 1);
   if (INSTR) st.nodes++;
   for (;;) {
     if (letter == 4) {
       if (depth == 0) return false;
       --depth;
-      node = stk_node[depth]; letter = stk_meta[depth] & 7u; lev_in = stk_meta[depth] >> 4;
+      node = stk_node[depth]; letter = stk_letter[depth];
+      path &= (1u << (2 * depth)) - 1u;
       na = __ldg(ix.nodes + 2 * (size_t)node); nb = __ldg(ix.nodes + 2 * (size_t)node + 1);
       continue;
     }
@@ -112,64 +100,158 @@ __device__ bool walk_trie(const DevIndex& ix, const uint8_t* __restrict__ s_lev,
       default: w0 = nb.z; w1 = nb.w; break;
     }
     const uint32_t flag = w0 & 3u;
-    if (flag == 0) { ++letter; continue; }
-    const uint32_t lev = lev_next(s_lev, M, pw, depth, letter, lev_in);
-    if (lev == 14) { ++letter; continue; }
+    const uint32_t tp = path | (letter << (2 * depth));
+    if (flag == 0 || !viable_bits(P, tp, depth + 1)) { ++letter; continue; }   // empty element or automaton dead (:122-147)
     if (flag == 1) {
-      stk_node[depth] = node; stk_meta[depth] = (uint8_t)((letter + 1) | (lev_in << 4));
-      ++depth; node = w1; lev_in = lev; letter = 0;
+      stk_node[depth] = node; stk_letter[depth] = (uint8_t)(letter + 1);
+      path = tp; ++depth; node = w1; letter = 0;
       na = __ldg(ix.nodes + 2 * (size_t)node); nb = __ldg(ix.nodes + 2 * (size_t)node + 1);
       if (INSTR) st.nodes++;
       continue;
     }
-    // bucket (:176-292)
-    const uint32_t cnt = w0 >> 2, nchars = pw - depth;
+    const uint32_t cnt = w0 >> 2;                                               // bucket (:176-292)
     if (INSTR) st.buckets++;
     const uint2* __restrict__ e = ix.entries + w1;
     for (uint32_t k = 0; k < cnt; ++k) {
       const uint2 en = __ldg(e + k);
       if (INSTR) st.entries++;
-      uint32_t tail = en.x, depth_b = depth, s = lev;
-      bool local_accept = false, zero = false;
-      for (uint32_t j = 0; j < nchars; ++j) {
-        ++depth_b;
-        s = lev_next(s_lev, M, pw, depth_b, tail & 3u, s);
-        if (s == 14) break;
-        if (depth_b >= pw - 2) {
-          if (s >= 8) local_accept = true;                          // 1-error match (:232-235)
-          if (depth_b == pw - 1 && s == 9) zero = !full_search;     // 0-error match (:237-246)
-        }
-        if (local_accept) {
-          if (zero) {                                               // :256-262
-            hits.n = 1; hits.buf[0] = en.y; hits.overflow = false;
-            return true;
-          }
-          bool dup = false;                                         // :265-277
-          for (uint32_t f = 0; f < hits.n && f < hits.cap; ++f) if (hits.buf[f * hits.stride] == en.y) { dup = true; break; }
-          if (dup) break;
-          if (hits.n < hits.cap) hits.buf[hits.n * hits.stride] = en.y; else hits.overflow = true;
-          hits.n++;
-        }
-        tail >>= 2;
-      }
+      if (apply_entry(classify_bits(P, tp | (en.x << (2 * (depth + 1))), pw), en.y, full_search, hits)) return true;
     }
     ++letter;
   }
 }
 
-// both sub-searches of one window (paralleltraversal.cpp:129-249); V = the lnwin-mer, first base most significant
+// ---------------------------------------------------------------------------------------------
+// Cooperative sub-search of 32 windows at once: one window per lane for the short, divergent trie NODE
+// walk; then the visited buckets are cut into tasks of <= kTaskEntries entries, compacted across the
+// warp, and classified one task per lane (uniform arithmetic, no table); finally each lane replays the
+// reference's DFS-order semantics (0-error exit, per-window de-duplication) over the codes of its window.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTaskMax = 256;      // tasks per 32-window round kept in shared memory
+constexpr int kTaskEntries = 8;    // entries per task
+constexpr int kEntryCap = 512;     // classification codes per round kept in shared memory
+constexpr uint32_t kTaskEnd = 0xFFFFu;
+
+struct CoopSmem {                  // per warp, ~4.4 KB
+  uint2 flat[kTaskMax];            // {first entry index, cnt | (depth+1)<<4 | path<<8}
+  uint16_t start[kTaskMax];        // first code slot of the task
+  uint16_t next[kTaskMax];         // next task of the same window, DFS order (kTaskEnd = last)
+  uint8_t lane[kTaskMax];          // owning window (lane)
+  uint8_t code[kEntryCap];
+  uint32_t P[32];
+  uint32_t ntask, nentry;
+};
+
+// trie NODE walk only: records the buckets the DFS would visit, in DFS order, as a linked list of tasks of
+// <= kTaskEntries entries.  Returns false if the shared buffers overflowed (the caller then searches this
+// window with walk_trie instead).
 template <bool INSTR>
-__device__ bool seed_window(const DevIndex& ix, const uint8_t* __restrict__ s_lev, uint64_t V, bool full_search, LaneHits& hits,
-                            SeedStats& st) {
+__device__ bool walk_nodes(const DevIndex& ix, uint32_t root, uint32_t P, CoopSmem& sm, unsigned lane, uint32_t& head, SeedStats& st) {
+  uint32_t stk_node[16];
+  uint8_t stk_letter[16];
+  uint32_t depth = 0, node = root, letter = 0, path = 0, last = kTaskEnd;
+  uint4 na = __ldg(ix.nodes + 2 * (size_t)node), nb = __ldg(ix.nodes + 2 * (size_t)node + 1);
+  if (INSTR) st.nodes++;
+  for (;;) {
+    if (letter == 4) {
+      if (depth == 0) return true;
+      --depth;
+      node = stk_node[depth]; letter = stk_letter[depth];
+      path &= (1u << (2 * depth)) - 1u;
+      na = __ldg(ix.nodes + 2 * (size_t)node); nb = __ldg(ix.nodes + 2 * (size_t)node + 1);
+      continue;
+    }
+    uint32_t w0, w1;
+    switch (letter) {
+      case 0: w0 = na.x; w1 = na.y; break;
+      case 1: w0 = na.z; w1 = na.w; break;
+      case 2: w0 = nb.x; w1 = nb.y; break;
+      default: w0 = nb.z; w1 = nb.w; break;
+    }
+    const uint32_t flag = w0 & 3u;
+    const uint32_t tp = path | (letter << (2 * depth));
+    if (flag == 0 || !viable_bits(P, tp, depth + 1)) { ++letter; continue; }
+    if (flag == 1) {
+      stk_node[depth] = node; stk_letter[depth] = (uint8_t)(letter + 1);
+      path = tp; ++depth; node = w1; letter = 0;
+      na = __ldg(ix.nodes + 2 * (size_t)node); nb = __ldg(ix.nodes + 2 * (size_t)node + 1);
+      if (INSTR) st.nodes++;
+      continue;
+    }
+    if (INSTR) st.buckets++;
+    const uint32_t cnt = w0 >> 2;
+    if (INSTR) st.entries += cnt;
+    for (uint32_t c0 = 0; c0 < cnt; c0 += kTaskEntries) {
+      const uint32_t n = min(cnt - c0, (uint32_t)kTaskEntries);
+      const uint32_t slot = atomicAdd(&sm.ntask, 1u), es = atomicAdd(&sm.nentry, n);
+      if (slot >= (uint32_t)kTaskMax || es + n > (uint32_t)kEntryCap) {
+        if (slot < (uint32_t)kTaskMax) { sm.flat[slot] = make_uint2(0u, 0u); sm.start[slot] = 0; sm.next[slot] = (uint16_t)kTaskEnd; sm.lane[slot] = 0; }
+        return false;
+      }
+      sm.flat[slot] = make_uint2(w1 + c0, n | ((depth + 1) << 4) | (tp << 8));
+      sm.start[slot] = (uint16_t)es; sm.next[slot] = (uint16_t)kTaskEnd; sm.lane[slot] = (uint8_t)lane;
+      if (last == kTaskEnd) head = slot; else sm.next[last] = (uint16_t)slot;
+      last = slot;
+    }
+    ++letter;
+  }
+}
+
+// One sub-search (forward or mirror) for the 32 windows of a round.  `root`/`P` are per lane (root ==
+// kNoneDev: lane idle).  Appends to lh with the reference's de-duplication; sets zero.
+template <bool INSTR>
+__device__ void coop_subsearch(const DevIndex& ix, CoopSmem& sm, const uint32_t root, const uint32_t P, const bool full_search, LaneHits& lh,
+                               bool& zero, SeedStats& st) {
+  const unsigned lane = lane_id();
+  const uint32_t pw = ix.partialwin;
+  sm.P[lane] = P;
+  if (lane == 0) { sm.ntask = 0; sm.nentry = 0; }
+  __syncwarp();
+  uint32_t head = kTaskEnd;
+  bool slow = false;
+  if (root != kNoneDev) slow = !walk_nodes<INSTR>(ix, root, P, sm, lane, head, st);
+  __syncwarp();
+  const uint32_t ntask = min(sm.ntask, (uint32_t)kTaskMax);
+  // classify: one task (<= kTaskEntries consecutive entries of one bucket) per lane; pure arithmetic
+  for (uint32_t t = lane; t < ntask; t += 32) {
+    const uint2 tk = sm.flat[t];
+    const uint32_t cnt = tk.y & 0xFu, sh = 2 * ((tk.y >> 4) & 0xFu), path = tk.y >> 8, Pw = sm.P[sm.lane[t]];
+    const uint32_t es = sm.start[t];
+    if (es + cnt > (uint32_t)kEntryCap) continue;   // belongs to a window that overflowed: it is redone below
+    const uint2* __restrict__ ep = ix.entries + tk.x;
+#pragma unroll 4
+    for (uint32_t k = 0; k < cnt; ++k) sm.code[es + k] = (uint8_t)classify_bits(Pw, path | (__ldg(ep + k).x << sh), pw);
+  }
+  __syncwarp();
+  // replay the DFS-order semantics per window over its chain of tasks
+  if (!slow) {
+    for (uint32_t t = head; t != kTaskEnd && !zero; t = sm.next[t]) {
+      const uint2 tk = sm.flat[t];
+      const uint32_t cnt = tk.y & 0xFu, es = sm.start[t];
+      for (uint32_t k = 0; k < cnt; ++k) {
+        const uint32_t c = sm.code[es + k];
+        if ((c & 3u) == 0) continue;
+        if (apply_entry(c, __ldg(ix.entries + tk.x + k).y, full_search, lh)) { zero = true; break; }
+      }
+    }
+  } else {
+    zero = walk_trie<INSTR>(ix, root, P, full_search, lh, st);
+  }
+  __syncwarp();
+}
+
+// both sub-searches of one window, sequentially by one lane (paralleltraversal.cpp:129-249); V = the lnwin-mer
+template <bool INSTR>
+__device__ bool seed_window(const DevIndex& ix, uint64_t V, bool full_search, LaneHits& hits, SeedStats& st) {
   const uint32_t pw = ix.partialwin;
   const uint32_t keyf = (uint32_t)(V >> (2 * pw)), keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
   hits.n = 0;
   bool zero = false;
   const uint32_t rootF = __ldg(&ix.lookup[keyf]).x;                               // :161
-  if (rootF != kNoneDev) zero = walk_trie<INSTR>(ix, s_lev, rootF, build_masks(keyr, pw, true), full_search, hits, st);
+  if (rootF != kNoneDev) zero = walk_trie<INSTR>(ix, rootF, rev_chars(keyr, pw), full_search, hits, st);
   if (!zero) {                                                                    // :188
     const uint32_t rootR = __ldg(&ix.lookup[keyr]).y;                             // :215
-    if (rootR != kNoneDev) zero = walk_trie<INSTR>(ix, s_lev, rootR, build_masks(keyf, pw, false), full_search, hits, st);
+    if (rootR != kNoneDev) zero = walk_trie<INSTR>(ix, rootR, keyf, full_search, hits, st);
   }
   return zero;
 }
@@ -235,25 +317,23 @@ __global__ void pack_reads_kernel(DevBatch b, uint32_t* pk03, uint32_t* pk03alt,
   }
 }
 
-constexpr int kSeedWarpsPerCta = 8;
-constexpr int kLaneHitCap = 16;   // per-window hit slots in shared memory (fast path)
+constexpr int kSeedWarpsPerCta = 4;
+constexpr int kLaneHitCap = 128;  // ids per window in the per-warp HBM scratch (x scale on a retry)
 
 // The seed kernel.  grid-stride over reads, one warp per read.
-//   lane_hits_g: optional global per-lane buffers (retry path) [nwarps_total][cap_g][32]; nullptr -> shared memory, kLaneHitCap
+//   lane_hits_g: per-lane id buffers [total warps][cap_g][32]
 template <bool INSTR>
-__global__ void __launch_bounds__(kSeedWarpsPerCta * 32)
+__global__ void __launch_bounds__(kSeedWarpsPerCta * 32, 8)
 seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint32_t cap_g) {
-  __shared__ uint8_t s_lev[420];
-  __shared__ uint32_t s_hits[kSeedWarpsPerCta][kLaneHitCap][32];
-  for (int i = threadIdx.x; i < 420; i += blockDim.x) s_lev[i] = c_lev[i];
-  __syncthreads();
+  __shared__ CoopSmem s_coop[kSeedWarpsPerCta];
   const unsigned lane = lane_id();
   const uint32_t wic = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kSeedWarpsPerCta + wic, nwarps = gridDim.x * kSeedWarpsPerCta;
-  const uint32_t L = ix.lnwin;
+  const uint32_t L = ix.lnwin, pw = ix.partialwin;
+  const bool full = prm.is_full_search != 0;
+  CoopSmem& sm = s_coop[wic];
   LaneHits lh;
-  if (lane_hits_g) { lh.buf = lane_hits_g + (size_t)warp * cap_g * 32 + lane; lh.stride = 32; lh.cap = cap_g; }
-  else { lh.buf = &s_hits[wic][0][lane]; lh.stride = 32; lh.cap = kLaneHitCap; }
+  lh.buf = lane_hits_g + (size_t)warp * cap_g * 32 + lane; lh.stride = 32; lh.cap = cap_g;   // per-window ids live in a per-warp HBM scratch
   SeedStats st{0, 0, 0};
   uint32_t n_windows = 0, n_short = 0;
   const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);
@@ -286,13 +366,20 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
         bool active = q < npos;
         if (active && step == 1) active = (p % s0 == 0) || (p % s1 == 0) || (p % s2 == 0);
         lh.n = 0; lh.overflow = false;
+        uint64_t V = 0;
+        uint32_t keyf = 0, keyr = 0, rootF = kNoneDev, rootR = kNoneDev;
         if (active) {
-          uint64_t V;
           if (var == kVarFwd) V = window_fwd(pk, p, L);
           else V = revcomp_bits(window_fwd(var == kVarRevT ? pk : pka, len - p - L, L), L);
-          seed_window<INSTR>(ix, s_lev, V, prm.is_full_search != 0, lh, st);
+          keyf = (uint32_t)(V >> (2 * pw)); keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
+          rootF = __ldg(&ix.lookup[keyf]).x;                                      // paralleltraversal.cpp:161
           ++n_windows;
         }
+        bool zero = false;
+        // forward sub-search for all 32 windows, then the mirror sub-search for those without a 0-error hit (:188)
+        coop_subsearch<INSTR>(ix, sm, rootF, rev_chars(keyr, pw), full, lh, zero, st);   // P = w[9..18) ascending
+        if (active && !zero) rootR = __ldg(&ix.lookup[keyr]).y;                   // :215
+        coop_subsearch<INSTR>(ix, sm, rootR, keyf, full, lh, zero, st);                   // P = w[8..0] descending
         if (lh.overflow) flags |= kOvfSeedLane;
         const uint32_t n = lh.overflow ? 0u : lh.n;
         const uint32_t incl = warp_incl_scan_u32(n), tot = __shfl_sync(kFull, incl, 31);
@@ -342,22 +429,33 @@ __global__ void bin_kernel(DevBatch b) {
   b.bins[(size_t)bin * b.cnt_stride + slot] = b.r0 + i;
 }
 
-// unit-test kernel: explicit windows, one lane per window (smr_debug_seed_windows)
-__global__ void seed_debug_kernel(DevIndex ix, const uint8_t* seq03, const uint32_t* seq_off, const uint32_t* win_read,
-                                  const uint32_t* win_pos, uint32_t nwin, uint32_t* ids, uint32_t cap, uint32_t* counts,
-                                  uint8_t* zero, int full_search) {
-  __shared__ uint8_t s_lev[420];
-  for (int i = threadIdx.x; i < 420; i += blockDim.x) s_lev[i] = c_lev[i];
-  __syncthreads();
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nwin) return;
-  const uint8_t* s = seq03 + seq_off[win_read[k]] + win_pos[k];
+// unit-test kernel: explicit windows through the SAME cooperative path as seed_kernel (mode 0), or through
+// the per-lane DFS fallback only (mode 1) (smr_debug_seed_windows)
+__global__ void __launch_bounds__(kSeedWarpsPerCta * 32)
+seed_debug_kernel(DevIndex ix, const uint8_t* seq03, const uint32_t* seq_off, const uint32_t* win_read, const uint32_t* win_pos, uint32_t nwin,
+                  uint32_t* ids, uint32_t cap, uint32_t* counts, uint8_t* zero, int full_search, int mode) {
+  __shared__ CoopSmem s_coop[kSeedWarpsPerCta];
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;   // whole warps stay together: nwin is padded by the launch
+  const bool active = k < nwin;
+  const uint32_t pw = ix.partialwin;
   uint64_t V = 0;
-  for (uint32_t i = 0; i < ix.lnwin; ++i) V = (V << 2) | (s[i] & 3u);
-  LaneHits lh; lh.buf = ids + (size_t)k * cap; lh.stride = 1; lh.cap = cap; lh.n = 0; lh.overflow = false;
+  if (active) {
+    const uint8_t* sq = seq03 + seq_off[win_read[k]] + win_pos[k];
+    for (uint32_t i = 0; i < ix.lnwin; ++i) V = (V << 2) | (sq[i] & 3u);
+  }
+  LaneHits lh; lh.buf = ids + (size_t)(active ? k : 0) * cap; lh.stride = 1; lh.cap = active ? cap : 0; lh.n = 0; lh.overflow = false;
   SeedStats st{0, 0, 0};
-  const bool z = seed_window<false>(ix, s_lev, V, full_search != 0, lh, st);
-  counts[k] = lh.n; zero[k] = z ? 1 : 0;
+  bool z = false;
+  const bool full = full_search != 0;
+  if (mode == 0) {
+    CoopSmem& sm = s_coop[threadIdx.x >> 5];
+    const uint32_t keyf = (uint32_t)(V >> (2 * pw)), keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
+    const uint32_t rootF = active ? __ldg(&ix.lookup[keyf]).x : kNoneDev;
+    coop_subsearch<false>(ix, sm, rootF, rev_chars(keyr, pw), full, lh, z, st);
+    const uint32_t rootR = (active && !z) ? __ldg(&ix.lookup[keyr]).y : kNoneDev;
+    coop_subsearch<false>(ix, sm, rootR, keyf, full, lh, z, st);
+  } else if (active) z = seed_window<false>(ix, V, full, lh, st);
+  if (active) { counts[k] = lh.n; zero[k] = z ? 1 : 0; }
 }
 
 }  // namespace smr

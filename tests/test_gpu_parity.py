@@ -56,7 +56,8 @@ def test_seed_windows_match_oracle(aligner, golden, oracle_indexes):
             wr.append(r); wp.append(p)
     wr, wp = np.array(wr, np.uint32), np.array(wp, np.uint32)
     for slot, ix in enumerate(oracle_indexes):
-        ids, counts, zero = aligner.debug_seed_windows(slot, cat03, b.off, wr, wp, cap=64)
+      for fallback in (False, True):   # the cooperative search and the per-lane DFS it falls back to
+        ids, counts, zero = aligner.debug_seed_windows(slot, cat03, b.off, wr, wp, cap=64, fallback_path=fallback)
         nz = 0
         for k in range(wr.size):
             seq = cat03[int(b.off[wr[k]]):int(b.off[wr[k] + 1])]
