@@ -352,7 +352,9 @@ def main():
     value = total_reads_job / (tm[0] / 1000.0)
     e2e_value = total_reads_step * e2e_steps / (tm[1] / 1000.0)
     # roofline of the dominant kernel (seed search): algorithmic bytes per SURVEY 8(d), counters are per step per rank-sum
-    alg_bytes = counters["windows"] * 8 + counters["trie_nodes"] * 4 + counters["buckets"] * 4 + counters["bucket_entries"] * 8 + total_reads_job * READ_LEN * 16
+    # bytes the seed kernel must stream: per window two 16-byte lookup records, per scanned list entry 8 bytes
+    # (text + id), and the read bases once per (strand, index part) (DESIGN.md "seed kernel")
+    alg_bytes = counters["windows"] * 32 + counters["bucket_entries"] * 8 + total_reads_job * READ_LEN * 16
     peak, peak_src = peaks()
     seed_s = float(np.sum(seed_ms)) / 1000.0        # counters are summed over the K steps and all ranks; times are this rank's
     ach = alg_bytes / world / seed_s / 1e9 if seed_s > 0 else 0.0

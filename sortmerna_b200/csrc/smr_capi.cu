@@ -482,16 +482,15 @@ int smr_load_index_part(smr_ctx* ctx, uint32_t index_num, uint32_t part, const v
   std::vector<uint8_t> rseq(refseq_cat + ref_off[0], refseq_cat + ref_off[nref]);
   rseq.resize(rseq.size() + 64, 4);
   int rc;
-  const uint32_t* lk = nullptr; const FlatNode* nd = nullptr; const Entry* en = nullptr; const uint32_t* po = nullptr; const SeqPos* ps = nullptr;
+  const uint32_t* lk = nullptr; const Entry* en = nullptr; const uint32_t* po = nullptr; const SeqPos* ps = nullptr;
   const uint8_t* rs = nullptr; const uint32_t* ro = nullptr;
-  if ((rc = upload_vec(ctx, pt, fx.lookup, &lk))) return rc;
-  if ((rc = upload_vec(ctx, pt, fx.nodes, &nd))) return rc;
-  if ((rc = upload_vec(ctx, pt, fx.entries, &en))) return rc;
+  if ((rc = upload_vec(ctx, pt, fx.flookup, &lk))) return rc;
+  if ((rc = upload_vec(ctx, pt, fx.flist, &en))) return rc;
   if ((rc = upload_vec(ctx, pt, fx.pos_off, &po))) return rc;
   if ((rc = upload_vec(ctx, pt, fx.pos, &ps))) return rc;
   if ((rc = upload_vec(ctx, pt, rseq, &rs))) return rc;
   if ((rc = upload_vec(ctx, pt, roff, &ro))) return rc;
-  pt.d.lookup = (const uint2*)lk; pt.d.nodes = (const uint4*)nd; pt.d.entries = (const uint2*)en; pt.d.pos_off = po; pt.d.pos = (const uint2*)ps;
+  pt.d.flookup = (const uint4*)lk; pt.d.flist = (const uint2*)en; pt.d.pos_off = po; pt.d.pos = (const uint2*)ps;
   pt.d.refseq = rs; pt.d.ref_off = ro;
   pt.n_nodes = fx.nodes.size(); pt.n_entries = fx.entries.size(); pt.n_ids = pt.d.nids; pt.n_pos = fx.pos.size();
   ctx->parts.push_back(std::move(pt));

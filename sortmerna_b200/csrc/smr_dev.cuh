@@ -17,9 +17,8 @@ struct DevIndex {
   uint32_t nref, nids;
   uint32_t is_last;          // last (index,part) in --ref order (paralleltraversal.cpp:294)
   uint32_t slot;             // ordinal of this part in the context
-  const uint2* lookup;       // [4^partialwin] {root of trie_F, root of trie_R} (kNoneDev = none)
-  const uint4* nodes;        // 2 x uint4 per node: {w0,w1} x 4 elements
-  const uint2* entries;      // {tail, id}
+  const uint4* flookup;      // [4^partialwin] {offF, cntF, offR, cntR} into flist
+  const uint2* flist;        // {text (path + tail, partialwin+1 chars, first char lowest), id}, DFS order per (9-mer, direction)
   const uint32_t* pos_off;   // [nids+1]
   const uint2* pos;          // {pos, seq}, each id's list sorted by (seq,pos)
   const uint8_t* refseq;     // 0..4

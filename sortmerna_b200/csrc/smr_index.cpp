@@ -67,6 +67,19 @@ uint32_t parse_mini_trie(Reader& rd, FlatIndex& fx) {
   return rd.bad ? kNone : root.node;
 }
 
+// appends the entries of the mini trie rooted at `node` to fx.flist in the reference's DFS order
+void dfs_flatten(const FlatIndex& fx, std::vector<Entry>& out, uint32_t node, uint32_t depth, uint32_t path) {
+  for (uint32_t c = 0; c < 4; ++c) {
+    const uint32_t w0 = fx.nodes[node].w[2 * c], w1 = fx.nodes[node].w[2 * c + 1];
+    const uint32_t flag = w0 & 3u, tp = path | (c << (2 * depth));
+    if (flag == 1) dfs_flatten(fx, out, w1, depth + 1, tp);
+    else if (flag == 2) {
+      const uint32_t cnt = w0 >> 2;
+      for (uint32_t k = 0; k < cnt; ++k) out.push_back(Entry{tp | (fx.entries[w1 + k].tail << (2 * (depth + 1))), fx.entries[w1 + k].id});
+    }
+  }
+}
+
 }  // namespace
 
 std::string flatten_index(const void* kmer_file, size_t kmer_bytes, const void* trie_file, size_t trie_bytes,
@@ -92,6 +105,20 @@ std::string flatten_index(const void* kmer_file, size_t kmer_bytes, const void* 
     }
   }
   if (rd.o != trie_bytes) return "bursttrie file has trailing bytes";
+  // DFS-ordered flat lists (text = path + tail needs (partialwin+1)*2 <= 32 bits)
+  if (fx.partialwin + 1 > 16) return "lnwin too large for 32-bit packed texts";
+  fx.flookup.assign((size_t)limit * 4, 0);
+  fx.flist.reserve(fx.entries.size());
+  for (uint32_t i = 0; i < limit; ++i) {
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t root = fx.lookup[(size_t)i * 2 + j];
+      const size_t o = fx.flist.size();
+      if (root != kNone) dfs_flatten(fx, fx.flist, root, 0, 0);
+      fx.flookup[(size_t)i * 4 + 2 * j] = (uint32_t)o;
+      fx.flookup[(size_t)i * 4 + 2 * j + 1] = (uint32_t)(fx.flist.size() - o);
+      fx.max_list = std::max(fx.max_list, (uint32_t)(fx.flist.size() - o));
+    }
+  }
 
   Reader pr{(const uint8_t*)pos_file, pos_bytes};
   uint32_t n = pr.u32();

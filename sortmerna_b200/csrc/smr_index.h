@@ -25,6 +25,14 @@ struct FlatIndex {
   std::vector<uint32_t> kmer_count; // kmer::count per 9-mer (kept for the minoccur test, paralleltraversal.cpp:161)
   std::vector<FlatNode> nodes;
   std::vector<Entry> entries;
+  // DFS-ordered flat form of every mini burst trie (what the kernels read): for 9-mer k, direction d
+  // (0 = trie_F, 1 = trie_R) the list flist[flookup[4k+2d] .. +flookup[4k+2d+1]) holds one item per bucket
+  // entry in the order the reference's DFS visits them (elements A,C,G,T; child before next sibling; bucket
+  // order; traverse_bursttrie.cpp:117-295): {text, id} with text = trie path letters + bucket tail =
+  // partialwin+1 characters, 2 bits each, first character in the lowest bits.
+  std::vector<uint32_t> flookup;  // 4 words per 9-mer: offF, cntF, offR, cntR
+  std::vector<Entry> flist;       // {text, id}
+  uint32_t max_list = 0;
   std::vector<uint32_t> pos_off;  // id -> [pos_off[id], pos_off[id+1])
   std::vector<SeqPos> pos;        // every list sorted by (seq, pos)
   uint64_t n_buckets = 0;

@@ -18,16 +18,24 @@
 namespace smr {
 
 // ---------------------------------------------------------------------------------------------
-// The reference drives the trie DFS with a table-driven universal Levenshtein automaton for d=1
-// (traverse_bursttrie.cpp:68-98, bit-vectors from bitvector.cpp:56-132).  That automaton accepts at
-// depth d (d+1 text characters consumed) exactly when the edit distance between those d+1 characters
-// and the 9-nt half window is <= 1, is "alive" exactly when some prefix of the half window is within
-// distance 1 of the text so far, and reaches state 9 at depth 8 exactly on an exact match (checked
-// exhaustively against the table: tests/test_lev_equivalence.py, and by the GPU-vs-oracle window tests;
-// the oracle keeps the table).  The kernels therefore evaluate those three predicates with a few
-// bit-parallel operations on 2-bit packed strings instead of walking a table:
-//   P = the half window (pw chars), T = the text (trie path letters + bucket tail, pw+1 chars),
-//   both packed first character in the LOWEST two bits (the bucket tails' own layout).
+// How a window is searched here.
+//
+// The reference walks the mini burst trie of the window's exact 9-mer half in lock step with a table-driven
+// universal Levenshtein automaton for d=1 (traverse_bursttrie.cpp:68-298, bit-vectors bitvector.cpp:56-132),
+// pruning sub-tries the automaton rejects.  That automaton accepts at depth d exactly when the d+1 text
+// characters read so far are within one edit of the 9-nt other half, and reaches state 9 at depth 8 exactly
+// on an exact match (proved against the table and against dynamic-programming edit distance on millions of
+// cases: tests/test_lev_equivalence.py; the oracle keeps the table).  Pointer chasing and per-window DFS
+// stacks are the wrong shape for a GPU (the first version of this kernel ran with 2 of 32 lanes active), so:
+//   * at load time every mini trie is flattened into ONE contiguous list of its entries in the DFS order of
+//     the reference, each entry carrying its full text = trie path letters + bucket tail (smr_index.h);
+//   * a window search classifies EVERY entry of the list of its 9-mer with three bit-parallel predicates
+//     (smr_levbits.h) -- entries in sub-tries the reference would have pruned simply classify as "no match",
+//     so the outcome is the same, and the ~2.4x more entries cost less than the pruning did;
+//   * the 32 windows of a round are searched together: their lists form one entry stream, one entry per lane
+//     per step (coalesced 8-byte loads, no divergence); the few matching entries are compacted with
+//     ballot/popc into a shared list and each lane then replays the reference's order-dependent rules
+//     (0-error exit, per-window de-duplication, traverse_bursttrie.cpp:249-281) over its own matches.
 // ---------------------------------------------------------------------------------------------
 // reverse the order of the pw 2-bit characters of v
 __device__ __forceinline__ uint32_t rev_chars(uint32_t v, uint32_t pw) {
@@ -57,7 +65,7 @@ struct LaneHits {
   uint32_t* buf; uint32_t stride, cap, n; bool overflow;
 };
 
-struct SeedStats { uint32_t nodes, buckets, entries; };
+struct SeedStats { uint32_t entries; };
 
 // the reference's per-entry side effects (traverse_bursttrie.cpp:249-281) applied to a classification code;
 // returns true when the window search ends on a 0-error match
@@ -73,187 +81,48 @@ __device__ __forceinline__ bool apply_entry(uint32_t code, uint32_t id, bool ful
   return false;
 }
 
-// Sequential DFS of one mini burst trie for one window (traverse_bursttrie.cpp:100-298): used for the few
-// windows that overflow the cooperative buffers, and by the unit-test entry point.
-template <bool INSTR>
-__device__ bool walk_trie(const DevIndex& ix, uint32_t root, uint32_t P, bool full_search, LaneHits& hits, SeedStats& st) {
-  const uint32_t pw = ix.partialwin;
-  uint32_t stk_node[16];
-  uint8_t stk_letter[16];
-  uint32_t depth = 0, node = root, letter = 0, path = 0;
-  uint4 na = __ldg(ix.nodes + 2 * (size_t)node), nb = __ldg(ix.nodes + 2 * (size_t)node + 1);
-  if (INSTR) st.nodes++;
-  for (;;) {
-    if (letter == 4) {
-      if (depth == 0) return false;
-      --depth;
-      node = stk_node[depth]; letter = stk_letter[depth];
-      path &= (1u << (2 * depth)) - 1u;
-      na = __ldg(ix.nodes + 2 * (size_t)node); nb = __ldg(ix.nodes + 2 * (size_t)node + 1);
-      continue;
-    }
-    uint32_t w0, w1;
-    switch (letter) {
-      case 0: w0 = na.x; w1 = na.y; break;
-      case 1: w0 = na.z; w1 = na.w; break;
-      case 2: w0 = nb.x; w1 = nb.y; break;
-      default: w0 = nb.z; w1 = nb.w; break;
-    }
-    const uint32_t flag = w0 & 3u;
-    const uint32_t tp = path | (letter << (2 * depth));
-    if (flag == 0 || !viable_bits(P, tp, depth + 1)) { ++letter; continue; }   // empty element or automaton dead (:122-147)
-    if (flag == 1) {
-      stk_node[depth] = node; stk_letter[depth] = (uint8_t)(letter + 1);
-      path = tp; ++depth; node = w1; letter = 0;
-      na = __ldg(ix.nodes + 2 * (size_t)node); nb = __ldg(ix.nodes + 2 * (size_t)node + 1);
-      if (INSTR) st.nodes++;
-      continue;
-    }
-    const uint32_t cnt = w0 >> 2;                                               // bucket (:176-292)
-    if (INSTR) st.buckets++;
-    const uint2* __restrict__ e = ix.entries + w1;
-    for (uint32_t k = 0; k < cnt; ++k) {
-      const uint2 en = __ldg(e + k);
-      if (INSTR) st.entries++;
-      if (apply_entry(classify_bits(P, tp | (en.x << (2 * (depth + 1))), pw), en.y, full_search, hits)) return true;
-    }
-    ++letter;
-  }
-}
+constexpr int kAccCap = 192;   // matching entries buffered per flush
 
-// ---------------------------------------------------------------------------------------------
-// Cooperative sub-search of 32 windows at once: one window per lane for the short, divergent trie NODE
-// walk; then the visited buckets are cut into tasks of <= kTaskEntries entries, compacted across the
-// warp, and classified one task per lane (uniform arithmetic, no table); finally each lane replays the
-// reference's DFS-order semantics (0-error exit, per-window de-duplication) over the codes of its window.
-// ---------------------------------------------------------------------------------------------
-constexpr int kTaskMax = 256;      // tasks per 32-window round kept in shared memory
-constexpr int kTaskEntries = 8;    // entries per task
-constexpr int kEntryCap = 512;     // classification codes per round kept in shared memory
-constexpr uint32_t kTaskEnd = 0xFFFFu;
-
-struct CoopSmem {                  // per warp, ~4.4 KB
-  uint2 flat[kTaskMax];            // {first entry index, cnt | (depth+1)<<4 | path<<8}
-  uint16_t start[kTaskMax];        // first code slot of the task
-  uint16_t next[kTaskMax];         // next task of the same window, DFS order (kTaskEnd = last)
-  uint8_t lane[kTaskMax];          // owning window (lane)
-  uint8_t code[kEntryCap];
-  uint32_t P[32];
-  uint32_t ntask, nentry;
+struct CoopSmem {              // per warp
+  uint32_t id[kAccCap];
+  uint8_t meta[kAccCap];       // owner lane | code << 5
 };
 
-// trie NODE walk only: records the buckets the DFS would visit, in DFS order, as a linked list of tasks of
-// <= kTaskEntries entries.  Returns false if the shared buffers overflowed (the caller then searches this
-// window with walk_trie instead).
+// One sub-search (forward: trie_F list of the first half, pattern = second half; or mirror) for the 32 windows
+// of a round.  off/cnt: the lane's list in ix.flist (cnt == 0: lane idle).  Appends to lh; sets zero.
 template <bool INSTR>
-__device__ bool walk_nodes(const DevIndex& ix, uint32_t root, uint32_t P, CoopSmem& sm, unsigned lane, uint32_t& head, SeedStats& st) {
-  uint32_t stk_node[16];
-  uint8_t stk_letter[16];
-  uint32_t depth = 0, node = root, letter = 0, path = 0, last = kTaskEnd;
-  uint4 na = __ldg(ix.nodes + 2 * (size_t)node), nb = __ldg(ix.nodes + 2 * (size_t)node + 1);
-  if (INSTR) st.nodes++;
-  for (;;) {
-    if (letter == 4) {
-      if (depth == 0) return true;
-      --depth;
-      node = stk_node[depth]; letter = stk_letter[depth];
-      path &= (1u << (2 * depth)) - 1u;
-      na = __ldg(ix.nodes + 2 * (size_t)node); nb = __ldg(ix.nodes + 2 * (size_t)node + 1);
-      continue;
-    }
-    uint32_t w0, w1;
-    switch (letter) {
-      case 0: w0 = na.x; w1 = na.y; break;
-      case 1: w0 = na.z; w1 = na.w; break;
-      case 2: w0 = nb.x; w1 = nb.y; break;
-      default: w0 = nb.z; w1 = nb.w; break;
-    }
-    const uint32_t flag = w0 & 3u;
-    const uint32_t tp = path | (letter << (2 * depth));
-    if (flag == 0 || !viable_bits(P, tp, depth + 1)) { ++letter; continue; }
-    if (flag == 1) {
-      stk_node[depth] = node; stk_letter[depth] = (uint8_t)(letter + 1);
-      path = tp; ++depth; node = w1; letter = 0;
-      na = __ldg(ix.nodes + 2 * (size_t)node); nb = __ldg(ix.nodes + 2 * (size_t)node + 1);
-      if (INSTR) st.nodes++;
-      continue;
-    }
-    if (INSTR) st.buckets++;
-    const uint32_t cnt = w0 >> 2;
-    if (INSTR) st.entries += cnt;
-    for (uint32_t c0 = 0; c0 < cnt; c0 += kTaskEntries) {
-      const uint32_t n = min(cnt - c0, (uint32_t)kTaskEntries);
-      const uint32_t slot = atomicAdd(&sm.ntask, 1u), es = atomicAdd(&sm.nentry, n);
-      if (slot >= (uint32_t)kTaskMax || es + n > (uint32_t)kEntryCap) {
-        if (slot < (uint32_t)kTaskMax) { sm.flat[slot] = make_uint2(0u, 0u); sm.start[slot] = 0; sm.next[slot] = (uint16_t)kTaskEnd; sm.lane[slot] = 0; }
-        return false;
-      }
-      sm.flat[slot] = make_uint2(w1 + c0, n | ((depth + 1) << 4) | (tp << 8));
-      sm.start[slot] = (uint16_t)es; sm.next[slot] = (uint16_t)kTaskEnd; sm.lane[slot] = (uint8_t)lane;
-      if (last == kTaskEnd) head = slot; else sm.next[last] = (uint16_t)slot;
-      last = slot;
-    }
-    ++letter;
-  }
-}
-
-// One sub-search (forward or mirror) for the 32 windows of a round.  `root`/`P` are per lane (root ==
-// kNoneDev: lane idle).  Appends to lh with the reference's de-duplication; sets zero.
-template <bool INSTR>
-__device__ void coop_subsearch(const DevIndex& ix, CoopSmem& sm, const uint32_t root, const uint32_t P, const bool full_search, LaneHits& lh,
-                               bool& zero, SeedStats& st) {
+__device__ void coop_flat(const DevIndex& ix, CoopSmem& sm, const uint32_t off, const uint32_t cnt, const uint32_t P, const bool full_search,
+                          LaneHits& lh, bool& zero, SeedStats& st) {
   const unsigned lane = lane_id();
   const uint32_t pw = ix.partialwin;
-  sm.P[lane] = P;
-  if (lane == 0) { sm.ntask = 0; sm.nentry = 0; }
-  __syncwarp();
-  uint32_t head = kTaskEnd;
-  bool slow = false;
-  if (root != kNoneDev) slow = !walk_nodes<INSTR>(ix, root, P, sm, lane, head, st);
-  __syncwarp();
-  const uint32_t ntask = min(sm.ntask, (uint32_t)kTaskMax);
-  // classify: one task (<= kTaskEntries consecutive entries of one bucket) per lane; pure arithmetic
-  for (uint32_t t = lane; t < ntask; t += 32) {
-    const uint2 tk = sm.flat[t];
-    const uint32_t cnt = tk.y & 0xFu, sh = 2 * ((tk.y >> 4) & 0xFu), path = tk.y >> 8, Pw = sm.P[sm.lane[t]];
-    const uint32_t es = sm.start[t];
-    if (es + cnt > (uint32_t)kEntryCap) continue;   // belongs to a window that overflowed: it is redone below
-    const uint2* __restrict__ ep = ix.entries + tk.x;
-#pragma unroll 4
-    for (uint32_t k = 0; k < cnt; ++k) sm.code[es + k] = (uint8_t)classify_bits(Pw, path | (__ldg(ep + k).x << sh), pw);
-  }
-  __syncwarp();
-  // replay the DFS-order semantics per window over its chain of tasks
-  if (!slow) {
-    for (uint32_t t = head; t != kTaskEnd && !zero; t = sm.next[t]) {
-      const uint2 tk = sm.flat[t];
-      const uint32_t cnt = tk.y & 0xFu, es = sm.start[t];
-      for (uint32_t k = 0; k < cnt; ++k) {
-        const uint32_t c = sm.code[es + k];
-        if ((c & 3u) == 0) continue;
-        if (apply_entry(c, __ldg(ix.entries + tk.x + k).y, full_search, lh)) { zero = true; break; }
-      }
+  const uint32_t incl = warp_incl_scan_u32(cnt), E = __shfl_sync(kFull, incl, 31), excl = incl - cnt;
+  if (INSTR) st.entries += cnt;
+  uint32_t nacc = 0;
+  for (uint32_t e0 = 0; e0 < E; e0 += 32) {
+    const uint32_t e = e0 + lane;
+    uint32_t lo = 0;                         // owner = first lane whose inclusive sum exceeds e
+#pragma unroll
+    for (int stp = 16; stp > 0; stp >>= 1) { const uint32_t v = __shfl_sync(kFull, incl, lo + stp - 1); if (v <= e) lo += stp; }
+    lo = min(lo, 31u);
+    const uint32_t ex_own = __shfl_sync(kFull, excl, lo), off_own = __shfl_sync(kFull, off, lo), P_own = __shfl_sync(kFull, P, lo);
+    uint32_t code = 0, id = 0;
+    if (e < E) {
+      const uint2 en = __ldg(ix.flist + off_own + (e - ex_own));
+      code = classify_bits(P_own, en.x, pw); id = en.y;
     }
-  } else {
-    zero = walk_trie<INSTR>(ix, root, P, full_search, lh, st);
+    const unsigned m = __ballot_sync(kFull, (code & 3u) != 0);
+    if ((code & 3u) != 0) { const uint32_t slot = nacc + __popc(m & ((1u << lane) - 1)); sm.id[slot] = id; sm.meta[slot] = (uint8_t)(lo | (code << 5)); }
+    nacc += __popc(m);
+    if (nacc + 32 > (uint32_t)kAccCap || e0 + 32 >= E) {   // flush: every lane replays its own matches, in list order
+      __syncwarp();
+      for (uint32_t i = 0; i < nacc && !zero; ++i) {
+        const uint32_t mt = sm.meta[i];
+        if ((mt & 31u) == lane) zero = apply_entry(mt >> 5, sm.id[i], full_search, lh);
+      }
+      nacc = 0;
+      __syncwarp();
+    }
   }
-  __syncwarp();
-}
-
-// both sub-searches of one window, sequentially by one lane (paralleltraversal.cpp:129-249); V = the lnwin-mer
-template <bool INSTR>
-__device__ bool seed_window(const DevIndex& ix, uint64_t V, bool full_search, LaneHits& hits, SeedStats& st) {
-  const uint32_t pw = ix.partialwin;
-  const uint32_t keyf = (uint32_t)(V >> (2 * pw)), keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
-  hits.n = 0;
-  bool zero = false;
-  const uint32_t rootF = __ldg(&ix.lookup[keyf]).x;                               // :161
-  if (rootF != kNoneDev) zero = walk_trie<INSTR>(ix, rootF, rev_chars(keyr, pw), full_search, hits, st);
-  if (!zero) {                                                                    // :188
-    const uint32_t rootR = __ldg(&ix.lookup[keyr]).y;                             // :215
-    if (rootR != kNoneDev) zero = walk_trie<INSTR>(ix, rootR, keyf, full_search, hits, st);
-  }
-  return zero;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -334,7 +203,7 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
   CoopSmem& sm = s_coop[wic];
   LaneHits lh;
   lh.buf = lane_hits_g + (size_t)warp * cap_g * 32 + lane; lh.stride = 32; lh.cap = cap_g;   // per-window ids live in a per-warp HBM scratch
-  SeedStats st{0, 0, 0};
+  SeedStats st{0};
   uint32_t n_windows = 0, n_short = 0;
   const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);
   const bool do_fwd = !(single && prm.is_reverse), do_rev = !(single && prm.is_forward);
@@ -366,20 +235,23 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
         bool active = q < npos;
         if (active && step == 1) active = (p % s0 == 0) || (p % s1 == 0) || (p % s2 == 0);
         lh.n = 0; lh.overflow = false;
-        uint64_t V = 0;
-        uint32_t keyf = 0, keyr = 0, rootF = kNoneDev, rootR = kNoneDev;
+        uint32_t keyf = 0, keyr = 0;
+        uint4 lk_f = make_uint4(0, 0, 0, 0);
         if (active) {
+          uint64_t V;
           if (var == kVarFwd) V = window_fwd(pk, p, L);
           else V = revcomp_bits(window_fwd(var == kVarRevT ? pk : pka, len - p - L, L), L);
           keyf = (uint32_t)(V >> (2 * pw)); keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
-          rootF = __ldg(&ix.lookup[keyf]).x;                                      // paralleltraversal.cpp:161
+          lk_f = __ldg(&ix.flookup[keyf]);                                        // paralleltraversal.cpp:161
           ++n_windows;
         }
         bool zero = false;
-        // forward sub-search for all 32 windows, then the mirror sub-search for those without a 0-error hit (:188)
-        coop_subsearch<INSTR>(ix, sm, rootF, rev_chars(keyr, pw), full, lh, zero, st);   // P = w[9..18) ascending
-        if (active && !zero) rootR = __ldg(&ix.lookup[keyr]).y;                   // :215
-        coop_subsearch<INSTR>(ix, sm, rootR, keyf, full, lh, zero, st);                   // P = w[8..0] descending
+        // sub-search (a): exact first half, <= 1 error in the second half (P = w[9..18) ascending)
+        coop_flat<INSTR>(ix, sm, lk_f.x, lk_f.y, rev_chars(keyr, pw), full, lh, zero, st);
+        // sub-search (b), only without a 0-error hit (:188): exact second half, <= 1 error in the reversed first half
+        uint4 lk_r = make_uint4(0, 0, 0, 0);
+        if (active && !zero) lk_r = __ldg(&ix.flookup[keyr]);                      // :215
+        coop_flat<INSTR>(ix, sm, lk_r.z, lk_r.w, keyf, full, lh, zero, st);
         if (lh.overflow) flags |= kOvfSeedLane;
         const uint32_t n = lh.overflow ? 0u : lh.n;
         const uint32_t incl = warp_incl_scan_u32(n), tot = __shfl_sync(kFull, incl, 31);
@@ -408,11 +280,8 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
   const uint32_t ns = warp_sum_u32(n_short);
   if (lane == 0 && ns) atomicAdd(&b.counters[dcNumShort], (unsigned long long)ns);
   if (INSTR) {
-    const uint64_t w = warp_sum_u64(n_windows), nn = warp_sum_u64(st.nodes), nb = warp_sum_u64(st.buckets), ne = warp_sum_u64(st.entries);
-    if (lane == 0) {
-      atomicAdd(&b.counters[dcWindows], (unsigned long long)w); atomicAdd(&b.counters[dcNodes], (unsigned long long)nn);
-      atomicAdd(&b.counters[dcBuckets], (unsigned long long)nb); atomicAdd(&b.counters[dcEntries], (unsigned long long)ne);
-    }
+    const uint64_t w = warp_sum_u64(n_windows), ne = warp_sum_u64(st.entries);
+    if (lane == 0) { atomicAdd(&b.counters[dcWindows], (unsigned long long)w); atomicAdd(&b.counters[dcEntries], (unsigned long long)ne); }
   }
 }
 
@@ -429,8 +298,8 @@ __global__ void bin_kernel(DevBatch b) {
   b.bins[(size_t)bin * b.cnt_stride + slot] = b.r0 + i;
 }
 
-// unit-test kernel: explicit windows through the SAME cooperative path as seed_kernel (mode 0), or through
-// the per-lane DFS fallback only (mode 1) (smr_debug_seed_windows)
+// unit-test kernel: explicit windows through the SAME cooperative path as seed_kernel (mode 0), or by one
+// lane scanning its own list sequentially (mode 1) (smr_debug_seed_windows)
 __global__ void __launch_bounds__(kSeedWarpsPerCta * 32)
 seed_debug_kernel(DevIndex ix, const uint8_t* seq03, const uint32_t* seq_off, const uint32_t* win_read, const uint32_t* win_pos, uint32_t nwin,
                   uint32_t* ids, uint32_t cap, uint32_t* counts, uint8_t* zero, int full_search, int mode) {
@@ -444,17 +313,25 @@ seed_debug_kernel(DevIndex ix, const uint8_t* seq03, const uint32_t* seq_off, co
     for (uint32_t i = 0; i < ix.lnwin; ++i) V = (V << 2) | (sq[i] & 3u);
   }
   LaneHits lh; lh.buf = ids + (size_t)(active ? k : 0) * cap; lh.stride = 1; lh.cap = active ? cap : 0; lh.n = 0; lh.overflow = false;
-  SeedStats st{0, 0, 0};
+  SeedStats st{0};
   bool z = false;
   const bool full = full_search != 0;
+  const uint32_t keyf = (uint32_t)(V >> (2 * pw)), keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
+  const uint32_t Pf = rev_chars(keyr, pw), Pr = keyf;
   if (mode == 0) {
     CoopSmem& sm = s_coop[threadIdx.x >> 5];
-    const uint32_t keyf = (uint32_t)(V >> (2 * pw)), keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
-    const uint32_t rootF = active ? __ldg(&ix.lookup[keyf]).x : kNoneDev;
-    coop_subsearch<false>(ix, sm, rootF, rev_chars(keyr, pw), full, lh, z, st);
-    const uint32_t rootR = (active && !z) ? __ldg(&ix.lookup[keyr]).y : kNoneDev;
-    coop_subsearch<false>(ix, sm, rootR, keyf, full, lh, z, st);
-  } else if (active) z = seed_window<false>(ix, V, full, lh, st);
+    const uint4 lf = active ? __ldg(&ix.flookup[keyf]) : make_uint4(0, 0, 0, 0);
+    coop_flat<false>(ix, sm, lf.x, lf.y, Pf, full, lh, z, st);
+    const uint4 lr = (active && !z) ? __ldg(&ix.flookup[keyr]) : make_uint4(0, 0, 0, 0);
+    coop_flat<false>(ix, sm, lr.z, lr.w, Pr, full, lh, z, st);
+  } else if (active) {
+    const uint4 lf = __ldg(&ix.flookup[keyf]);
+    for (uint32_t i = 0; i < lf.y && !z; ++i) { const uint2 en = __ldg(ix.flist + lf.x + i); z = apply_entry(classify_bits(Pf, en.x, pw), en.y, full, lh); }
+    if (!z) {
+      const uint4 lr = __ldg(&ix.flookup[keyr]);
+      for (uint32_t i = 0; i < lr.w && !z; ++i) { const uint2 en = __ldg(ix.flist + lr.z + i); z = apply_entry(classify_bits(Pr, en.x, pw), en.y, full, lh); }
+    }
+  }
   if (active) { counts[k] = lh.n; zero[k] = z ? 1 : 0; }
 }
 
