@@ -119,7 +119,7 @@ int setup_arenas(smr_ctx* ctx) {
   uint32_t max_nref = 1;
   for (auto& pt : ctx->parts) max_nref = std::max(max_nref, pt.d.nref);
   ctx->hist_cap = max_nref;
-  ctx->cand_cap = pow2_ge(max_nref);
+  ctx->cand_cap = std::max(64u, max_nref);
   ctx->pair_cap = pow2_ge(4096u * ctx->scale);
   ctx->row_cap = ctx->max_len + 2 * 64 + 64;
   ctx->lis_warps = (uint32_t)ctx->sm_count * 4 * kLisWarpsPerCta;

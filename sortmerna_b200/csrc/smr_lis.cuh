@@ -26,7 +26,10 @@ constexpr int kPairsShared = 128;  // pairs / LIS arrays kept in shared memory u
 
 struct LisArena {            // per-warp scratch in HBM
   uint32_t* hist;            // [hist_cap] epoch<<20 | count, indexed by reference number
-  unsigned long long* cand;  // [cand_cap] (power of two)
+  unsigned long long* cand;  // [cand_cap] candidate keys in ascending reference order
+  unsigned long long* grp;   // [cand_cap] the group of candidates being processed (one count level, or all when <= 32)
+  uint32_t* bitmap;          // [ceil(hist_cap/32)] references that reached num_seeds votes
+  uint32_t* summary;         // [ceil(hist_cap/1024)] non-zero words of bitmap
   unsigned long long* pairs; // [pair_cap] (power of two) refpos<<32 | readpos
   uint32_t* lis_b; uint32_t* lis_p;  // [pair_cap]
   int32_t* rowH; int32_t* rowF;      // [row_cap]
@@ -48,16 +51,20 @@ __device__ __forceinline__ LisArena carve_arena(const LisGlobals& g, uint32_t wa
   uint8_t* p = g.arena_base + (size_t)warp * g.arena_stride;
   a.hist_cap = g.hist_cap; a.cand_cap = g.cand_cap; a.pair_cap = g.pair_cap; a.row_cap = g.row_cap;
   a.cand = (unsigned long long*)p; p += (size_t)g.cand_cap * 8;
+  a.grp = (unsigned long long*)p; p += (size_t)g.cand_cap * 8;
   a.pairs = (unsigned long long*)p; p += (size_t)g.pair_cap * 8;
   a.hist = (uint32_t*)p; p += (size_t)g.hist_cap * 4;
   a.lis_b = (uint32_t*)p; p += (size_t)g.pair_cap * 4;
   a.lis_p = (uint32_t*)p; p += (size_t)g.pair_cap * 4;
   a.rowH = (int32_t*)p; p += (size_t)g.row_cap * 4;
-  a.rowF = (int32_t*)p;
+  a.rowF = (int32_t*)p; p += (size_t)g.row_cap * 4;
+  a.bitmap = (uint32_t*)p; p += (size_t)((g.hist_cap + 31) / 32) * 4;
+  a.summary = (uint32_t*)p;
   return a;
 }
 __host__ __device__ inline size_t lis_arena_bytes(uint32_t hist_cap, uint32_t cand_cap, uint32_t pair_cap, uint32_t row_cap) {
-  size_t b = (size_t)cand_cap * 8 + (size_t)pair_cap * 8 + (size_t)hist_cap * 4 + (size_t)pair_cap * 8 + (size_t)row_cap * 8;
+  size_t b = (size_t)cand_cap * 16 + (size_t)pair_cap * 8 + (size_t)hist_cap * 4 + (size_t)pair_cap * 8 + (size_t)row_cap * 8 +
+             (size_t)((hist_cap + 31) / 32) * 4 + (size_t)((hist_cap + 1023) / 1024) * 4 + 64;
   return (b + 255) & ~(size_t)255;
 }
 
@@ -77,6 +84,21 @@ __device__ void warp_sort_u64(unsigned long long* a, uint32_t n_pow2) {
       __syncwarp();
     }
   }
+}
+// ascending sort of one 64-bit key per lane (pad with ~0ull), entirely in registers
+__device__ __forceinline__ unsigned long long warp_sort32_u64(unsigned long long key) {
+  const unsigned lane = lane_id();
+#pragma unroll
+  for (unsigned k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (unsigned j = k >> 1; j > 0; j >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(kFull, key, j);
+      const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+      const unsigned long long mn = key < other ? key : other, mx = key < other ? other : key;
+      key = (lower == up) ? mn : mx;
+    }
+  }
+  return key;
 }
 __device__ __forceinline__ uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
 
@@ -180,37 +202,97 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
         trans = c < ns && nn >= ns;
       }
       const unsigned tb = __ballot_sync(kFull, trans);
-      if (trans) { const uint32_t slot = ncand + __popc(tb & ((1u << lane) - 1)); if (slot < E.ar.cand_cap) E.ar.cand[slot] = seq; }
+      if (trans) {
+        const uint32_t slot = ncand + __popc(tb & ((1u << lane) - 1));
+        if (slot < 32u) E.ar.cand[slot] = seq;      // the first 32 in discovery order serve the small-list path
+        atomicOr(&E.ar.bitmap[seq >> 5], 1u << (seq & 31u));
+        atomicOr(&E.ar.summary[seq >> 10], 1u << ((seq >> 5) & 31u));
+      }
       ncand += __popc(tb);
       __syncwarp();
     }
   }
   if (ncand == 0) return;
   if (ncand > E.ar.cand_cap) { rc.flags |= kOvfPairs; return; }
+  __syncwarp();
   // ---- 2. order candidates: count desc, reference number asc (alignment.cpp:143-148) ----
-  const uint32_t nc2 = next_pow2(ncand);
-  for (uint32_t i = lane; i < nc2; i += 32) {
+  // Small lists (the common case) are sorted in registers.  Large ones -- reads from conserved regions vote for
+  // thousands of references -- are never sorted: the bitmap yields them in ascending reference order and they
+  // are then taken one count level at a time, which is the same order.
+  const bool by_level = ncand > 32u;
+  uint32_t level = 0;
+  if (!by_level) {
     unsigned long long key = ~0ull;
-    if (i < ncand) { const uint32_t seq = (uint32_t)E.ar.cand[i]; const uint32_t c = E.ar.hist[seq] & 0xFFFFFu; key = ((unsigned long long)(0xFFFFFu - c) << 32) | seq; }
-    E.ar.cand[i] = key;
+    if (lane < ncand) {
+      const uint32_t seq = (uint32_t)E.ar.cand[lane]; const uint32_t c = E.ar.hist[seq] & 0xFFFFFu;
+      key = ((unsigned long long)(0xFFFFFu - c) << 32) | seq;
+      E.ar.bitmap[seq >> 5] = 0; E.ar.summary[seq >> 10] = 0;
+    }
+    key = warp_sort32_u64(key);
+    E.ar.grp[lane] = key;
+  } else {
+    const uint32_t n_sum = (E.ar.hist_cap + 1023u) / 1024u;
+    uint32_t out = 0;
+    for (uint32_t s0w = 0; s0w < n_sum; s0w += 32) {
+      uint32_t sw = 0;
+      if (s0w + lane < n_sum) { sw = E.ar.summary[s0w + lane]; if (sw) E.ar.summary[s0w + lane] = 0; }
+      unsigned lanes = __ballot_sync(kFull, sw != 0);
+      while (lanes) {
+        const int L = __ffs(lanes) - 1; lanes &= lanes - 1;
+        const uint32_t w = __shfl_sync(kFull, sw, L), base_word = (s0w + L) * 32u;
+        uint32_t bw = 0;
+        if ((w >> lane) & 1u) { bw = E.ar.bitmap[base_word + lane]; E.ar.bitmap[base_word + lane] = 0; }
+        const uint32_t pc = __popc(bw), incl = warp_incl_scan_u32(pc), tot = __shfl_sync(kFull, incl, 31);
+        uint32_t pos = out + incl - pc;
+        while (bw) {
+          const uint32_t bit = __ffs(bw) - 1; bw &= bw - 1;
+          const uint32_t seq = (base_word + lane) * 32u + bit, c = E.ar.hist[seq] & 0xFFFFFu;
+          if (pos < E.ar.cand_cap) E.ar.cand[pos] = ((unsigned long long)(0xFFFFFu - c) << 32) | seq;
+          ++pos; level = max(level, c);
+        }
+        out += tot;
+      }
+    }
+    if (out != ncand) { rc.flags |= kErrTrace; return; }   // internal consistency
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) level = max(level, __shfl_xor_sync(kFull, level, o2));
   }
   __syncwarp();
-  warp_sort_u64(E.ar.cand, nc2);
 
   // ---- 3. candidates in order (alignment.cpp:150-508) ----
-  bool is_aligned = false, is_search_candidates = true;
+  bool is_aligned = false, is_search_candidates = true, first_cand = true, stop_all = false;
   uint32_t prev_occur = 0;
   const uint64_t rlen = rc.len, lnwin = ix.lnwin;
   const uint32_t N = (uint32_t)o.num_alignments;
   AlnWork* slots = E.g->aln_work + (size_t)rc.r * E.g->slots;
   const SwScore sc{o.match, o.mismatch, o.score_N, o.gap_open, o.gap_ext};
 
-  for (uint32_t k = 0; k < ncand && is_search_candidates; ++k) {
-    const unsigned long long ck = E.ar.cand[k];
+  for (;;) {
+    // the next group: everything (sorted) for small lists, else the members of the current count level
+    uint32_t ngrp = ncand, next_level = 0;
+    if (by_level) {
+      if (level == 0) break;
+      ngrp = 0;
+      for (uint32_t i0 = 0; i0 < ncand; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        unsigned long long key = 0; uint32_t c = 0;
+        if (i < ncand) { key = E.ar.cand[i]; c = 0xFFFFFu - (uint32_t)(key >> 32); }
+        const bool pick = i < ncand && c == level;
+        const unsigned pm = __ballot_sync(kFull, pick);
+        if (pick) E.ar.grp[ngrp + __popc(pm & ((1u << lane) - 1))] = key;
+        ngrp += __popc(pm);
+        if (i < ncand && c < level) next_level = max(next_level, c);
+      }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) next_level = max(next_level, __shfl_xor_sync(kFull, next_level, o2));
+      __syncwarp();
+    }
+  for (uint32_t k = 0; k < ngrp && is_search_candidates; ++k) {
+    const unsigned long long ck = E.ar.grp[k];
     const uint32_t max_ref = (uint32_t)ck, max_occur = 0xFFFFFu - (uint32_t)(ck >> 32);
-    if (max_occur < (uint32_t)o.num_seeds) break;                                            // :158
-    if (is_aligned && o.min_lis > 0 && k > 0 && max_occur < prev_occur) { --rc.best; if (rc.best < 1) break; }  // :165-169
-    prev_occur = max_occur;
+    if (max_occur < (uint32_t)o.num_seeds) { stop_all = true; break; }                       // :158
+    if (is_aligned && o.min_lis > 0 && !first_cand && max_occur < prev_occur) { --rc.best; if (rc.best < 1) { stop_all = true; break; } }  // :165-169
+    prev_occur = max_occur; first_cand = false;
 
     // gather (refpos, readpos) pairs of this reference (:181-201)
     const uint32_t np = max_occur;
@@ -240,10 +322,18 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
     }
     __syncwarp();
     if (filled != np) { rc.flags |= kErrTrace; return; }   // internal consistency: votes == gathered pairs
-    const uint32_t np2 = next_pow2(np);
-    for (uint32_t i = np + lane; i < np2; i += 32) P[i] = ~0ull;
-    __syncwarp();
-    warp_sort_u64(P, np2);
+    if (np <= 32u) {
+      unsigned long long key = lane < np ? P[lane] : ~0ull;
+      __syncwarp();
+      key = warp_sort32_u64(key);
+      if (lane < np) P[lane] = key;
+      __syncwarp();
+    } else {
+      const uint32_t np2 = next_pow2(np);
+      for (uint32_t i = np + lane; i < np2; i += 32) P[i] = ~0ull;
+      __syncwarp();
+      warp_sort_u64(P, np2);
+    }
 
     // sliding window over the sorted pairs (:205-507)
     uint32_t it = 0, f = 0;
@@ -338,6 +428,9 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
       } else { begin_ref = (uint32_t)(P[f] >> 32); begin_read = (uint32_t)P[f]; }
     }
     __syncwarp();
+  }
+    if (!by_level || stop_all || !is_search_candidates) break;
+    level = next_level;
   }
 }
 
