@@ -16,7 +16,7 @@ import numpy as np
 from . import hostio
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsmr_b200.so")
+LIB_PATH = os.environ.get("SMR_LIB_PATH") or os.path.join(HERE, "libsmr_b200.so")  # override: kernel-variant experiments only
 
 STATUS = {0: "SMR_OK", 1: "SMR_ERR_CUDA", 2: "SMR_ERR_ARG", 3: "SMR_ERR_INDEX", 4: "SMR_ERR_UNSUPPORTED",
           5: "SMR_ERR_CAPACITY", 6: "SMR_ERR_NO_DEVICE"}

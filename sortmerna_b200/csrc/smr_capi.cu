@@ -38,6 +38,7 @@ struct smr_ctx {
   uint32_t n_index_files = 0;
   int sm_count = 148;
   uint32_t chunk_reads = 1u << 20;
+  uint32_t lis_ctas_per_sm = 4;   // persistent CTAs of the candidate kernel per SM (matches its __launch_bounds__)
 
   // resident batch
   uint32_t nreads = 0; uint64_t total_nt = 0; uint32_t max_len = 0;
@@ -98,6 +99,7 @@ DevParams to_dev(const smr_params& p) {
   d.num_seeds = p.num_seeds; d.min_lis = p.min_lis; d.edges = p.edges; d.edges_is_percent = p.edges_is_percent;
   d.num_alignments = p.num_alignments; d.is_best = p.is_best; d.is_forward = p.is_forward; d.is_reverse = p.is_reverse;
   d.is_full_search = p.is_full_search;
+  d.one = 1;
   return d;
 }
 
@@ -122,7 +124,7 @@ int setup_arenas(smr_ctx* ctx) {
   ctx->cand_cap = std::max(64u, max_nref);
   ctx->pair_cap = pow2_ge(4096u * ctx->scale);
   ctx->row_cap = ctx->max_len + 2 * 64 + 64;
-  ctx->lis_warps = (uint32_t)ctx->sm_count * 4 * kLisWarpsPerCta;
+  ctx->lis_warps = (uint32_t)ctx->sm_count * ctx->lis_ctas_per_sm * kLisWarpsPerCta;
   ctx->lis_stride = lis_arena_bytes(ctx->hist_cap, ctx->cand_cap, ctx->pair_cap, ctx->row_cap);
   // keep the arena total under ~8 GB: fewer persistent warps for huge reference sets
   const size_t budget = (size_t)8 << 30;
@@ -441,6 +443,7 @@ int smr_init(int device, smr_ctx** out) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return SMR_ERR_NO_DEVICE; }
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SMR_ERR_CUDA; }
+  if (const char* e = getenv("SMR_LIS_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 16) ctx->lis_ctas_per_sm = (uint32_t)v; }
   *out = ctx;
   return SMR_OK;
 }

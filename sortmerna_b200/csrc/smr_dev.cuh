@@ -30,6 +30,7 @@ struct DevParams {
   int32_t num_seeds, min_lis, edges, edges_is_percent;
   int32_t num_alignments, is_best;
   int32_t is_forward, is_reverse, is_full_search;
+  int32_t one;   // 1 (run-time constant, see SwScore::one)
 };
 
 // Per-read carried state = the KVDB blob of the reference (read.cpp:429-462) + pass-local flags.

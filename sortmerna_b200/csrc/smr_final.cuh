@@ -47,7 +47,7 @@ finalize_kernel(DevBatch b, DevParams prm, FinalGlobals g) {
   int32_t* rowH = (int32_t*)p; p += (size_t)g.row_cap * 4;
   int32_t* rowF = (int32_t*)p; p += (size_t)g.row_cap * 4;
   A.dir = (int8_t*)p;
-  const SwScore sc{prm.match, prm.mismatch, prm.score_N, prm.gap_open, prm.gap_ext};
+  const SwScore sc{prm.match, prm.mismatch, prm.score_N, prm.gap_open, prm.gap_ext, prm.one};
   const uint32_t total = b.nreads * g.slots;
   for (;;) {
     uint32_t wi = 0;
@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kFinalWarpsPerCta * 32)
 ssw_debug_kernel(const uint8_t* qcat, const uint32_t* qoff, const uint8_t* tcat, const uint32_t* toff, uint32_t npairs, uint32_t filters,
                  DevParams prm, int32_t* out, uint32_t* cigars, uint32_t cigar_cap, FinalGlobals g) {
   __shared__ __align__(16) uint8_t s_ref[kFinalWarpsPerCta][kRefStage + 64];
+  __shared__ int32_t s_prof[kFinalWarpsPerCta][kProfWords];
   const unsigned lane = lane_id();
   const uint32_t warp = blockIdx.x * kFinalWarpsPerCta + (threadIdx.x >> 5), nwarps = gridDim.x * kFinalWarpsPerCta;
   uint8_t* p = g.arena_base + (size_t)warp * g.arena_stride;
@@ -112,14 +113,14 @@ ssw_debug_kernel(const uint8_t* qcat, const uint32_t* qoff, const uint8_t* tcat,
   int32_t* rowH = (int32_t*)p; p += (size_t)g.row_cap * 4;
   int32_t* rowF = (int32_t*)p; p += (size_t)g.row_cap * 4;
   A.dir = (int8_t*)p;
-  const SwScore sc{prm.match, prm.mismatch, prm.score_N, prm.gap_open, prm.gap_ext};
+  const SwScore sc{prm.match, prm.mismatch, prm.score_N, prm.gap_open, prm.gap_ext, prm.one};
   for (uint32_t k = warp; k < npairs; k += nwarps) {
     const int32_t m = (int32_t)(qoff[k + 1] - qoff[k]), n = (int32_t)(toff[k + 1] - toff[k]);
     const SeqView q{qcat + qoff[k], 0, 1, false}, t{tcat + toff[k], 0, 1, false};
     int32_t* o = out + (size_t)k * 6;
     SwEnd f = sw_forward(q, m, t, n, sc, rowH, rowF);
     // the score-only kernel of the candidate loop must agree with the arg-max kernel
-    if (sw_score(q, m, t, n, sc, s_ref[threadIdx.x >> 5], rowH, rowF) != f.score) f.score = -12345;
+    if (sw_score(q, m, t, n, sc, s_ref[threadIdx.x >> 5], s_prof[threadIdx.x >> 5], rowH, rowF) != f.score) f.score = -12345;
     int32_t rb = -1, qb = -1, nc = 0;
     if ((uint32_t)(f.score & 0xFFFF) >= filters && f.score > 0) {
       const SwEnd rev = sw_forward(q.reversed_prefix(f.read), f.read + 1, t.reversed_prefix(f.ref), f.ref + 1, sc, rowH, rowF);

@@ -153,6 +153,7 @@ struct PassEnv {
   LisArena ar; uint32_t* epoch_ptr; uint32_t epoch;
   unsigned long long* s_pairs; uint32_t* s_b; uint32_t* s_p;   // shared-memory fast buffers (kPairsShared)
   uint8_t* s_ref;                                               // staged reference window (kRefStage + 64)
+  int32_t* s_prof;                                              // query profile (kProfWords)
   const uint2* hits; uint32_t nh;                               // hit region of (current part, current read)
   unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls;
 };
@@ -265,7 +266,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   const uint64_t rlen = rc.len, lnwin = ix.lnwin;
   const uint32_t N = (uint32_t)o.num_alignments;
   AlnWork* slots = E.g->aln_work + (size_t)rc.r * E.g->slots;
-  const SwScore sc{o.match, o.mismatch, o.score_N, o.gap_open, o.gap_ext};
+  const SwScore sc{o.match, o.mismatch, o.score_N, o.gap_open, o.gap_ext, o.one};
 
   for (;;) {
     // the next group: everything (sorted) for small lists, else the members of the current count level
@@ -378,7 +379,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
           else q = SeqView{B.seq04 + rc.seq_base, (int32_t)(rc.len - 1 - aqs), -1, true};
           const SeqView t{ix.refseq + __ldg(ix.ref_off + max_ref), (int32_t)win_start, 1, false};
           int32_t sw = 0;
-          if (qlen > 0 && alen > 0 && (uint32_t)alen <= E.ar.row_cap) sw = sw_score(q, qlen, t, (int32_t)alen, sc, E.s_ref, E.ar.rowH, E.ar.rowF);
+          if (qlen > 0 && alen > 0 && (uint32_t)alen <= E.ar.row_cap) sw = sw_score(q, qlen, t, (int32_t)alen, sc, E.s_ref, E.s_prof, E.ar.rowH, E.ar.rowF);
           E.n_sw_calls++; E.n_sw_cells += (unsigned long long)alen * (unsigned long long)(qlen > 0 ? qlen : 0);
           const uint32_t score1 = (uint32_t)sw & 0xFFFFu;                                   // s_align.score1 is uint16
           is_aligned = score1 > ix.minimal_score;                                           // :388
@@ -490,6 +491,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   __shared__ uint32_t s_b[kLisWarpsPerCta][kPairsShared];
   __shared__ uint32_t s_p[kLisWarpsPerCta][kPairsShared];
   __shared__ __align__(16) uint8_t s_ref[kLisWarpsPerCta][kRefStage + 64];
+  __shared__ int32_t s_prof[kLisWarpsPerCta][kProfWords];
   __shared__ uint32_t s_bin_start[kCostBins + 1];
   const unsigned lane = lane_id();
   const uint32_t wic = threadIdx.x >> 5, warp = blockIdx.x * kLisWarpsPerCta + wic;
@@ -503,7 +505,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   E.b = &b; E.prm = &prm; E.g = &g;
   E.ar = carve_arena(g, warp);
   E.epoch_ptr = g.epochs + warp; E.epoch = *E.epoch_ptr;
-  E.s_pairs = s_pairs[wic]; E.s_b = s_b[wic]; E.s_p = s_p[wic]; E.s_ref = s_ref[wic];
+  E.s_pairs = s_pairs[wic]; E.s_b = s_b[wic]; E.s_p = s_p[wic]; E.s_ref = s_ref[wic]; E.s_prof = s_prof[wic];
   E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = 0;
   const uint32_t nwork = s_bin_start[kCostBins];
   const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);

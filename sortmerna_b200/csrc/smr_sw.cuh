@@ -29,7 +29,7 @@ struct SeqView {
   __device__ __forceinline__ SeqView reversed_prefix(int32_t end) const { return SeqView{base, start + end * step, -step, comp}; }
 };
 
-struct SwScore { int32_t match, mismatch, sN, go, ge; };
+struct SwScore { int32_t match, mismatch, sN, go, ge, one; };  // one == 1 at run time (keeps IMADs on the fma pipe)
 struct SwEnd { int32_t score, ref, read; };
 
 // Forward score pass.  q: query (m rows), t: target (n columns).  rowH/rowF: scratch of >= n ints each,
@@ -123,78 +123,90 @@ __device__ __noinline__ SwEnd sw_forward(const SeqView q, const int32_t m, const
 // Score-only forward pass: the hot loop of the candidate kernel.  Accept / replace / stop decisions
 // of compute_lis_alignment only consume score1 (alignment.cpp:388-469), so the arg-max bookkeeping of
 // sw_warp is left to the finalize kernel, which re-runs the forward pass for the few alignments that
-// end up stored.  The reference window is staged in shared memory with 32 sentinel bytes (value 6,
-// never equal to a query code) on both sides, so lanes need no "column in range" predicate: columns
-// outside [0,n) only ever produce values strictly below the running maximum (every step away from a
-// real cell costs a mismatch or a gap), and real cells never read them.
-// Requires m <= 32*R, mismatch < 0, gap_open > 0.  FASTN: score_N == mismatch (the default), which
-// makes "reference base is N" need no special case.
+// end up stored.  The reference window is staged in shared memory with 32 sentinel columns on both
+// sides, so lanes need no "column in range" predicate: columns outside [0,n) only ever produce values
+// strictly below the running maximum (every step away from a real cell costs a mismatch or a gap), and
+// real cells never read them.  Requires m <= 256, n <= kRefStage, mismatch < 0, score_N < 0, gap_open > 0.
 // ---------------------------------------------------------------------------------------------
-constexpr int kRefStage = 448;  // staged window bytes per warp; longer windows use sw_warp
+constexpr int kRefStage = 448;    // staged window bytes per warp; longer windows use sw_warp
+constexpr int kProfTables = 6;    // reference letter A,C,G,T,N + the out-of-window sentinel
+constexpr int kProfWords = kProfTables * 32 * 8;   // query profile per warp: [table][row-in-lane r][lane], R <= 8
 
-template <int R, bool FASTN>
-__device__ int32_t sw_score_warp(const SeqView q, const int32_t m, const uint8_t* __restrict__ s_ref, const int32_t n, const SwScore sc) {
+// The profile turns the per-cell "compare + select" of the substitution score into one conflict-free shared
+// load: the candidate kernel is bound by the ALU pipe (ncu: alu pipe 70-76 % of peak, fma pipe 8 %), so the
+// cell update is arranged to need only the max-type instructions there -- VIMNMX3.relu for H, VIADDMNMX for E
+// and F, one VIMNMX3 per two cells for the running maximum -- while the two plain additions go to the FMA pipe
+// as IMADs (multiplication by a run-time 1) and the score comes from the LSU pipe.
+template <int R>
+__device__ int32_t sw_score_warp(const int32_t* __restrict__ s_prof, const uint8_t* __restrict__ s_ref, const int32_t n, const SwScore sc) {
   const int lane = (int)lane_id();
-  const int32_t i0 = lane * R;
-  int32_t qc[R], qmis[R], Hp[R], E[R];
+  int32_t Hp[R], E[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int32_t i = i0 + r;
-    const uint32_t c = i < m ? q.at(i) : 7u;
-    qmis[r] = c == 7u ? -(1 << 20) : (c >= 4u ? sc.sN : sc.mismatch);
-    qc[r] = c >= 4u ? (c == 7u ? 7 : 5) : (int32_t)c;
-    Hp[r] = 0; E[r] = 0;
-  }
+  for (int r = 0; r < R; ++r) { Hp[r] = 0; E[r] = 0; }
   int32_t diagH = 0, outH = 0, outF = 0, best = 0;
   const uint8_t* colp = s_ref + 32 - lane;
+  const int32_t* prow = s_prof + lane;
   const int32_t nsteps = n + 31;
-  const int32_t nge = -sc.ge;
+  const int32_t nge = -sc.ge, ngo = -sc.go, one = sc.one;
 #pragma unroll 2
   for (int32_t ts = 0; ts < nsteps; ++ts) {
-    const int32_t rc = colp[ts];
+    const int32_t* pt = prow + (int32_t)colp[ts] * (R * 32);
     int32_t upH = __shfl_up_sync(kFull, outH, 1), upF = __shfl_up_sync(kFull, outF, 1);
     if (lane == 0) { upH = 0; upF = 0; }
-    int32_t diag = diagH, F = upF, colmax = 0;
+    int32_t diag = diagH, F = upF, h_prev = 0;
     diagH = upH;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int32_t miss = FASTN ? qmis[r] : (rc == 4 ? sc.sN : qmis[r]);
-      const int32_t s = (rc == qc[r]) ? sc.match : miss;
-      const int32_t h = __vimax3_s32_relu(diag + s, E[r], F);
+      const int32_t h = __vimax3_s32_relu(diag * one + pt[r * 32], E[r], F);   // IMAD (fma pipe) + VIMNMX3.relu
       diag = Hp[r]; Hp[r] = h;
-      const int32_t open = h - sc.go;
+      const int32_t open = h * one + ngo;                                       // IMAD
       E[r] = __viaddmax_s32(E[r], nge, open);
       F = __viaddmax_s32(F, nge, open);
-      colmax = max(colmax, h);
+      if (r & 1) best = __vimax3_s32(best, h, h_prev); else h_prev = h;
     }
+    if (R & 1) best = max(best, h_prev);
     outH = Hp[R - 1]; outF = F;
-    best = max(best, colmax);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(kFull, best, o));
   return best;
 }
 
-template <bool FASTN>
-__device__ __noinline__ int32_t sw_score_dispatch(const SeqView q, const int32_t m, const uint8_t* s_ref, const int32_t n, const SwScore sc) {
-  if (m <= 32) return sw_score_warp<1, FASTN>(q, m, s_ref, n, sc);
-  if (m <= 64) return sw_score_warp<2, FASTN>(q, m, s_ref, n, sc);
-  if (m <= 96) return sw_score_warp<3, FASTN>(q, m, s_ref, n, sc);
-  if (m <= 128) return sw_score_warp<4, FASTN>(q, m, s_ref, n, sc);
-  if (m <= 160) return sw_score_warp<5, FASTN>(q, m, s_ref, n, sc);
-  if (m <= 192) return sw_score_warp<6, FASTN>(q, m, s_ref, n, sc);
-  return sw_score_warp<8, FASTN>(q, m, s_ref, n, sc);
+template <int R>
+__device__ __noinline__ int32_t sw_score_run(const SeqView q, const int32_t m, int32_t* __restrict__ s_prof, const uint8_t* __restrict__ s_ref,
+                                             const int32_t n, const SwScore sc) {
+  const int lane = (int)lane_id();
+  // profile: table tb, row r of this lane, at s_prof[(tb*R + r)*32 + lane]  (mat[ref*5+read], read.cpp:274-288)
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int32_t i = lane * R + r;
+    const uint32_t c = i < m ? q.at(i) : 7u;
+    const int32_t mis = c == 7u ? -(1 << 20) : (c >= 4u ? sc.sN : sc.mismatch);
+#pragma unroll
+    for (int tb = 0; tb < 4; ++tb) s_prof[(tb * R + r) * 32 + lane] = (c == (uint32_t)tb) ? sc.match : mis;
+    s_prof[(4 * R + r) * 32 + lane] = c == 7u ? -(1 << 20) : sc.sN;   // reference N
+    s_prof[(5 * R + r) * 32 + lane] = mis;                            // outside the window: never a match
+  }
+  __syncwarp();
+  return sw_score_warp<R>(s_prof, s_ref, n, sc);
 }
 
-// score of the best local alignment of q (m rows) against t (n columns); s_ref = kRefStage+64 bytes of shared memory
-__device__ int32_t sw_score(const SeqView q, const int32_t m, const SeqView t, const int32_t n, const SwScore sc, uint8_t* s_ref,
+// score of the best local alignment of q (m rows) against t (n columns); s_ref = kRefStage+64 bytes and s_prof =
+// kProfWords ints of shared memory owned by this warp
+__device__ int32_t sw_score(const SeqView q, const int32_t m, const SeqView t, const int32_t n, const SwScore sc, uint8_t* s_ref, int32_t* s_prof,
                             int32_t* rowH, int32_t* rowF) {
   if (m > 256 || n > kRefStage || sc.mismatch >= 0 || sc.go <= 0 || sc.sN >= 0) return sw_forward(q, m, t, n, sc, rowH, rowF).score;
   const int lane = (int)lane_id();
   __syncwarp();
-  for (int32_t i = lane; i < n + 64; i += 32) { const int32_t j = i - 32; s_ref[i] = (j >= 0 && j < n) ? (uint8_t)t.at(j) : (uint8_t)6; }
-  __syncwarp();
-  return sc.sN == sc.mismatch ? sw_score_dispatch<true>(q, m, s_ref, n, sc) : sw_score_dispatch<false>(q, m, s_ref, n, sc);
+  // staged window: table index per column, sentinel table (5) for 32 columns on both sides
+  for (int32_t i = lane; i < n + 64; i += 32) { const int32_t j = i - 32; s_ref[i] = (j >= 0 && j < n) ? (uint8_t)min(t.at(j), 4u) : (uint8_t)5; }
+  if (m <= 32) return sw_score_run<1>(q, m, s_prof, s_ref, n, sc);
+  if (m <= 64) return sw_score_run<2>(q, m, s_prof, s_ref, n, sc);
+  if (m <= 96) return sw_score_run<3>(q, m, s_prof, s_ref, n, sc);
+  if (m <= 128) return sw_score_run<4>(q, m, s_prof, s_ref, n, sc);
+  if (m <= 160) return sw_score_run<5>(q, m, s_prof, s_ref, n, sc);
+  if (m <= 192) return sw_score_run<6>(q, m, s_prof, s_ref, n, sc);
+  return sw_score_run<8>(q, m, s_prof, s_ref, n, sc);
 }
 
 // ---------------------------------------------------------------------------------------------
