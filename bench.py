@@ -339,9 +339,10 @@ def main():
     cnt_names = list(api.CNT_NAMES)
     vec = csum
     tm = np.array([step_ms, e2e_s * 1000.0, wall_ms], dtype=np.float64)
-    if world > 1:
-        tv = torch.from_numpy(vec).cuda(); dist.all_reduce(tv); vec = tv.cpu().numpy()
-        tt = torch.from_numpy(tm).cuda(); dist.all_reduce(tt, op=dist.ReduceOp.MAX); tm = tt.cpu().numpy()
+    from sortmerna_b200 import shard
+    dev = torch.device("cuda", local_rank)
+    vec = shard.allreduce_counters(vec, dev)       # the path's only collective (NCCL): Readstats counters, SUM
+    tm = shard.allreduce_max(tm, dev)              # device-side timings: max over ranks
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -386,7 +386,8 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
   if (out.counters) {
     static const int mapc[][2] = {{SMR_CNT_NUM_SHORT, dcNumShort}, {SMR_CNT_SW_CALLS, dcSwCalls}, {SMR_CNT_SW_CELLS, dcSwCells},
                                   {SMR_CNT_WINDOWS, dcWindows}, {SMR_CNT_TRIE_NODES, dcNodes}, {SMR_CNT_BUCKETS, dcBuckets},
-                                  {SMR_CNT_BUCKET_ENTRIES, dcEntries}, {SMR_CNT_POS_ENTRIES, dcPosEntries}, {SMR_CNT_LIS_CALLS, dcLisCalls}};
+                                  {SMR_CNT_BUCKET_ENTRIES, dcEntries}, {SMR_CNT_POS_ENTRIES, dcPosEntries}, {SMR_CNT_LIS_CALLS, dcLisCalls},
+                                  {10, dcMaxReadCycles}, {11, dcSumReadCycles}, {12, dcLisKernelCycles}};
     for (auto& m : mapc) if ((uint32_t)m[0] < out.n_counters) out.counters[m[0]] += cnt[m[1]];
   }
   return rc;

@@ -508,6 +508,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   E.s_pairs = s_pairs[wic]; E.s_b = s_b[wic]; E.s_p = s_p[wic]; E.s_ref = s_ref[wic]; E.s_prof = s_prof[wic];
   E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = 0;
   const uint32_t nwork = s_bin_start[kCostBins];
+  unsigned long long t_max = 0, t_sum = 0; const long long t_k0 = clock64();
   const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);
   for (;;) {
     uint32_t wi = 0;
@@ -517,6 +518,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     uint32_t k = 0;
     while (wi >= s_bin_start[k + 1]) ++k;
     const uint32_t r = b.bins[(size_t)(kCostBins - 1 - k) * b.cnt_stride + (wi - s_bin_start[k])];
+    const long long t_read0 = clock64();
     ReadCtx rc;
     rc.r = r; rc.seq_base = b.seq_off[r]; rc.len = b.seq_off[r + 1] - rc.seq_base;
     rc.hasn = b.has_n[r] != 0; rc.flags = 0;
@@ -549,12 +551,15 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
       __syncwarp();
     }
     if (rc.flags && lane == 0) atomicOr(&b.flags[r], rc.flags);
+    { const unsigned long long dt = (unsigned long long)(clock64() - t_read0); t_max = dt > t_max ? dt : t_max; t_sum += dt; }
     __syncwarp();
   }
   if (lane == 0) {
     *E.epoch_ptr = E.epoch;
     atomicAdd(&b.counters[dcSwCalls], E.n_sw_calls); atomicAdd(&b.counters[dcSwCells], E.n_sw_cells);
     atomicAdd(&b.counters[dcPosEntries], E.n_pos_entries); atomicAdd(&b.counters[dcLisCalls], E.n_lis_calls);
+    atomicMax(&b.counters[dcMaxReadCycles], t_max); atomicAdd(&b.counters[dcSumReadCycles], t_sum);
+    atomicMax(&b.counters[dcLisKernelCycles], (unsigned long long)(clock64() - t_k0));
   }
 }
 
