@@ -107,6 +107,12 @@ __device__ SwEnd sw_warp(const SeqView q, const int32_t m, const SeqView t, cons
   return e;
 }
 
+// one instantiation for any shape (row blocks of 256 rows): the rarely taken fallback of the candidate kernel
+__device__ __noinline__ SwEnd sw_forward_any(const SeqView q, const int32_t m, const SeqView t, const int32_t n, const SwScore sc,
+                                             int32_t* rowH, int32_t* rowF) {
+  return sw_warp<8>(q, m, t, n, sc, rowH, rowF);
+}
+
 // dispatch on the query length: the smallest R with 32*R >= m (R = 8 and row blocks beyond 256 rows)
 __device__ __noinline__ SwEnd sw_forward(const SeqView q, const int32_t m, const SeqView t, const int32_t n, const SwScore sc,
                                          int32_t* rowH, int32_t* rowF) {
@@ -137,6 +143,12 @@ constexpr int kProfWords = kProfTables * 32 * 8;   // query profile per warp: [t
 // cell update is arranged to need only the max-type instructions there -- VIMNMX3.relu for H, VIADDMNMX for E
 // and F, one VIMNMX3 per two cells for the running maximum -- while the two plain additions go to the FMA pipe
 // as IMADs (multiplication by a run-time 1) and the score comes from the LSU pipe.
+// The cell update is arranged so that the only loop-carried chain down a lane's R rows is ONE instruction per
+// row.  With X = max(0, diag + s, E) (independent of F) we have H = max(X, F) and, because gap_ext <= gap_open,
+//   F(r+1) = max(F(r) - ge, H(r) - go) = max(F(r) - ge, X(r) - go),
+// so all X(r), X(r) - go are computed first (instruction-level parallel), the F chain is R dependent VIADDMNMX,
+// and H, E follow in parallel again.  (The kernel is latency-bound: ncu shows ~50 % issue utilisation with the
+// alu pipe at 44 %, so a shorter dependency chain is worth a few extra IMADs on the idle fma pipe.)
 template <int R>
 __device__ int32_t sw_score_warp(const int32_t* __restrict__ s_prof, const uint8_t* __restrict__ s_ref, const int32_t n, const SwScore sc) {
   const int lane = (int)lane_id();
@@ -148,24 +160,45 @@ __device__ int32_t sw_score_warp(const int32_t* __restrict__ s_prof, const uint8
   const int32_t* prow = s_prof + lane;
   const int32_t nsteps = n + 31;
   const int32_t nge = -sc.ge, ngo = -sc.go, one = sc.one;
-#pragma unroll 2
+  // software pipeline: the substitution scores of the next column are fetched while this one is computed
+  int32_t sc_cur[R];
+  {
+    const int32_t* pt = prow + (int32_t)colp[0] * (R * 32);
+#pragma unroll
+    for (int r = 0; r < R; ++r) sc_cur[r] = pt[r * 32];
+  }
   for (int32_t ts = 0; ts < nsteps; ++ts) {
-    const int32_t* pt = prow + (int32_t)colp[ts] * (R * 32);
+    int32_t sc_next[R];
+    {
+      const int32_t* pt = prow + (int32_t)colp[ts + 1] * (R * 32);   // colp[nsteps] is still inside the trailing sentinels
+#pragma unroll
+      for (int r = 0; r < R; ++r) sc_next[r] = pt[r * 32];
+    }
     int32_t upH = __shfl_up_sync(kFull, outH, 1), upF = __shfl_up_sync(kFull, outF, 1);
     if (lane == 0) { upH = 0; upF = 0; }
-    int32_t diag = diagH, F = upF, h_prev = 0;
-    diagH = upH;
+    int32_t X[R], Xgo[R], F[R + 1];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int32_t h = __vimax3_s32_relu(diag * one + pt[r * 32], E[r], F);   // IMAD (fma pipe) + VIMNMX3.relu
-      diag = Hp[r]; Hp[r] = h;
-      const int32_t open = h * one + ngo;                                       // IMAD
-      E[r] = __viaddmax_s32(E[r], nge, open);
-      F = __viaddmax_s32(F, nge, open);
-      if (r & 1) best = __vimax3_s32(best, h, h_prev); else h_prev = h;
+      const int32_t diag = r == 0 ? diagH : Hp[r - 1];
+      X[r] = __vimax_s32_relu(diag * one + sc_cur[r], E[r]);
+      Xgo[r] = X[r] * one + ngo;
     }
-    if (R & 1) best = max(best, h_prev);
-    outH = Hp[R - 1]; outF = F;
+    diagH = upH;
+    F[0] = upF;
+#pragma unroll
+    for (int r = 0; r < R; ++r) F[r + 1] = __viaddmax_s32(F[r], nge, Xgo[r]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int32_t h = max(X[r], F[r]);
+      E[r] = __vimax3_s32(E[r] * one + nge, Xgo[r], F[r] * one + ngo);
+      Hp[r] = h;
+    }
+#pragma unroll
+    for (int r = 0; r + 1 < R; r += 2) best = __vimax3_s32(best, Hp[r], Hp[r + 1]);
+    if (R & 1) best = max(best, Hp[R - 1]);
+    outH = Hp[R - 1]; outF = F[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) sc_cur[r] = sc_next[r];
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(kFull, best, o));
@@ -195,7 +228,7 @@ __device__ __noinline__ int32_t sw_score_run(const SeqView q, const int32_t m, i
 // kProfWords ints of shared memory owned by this warp
 __device__ int32_t sw_score(const SeqView q, const int32_t m, const SeqView t, const int32_t n, const SwScore sc, uint8_t* s_ref, int32_t* s_prof,
                             int32_t* rowH, int32_t* rowF) {
-  if (m > 256 || n > kRefStage || sc.mismatch >= 0 || sc.go <= 0 || sc.sN >= 0) return sw_forward(q, m, t, n, sc, rowH, rowF).score;
+  if (m > 256 || n > kRefStage || sc.mismatch >= 0 || sc.go <= 0 || sc.sN >= 0 || sc.ge > sc.go) return sw_forward_any(q, m, t, n, sc, rowH, rowF).score;
   const int lane = (int)lane_id();
   __syncwarp();
   // staged window: table index per column, sentinel table (5) for 32 columns on both sides
