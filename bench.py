@@ -241,7 +241,7 @@ def main():
             return
         fastas, idx_dir, prefixes, refs, stats, built = load_databases()
         pool = DbPool(refs)
-        sample = args.cpu_sample or int(min(200_000, max(5_000, 1_500 * cores)))
+        sample = args.cpu_sample or int(min(40_000, max(4_000, 300 * cores)))   # ~5 s of reference CPU time per step
         vals, secs = [], []
         for s in range(args.warmup + args.steps):
             if s < args.warmup and s > 0:

@@ -78,7 +78,8 @@ enum {
   SMR_CNT_BUCKET_ENTRIES = 7,/* bucket entries visited */
   SMR_CNT_POS_ENTRIES = 8,   /* position entries touched by candidate voting */
   SMR_CNT_LIS_CALLS = 9,     /* compute_lis_alignment-equivalent calls */
-  SMR_CNT_FIXED = 16         /* reads_matched_per_db[i] lives at counters[SMR_CNT_FIXED + i] */
+  /* 10..22: warp-cycle accounting of the candidate kernel (max per read, sum, kernel, then per phase) */
+  SMR_CNT_FIXED = 32         /* reads_matched_per_db[i] lives at counters[SMR_CNT_FIXED + i] */
 };
 
 /* -- lifetime ------------------------------------------------------------------------------- */

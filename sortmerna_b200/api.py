@@ -27,8 +27,9 @@ SYMBOLS = ["smr_init", "smr_destroy", "smr_last_error", "smr_device_count", "smr
            "smr_run_resident", "smr_download_results", "smr_last_timings", "smr_debug_seed_windows", "smr_debug_ssw"]
 
 CNT_NAMES = ("num_aligned", "num_short", "sw_calls", "sw_cells", "windows", "trie_nodes", "buckets",
-             "bucket_entries", "pos_entries", "lis_calls", "dbg_max_read_cycles", "dbg_sum_read_cycles", "dbg_lis_kernel_cycles")
-CNT_FIXED = 16
+             "bucket_entries", "pos_entries", "lis_calls", "dbg_max_read_cycles", "dbg_sum_read_cycles", "dbg_lis_kernel_cycles",
+             "cyc_vote", "cyc_order", "cyc_group", "cyc_prep", "cyc_sw_setup", "cyc_sw_loop", "cyc_book")
+CNT_FIXED = 32
 
 
 class Params(C.Structure):

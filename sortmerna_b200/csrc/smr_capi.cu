@@ -50,7 +50,7 @@ struct smr_ctx {
   DevBuf lis_arena, lis_epochs, final_arena, lane_hits;
   uint32_t lis_warps = 0, final_warps = 0;
   size_t lis_stride = 0, final_stride = 0;
-  uint32_t hist_cap = 0, cand_cap = 0, pair_cap = 0, row_cap = 0, cap_w = 0, cap_cig = 0; size_t cap_dir = 0;
+  uint32_t hist_cap = 0, cand_cap = 0, pair_cap = 0, row_cap = 0, pall_cap = 0, cap_w = 0, cap_cig = 0; size_t cap_dir = 0;
   uint32_t lane_hits_cap = 0, lane_hits_warps = 0;
   uint64_t cigar_cap_dev = 0;
   uint32_t scale = 1;         // scratch scale of the current run (1 = fast path)
@@ -125,7 +125,8 @@ int setup_arenas(smr_ctx* ctx) {
   ctx->pair_cap = pow2_ge(4096u * ctx->scale);
   ctx->row_cap = ctx->max_len + 2 * 64 + 64;
   ctx->lis_warps = (uint32_t)ctx->sm_count * ctx->lis_ctas_per_sm * kLisWarpsPerCta;
-  ctx->lis_stride = lis_arena_bytes(ctx->hist_cap, ctx->cand_cap, ctx->pair_cap, ctx->row_cap);
+  ctx->pall_cap = 32768u * ctx->scale;
+  ctx->lis_stride = lis_arena_bytes(ctx->hist_cap, ctx->cand_cap, ctx->pair_cap, ctx->row_cap, ctx->pall_cap);
   // keep the arena total under ~8 GB: fewer persistent warps for huge reference sets
   const size_t budget = (size_t)8 << 30;
   while (ctx->lis_warps > 64 && ctx->lis_stride * ctx->lis_warps > budget) ctx->lis_warps /= 2;
@@ -289,7 +290,7 @@ int run_impl(smr_ctx* ctx) {
     {
       LisGlobals lg{};
       lg.arena_base = (uint8_t*)ctx->lis_arena.p; lg.arena_stride = ctx->lis_stride;
-      lg.hist_cap = ctx->hist_cap; lg.cand_cap = ctx->cand_cap; lg.pair_cap = ctx->pair_cap; lg.row_cap = ctx->row_cap;
+      lg.hist_cap = ctx->hist_cap; lg.cand_cap = ctx->cand_cap; lg.pair_cap = ctx->pair_cap; lg.row_cap = ctx->row_cap; lg.pall_cap = ctx->pall_cap;
       lg.epochs = (uint32_t*)ctx->lis_epochs.p; lg.aln_work = (AlnWork*)ctx->aln_work.p; lg.slots = slots; lg.work_next = sc.lis_next;
       lg.parts = (const DevIndex*)ctx->parts_dev.p; lg.nparts = (uint32_t)hp.size();
       lis_kernel<<<ctx->lis_warps / kLisWarpsPerCta, kLisWarpsPerCta * 32, 0, ctx->stream>>>(b, dp, lg);
@@ -387,7 +388,8 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
     static const int mapc[][2] = {{SMR_CNT_NUM_SHORT, dcNumShort}, {SMR_CNT_SW_CALLS, dcSwCalls}, {SMR_CNT_SW_CELLS, dcSwCells},
                                   {SMR_CNT_WINDOWS, dcWindows}, {SMR_CNT_TRIE_NODES, dcNodes}, {SMR_CNT_BUCKETS, dcBuckets},
                                   {SMR_CNT_BUCKET_ENTRIES, dcEntries}, {SMR_CNT_POS_ENTRIES, dcPosEntries}, {SMR_CNT_LIS_CALLS, dcLisCalls},
-                                  {10, dcMaxReadCycles}, {11, dcSumReadCycles}, {12, dcLisKernelCycles}};
+                                  {10, dcMaxReadCycles}, {11, dcSumReadCycles}, {12, dcLisKernelCycles},
+                                  {13, dcCycVote}, {14, dcCycOrder}, {15, dcCycGroup}, {16, dcCycPrep}, {17, dcCycSwSetup}, {18, dcCycSwLoop}, {19, dcCycBook}};
     for (auto& m : mapc) if ((uint32_t)m[0] < out.n_counters) out.counters[m[0]] += cnt[m[1]];
   }
   return rc;

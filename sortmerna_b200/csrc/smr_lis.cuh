@@ -28,6 +28,8 @@ struct LisArena {            // per-warp scratch in HBM
   uint32_t* hist;            // [hist_cap] epoch<<20 | count, indexed by reference number
   unsigned long long* cand;  // [cand_cap] candidate keys in ascending reference order
   unsigned long long* grp;   // [cand_cap] the group of candidates being processed (one count level, or all when <= 32)
+  unsigned long long* pall;  // [pall_cap] (refpos<<32 | readpos) of ALL candidates of a call, grouped per reference
+  uint32_t pall_cap;
   uint32_t* bitmap;          // [ceil(hist_cap/32)] references that reached num_seeds votes
   uint32_t* summary;         // [ceil(hist_cap/1024)] non-zero words of bitmap
   unsigned long long* pairs; // [pair_cap] (power of two) refpos<<32 | readpos
@@ -38,7 +40,7 @@ struct LisArena {            // per-warp scratch in HBM
 
 struct LisGlobals {
   uint8_t* arena_base; size_t arena_stride;   // per-warp arena
-  uint32_t hist_cap, cand_cap, pair_cap, row_cap;
+  uint32_t hist_cap, cand_cap, pair_cap, row_cap, pall_cap;
   uint32_t* epochs;                            // [total warps]
   AlnWork* aln_work;                           // [nreads * slots]
   uint32_t slots;
@@ -59,12 +61,14 @@ __device__ __forceinline__ LisArena carve_arena(const LisGlobals& g, uint32_t wa
   a.rowH = (int32_t*)p; p += (size_t)g.row_cap * 4;
   a.rowF = (int32_t*)p; p += (size_t)g.row_cap * 4;
   a.bitmap = (uint32_t*)p; p += (size_t)((g.hist_cap + 31) / 32) * 4;
-  a.summary = (uint32_t*)p;
+  a.summary = (uint32_t*)p; p += (size_t)((g.hist_cap + 1023) / 1024) * 4;
+  p = (uint8_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+  a.pall = (unsigned long long*)p; a.pall_cap = g.pall_cap;
   return a;
 }
-__host__ __device__ inline size_t lis_arena_bytes(uint32_t hist_cap, uint32_t cand_cap, uint32_t pair_cap, uint32_t row_cap) {
+__host__ __device__ inline size_t lis_arena_bytes(uint32_t hist_cap, uint32_t cand_cap, uint32_t pair_cap, uint32_t row_cap, uint32_t pall_cap) {
   size_t b = (size_t)cand_cap * 16 + (size_t)pair_cap * 8 + (size_t)hist_cap * 4 + (size_t)pair_cap * 8 + (size_t)row_cap * 8 +
-             (size_t)((hist_cap + 31) / 32) * 4 + (size_t)((hist_cap + 1023) / 1024) * 4 + 64;
+             (size_t)((hist_cap + 31) / 32) * 4 + (size_t)((hist_cap + 1023) / 1024) * 4 + 64 + (size_t)pall_cap * 8;
   return (b + 255) & ~(size_t)255;
 }
 
@@ -156,7 +160,11 @@ struct PassEnv {
   int32_t* s_prof;                                              // query profile (kProfWords)
   const uint2* hits; uint32_t nh;                               // hit region of (current part, current read)
   unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls;
+  unsigned long long cyc[8];                                    // warp cycles per phase: vote, order, group, prep, sw setup, sw loop, book
 };
+
+__device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score, const uint32_t ncand, const bool by_level,
+                               uint32_t level, const bool grouped);
 
 // compute_lis_alignment (alignment.cpp:100-509).  Uniform control flow; warp-parallel inner scans.
 __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score) {
@@ -167,9 +175,10 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   const uint32_t nh = E.nh;
   const uint32_t ns = (uint32_t)max(o.num_seeds, 1);
   E.n_lis_calls++;
+  long long tph = clock64();
 
   // ---- 1. votes per reference (alignment.cpp:118-138) ----
-  if (++E.epoch >= 4096u) {   // epoch tag wrapped: clear the histogram once
+  if (++E.epoch >= 2048u) {   // epoch tag wrapped (11 bits: bit 31 of a histogram word marks a pair cursor): clear once
     for (uint32_t i = lane; i < E.ar.hist_cap; i += 32) E.ar.hist[i] = 0;
     E.epoch = 1; __syncwarp();
   }
@@ -213,6 +222,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
       __syncwarp();
     }
   }
+  { const long long t2 = clock64(); E.cyc[0] += (unsigned long long)(t2 - tph); tph = t2; }
   if (ncand == 0) return;
   if (ncand > E.ar.cand_cap) { rc.flags |= kOvfPairs; return; }
   __syncwarp();
@@ -231,6 +241,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
     }
     key = warp_sort32_u64(key);
     E.ar.grp[lane] = key;
+    E.ar.cand[lane] = key;   // (kept for the cursor clean-up; grp is the working group buffer)
   } else {
     const uint32_t n_sum = (E.ar.hist_cap + 1023u) / 1024u;
     uint32_t out = 0;
@@ -260,6 +271,74 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   }
   __syncwarp();
 
+  { const long long t2 = clock64(); E.cyc[1] += (unsigned long long)(t2 - tph); tph = t2; }
+  // ---- 2b. group the (refpos, readpos) pairs of ALL candidates in one pass over the position lists ----
+  // (the reference rescans every list once per candidate, alignment.cpp:181-194; with thousands of candidates a
+  //  per-candidate gather -- even by binary search -- dominates, so the pairs are scattered into per-reference
+  //  segments with one atomic cursor per reference, kept in the vote histogram word, bit 31 = "cursor")
+  bool grouped = false;
+  {
+    uint32_t running = 0;
+    const unsigned long long* list = E.ar.cand;
+    uint32_t tc = 0;
+    for (uint32_t i0 = 0; i0 < ncand; i0 += 32) { const uint32_t i = i0 + lane; if (i < ncand) tc += 0xFFFFFu - (uint32_t)(list[i] >> 32); }
+    tc = warp_sum_u32(tc);
+    if (tc <= E.ar.pall_cap && ncand > 1) {
+      for (uint32_t i0 = 0; i0 < ncand; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        uint32_t c = 0, seq = 0;
+        if (i < ncand) { const unsigned long long key = list[i]; c = 0xFFFFFu - (uint32_t)(key >> 32); seq = (uint32_t)key; }
+        const uint32_t incl = warp_incl_scan_u32(c), tot = __shfl_sync(kFull, incl, 31);
+        if (i < ncand) E.ar.hist[seq] = 0x80000000u | (running + incl - c);
+        running += tot;
+      }
+      __syncwarp();
+      for (uint32_t h0 = 0; h0 < nh; h0 += 32) {
+        const uint32_t h = h0 + lane;
+        uint32_t o_l = 0, s_l = 0, w_l = 0;
+        if (h < nh) {
+          const uint2 hv = hits[h];
+          if (hit_selected(hv, rc, s0, s1, s2)) { o_l = __ldg(ix.pos_off + hv.x); s_l = __ldg(ix.pos_off + hv.x + 1) - o_l; w_l = hv.y & kWinMask; }
+        }
+        const uint32_t incl = warp_incl_scan_u32(s_l), tot = __shfl_sync(kFull, incl, 31), excl = incl - s_l;
+        for (uint32_t e0 = 0; e0 < tot; e0 += 32) {
+          const uint32_t e = e0 + lane;
+          uint32_t lo = 0;
+#pragma unroll
+          for (int stp = 16; stp > 0; stp >>= 1) { const uint32_t v = __shfl_sync(kFull, incl, lo + stp - 1); if (v <= e) lo += stp; }
+          lo = min(lo, 31u);
+          const uint32_t o_own = __shfl_sync(kFull, o_l, lo), ex_own = __shfl_sync(kFull, excl, lo), w_own = __shfl_sync(kFull, w_l, lo);
+          if (e < tot) {
+            const uint2 ps = __ldg(&ix.pos[o_own + (e - ex_own)]);
+            if (ps.y < E.ar.hist_cap && (E.ar.hist[ps.y] & 0x80000000u)) {
+              const uint32_t slot = atomicAdd(&E.ar.hist[ps.y], 1u) & 0x7FFFFFFFu;
+              E.ar.pall[slot] = ((unsigned long long)ps.x << 32) | w_own;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      grouped = true;
+    }
+  }
+  { const long long t2 = clock64(); E.cyc[2] += (unsigned long long)(t2 - tph); tph = t2; }
+  run_candidates(E, rc, search, max_SW_score, ncand, by_level, level, grouped);
+  __syncwarp();
+  if (grouped) {   // the cursors must not survive the call: histogram words are epoch-tagged votes otherwise
+    const unsigned long long* list = E.ar.cand;
+    for (uint32_t i = lane; i < ncand; i += 32) E.ar.hist[(uint32_t)list[i]] = 0;
+    __syncwarp();
+  }
+}
+
+// candidates in order (alignment.cpp:150-508); returns through rc.flags on scratch overflow
+__device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score, const uint32_t ncand, const bool by_level,
+                               uint32_t level, const bool grouped) {
+  const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
+  const unsigned lane = lane_id();
+  const uint32_t s0 = ix.skip[0], s1 = ix.skip[1], s2 = ix.skip[2];
+  const uint2* hits = E.hits;
+  const uint32_t nh = E.nh;
   // ---- 3. candidates in order (alignment.cpp:150-508) ----
   bool is_aligned = false, is_search_candidates = true, first_cand = true, stop_all = false;
   uint32_t prev_occur = 0;
@@ -295,6 +374,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
     if (is_aligned && o.min_lis > 0 && !first_cand && max_occur < prev_occur) { --rc.best; if (rc.best < 1) { stop_all = true; break; } }  // :165-169
     prev_occur = max_occur; first_cand = false;
 
+    long long tc0 = clock64();
     // gather (refpos, readpos) pairs of this reference (:181-201)
     const uint32_t np = max_occur;
     unsigned long long* P; uint32_t* lb; uint32_t* lp;
@@ -302,6 +382,11 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
     else if (np <= E.ar.pair_cap) { P = E.ar.pairs; lb = E.ar.lis_b; lp = E.ar.lis_p; }
     else { rc.flags |= kOvfPairs; return; }
     uint32_t filled = 0;
+    if (grouped) {   // the pairs of this reference were grouped by the one-pass scatter
+      const uint32_t seg_end = E.ar.hist[max_ref] & 0x7FFFFFFFu, seg = seg_end - np;
+      for (uint32_t i = lane; i < np; i += 32) P[i] = E.ar.pall[seg + i];
+      filled = np;
+    } else
     for (uint32_t h0 = 0; h0 < nh; h0 += 32) {
       const uint32_t h = h0 + lane;
       uint32_t first = 0, cnt = 0, win = 0;
@@ -378,8 +463,10 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
           if (!rc.reversed) q = SeqView{B.seq04 + rc.seq_base, (int32_t)aqs, 1, false};
           else q = SeqView{B.seq04 + rc.seq_base, (int32_t)(rc.len - 1 - aqs), -1, true};
           const SeqView t{ix.refseq + __ldg(ix.ref_off + max_ref), (int32_t)win_start, 1, false};
+          { const long long t2 = clock64(); E.cyc[3] += (unsigned long long)(t2 - tc0); tc0 = t2; }
           int32_t sw = 0;
-          if (qlen > 0 && alen > 0 && (uint32_t)alen <= E.ar.row_cap) sw = sw_score(q, qlen, t, (int32_t)alen, sc, E.s_ref, E.s_prof, E.ar.rowH, E.ar.rowF);
+          if (qlen > 0 && alen > 0 && (uint32_t)alen <= E.ar.row_cap) sw = sw_score(q, qlen, t, (int32_t)alen, sc, E.s_ref, E.s_prof, E.ar.rowH, E.ar.rowF, &E.cyc[4]);
+          { const long long t2 = clock64(); E.cyc[5] += (unsigned long long)(t2 - tc0); tc0 = t2; }
           E.n_sw_calls++; E.n_sw_cells += (unsigned long long)alen * (unsigned long long)(qlen > 0 ? qlen : 0);
           const uint32_t score1 = (uint32_t)sw & 0xFFFFu;                                   // s_align.score1 is uint16
           is_aligned = score1 > ix.minimal_score;                                           // :388
@@ -428,6 +515,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
         if (it != np) { begin_ref = (uint32_t)(P[it] >> 32); begin_read = (uint32_t)P[it]; } else break;
       } else { begin_ref = (uint32_t)(P[f] >> 32); begin_read = (uint32_t)P[f]; }
     }
+    { const long long t2 = clock64(); E.cyc[6] += (unsigned long long)(t2 - tc0); }
     __syncwarp();
   }
     if (!by_level || stop_all || !is_search_candidates) break;
@@ -507,6 +595,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   E.epoch_ptr = g.epochs + warp; E.epoch = *E.epoch_ptr;
   E.s_pairs = s_pairs[wic]; E.s_b = s_b[wic]; E.s_p = s_p[wic]; E.s_ref = s_ref[wic]; E.s_prof = s_prof[wic];
   E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = 0;
+  for (int i = 0; i < 8; ++i) E.cyc[i] = 0;
   const uint32_t nwork = s_bin_start[kCostBins];
   unsigned long long t_max = 0, t_sum = 0; const long long t_k0 = clock64();
   const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);
@@ -558,6 +647,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     *E.epoch_ptr = E.epoch;
     atomicAdd(&b.counters[dcSwCalls], E.n_sw_calls); atomicAdd(&b.counters[dcSwCells], E.n_sw_cells);
     atomicAdd(&b.counters[dcPosEntries], E.n_pos_entries); atomicAdd(&b.counters[dcLisCalls], E.n_lis_calls);
+    for (int i = 0; i < 7; ++i) atomicAdd(&b.counters[dcCycVote + i], E.cyc[i]);
     atomicMax(&b.counters[dcMaxReadCycles], t_max); atomicAdd(&b.counters[dcSumReadCycles], t_sum);
     atomicMax(&b.counters[dcLisKernelCycles], (unsigned long long)(clock64() - t_k0));
   }

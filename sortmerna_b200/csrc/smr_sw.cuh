@@ -227,12 +227,15 @@ __device__ __noinline__ int32_t sw_score_run(const SeqView q, const int32_t m, i
 // score of the best local alignment of q (m rows) against t (n columns); s_ref = kRefStage+64 bytes and s_prof =
 // kProfWords ints of shared memory owned by this warp
 __device__ int32_t sw_score(const SeqView q, const int32_t m, const SeqView t, const int32_t n, const SwScore sc, uint8_t* s_ref, int32_t* s_prof,
-                            int32_t* rowH, int32_t* rowF) {
+                            int32_t* rowH, int32_t* rowF, unsigned long long* cyc_setup = nullptr) {
+  const long long t_s0 = clock64();
   if (m > 256 || n > kRefStage || sc.mismatch >= 0 || sc.go <= 0 || sc.sN >= 0 || sc.ge > sc.go) return sw_forward_any(q, m, t, n, sc, rowH, rowF).score;
   const int lane = (int)lane_id();
   __syncwarp();
   // staged window: table index per column, sentinel table (5) for 32 columns on both sides
   for (int32_t i = lane; i < n + 64; i += 32) { const int32_t j = i - 32; s_ref[i] = (j >= 0 && j < n) ? (uint8_t)min(t.at(j), 4u) : (uint8_t)5; }
+  __syncwarp();
+  if (cyc_setup) *cyc_setup += (unsigned long long)(clock64() - t_s0);
   if (m <= 32) return sw_score_run<1>(q, m, s_prof, s_ref, n, sc);
   if (m <= 64) return sw_score_run<2>(q, m, s_prof, s_ref, n, sc);
   if (m <= 96) return sw_score_run<3>(q, m, s_prof, s_ref, n, sc);
