@@ -270,6 +270,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     t_setup = time.time()
+    if world > 1:       # the index cache is built once (rank 0), the other ranks wait and then only read it
+        if rank == 0:
+            load_databases()
+        dist.barrier()
     fastas, idx_dir, prefixes, refs, stats, built = load_databases()
     n_job = args.reads
     n = max(1, n_job // args.steps)                   # reads per step (batch) per GPU
