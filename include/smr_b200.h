@@ -142,6 +142,9 @@ int smr_last_timings(const smr_ctx*, double out[8]);
 int smr_debug_seed_windows(smr_ctx*, uint32_t part_slot, const uint8_t* seq_cat, const uint64_t* seq_off,
                            uint32_t nreads, const uint32_t* win_read, const uint32_t* win_pos, uint32_t nwin,
                            uint32_t* ids, uint32_t cap, uint32_t* counts, uint8_t* zero);
+/* measured peak of dependent-free DPX (VIADDMNMX) thread-operations per second on this device, in 1e9/s:
+ * the denominator of the Smith-Waterman roofline */
+int smr_debug_dpx_peak(smr_ctx*, double* giga_ops_per_s);
 /* ssw_align(flag=2) equivalents on explicit (query, target) pairs:
  * out[k*6..] = score1, ref_begin1, ref_end1, read_begin1, read_end1, cigar_len; cigars at k*cigar_cap */
 int smr_debug_ssw(smr_ctx*, const uint8_t* q_cat, const uint64_t* q_off, const uint8_t* t_cat,

@@ -24,7 +24,8 @@ STATUS = {0: "SMR_OK", 1: "SMR_ERR_CUDA", 2: "SMR_ERR_ARG", 3: "SMR_ERR_INDEX", 
 # every symbol include/smr_b200.h declares
 SYMBOLS = ["smr_init", "smr_destroy", "smr_last_error", "smr_device_count", "smr_load_index_part",
            "smr_set_minimal_score", "smr_set_params", "smr_index_info", "smr_align_batch", "smr_upload_batch",
-           "smr_run_resident", "smr_download_results", "smr_last_timings", "smr_debug_seed_windows", "smr_debug_ssw"]
+           "smr_run_resident", "smr_download_results", "smr_last_timings", "smr_debug_seed_windows", "smr_debug_ssw",
+           "smr_debug_dpx_peak"]
 
 CNT_NAMES = ("num_aligned", "num_short", "sw_calls", "sw_cells", "windows", "trie_nodes", "buckets",
              "bucket_entries", "pos_entries", "lis_calls", "dbg_max_read_cycles", "dbg_sum_read_cycles", "dbg_lis_kernel_cycles",
@@ -193,6 +194,12 @@ class Aligner:
         self.L.smr_last_timings(self.h, _ptr(out))
         return dict(total_ms=out[0], seed_ms=out[1], lis_ms=out[2], final_ms=out[3], h2d_ms=out[4], d2h_ms=out[5],
                     launches=int(out[6]))
+
+    def dpx_peak(self) -> float:
+        """measured dependent-free DPX thread-ops/s (1e9/s) on this device"""
+        v = C.c_double(0)
+        self._check(self.L.smr_debug_dpx_peak(self.h, C.byref(v)), "smr_debug_dpx_peak")
+        return v.value
 
     # ---- unit-test entry points ----
     def debug_seed_windows(self, part_slot, cat03, off, win_read, win_pos, cap=64, fallback_path=False):

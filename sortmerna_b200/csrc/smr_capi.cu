@@ -591,6 +591,29 @@ int smr_last_timings(const smr_ctx* ctx, double out[8]) {
   return SMR_OK;
 }
 
+int smr_debug_dpx_peak(smr_ctx* ctx, double* giga_ops_per_s) {
+  if (!ctx || !giga_ops_per_s) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  int32_t* d = nullptr;
+  CK(cudaMalloc(&d, 64));
+  const int iters = 1 << 14, ctas = ctx->sm_count * 8, thr = 256;
+  cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1);
+  double best = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(e0, ctx->stream));
+    dpx_peak_kernel<<<ctas, thr, 0, ctx->stream>>>(d, iters, -2, -1000000);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double ops = (double)ctas * thr * iters * 8.0;
+    if (rep > 0) best = std::max(best, ops / (ms * 1e-3) / 1e9);
+  }
+  cudaFree(d);
+  *giga_ops_per_s = best;
+  return SMR_OK;
+}
+
 int smr_debug_seed_windows(smr_ctx* ctx, uint32_t part_slot, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads,
                            const uint32_t* win_read, const uint32_t* win_pos, uint32_t nwin, uint32_t* ids, uint32_t cap, uint32_t* counts,
                            uint8_t* zero) {

@@ -138,4 +138,15 @@ ssw_debug_kernel(const uint8_t* qcat, const uint32_t* qoff, const uint8_t* tcat,
   }
 }
 
+// DPX issue-rate micro-benchmark: 8 independent VIADDMNMX chains per thread (the dependent-free peak SURVEY 8(d)
+// asks to measure on the box instead of quoting a datasheet).  out[0] receives a value so nothing is optimised away.
+__global__ void dpx_peak_kernel(int32_t* out, int iters, int32_t a, int32_t b) {
+  int32_t x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = __viaddmax_s32(x0, a, b); x1 = __viaddmax_s32(x1, a, b); x2 = __viaddmax_s32(x2, a, b); x3 = __viaddmax_s32(x3, a, b);
+    x4 = __viaddmax_s32(x4, a, b); x5 = __viaddmax_s32(x5, a, b); x6 = __viaddmax_s32(x6, a, b); x7 = __viaddmax_s32(x7, a, b);
+  }
+  if ((x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7) == 0x7fffffff) out[0] = x0;
+}
+
 }  // namespace smr

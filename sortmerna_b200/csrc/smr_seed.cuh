@@ -226,47 +226,47 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
     const uint32_t npos = (len - L) / step + 1;          // positions q*step, q < npos
     const size_t region = hit_base(b, ix.slot, r); const uint32_t region_cap = hit_cap(b, r);
     uint32_t total = 0, flags = 0, cost = 0;
+    // the windows of all strand variants form one sequence (variant-major), 32 per round
     const uint32_t nvar = hasn ? 3u : 2u;
-    for (uint32_t var = 0; var < nvar; ++var) {
-      if (var == kVarFwd && !do_fwd) continue;
-      if (var != kVarFwd && !do_rev) continue;
-      for (uint32_t q0 = 0; q0 < npos; q0 += 32) {
-        const uint32_t q = q0 + lane, p = q * step;
-        bool active = q < npos;
-        if (active && step == 1) active = (p % s0 == 0) || (p % s1 == 0) || (p % s2 == 0);
-        lh.n = 0; lh.overflow = false;
-        uint32_t keyf = 0, keyr = 0;
-        uint4 lk_f = make_uint4(0, 0, 0, 0);
-        if (active) {
-          uint64_t V;
-          if (var == kVarFwd) V = window_fwd(pk, p, L);
-          else V = revcomp_bits(window_fwd(var == kVarRevT ? pk : pka, len - p - L, L), L);
-          keyf = (uint32_t)(V >> (2 * pw)); keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
-          lk_f = __ldg(&ix.flookup[keyf]);                                        // paralleltraversal.cpp:161
-          ++n_windows;
-        }
-        bool zero = false;
-        // sub-search (a): exact first half, <= 1 error in the second half (P = w[9..18) ascending)
-        coop_flat<INSTR>(ix, sm, lk_f.x, lk_f.y, rev_chars(keyr, pw), full, lh, zero, st);
-        // sub-search (b), only without a 0-error hit (:188): exact second half, <= 1 error in the reversed first half
-        uint4 lk_r = make_uint4(0, 0, 0, 0);
-        if (active && !zero) lk_r = __ldg(&ix.flookup[keyr]);                      // :215
-        coop_flat<INSTR>(ix, sm, lk_r.z, lk_r.w, keyf, full, lh, zero, st);
-        if (lh.overflow) flags |= kOvfSeedLane;
-        const uint32_t n = lh.overflow ? 0u : lh.n;
-        const uint32_t incl = warp_incl_scan_u32(n), tot = __shfl_sync(kFull, incl, 31);
-        if (total + tot > region_cap) { flags |= kOvfSeedRegion; }
-        else {
-          const size_t base = region + total + incl - n;
-          for (uint32_t k = 0; k < n; ++k) {
-            const uint32_t id = lh.buf[k * lh.stride];
-            b.hits[base + k] = make_uint2(id, p | (var << 24));
-            cost += __ldg(ix.pos_off + id + 1) - __ldg(ix.pos_off + id);
-          }
-        }
-        total += tot;
-        __syncwarp();
+    const uint32_t v_lo = do_fwd ? 0u : 1u, v_hi = do_rev ? nvar : 1u;      // variants searched: [v_lo, v_hi)
+    const uint32_t nq = (v_hi - v_lo) * npos;
+    for (uint32_t q0 = 0; q0 < nq; q0 += 32) {
+      const uint32_t qq = q0 + lane;
+      const uint32_t var = v_lo + qq / npos, p = (qq % npos) * step;
+      bool active = qq < nq;
+      if (active && step == 1) active = (p % s0 == 0) || (p % s1 == 0) || (p % s2 == 0);
+      lh.n = 0; lh.overflow = false;
+      uint32_t keyf = 0, keyr = 0;
+      uint4 lk_f = make_uint4(0, 0, 0, 0);
+      if (active) {
+        uint64_t V;
+        if (var == kVarFwd) V = window_fwd(pk, p, L);
+        else V = revcomp_bits(window_fwd(var == kVarRevT ? pk : pka, len - p - L, L), L);
+        keyf = (uint32_t)(V >> (2 * pw)); keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
+        lk_f = __ldg(&ix.flookup[keyf]);                                        // paralleltraversal.cpp:161
+        ++n_windows;
       }
+      bool zero = false;
+      // sub-search (a): exact first half, <= 1 error in the second half (P = w[9..18) ascending)
+      coop_flat<INSTR>(ix, sm, lk_f.x, lk_f.y, rev_chars(keyr, pw), full, lh, zero, st);
+      // sub-search (b), only without a 0-error hit (:188): exact second half, <= 1 error in the reversed first half
+      uint4 lk_r = make_uint4(0, 0, 0, 0);
+      if (active && !zero) lk_r = __ldg(&ix.flookup[keyr]);                      // :215
+      coop_flat<INSTR>(ix, sm, lk_r.z, lk_r.w, keyf, full, lh, zero, st);
+      if (lh.overflow) flags |= kOvfSeedLane;
+      const uint32_t n = lh.overflow ? 0u : lh.n;
+      const uint32_t incl = warp_incl_scan_u32(n), tot = __shfl_sync(kFull, incl, 31);
+      if (total + tot > region_cap) { flags |= kOvfSeedRegion; }
+      else {
+        const size_t base = region + total + incl - n;
+        for (uint32_t k = 0; k < n; ++k) {
+          const uint32_t id = lh.buf[k * lh.stride];
+          b.hits[base + k] = make_uint2(id, p | (var << 24));
+          cost += __ldg(ix.pos_off + id + 1) - __ldg(ix.pos_off + id);
+        }
+      }
+      total += tot;
+      __syncwarp();
     }
     flags = __reduce_or_sync(kFull, flags);
     cost = warp_sum_u32(min(cost, 1u << 24));
