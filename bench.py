@@ -372,14 +372,26 @@ def main():
     sw_kernel_rate = cells_per_rank / lis_s / 1e12 if lis_s > 0 else 0.0            # whole kernel (votes, LIS, ... included)
     sw_loop_rate = cells_per_rank / (lis_s * sw_loop_frac) / 1e12 if lis_s * sw_loop_frac > 0 else 0.0
     sw_peak = dpx / 3.5 / 1e3                        # Tcell-updates/s
+    tr = {}
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+    except Exception:
+        pass
+    def _traffic(kernel):   # ncu DRAM bytes of the committed capture, scaled to the reads of one launch of this run
+        if kernel in tr and tr.get("reads_in_captured_launch"):
+            return int(tr[kernel]["dram_bytes"] * n / tr["reads_in_captured_launch"])
+        return None
     roof_sw = {"bound": "integer (alu pipe, DPX)", "kernel": "lis_kernel (candidates + Smith-Waterman score pass)",
                "achieved": sw_kernel_rate, "peak": sw_peak, "unit": "Tcell-updates/s", "frac": sw_kernel_rate / sw_peak if sw_peak else None,
-               "traffic": None, "achieved_in_sw_loop_only": sw_loop_rate, "frac_in_sw_loop_only": sw_loop_rate / sw_peak if sw_peak else None,
+               "traffic": _traffic("lis_kernel"), "traffic_unit": "DRAM bytes per launch (ncu capture scaled by reads per launch)",
+               "achieved_in_sw_loop_only": sw_loop_rate, "frac_in_sw_loop_only": sw_loop_rate / sw_peak if sw_peak else None,
                "sw_loop_share_of_kernel_warp_cycles": sw_loop_frac,
                "peak_source": f"measured now: {dpx:.0f} G dependent-free VIADDMNMX thread-ops/s (smr_debug_dpx_peak) / 3.5 such instructions per cell",
                "cells_per_step": int(cells_per_rank / args.steps), "kernel_ms_per_step": float(np.mean(lis_ms))}
     roof_seed = {"bound": "hbm", "kernel": "seed_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": int(alg_bytes / world / args.steps),
+                 "traffic": _traffic("seed_kernel"), "traffic_unit": "DRAM bytes of ONE launch (index part 0 of 8; ncu capture scaled by reads per launch)",
+                 "algorithmic_bytes_per_launch": int(alg_bytes / world / args.steps / max(1, info["parts"])),
+                 "peak_source": peak_src, "algorithmic_bytes_per_step": int(alg_bytes / world / args.steps),
                  "kernel_ms_per_step": float(np.mean(seed_ms))}
     out = {
         "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
