@@ -51,3 +51,25 @@ def load_case(name):
 
 def case_names():
     return sorted(d[5:] for d in os.listdir(GOLDEN) if d.startswith("case_"))
+
+
+@pytest.fixture(scope="session")
+def golden_t0():
+    """BASELINE config 1: the 1.5 kb read of data/test_read.fasta vs data/test_ref.fasta (single-line copies), with the
+    reference's own index and output (tests/golden/t0/, made by make_golden.make_t0)."""
+    from sortmerna_b200 import hostio
+    d = tempfile.mkdtemp(prefix="smr_idx_t0_")
+    src = os.path.join(GOLDEN, "t0", "idx")
+    for fn in os.listdir(src):
+        if fn.endswith(".gz"):
+            with gzip.open(os.path.join(src, fn), "rb") as fi, open(os.path.join(d, fn[:-3]), "wb") as fo:
+                shutil.copyfileobj(fi, fo)
+        else:
+            shutil.copy(os.path.join(src, fn), d)
+    refs = hostio.load_references(os.path.join(GOLDEN, "t0", "db_t0.fasta"))
+    prefix = hostio.find_index_prefixes(d)["db_t0.fasta"]
+    batch = hostio.load_reads(os.path.join(GOLDEN, "t0", "reads_t0.fasta"))
+    with open(os.path.join(GOLDEN, "t0", "expected.json")) as f:
+        exp = json.load(f)
+    yield dict(refs=refs, prefix=prefix, stats=hostio.parse_stats(prefix), batch=batch, exp=exp)
+    shutil.rmtree(d, ignore_errors=True)

@@ -159,3 +159,19 @@ def test_edge_batches(aligner, golden, oracle_indexes):
     g1 = aligner.align(one.cat, one.off)
     w1 = ora.align(oracle_indexes, [0, 1], [0, 0], 2, golden["refs"], [37, 36], [18, 9, 3, 18, 9, 3], ora.default_params(), one)
     assert_same_results(g1, w1, "single")
+
+
+def test_long_read_t0(golden_t0):
+    """BASELINE config 1: a 1.5 kb read (several SW row blocks, score > 255) -- identical to the oracle and to the reference SAM row."""
+    ora = _ora()
+    g = golden_t0
+    a = api.Aligner(0)
+    a.set_params(api.default_params())
+    a.load_index_part(0, 0, g["prefix"], g["refs"], g["exp"]["log"]["minimal_score"][0], (18, 9, 3), g["stats"].lnwin)
+    got = a.align(g["batch"].cat, g["batch"].off)
+    ix = ora.OracleIndex(g["prefix"], 0, g["stats"].lnwin)
+    want = ora.align([ix], [0], [0], 1, [g["refs"]], g["exp"]["log"]["minimal_score"], [18, 9, 3], ora.default_params(), g["batch"])
+    assert_same_results(got, want, "t0")
+    rows = hostio.format_sam_rows(g["batch"], [g["refs"]], got["res"], got["alns"], got["cigar"], got["slots"])
+    assert rows == g["exp"]["sam"]
+    a.close()

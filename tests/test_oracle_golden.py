@@ -62,3 +62,13 @@ def test_empty_and_short_batches(golden, oracle_indexes):
     batch = hostio.pack_reads(["@e", "@s", "@x"], [b"", b"ACGTACGTAC", b"ACGTNNNN"])
     out = ora.align(oracle_indexes, [0, 1], [0, 0], 2, golden["refs"], [37, 36], [18, 9, 3, 18, 9, 3], prm, batch)
     assert int(out["res"]["is_hit"].sum()) == 0 and out["counters"]["num_short_last"] == 3
+
+
+def test_oracle_long_read_t0(golden_t0):
+    """BASELINE config 1 (t0/t2 of the reference's suite): 1.5 kb read, int16 'word' SW path, 30-op CIGAR."""
+    g = golden_t0
+    ix = ora.OracleIndex(g["prefix"], 0, g["stats"].lnwin)
+    out = ora.align([ix], [0], [0], 1, [g["refs"]], g["exp"]["log"]["minimal_score"], [18, 9, 3], ora.default_params(), g["batch"])
+    rows = hostio.format_sam_rows(g["batch"], [g["refs"]], out["res"], out["alns"], out["cigar"], out["slots"])
+    assert rows == g["exp"]["sam"]
+    assert int(out["alns"]["score1"][0]) > 255   # the byte kernel overflowed in the reference: word path
