@@ -47,7 +47,8 @@ struct smr_ctx {
   DevBuf seq04, seq_off, pk03, pk03alt, pk_off, has_n, hit_cnt, flags, state, hit_db, aln_work, out_aln;
   DevBuf hits, cost, bins, scalars, counters, cigar_pool, parts_dev;
   size_t hits_stride = 0; uint32_t cnt_stride = 0;
-  DevBuf lis_arena, lis_epochs, final_arena, lane_hits;
+  DevBuf lis_arena, lis_epochs, final_arena, lane_hits, tb_arena, tb_jobs;
+  uint32_t tb_threads = 0, tb_cap_w = 0, tb_cap_cig = 0; size_t tb_cap_dir = 0, tb_stride = 0;
   uint32_t lis_warps = 0, final_warps = 0;
   size_t lis_stride = 0, final_stride = 0;
   uint32_t hist_cap = 0, cand_cap = 0, pair_cap = 0, row_cap = 0, pall_cap = 0, cap_w = 0, cap_cig = 0; size_t cap_dir = 0;
@@ -145,6 +146,14 @@ int setup_arenas(smr_ctx* ctx) {
   ctx->final_stride = final_arena_bytes(ctx->cap_w, ctx->cap_cig, ctx->row_cap, ctx->cap_dir);
   while (ctx->final_warps > 64 && ctx->final_stride * ctx->final_warps > budget) ctx->final_warps /= 2;
   if (int rc = ensure(ctx, ctx->final_arena, ctx->final_stride * ctx->final_warps)) return rc;
+  // traceback stage: one thread per alignment, 1024 threads per SM
+  ctx->tb_threads = (uint32_t)ctx->sm_count * 1024u;
+  ctx->tb_cap_w = 2 * 32 * ctx->scale + 8;                       // band widths up to 32*scale
+  ctx->tb_cap_cig = 128 * ctx->scale;
+  ctx->tb_cap_dir = (size_t)12288 * ctx->scale;                  // (2*band+1) * readLen * 3 bytes
+  ctx->tb_stride = ((size_t)ctx->tb_cap_w * 12 + (size_t)ctx->tb_cap_cig * 4 + ctx->tb_cap_dir + 255) & ~(size_t)255;
+  while (ctx->tb_threads > 4096 && ctx->tb_stride * ctx->tb_threads > budget) ctx->tb_threads /= 2;
+  if (int rc = ensure(ctx, ctx->tb_arena, ctx->tb_stride * ctx->tb_threads)) return rc;
   ctx->lane_hits_cap = kLaneHitCap * ctx->scale;
   ctx->lane_hits_warps = ctx->scale == 1 ? (uint32_t)ctx->sm_count * 8 * kSeedWarpsPerCta : 1024u;
   if (int rc = ensure(ctx, ctx->lane_hits, (size_t)ctx->lane_hits_warps * ctx->lane_hits_cap * 32 * 4)) return rc;
@@ -309,8 +318,14 @@ int run_impl(smr_ctx* ctx) {
     fg.parts = (const DevIndex*)ctx->parts_dev.p; fg.aln_work = (const AlnWork*)ctx->aln_work.p; fg.out = (OutAln*)ctx->out_aln.p;
     fg.slots = slots; fg.cigar_pool = (uint32_t*)ctx->cigar_pool.p; fg.cigar_cap = ctx->cigar_cap_dev; fg.cigar_used = sc.cigar_used;
     fg.work_next = sc.fin_next;
+    if ((rc = ensure(ctx, ctx->tb_jobs, (size_t)n * slots * sizeof(TraceJob)))) return rc;
+    fg.jobs = (TraceJob*)ctx->tb_jobs.p; fg.tb_arena = (uint8_t*)ctx->tb_arena.p; fg.tb_stride = ctx->tb_stride;
+    fg.tb_cap_w = ctx->tb_cap_w; fg.tb_cap_cig = ctx->tb_cap_cig; fg.tb_cap_dir = ctx->tb_cap_dir;
     finalize_kernel<<<ctx->final_warps / kFinalWarpsPerCta, kFinalWarpsPerCta * 32, 0, ctx->stream>>>(b, dp, fg);
     CK(cudaGetLastError());
+    traceback_kernel<<<ctx->tb_threads / 128, 128, 0, ctx->stream>>>(b, dp, fg);
+    CK(cudaGetLastError());
+    ctx->n_launch += 1;
     CK(cudaEventRecord(f1, ctx->stream));
     spans.push_back({evi - 2, 1});
     ctx->n_launch += 1;
@@ -457,7 +472,7 @@ void smr_destroy(smr_ctx* ctx) {
   for (auto& pt : ctx->parts) for (void* p : pt.owned) cudaFree(p);
   DevBuf* bufs[] = {&ctx->seq04, &ctx->seq_off, &ctx->pk03, &ctx->pk03alt, &ctx->pk_off, &ctx->has_n, &ctx->hit_cnt, &ctx->flags, &ctx->state,
                     &ctx->hit_db, &ctx->aln_work, &ctx->out_aln, &ctx->hits, &ctx->cost, &ctx->bins, &ctx->scalars, &ctx->counters, &ctx->cigar_pool,
-                    &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->final_arena, &ctx->lane_hits};
+                    &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs};
   for (DevBuf* b : bufs) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -18,6 +18,14 @@ struct OutAln {
   uint8_t strand, pad;
 };
 
+// what the traceback stage needs for one stored alignment (filled by finalize_kernel)
+struct TraceJob {
+  uint32_t valid;          // 1 = traceback wanted
+  uint32_t idx_slot, ref_num, ref_off;   // reference window start = refseq[ref_off[ref_num] + ref_off]
+  int32_t q_start, q_step;               // query view start / step into seq04 of the read (step -1 + complement for the minus strand)
+  int32_t rl, ql, score, band;
+};
+
 struct FinalGlobals {
   uint8_t* arena_base; size_t arena_stride;
   uint32_t cap_w, cap_cig, row_cap; size_t cap_dir;
@@ -25,6 +33,9 @@ struct FinalGlobals {
   const AlnWork* aln_work; OutAln* out; uint32_t slots;
   uint32_t* cigar_pool; unsigned long long cigar_cap; unsigned long long* cigar_used;
   uint32_t* work_next;
+  // traceback stage (one THREAD per alignment)
+  struct TraceJob* jobs;             // [nreads_chunk * slots]
+  uint8_t* tb_arena; size_t tb_stride; uint32_t tb_cap_w, tb_cap_cig; size_t tb_cap_dir;
 };
 __host__ __device__ inline size_t final_arena_bytes(uint32_t cap_w, uint32_t cap_cig, uint32_t row_cap, size_t cap_dir) {
   size_t b = (size_t)cap_w * 12 + (size_t)cap_cig * 4 + (size_t)row_cap * 8 + cap_dir;
@@ -35,11 +46,13 @@ constexpr int kFinalWarpsPerCta = 4;
 
 __global__ void __launch_bounds__(kFinalWarpsPerCta * 32)
 finalize_kernel(DevBatch b, DevParams prm, FinalGlobals g) {
+  __shared__ __align__(16) uint8_t s_ref[kFinalWarpsPerCta][kRefStage + 64];
+  __shared__ int32_t s_prof[kFinalWarpsPerCta][kProfWords];
   const unsigned lane = lane_id();
   const uint32_t warp = blockIdx.x * kFinalWarpsPerCta + (threadIdx.x >> 5);
   uint8_t* p = g.arena_base + (size_t)warp * g.arena_stride;
   TraceArena A;
-  A.cap_w = g.cap_w; A.cap_cig = g.cap_cig; A.cap_dir = g.cap_dir;
+  A.cap_w = g.cap_w; A.cap_cig = g.cap_cig; A.cap_dir = g.cap_dir; A.stride = 1;
   A.hb = (int32_t*)p; p += (size_t)g.cap_w * 4;
   A.eb = (int32_t*)p; p += (size_t)g.cap_w * 4;
   A.hc = (int32_t*)p; p += (size_t)g.cap_w * 4;
@@ -55,7 +68,7 @@ finalize_kernel(DevBatch b, DevParams prm, FinalGlobals g) {
     wi = __shfl_sync(kFull, wi, 0);
     if (wi >= total) break;
     const uint32_t r = b.r0 + wi / g.slots, k = wi % g.slots;
-    if (k >= b.state[r].n_align || b.flags[r]) continue;
+    if (k >= b.state[r].n_align || b.flags[r]) { if (lane == 0) g.jobs[(size_t)wi].valid = 0; continue; }
     const AlnWork a = g.aln_work[(size_t)r * g.slots + k];
     const DevIndex& ix = g.parts[a.idx_slot];
     const uint32_t seq_base = b.seq_off[r], len = b.seq_off[r + 1] - seq_base;
@@ -64,34 +77,64 @@ finalize_kernel(DevBatch b, DevParams prm, FinalGlobals g) {
     const SeqView t{ix.refseq + ix.ref_off[a.ref_num], (int32_t)a.win_ref_start, 1, false};
     // forward pass again, now with the end-point tie-breaks (ssw.c:310-336), then the reverse pass over
     // the prefixes that end at the forward optimum (ssw.c:899-915)
-    const SwEnd fwd = sw_forward(q, (int32_t)a.q_len, t, (int32_t)a.win_len, sc, rowH, rowF);
-    if ((uint32_t)(fwd.score & 0xFFFF) != a.score1) { if (lane == 0) atomicOr(&b.flags[r], kErrTrace); continue; }
+    uint8_t* sr = s_ref[threadIdx.x >> 5]; int32_t* sp = s_prof[threadIdx.x >> 5];
+    const SwEnd fwd = sw_locate(q, (int32_t)a.q_len, t, (int32_t)a.win_len, sc, (int32_t)a.score1, sr, sp, rowH, rowF);
+    if ((uint32_t)(fwd.score & 0xFFFF) != a.score1) { if (lane == 0) { atomicOr(&b.flags[r], kErrTrace); g.jobs[(size_t)wi].valid = 0; } continue; }
     const int32_t a_ref_end = fwd.ref, a_read_end = fwd.read;
-    const SwEnd rev = sw_forward(q.reversed_prefix(a_read_end), a_read_end + 1, t.reversed_prefix(a_ref_end), a_ref_end + 1, sc, rowH, rowF);
+    const SwEnd rev = sw_locate(q.reversed_prefix(a_read_end), a_read_end + 1, t.reversed_prefix(a_ref_end), a_ref_end + 1, sc, (int32_t)a.score1, sr, sp, rowH, rowF);
+    if (rev.score != (int32_t)a.score1) { if (lane == 0) { atomicOr(&b.flags[r], kErrTrace); g.jobs[(size_t)wi].valid = 0; } continue; }
     const int32_t ref_begin = a_ref_end - rev.ref, read_begin = a_read_end - rev.read;
     const int32_t rl = a_ref_end - ref_begin + 1, ql = a_read_end - read_begin + 1;
     const int32_t band = (rl > ql ? rl - ql : ql - rl) + 1;                                  // ssw.c:924
-    for (uint32_t i = lane; i < g.cap_w; i += 32) { A.hb[i] = 0; A.eb[i] = 0; A.hc[i] = 0; }
-    __syncwarp();
-    int32_t nc = 0;
-    if (lane == 0) nc = banded_traceback_lane(t.sub(ref_begin), q.sub(read_begin), rl, ql, (int32_t)a.score1, sc, band, A);
-    nc = __shfl_sync(kFull, nc, 0);
-    __syncwarp();
-    if (nc < 0) { if (lane == 0) atomicOr(&b.flags[r], nc == -1 ? kOvfTrace : kErrTrace); continue; }
-    unsigned long long off = 0;
-    if (lane == 0) off = atomicAdd(g.cigar_used, (unsigned long long)nc);
-    off = __shfl_sync(kFull, off, 0);
-    if (off + (unsigned long long)nc > g.cigar_cap) { if (lane == 0) atomicOr(&b.flags[r], kOvfCigar); continue; }
-    for (int32_t i = lane; i < nc; i += 32) g.cigar_pool[off + i] = A.cig[nc - 1 - i];        // ssw.c:750-758 (reverse)
     if (lane == 0) {
       OutAln o;
-      o.cigar_off = (uint32_t)off; o.cigar_len = (uint32_t)nc; o.ref_num = a.ref_num;
+      o.cigar_off = 0; o.cigar_len = 0; o.ref_num = a.ref_num;
       o.ref_begin1 = ref_begin + (int32_t)a.win_ref_start; o.ref_end1 = a_ref_end + (int32_t)a.win_ref_start;   // alignment.cpp:396-399
       o.read_begin1 = read_begin + (int32_t)a.q_start; o.read_end1 = a_read_end + (int32_t)a.q_start;
       o.readlen = len; o.score1 = a.score1; o.part = a.part; o.index_num = a.index_num; o.strand = a.strand; o.pad = 0;
       g.out[(size_t)r * g.slots + k] = o;
+      TraceJob j;
+      const SeqView qs = q.sub(read_begin);
+      j.valid = 1; j.idx_slot = a.idx_slot; j.ref_num = a.ref_num; j.ref_off = a.win_ref_start + (uint32_t)ref_begin;
+      j.q_start = qs.start; j.q_step = qs.step; j.rl = rl; j.ql = ql; j.score = (int32_t)a.score1; j.band = band;
+      g.jobs[(size_t)wi] = j;
     }
     __syncwarp();
+  }
+}
+
+// banded_sw (ssw.c:577-773) for every stored alignment, one THREAD per alignment (the DP rows are a serial chain of
+// 3..2*band+1 cells; 32 alignments per warp keep the lanes busy where one-lane-per-warp left 31 idle)
+__global__ void __launch_bounds__(128)
+traceback_kernel(DevBatch b, DevParams prm, FinalGlobals g) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const uint32_t lane = threadIdx.x & 31;
+  // the 32 arenas of a warp are interleaved element-wise: lanes walking their own band in step touch consecutive addresses
+  uint8_t* p = g.tb_arena + (size_t)(tid >> 5) * g.tb_stride * 32;
+  TraceArena A;
+  A.cap_w = g.tb_cap_w; A.cap_cig = g.tb_cap_cig; A.cap_dir = g.tb_cap_dir; A.stride = 32;
+  A.hb = (int32_t*)p + lane; p += (size_t)g.tb_cap_w * 4 * 32;
+  A.eb = (int32_t*)p + lane; p += (size_t)g.tb_cap_w * 4 * 32;
+  A.hc = (int32_t*)p + lane; p += (size_t)g.tb_cap_w * 4 * 32;
+  A.cig = (uint32_t*)p + lane; p += (size_t)g.tb_cap_cig * 4 * 32;
+  A.dir = (int8_t*)p + lane;
+  const SwScore sc{prm.match, prm.mismatch, prm.score_N, prm.gap_open, prm.gap_ext, prm.one};
+  const uint32_t total = b.nreads * g.slots;
+  for (uint32_t wi = tid; wi < total; wi += nthreads) {
+    const TraceJob j = g.jobs[wi];
+    if (!j.valid) continue;
+    const uint32_t r = b.r0 + wi / g.slots, k = wi % g.slots;
+    const DevIndex& ix = g.parts[j.idx_slot];
+    const SeqView t{ix.refseq + ix.ref_off[j.ref_num], (int32_t)j.ref_off, 1, false};
+    const SeqView q{b.seq04 + b.seq_off[r], j.q_start, j.q_step, j.q_step < 0};
+    for (uint32_t i = 0; i < g.tb_cap_w; ++i) { A.hb[i * 32] = 0; A.eb[i * 32] = 0; A.hc[i * 32] = 0; }
+    const int32_t nc = banded_traceback_lane(t, q, j.rl, j.ql, j.score, sc, j.band, A);
+    if (nc < 0) { atomicOr(&b.flags[r], nc == -1 ? kOvfTrace : kErrTrace); continue; }
+    const unsigned long long off = atomicAdd(g.cigar_used, (unsigned long long)nc);
+    if (off + (unsigned long long)nc > g.cigar_cap) { atomicOr(&b.flags[r], kOvfCigar); continue; }
+    for (int32_t i = 0; i < nc; ++i) g.cigar_pool[off + i] = A.cig[(size_t)(nc - 1 - i) * 32];        // ssw.c:750-758 (reverse)
+    OutAln* o = g.out + (size_t)r * g.slots + k;
+    o->cigar_off = (uint32_t)off; o->cigar_len = (uint32_t)nc;
   }
 }
 
@@ -105,7 +148,7 @@ ssw_debug_kernel(const uint8_t* qcat, const uint32_t* qoff, const uint8_t* tcat,
   const uint32_t warp = blockIdx.x * kFinalWarpsPerCta + (threadIdx.x >> 5), nwarps = gridDim.x * kFinalWarpsPerCta;
   uint8_t* p = g.arena_base + (size_t)warp * g.arena_stride;
   TraceArena A;
-  A.cap_w = g.cap_w; A.cap_cig = g.cap_cig; A.cap_dir = g.cap_dir;
+  A.cap_w = g.cap_w; A.cap_cig = g.cap_cig; A.cap_dir = g.cap_dir; A.stride = 1;
   A.hb = (int32_t*)p; p += (size_t)g.cap_w * 4;
   A.eb = (int32_t*)p; p += (size_t)g.cap_w * 4;
   A.hc = (int32_t*)p; p += (size_t)g.cap_w * 4;
@@ -121,6 +164,10 @@ ssw_debug_kernel(const uint8_t* qcat, const uint32_t* qoff, const uint8_t* tcat,
     SwEnd f = sw_forward(q, m, t, n, sc, rowH, rowF);
     // the score-only kernel of the candidate loop must agree with the arg-max kernel
     if (sw_score(q, m, t, n, sc, s_ref[threadIdx.x >> 5], s_prof[threadIdx.x >> 5], rowH, rowF) != f.score) f.score = -12345;
+    if (f.score > 0) {   // the score-known locate kernel (finalize) must agree with the arg-max kernel on the end point
+      const SwEnd l = sw_locate(q, m, t, n, sc, f.score, s_ref[threadIdx.x >> 5], s_prof[threadIdx.x >> 5], rowH, rowF);
+      if (l.ref != f.ref || l.read != f.read) f.score = -12346;
+    }
     int32_t rb = -1, qb = -1, nc = 0;
     if ((uint32_t)(f.score & 0xFFFF) >= filters && f.score > 0) {
       const SwEnd rev = sw_forward(q.reversed_prefix(f.read), f.read + 1, t.reversed_prefix(f.ref), f.ref + 1, sc, rowH, rowF);

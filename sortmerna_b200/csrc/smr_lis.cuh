@@ -465,7 +465,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
           const SeqView t{ix.refseq + __ldg(ix.ref_off + max_ref), (int32_t)win_start, 1, false};
           { const long long t2 = clock64(); E.cyc[3] += (unsigned long long)(t2 - tc0); tc0 = t2; }
           int32_t sw = 0;
-          if (qlen > 0 && alen > 0 && (uint32_t)alen <= E.ar.row_cap) sw = sw_score(q, qlen, t, (int32_t)alen, sc, E.s_ref, E.s_prof, E.ar.rowH, E.ar.rowF, &E.cyc[4]);
+          if (qlen > 0 && alen > 0 && (uint32_t)alen <= E.ar.row_cap) sw = sw_score(q, qlen, t, (int32_t)alen, sc, E.s_ref, E.s_prof, E.ar.rowH, E.ar.rowF);
           { const long long t2 = clock64(); E.cyc[5] += (unsigned long long)(t2 - tc0); tc0 = t2; }
           E.n_sw_calls++; E.n_sw_cells += (unsigned long long)alen * (unsigned long long)(qlen > 0 ? qlen : 0);
           const uint32_t score1 = (uint32_t)sw & 0xFFFFu;                                   // s_align.score1 is uint16

@@ -149,13 +149,18 @@ constexpr int kProfWords = kProfTables * 32 * 8;   // query profile per warp: [t
 // so all X(r), X(r) - go are computed first (instruction-level parallel), the F chain is R dependent VIADDMNMX,
 // and H, E follow in parallel again.  (The kernel is latency-bound: ncu shows ~50 % issue utilisation with the
 // alu pipe at 44 %, so a shorter dependency chain is worth a few extra IMADs on the idle fma pipe.)
-template <int R>
-__device__ int32_t sw_score_warp(const int32_t* __restrict__ s_prof, const uint8_t* __restrict__ s_ref, const int32_t n, const SwScore sc) {
+// FIND = false: returns the best score.  FIND = true: `target` is the (known) best score; returns the position of the first
+// cell holding it in the reference's order (smallest column, then smallest row: ssw.c:310-336) packed as column<<16 | row,
+// or -1 if no cell equals target.
+template <int R, bool FIND>
+__device__ int32_t sw_score_warp(const int32_t* __restrict__ s_prof, const uint8_t* __restrict__ s_ref, const int32_t n, const SwScore sc,
+                                 const int32_t target) {
   const int lane = (int)lane_id();
   int32_t Hp[R], E[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) { Hp[r] = 0; E[r] = 0; }
   int32_t diagH = 0, outH = 0, outF = 0, best = 0;
+  int32_t found = 0x7FFFFFFF;   // FIND: column<<16 | row of this lane's first hit
   const uint8_t* colp = s_ref + 32 - lane;
   const int32_t* prow = s_prof + lane;
   const int32_t nsteps = n + 31;
@@ -193,21 +198,35 @@ __device__ int32_t sw_score_warp(const int32_t* __restrict__ s_prof, const uint8
       E[r] = __vimax3_s32(E[r] * one + nge, Xgo[r], F[r] * one + ngo);
       Hp[r] = h;
     }
+    if (FIND) {
+      if (found == 0x7FFFFFFF) {
+        int32_t rr = -1;
 #pragma unroll
-    for (int r = 0; r + 1 < R; r += 2) best = __vimax3_s32(best, Hp[r], Hp[r + 1]);
-    if (R & 1) best = max(best, Hp[R - 1]);
+        for (int r = R - 1; r >= 0; --r) if (Hp[r] == target) rr = r;
+        if (rr >= 0) found = ((ts - lane) << 16) | (lane * R + rr);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r + 1 < R; r += 2) best = __vimax3_s32(best, Hp[r], Hp[r + 1]);
+      if (R & 1) best = max(best, Hp[R - 1]);
+    }
     outH = Hp[R - 1]; outF = F[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) sc_cur[r] = sc_next[r];
+  }
+  if (FIND) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(kFull, found, o));
+    return found == 0x7FFFFFFF ? -1 : found;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(kFull, best, o));
   return best;
 }
 
-template <int R>
+template <int R, bool FIND>
 __device__ __noinline__ int32_t sw_score_run(const SeqView q, const int32_t m, int32_t* __restrict__ s_prof, const uint8_t* __restrict__ s_ref,
-                                             const int32_t n, const SwScore sc) {
+                                             const int32_t n, const SwScore sc, const int32_t target) {
   const int lane = (int)lane_id();
   // profile: table tb, row r of this lane, at s_prof[(tb*R + r)*32 + lane]  (mat[ref*5+read], read.cpp:274-288)
 #pragma unroll
@@ -221,28 +240,46 @@ __device__ __noinline__ int32_t sw_score_run(const SeqView q, const int32_t m, i
     s_prof[(5 * R + r) * 32 + lane] = mis;                            // outside the window: never a match
   }
   __syncwarp();
-  return sw_score_warp<R>(s_prof, s_ref, n, sc);
+  return sw_score_warp<R, FIND>(s_prof, s_ref, n, sc, target);
+}
+
+// can the staged-window kernels handle this shape / these scores?
+__device__ __forceinline__ bool sw_fast_ok(const int32_t m, const int32_t n, const SwScore sc) {
+  return m <= 256 && n <= kRefStage && sc.mismatch < 0 && sc.go > 0 && sc.sN < 0 && sc.ge <= sc.go;
+}
+
+template <bool FIND>
+__device__ int32_t sw_fast(const SeqView q, const int32_t m, const SeqView t, const int32_t n, const SwScore sc, uint8_t* s_ref, int32_t* s_prof,
+                           const int32_t target) {
+  const int lane = (int)lane_id();
+  __syncwarp();
+  // staged window: table index per column, sentinel table (5) for 32 columns on both sides
+  for (int32_t i = lane; i < n + 64; i += 32) { const int32_t j = i - 32; s_ref[i] = (j >= 0 && j < n) ? (uint8_t)min(t.at(j), 4u) : (uint8_t)5; }
+  __syncwarp();
+  if (m <= 32) return sw_score_run<1, FIND>(q, m, s_prof, s_ref, n, sc, target);
+  if (m <= 64) return sw_score_run<2, FIND>(q, m, s_prof, s_ref, n, sc, target);
+  if (m <= 96) return sw_score_run<3, FIND>(q, m, s_prof, s_ref, n, sc, target);
+  if (m <= 128) return sw_score_run<4, FIND>(q, m, s_prof, s_ref, n, sc, target);
+  if (m <= 160) return sw_score_run<5, FIND>(q, m, s_prof, s_ref, n, sc, target);
+  if (m <= 192) return sw_score_run<6, FIND>(q, m, s_prof, s_ref, n, sc, target);
+  return sw_score_run<8, FIND>(q, m, s_prof, s_ref, n, sc, target);
 }
 
 // score of the best local alignment of q (m rows) against t (n columns); s_ref = kRefStage+64 bytes and s_prof =
 // kProfWords ints of shared memory owned by this warp
 __device__ int32_t sw_score(const SeqView q, const int32_t m, const SeqView t, const int32_t n, const SwScore sc, uint8_t* s_ref, int32_t* s_prof,
                             int32_t* rowH, int32_t* rowF, unsigned long long* cyc_setup = nullptr) {
-  const long long t_s0 = clock64();
-  if (m > 256 || n > kRefStage || sc.mismatch >= 0 || sc.go <= 0 || sc.sN >= 0 || sc.ge > sc.go) return sw_forward_any(q, m, t, n, sc, rowH, rowF).score;
-  const int lane = (int)lane_id();
-  __syncwarp();
-  // staged window: table index per column, sentinel table (5) for 32 columns on both sides
-  for (int32_t i = lane; i < n + 64; i += 32) { const int32_t j = i - 32; s_ref[i] = (j >= 0 && j < n) ? (uint8_t)min(t.at(j), 4u) : (uint8_t)5; }
-  __syncwarp();
-  if (cyc_setup) *cyc_setup += (unsigned long long)(clock64() - t_s0);
-  if (m <= 32) return sw_score_run<1>(q, m, s_prof, s_ref, n, sc);
-  if (m <= 64) return sw_score_run<2>(q, m, s_prof, s_ref, n, sc);
-  if (m <= 96) return sw_score_run<3>(q, m, s_prof, s_ref, n, sc);
-  if (m <= 128) return sw_score_run<4>(q, m, s_prof, s_ref, n, sc);
-  if (m <= 160) return sw_score_run<5>(q, m, s_prof, s_ref, n, sc);
-  if (m <= 192) return sw_score_run<6>(q, m, s_prof, s_ref, n, sc);
-  return sw_score_run<8>(q, m, s_prof, s_ref, n, sc);
+  if (!sw_fast_ok(m, n, sc)) return sw_forward_any(q, m, t, n, sc, rowH, rowF).score;
+  return sw_fast<false>(q, m, t, n, sc, s_ref, s_prof, 0);
+}
+
+// end point of the best local alignment whose score `target` is already known (finalize: forward and reverse pass)
+__device__ SwEnd sw_locate(const SeqView q, const int32_t m, const SeqView t, const int32_t n, const SwScore sc, const int32_t target,
+                           uint8_t* s_ref, int32_t* s_prof, int32_t* rowH, int32_t* rowF) {
+  if (!sw_fast_ok(m, n, sc) || target <= 0) return sw_forward(q, m, t, n, sc, rowH, rowF);
+  const int32_t f = sw_fast<true>(q, m, t, n, sc, s_ref, s_prof, target);
+  if (f < 0) return SwEnd{0, -1, 0};
+  return SwEnd{target, f >> 16, f & 0xFFFF};
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -256,6 +293,8 @@ struct TraceArena {
   int8_t* dir; size_t cap_dir;            // direction matrix
   uint32_t* cig; uint32_t cap_cig;        // cigar scratch (reverse order)
   uint32_t cap_w;
+  uint32_t stride;                        // element k of every array lives at [k * stride]: 1 = private contiguous arena,
+                                          // 32 = arenas of the 32 lanes of a warp interleaved (coalesced when lanes run in step)
 };
 
 // returns: >=0 cigar length (cig holds the ops in REVERSE order), -1 arena too small, -2 trace back error
@@ -263,44 +302,45 @@ __device__ int32_t banded_traceback_lane(const SeqView t, const SeqView q, const
                                          const SwScore sc, int32_t band_width, TraceArena& A) {
   // the caller zeroes hb/eb/hc[0..cap_w) (the reference's band rows keep their contents across the
   // band-doubling iterations, ssw.c:601-606; only the cells named below are reset per iteration)
+  const size_t S = A.stride;
   int32_t maxv = 0, width = 0, width_d = 0;
   do {
     width = band_width * 2 + 3; width_d = band_width * 2 + 1;
     if ((uint32_t)(width + 1) > A.cap_w) return -1;
     if ((size_t)width_d * readLen * 3 + 8 > A.cap_dir) return -1;
-    for (int32_t j = 1; j < width - 1; ++j) A.hb[j] = 0;
+    for (int32_t j = 1; j < width - 1; ++j) A.hb[j * S] = 0;
     for (int32_t i = 0; i < readLen; ++i) {
       const int32_t beg = max(0, i - band_width), end = min(refLen - 1, i + band_width);
       const int32_t edge = end + 1 < width - 1 ? end + 1 : width - 1;
       int32_t f = 0, u = 0;
-      A.hb[0] = 0; A.eb[0] = 0; A.hb[edge] = 0; A.eb[edge] = 0; A.hc[0] = 0;
-      int8_t* dl = A.dir + (size_t)width_d * i * 3;
+      A.hb[0] = 0; A.eb[0] = 0; A.hb[edge * S] = 0; A.eb[edge * S] = 0; A.hc[0] = 0;
+      int8_t* dl = A.dir + (size_t)width_d * i * 3 * S;
       const uint32_t qi = q.at(i);
       for (int32_t j = beg; j <= end; ++j) {
         u = band_u(band_width, i, j);
         const int32_t up = band_u(band_width, i - 1, j), lf = band_u(band_width, i, j - 1), dg = band_u(band_width, i - 1, j - 1);
         const int32_t de = band_d(band_width, i, j, 0), df = de + 1, dh = de + 2;
-        int32_t t1 = i == 0 ? -sc.go : A.hb[up] - sc.go;
-        int32_t t2 = i == 0 ? -sc.ge : A.eb[up] - sc.ge;
+        int32_t t1 = i == 0 ? -sc.go : A.hb[up * S] - sc.go;
+        int32_t t2 = i == 0 ? -sc.ge : A.eb[up * S] - sc.ge;
         const int32_t ev = t1 > t2 ? t1 : t2;
-        A.eb[u] = ev;
+        A.eb[u * S] = ev;
         const int8_t cde = t1 > t2 ? 3 : 2;
-        dl[de] = cde;
-        t1 = A.hc[lf] - sc.go; t2 = f - sc.ge;
+        dl[de * S] = cde;
+        t1 = A.hc[lf * S] - sc.go; t2 = f - sc.ge;
         f = t1 > t2 ? t1 : t2;
         const int8_t cdf = t1 > t2 ? 5 : 4;
-        dl[df] = cdf;
+        dl[df * S] = cdf;
         const int32_t e1 = ev > 0 ? ev : 0, f1 = f > 0 ? f : 0;
         t1 = e1 > f1 ? e1 : f1;
         const uint32_t tj = t.at(j);
         const int32_t s = (tj >= 4u || qi >= 4u) ? sc.sN : (tj == qi ? sc.match : sc.mismatch);
-        t2 = A.hb[dg] + s;
+        t2 = A.hb[dg * S] + s;
         const int32_t hv = t1 > t2 ? t1 : t2;
-        A.hc[u] = hv;
+        A.hc[u * S] = hv;
         if (hv > maxv) maxv = hv;
-        dl[dh] = (t1 <= t2) ? (int8_t)1 : (e1 > f1 ? cde : cdf);
+        dl[dh * S] = (t1 <= t2) ? (int8_t)1 : (e1 > f1 ? cde : cdf);
       }
-      for (int32_t j = 1; j <= u; ++j) A.hb[j] = A.hc[j];
+      for (int32_t j = 1; j <= u; ++j) A.hb[j * S] = A.hc[j * S];
     }
     band_width *= 2;
   } while (maxv < score);
@@ -308,15 +348,15 @@ __device__ int32_t banded_traceback_lane(const SeqView t, const SeqView q, const
   // trace back (ssw.c:674-747)
   int32_t i = readLen - 1, j = refLen - 1, run = 0, cur_op = 0, op = 0, which = 2;
   uint32_t l = 0;
-  const int8_t* dl = A.dir + (size_t)width_d * (readLen - 1) * 3;
+  int64_t row_off = (int64_t)width_d * (readLen - 1) * 3;     // element offset of the current row in the direction matrix
   while (i > 0) {
     const int32_t tt = band_d(band_width, i, j, which);
-    const int64_t abs_off = (dl - A.dir) + tt;        // same linear layout as the reference's direction array
+    const int64_t abs_off = row_off + tt;        // same linear layout as the reference's direction array
     if (abs_off < 0 || abs_off >= (int64_t)width_d * readLen * 3) return -2;
-    switch (dl[tt]) {
-      case 1: --i; --j; which = 2; dl -= width_d * 3; op = 0; break;
-      case 2: --i; which = 0; dl -= width_d * 3; op = 1; break;
-      case 3: --i; which = 2; dl -= width_d * 3; op = 1; break;
+    switch (A.dir[abs_off * S]) {
+      case 1: --i; --j; which = 2; row_off -= width_d * 3; op = 0; break;
+      case 2: --i; which = 0; row_off -= width_d * 3; op = 1; break;
+      case 3: --i; which = 2; row_off -= width_d * 3; op = 1; break;
       case 4: --j; which = 1; op = 2; break;
       case 5: --j; which = 2; op = 2; break;
       default: return -2;
@@ -324,12 +364,12 @@ __device__ int32_t banded_traceback_lane(const SeqView t, const SeqView q, const
     if (op == cur_op) ++run;
     else {
       if (l >= A.cap_cig) return -1;
-      A.cig[l++] = (uint32_t)run << 4 | (uint32_t)cur_op; cur_op = op; run = 1;
+      A.cig[(l++) * S] = (uint32_t)run << 4 | (uint32_t)cur_op; cur_op = op; run = 1;
     }
   }
   if (l + 2 > A.cap_cig) return -1;
-  if (op == 0) A.cig[l++] = (uint32_t)(run + 1) << 4;
-  else { A.cig[l++] = (uint32_t)run << 4 | (uint32_t)op; A.cig[l++] = 16u; }
+  if (op == 0) A.cig[(l++) * S] = (uint32_t)(run + 1) << 4;
+  else { A.cig[(l++) * S] = (uint32_t)run << 4 | (uint32_t)op; A.cig[(l++) * S] = 16u; }
   return (int32_t)l;
 }
 
