@@ -148,17 +148,26 @@ def write_fastq(path, reads):
 
 
 # ------------------------------------------------------------------------------------------------
-def load_databases():
+def load_databases(native_index=True):
     stage_data.stage_inputs() if os.path.isdir(stage_data.REF_DATA) else None
     fastas = [stage_data.db_path(n) for n in stage_data.DBS]
     missing = [f for f in fastas if not os.path.exists(f)]
     if missing:
         raise SystemExit(f"missing database FASTA files {missing}: run tools/stage_data.py where /root/reference exists")
-    idx_dir, built = stage_data.ensure_indexes(fastas)
+    if not native_index:
+        return fastas, None, None, [hostio.load_references(f) for f in fastas], None, {}
+    idx_dir, built = stage_data.ensure_indexes(fastas)   # smr_build_index (our builder), 8 databases in parallel
     pre = hostio.find_index_prefixes(idx_dir)
     refs = [hostio.load_references(f) for f in fastas]
     stats = [hostio.parse_stats(pre[os.path.basename(f)]) for f in fastas]
     return fastas, idx_dir, [pre[os.path.basename(f)] for f in fastas], refs, stats, built
+
+
+def reference_index_dir(fastas):
+    """The reference legs (cpu_baseline, --impl reference) run the unmodified binary on the index ITS OWN builder makes
+    (data_cache/idx_ref; one process per database, outside every timed region) -- never on files our builder wrote."""
+    d, _ = stage_data.ensure_indexes(fastas, os.path.join(stage_data.CACHE, "idx_ref"), builder="reference")
+    return d
 
 
 def minimal_scores(stats, fastas, nreads_total):
@@ -239,7 +248,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        fastas, idx_dir, prefixes, refs, stats, built = load_databases()
+        fastas, _, _, refs, _, _ = load_databases(native_index=False)
+        idx_dir = reference_index_dir(fastas)
         pool = DbPool(refs)
         sample = args.cpu_sample or int(min(40_000, max(4_000, 300 * cores)))   # ~5 s of reference CPU time per step
         vals, secs = [], []
@@ -413,7 +423,7 @@ def main():
     }
     if not args.no_cpu_baseline:
         sample = args.cpu_sample or int(min(100_000, max(5_000, 1_000 * cores)))
-        v, t, total, _ = run_reference_sample(fastas, idx_dir, first_reads[:sample], cores)
+        v, t, total, _ = run_reference_sample(fastas, reference_index_dir(fastas), first_reads[:sample], cores)
         out["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference",
                                "sample": f"first {sample} reads of the same synthetic workload vs the 8 databases, reference CPU build "
                                          f"(oracle/_ref/sortmerna_ref -threads {cores}), alignment loops {t:.1f} s (index loading excluded; "

@@ -64,6 +64,26 @@ typedef struct {
   uint8_t strand, pad;
 } smr_aln;
 
+/* Index builder (host code, no GPU needed).  Replaces build_index (src/sortmerna/indexdb.cpp:1119-2095): writes
+ * <out_prefix>.kmer_P.dat / .bursttrie_P.dat / .pos_P.dat for every part P and <out_prefix>.stats in the reference's on-disk
+ * format -- the files Index::load (index.cpp:143-357), Refstats::load (refstats.cpp:103-190) and smr_load_index_part read.
+ * Content is that of the reference's builder (same windows, alphabet map, burst tries, counts, position lists, part split);
+ * only the arbitrary numbering of the unique L-mers differs (order of first occurrence instead of a CMPH hash value).
+ * lnwin = -L (18), interval = -interval (1), max_pos = -max_pos (10000; 0 = all), max_mb = -m (3072).
+ * report6 (optional): parts, sequences, windows, unique L-mers, trie nodes, bytes written.  err: message buffer. */
+int smr_build_index(const char* fasta_path, const char* out_prefix, uint32_t lnwin, uint32_t interval, uint32_t max_pos,
+                    double max_mb, uint64_t* report6, char* err, size_t err_cap);
+
+/* Report-side arithmetic of one stored alignment = Read::calc_miss_gap_match (src/sortmerna/read.cpp:547-589), computed on the
+ * GPU from the CIGAR it has just produced: what %id / %cov / NM:i / BLAST columns 3,5,6 are derived from. */
+typedef struct {
+  uint32_t n_miss, n_gap, n_match;
+  /* n_match as denovo_stats_run obtains it (src/sortmerna/processor.cpp:329-357): that caller does NOT reverse-complement
+   * the read first, so for a reverse-strand alignment the CIGAR is walked over the forward read.  Reproduced as is, because
+   * n_yid_ycov / n_yid_ncov / n_nid_ycov / n_denovo and aligned_denovo.* depend on it; equals n_match on the forward strand. */
+  uint32_t n_match_denovo;
+} smr_aln_stats;
+
 /* Counters.  The first block is Readstats (include/readstats.hpp:77-84) as mutated by this path;
  * it is what the single NCCL all-reduce sums across GPUs.  The second block is instrumentation
  * used for the roofline arithmetic. */
@@ -119,6 +139,10 @@ int smr_align_batch(smr_ctx*, const uint8_t* seq_cat, const uint64_t* seq_off, u
                     smr_read_result* results, smr_aln* alns,
                     uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used,
                     uint64_t* counters, uint32_t n_counters);
+
+/* Optional: where the next smr_align_batch / smr_download_results stores smr_aln_stats for every stored alignment (same
+ * indexing as alns[]; nullptr = do not compute).  Host buffer of nreads * max(1,num_alignments) entries. */
+int smr_set_stats_buffer(smr_ctx*, smr_aln_stats* stats);
 
 /* Same work with the batch already resident: upload once, run many times (bench `value` leg). */
 int smr_upload_batch(smr_ctx*, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads);

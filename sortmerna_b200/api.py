@@ -25,7 +25,7 @@ STATUS = {0: "SMR_OK", 1: "SMR_ERR_CUDA", 2: "SMR_ERR_ARG", 3: "SMR_ERR_INDEX", 
 SYMBOLS = ["smr_init", "smr_destroy", "smr_last_error", "smr_device_count", "smr_load_index_part",
            "smr_set_minimal_score", "smr_set_params", "smr_index_info", "smr_align_batch", "smr_upload_batch",
            "smr_run_resident", "smr_download_results", "smr_last_timings", "smr_debug_seed_windows", "smr_debug_ssw",
-           "smr_debug_dpx_peak"]
+           "smr_debug_dpx_peak", "smr_set_stats_buffer", "smr_build_index"]
 
 CNT_NAMES = ("num_aligned", "num_short", "sw_calls", "sw_cells", "windows", "trie_nodes", "buckets",
              "bucket_entries", "pos_entries", "lis_calls", "dbg_max_read_cycles", "dbg_sum_read_cycles", "dbg_lis_kernel_cycles",
@@ -57,6 +57,8 @@ ALN_DTYPE = np.dtype([("cigar_off", "<u4"), ("cigar_len", "<u4"), ("ref_num", "<
                       ("ref_end1", "<i4"), ("read_begin1", "<i4"), ("read_end1", "<i4"), ("readlen", "<u4"),
                       ("score1", "<u2"), ("part", "<u2"), ("index_num", "<u2"), ("strand", "u1"), ("pad", "u1")])
 
+STATS_DTYPE = np.dtype([("n_miss", "<u4"), ("n_gap", "<u4"), ("n_match", "<u4"), ("n_match_denovo", "<u4")])
+
 _lib = None
 
 
@@ -81,6 +83,20 @@ def load_library():
 
 def _ptr(a):
     return C.c_void_p(a.ctypes.data)
+
+
+def build_index(fasta: str, out_prefix: str, lnwin: int = 18, interval: int = 1, max_pos: int = 10000, max_mb: float = 3072.0) -> dict:
+    """smr_build_index: the native stand-in for the reference's `build_index` (indexdb.cpp:1119-2095).  Host code only (no GPU
+    needed); writes <out_prefix>.{kmer,bursttrie,pos}_P.dat + .stats.  Defaults = the reference's (-L 18 -interval 1 -max_pos 10000 -m 3072)."""
+    L = load_library()
+    L.smr_build_index.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.POINTER(C.c_uint64),
+                                  C.c_char_p, C.c_size_t]
+    rep = (C.c_uint64 * 6)()
+    err = C.create_string_buffer(1024)
+    rc = L.smr_build_index(os.fsencode(fasta), os.fsencode(out_prefix), lnwin, interval, max_pos, float(max_mb), rep, err, len(err))
+    if rc != 0:
+        raise SmrError(f"smr_build_index({fasta}): {err.value.decode(errors='replace')}")
+    return dict(zip(("parts", "numseq", "windows", "unique_lmers", "trie_nodes", "bytes_written"), (int(x) for x in rep)))
 
 
 class SmrError(RuntimeError):
@@ -159,17 +175,24 @@ class Aligner:
         return dict(res=res, alns=alns, cigar=pool[: used], matched=counters[CNT_FIXED:].copy(), counters=cnt,
                     slots=slots, timings=self.timings())
 
-    def align(self, cat: np.ndarray, off: np.ndarray):
-        """smr_align_batch: host buffers in, host results out (H2D and D2H inside the call)."""
+    def align(self, cat: np.ndarray, off: np.ndarray, with_stats: bool = False):
+        """smr_align_batch: host buffers in, host results out (H2D and D2H inside the call).
+        with_stats: also return calc_miss_gap_match per stored alignment (out["stats"], computed on the GPU)."""
         cat = np.ascontiguousarray(cat, np.uint8)
         off = np.ascontiguousarray(off, np.uint64)
         n = off.size - 1
         slots, res, alns, pool, cap, counters = self._outputs(n)
+        stats = np.zeros(n * slots, STATS_DTYPE) if with_stats else None
+        self._check(self.L.smr_set_stats_buffer(self.h, _ptr(stats) if with_stats else C.c_void_p(0)), "smr_set_stats_buffer")
         used = C.c_uint64(0)
         rc = self.L.smr_align_batch(self.h, _ptr(cat), _ptr(off), C.c_uint32(n), _ptr(res), _ptr(alns), _ptr(pool),
                                     C.c_uint64(cap), C.byref(used), _ptr(counters), C.c_uint32(counters.size))
         self._check(rc, "smr_align_batch")
-        return self._pack(res, alns, pool, used.value, counters, slots)
+        self.L.smr_set_stats_buffer(self.h, C.c_void_p(0))
+        out = self._pack(res, alns, pool, used.value, counters, slots)
+        if with_stats:
+            out["stats"] = stats
+        return out
 
     def upload(self, cat: np.ndarray, off: np.ndarray):
         cat = np.ascontiguousarray(cat, np.uint8)

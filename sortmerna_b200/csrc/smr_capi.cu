@@ -47,7 +47,8 @@ struct smr_ctx {
   DevBuf seq04, seq_off, pk03, pk03alt, pk_off, has_n, hit_cnt, flags, state, hit_db, aln_work, out_aln;
   DevBuf hits, cost, bins, scalars, counters, cigar_pool, parts_dev;
   size_t hits_stride = 0; uint32_t cnt_stride = 0;
-  DevBuf lis_arena, lis_epochs, final_arena, lane_hits, tb_arena, tb_jobs;
+  DevBuf lis_arena, lis_epochs, final_arena, lane_hits, tb_arena, tb_jobs, aln_stats;
+  smr_aln_stats* host_stats = nullptr;   // optional output of the report arithmetic
   uint32_t tb_threads = 0, tb_cap_w = 0, tb_cap_cig = 0; size_t tb_cap_dir = 0, tb_stride = 0;
   uint32_t lis_warps = 0, final_warps = 0;
   size_t lis_stride = 0, final_stride = 0;
@@ -321,6 +322,11 @@ int run_impl(smr_ctx* ctx) {
     if ((rc = ensure(ctx, ctx->tb_jobs, (size_t)n * slots * sizeof(TraceJob)))) return rc;
     fg.jobs = (TraceJob*)ctx->tb_jobs.p; fg.tb_arena = (uint8_t*)ctx->tb_arena.p; fg.tb_stride = ctx->tb_stride;
     fg.tb_cap_w = ctx->tb_cap_w; fg.tb_cap_cig = ctx->tb_cap_cig; fg.tb_cap_dir = ctx->tb_cap_dir;
+    fg.stats = nullptr;
+    if (ctx->host_stats) {
+      if ((rc = ensure(ctx, ctx->aln_stats, (size_t)nreads * slots * sizeof(AlnStats)))) return rc;
+      fg.stats = (AlnStats*)ctx->aln_stats.p;
+    }
     finalize_kernel<<<ctx->final_warps / kFinalWarpsPerCta, kFinalWarpsPerCta * 32, 0, ctx->stream>>>(b, dp, fg);
     CK(cudaGetLastError());
     traceback_kernel<<<ctx->tb_threads / 128, 128, 0, ctx->stream>>>(b, dp, fg);
@@ -358,6 +364,8 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
   CK(cudaEventRecord(e0, ctx->stream));
   std::vector<ReadState> st(n); std::vector<uint32_t> fl(n); std::vector<uint16_t> hdb(n);
   std::vector<OutAln> oa((size_t)n * slots);
+  std::vector<AlnStats> ast;
+  if (ctx->host_stats) { ast.resize((size_t)n * slots); CK(cudaMemcpyAsync(ast.data(), ctx->aln_stats.p, ast.size() * sizeof(AlnStats), cudaMemcpyDeviceToHost, ctx->stream)); }
   unsigned long long used = 0;
   std::vector<unsigned long long> cnt(dcCount + 64);
   CK(cudaMemcpyAsync(st.data(), ctx->state.p, (size_t)n * sizeof(ReadState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -392,6 +400,7 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
       a.cigar_off = (uint32_t)out.cigar_used; a.cigar_len = d.cigar_len; out.cigar_used += d.cigar_len;
       a.ref_num = d.ref_num; a.ref_begin1 = d.ref_begin1; a.ref_end1 = d.ref_end1; a.read_begin1 = d.read_begin1; a.read_end1 = d.read_end1;
       a.readlen = d.readlen; a.score1 = d.score1; a.part = d.part; a.index_num = d.index_num; a.strand = d.strand;
+      if (ctx->host_stats) { const AlnStats& st2 = ast[(size_t)r * slots + k]; ctx->host_stats[(size_t)dst * slots + k] = smr_aln_stats{st2.n_miss, st2.n_gap, st2.n_match, st2.n_match_denovo}; }
     }
     if (s.is_hit && out.counters) {
       if (out.n_counters > SMR_CNT_NUM_ALIGNED) out.counters[SMR_CNT_NUM_ALIGNED]++;
@@ -472,7 +481,7 @@ void smr_destroy(smr_ctx* ctx) {
   for (auto& pt : ctx->parts) for (void* p : pt.owned) cudaFree(p);
   DevBuf* bufs[] = {&ctx->seq04, &ctx->seq_off, &ctx->pk03, &ctx->pk03alt, &ctx->pk_off, &ctx->has_n, &ctx->hit_cnt, &ctx->flags, &ctx->state,
                     &ctx->hit_db, &ctx->aln_work, &ctx->out_aln, &ctx->hits, &ctx->cost, &ctx->bins, &ctx->scalars, &ctx->counters, &ctx->cigar_pool,
-                    &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs};
+                    &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs, &ctx->aln_stats};
   for (DevBuf* b : bufs) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -554,6 +563,12 @@ int smr_align_batch(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_of
   int rc = align_impl(ctx, seq_cat, seq_off, nreads, out, nullptr, 0);
   if (cigar_used) *cigar_used = out.cigar_used;
   return rc;
+}
+
+int smr_set_stats_buffer(smr_ctx* ctx, smr_aln_stats* stats) {
+  if (!ctx) return SMR_ERR_ARG;
+  ctx->host_stats = stats;
+  return SMR_OK;
 }
 
 int smr_upload_batch(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads) {

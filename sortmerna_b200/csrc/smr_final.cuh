@@ -26,6 +26,8 @@ struct TraceJob {
   int32_t rl, ql, score, band;
 };
 
+struct AlnStats { uint32_t n_miss, n_gap, n_match, n_match_denovo; };   // layout of smr_aln_stats
+
 struct FinalGlobals {
   uint8_t* arena_base; size_t arena_stride;
   uint32_t cap_w, cap_cig, row_cap; size_t cap_dir;
@@ -36,6 +38,7 @@ struct FinalGlobals {
   // traceback stage (one THREAD per alignment)
   struct TraceJob* jobs;             // [nreads_chunk * slots]
   uint8_t* tb_arena; size_t tb_stride; uint32_t tb_cap_w, tb_cap_cig; size_t tb_cap_dir;
+  AlnStats* stats;                   // [nreads * slots] or nullptr
 };
 __host__ __device__ inline size_t final_arena_bytes(uint32_t cap_w, uint32_t cap_cig, uint32_t row_cap, size_t cap_dir) {
   size_t b = (size_t)cap_w * 12 + (size_t)cap_cig * 4 + (size_t)row_cap * 8 + cap_dir;
@@ -135,6 +138,25 @@ traceback_kernel(DevBatch b, DevParams prm, FinalGlobals g) {
     for (int32_t i = 0; i < nc; ++i) g.cigar_pool[off + i] = A.cig[(size_t)(nc - 1 - i) * 32];        // ssw.c:750-758 (reverse)
     OutAln* o = g.out + (size_t)r * g.slots + k;
     o->cigar_off = (uint32_t)off; o->cigar_len = (uint32_t)nc;
+    if (g.stats) {   // Read::calc_miss_gap_match (read.cpp:547-589): walk the CIGAR over the 0-4 codes of reference and read
+      // qd: the read as denovo_stats_run sees it (processor.cpp:329-333: 0-4 codes, never reverse-complemented)
+      const SeqView qd{b.seq04 + b.seq_off[r], o->read_begin1, 1, false};
+      uint32_t miss = 0, gap = 0, match = 0, match_d = 0;
+      int32_t x = 0, y = 0;
+      for (int32_t i = nc - 1; i >= 0; --i) {
+        const uint32_t c = A.cig[(size_t)i * 32], op = c & 0xFu, ln = c >> 4;
+        if (op == 0) {
+          for (uint32_t u = 0; u < ln; ++u, ++x, ++y) {
+            const uint32_t tc = t.at(x);
+            if (tc != q.at(y)) ++miss; else ++match;
+            match_d += tc == qd.at(y);
+          }
+        }
+        else if (op == 1) { y += (int32_t)ln; gap += ln; }
+        else { x += (int32_t)ln; gap += ln; }
+      }
+      g.stats[(size_t)r * g.slots + k] = AlnStats{miss, gap, match, match_d};
+    }
   }
 }
 

@@ -183,6 +183,99 @@ def minimal_score(stats: IndexStats, lam: float, K: float, all_reads_len: int, a
     return int(math.log(evalue / (K * full_ref * full_read)) / -lam) & 0xFFFFFFFF
 
 
+def evalue_params(stats: IndexStats, K: float, all_reads_len: int, all_reads_count: int) -> tuple:
+    """the length-corrected (full_ref, full_read) of refstats.cpp:236-257 that the E-value of a BLAST row uses"""
+    entropy = -sum(p * math.log2(p) for p in stats.background_freq)
+    full_ref, full_read = stats.full_ref, all_reads_len
+    expect_L = int(math.log(K * full_ref * full_read) / entropy)
+    if full_ref > expect_L * stats.numseq:
+        full_ref -= expect_L * stats.numseq
+    full_read -= expect_L * all_reads_count
+    return full_ref, full_read
+
+
+def _g3(x: float) -> str:
+    """what `ss.precision(3); ss << x` prints (C++ general format, 3 significant digits)"""
+    return f"{x:.3g}"
+
+
+def format_blast_rows(batch: "ReadBatch", refs_by_index: list, results, alns, cigar_pool, slots: int, stats, gumbel: list,
+                      ev_params: list) -> list:
+    """Tabular BLAST rows with the optional columns 'cigar qcov qstrand' as ReportBlast::append prints them
+    (src/sortmerna/report_blast.cpp:99-365).  stats[i] = (n_miss, n_gap, n_match) of alignment i -- from the GPU
+    (smr_aln_stats) or from calc_miss_gap_match; gumbel[index] = (lambda, K); ev_params[index] = (full_ref, full_read)."""
+    import numpy as _np
+    rows = []
+    for r in range(batch.n):
+        na = int(results["n_align"][r])
+        name = seq_id(batch.headers[r])
+        rlen = len(batch.seqs[r])
+        for a in range(na):
+            al = alns[r * slots + a]
+            st = stats[r * slots + a]
+            idx = int(al["index_num"])
+            lam, K = gumbel[idx]
+            full_ref, full_read = ev_params[idx]
+            score = int(al["score1"])
+            bitscore = int(_np.float32(_np.float32(lam * score - math.log(K)) / _np.float32(math.log(2))))   # report_blast.cpp:117-119
+            evalue = K * full_ref * full_read * math.exp(-lam * score)                                      # :121-126
+            miss, gap, match = int(st["n_miss"]), int(st["n_gap"]), int(st["n_match"])
+            pid = match / (miss + gap + match)
+            cov = abs(int(al["read_end1"]) - int(al["read_begin1"]) + 1) / int(al["readlen"])
+            cig = cigar_pool[int(al["cigar_off"]):int(al["cigar_off"]) + int(al["cigar_len"])]
+            cs = (f"{int(al['read_begin1'])}S" if int(al["read_begin1"]) else "") + cigar_string(cig)
+            end_mask = rlen - int(al["read_end1"]) - 1
+            if end_mask > 0:
+                cs += f"{end_mask}S"
+            refs = refs_by_index[idx]
+            rows.append("\t".join([name, refs.ids[int(al["ref_num"])], _g3(pid * 100), str(int(al["read_end1"]) - int(al["read_begin1"]) + 1),
+                                   str(miss), str(gap), str(int(al["read_begin1"]) + 1), str(int(al["read_end1"]) + 1),
+                                   str(int(al["ref_begin1"]) + 1), str(int(al["ref_end1"]) + 1), _g3(evalue), str(bitscore), cs,
+                                   _g3(cov * 100), "+" if bool(al["strand"]) else "-"]))
+    return rows
+
+
+def host_aln_stats(batch: "ReadBatch", refs_by_index: list, results, alns, cigar_pool, slots: int):
+    """calc_miss_gap_match on the host (numpy) for every stored alignment: the CPU twin of smr_aln_stats, used by the tests."""
+    out = np.zeros(batch.n * slots, dtype=[("n_miss", "<u4"), ("n_gap", "<u4"), ("n_match", "<u4"), ("n_match_denovo", "<u4")])
+    for r in range(batch.n):
+        enc = batch.cat[int(batch.off[r]):int(batch.off[r + 1])]
+        for a in range(int(results["n_align"][r])):
+            al = alns[r * slots + a]
+            refs = refs_by_index[int(al["index_num"])]
+            e04 = enc if bool(al["strand"]) else np.where(enc < 4, 3 - enc, 4)[::-1]
+            rseq = refs.cat[int(refs.off[int(al["ref_num"])]):int(refs.off[int(al["ref_num"]) + 1])]
+            cig = cigar_pool[int(al["cigar_off"]):int(al["cigar_off"]) + int(al["cigar_len"])]
+            m = calc_miss_gap_match(rseq, e04, al, cig)
+            # denovo_stats_run (processor.cpp:329-357) walks the same CIGAR over the read WITHOUT reverse-complementing it
+            md = m if bool(al["strand"]) else calc_miss_gap_match(rseq, enc, al, cig)
+            out[r * slots + a] = (m[0], m[1], m[2], md[2])
+    return out
+
+
+def denovo_classes(results, alns, slots: int, stats, min_id: float, min_cov: float):
+    """denovo_stats_run (processor.cpp:329-357) from smr_aln_stats: per read the four counters
+    (c_yid_ycov, n_yid_ncov, n_nid_ycov, n_denovo) over its stored alignments; their column sums are Readstats'
+    n_yid_ycov / n_yid_ncov / n_nid_ycov / num_denovo.  Returns an (nreads, 4) uint32 array."""
+    n = results.shape[0]
+    out = np.zeros((n, 4), np.uint32)
+    for r in range(n):
+        for a in range(int(results["n_align"][r])):
+            al, st = alns[r * slots + a], stats[r * slots + a]
+            tot = int(st["n_miss"]) + int(st["n_gap"]) + int(st["n_match"])
+            idv = int(st["n_match_denovo"]) / tot
+            cov = abs(int(al["read_end1"]) - int(al["read_begin1"]) + 1) / int(al["readlen"])
+            is_id = math.floor(idv * 1000.0 + 0.5) / 1000.0 >= min_id      # :336-339 round to 3 decimals
+            is_cov = math.floor(cov * 1000.0 + 0.5) / 1000.0 >= min_cov
+            out[r, 0 if (is_id and is_cov) else 1 if is_id else 2 if is_cov else 3] += 1
+    return out
+
+
+def is_denovo_read(classes: np.ndarray) -> np.ndarray:
+    """output.cpp:130-141 (single-end): the read goes to aligned_denovo.* when n_denovo > 0 and the other three are 0"""
+    return (classes[:, 3] > 0) & (classes[:, 0] == 0) & (classes[:, 1] == 0) & (classes[:, 2] == 0)
+
+
 _OPS = "MID"
 
 

@@ -49,6 +49,11 @@ def load_case(name):
         return json.load(f)
 
 
+def load_denovo():
+    with open(os.path.join(GOLDEN, "denovo.json")) as f:
+        return json.load(f)
+
+
 def case_names():
     return sorted(d[5:] for d in os.listdir(GOLDEN) if d.startswith("case_"))
 

@@ -7,6 +7,8 @@ and oracle/_ref/sortmerna_ref exist):
   idx/*.dat.gz, idx/*.stats     the reference's own index of the two slices
   case_*/expected.json          what the UNMODIFIED reference binary printed for each option set:
                                 SAM rows, aligned.log numbers (minimal scores, totals, coverage)
+  denovo.json                   denovo_stats counts + aligned_denovo read ids for -id/-coverage option sets
+                                (python tests/golden/make_golden.py denovo regenerates only this file)
 
 Usage: python tests/golden/make_golden.py
 """
@@ -170,7 +172,36 @@ def make_t0(tmp):
     print("t0", log["passing"], log["minimal_score"], [x.split("\t")[5][:60] + " " + x.split("\t")[11] for x in sam])
 
 
+DENOVO_CASES = {"default": [], "best3": ["-num_alignments", "3"], "rev_only": ["-R"], "loose": ["-num_alignments", "2"]}
+DENOVO_ARGS = {"default": ("0.97", "0.97"), "best3": ("0.97", "0.97"), "rev_only": ("0.9", "0.9"), "loose": ("0.85", "0.5")}
+
+
+def make_denovo():
+    """denovo.json: what denovo_stats (processor.cpp:287-438) counted and which reads went to aligned_denovo.fq
+    (output.cpp:130-141) for '-otu_map -de_novo_otu -id X -coverage Y' on the golden reads."""
+    import re
+    arc_p, bac_p, reads_p = (os.path.join(HERE, f) for f in ("db_arc.fasta", "db_bac.fasta", "reads_mix.fq"))
+    tmp = tempfile.mkdtemp(prefix="smr_golden_dn_")
+    res = {}
+    for case, extra in DENOVO_CASES.items():
+        mid, mcov = DENOVO_ARGS[case]
+        r = ora.run_reference([arc_p, bac_p], reads_p, os.path.join(tmp, case),
+                              extra=["-fastx", "-otu_map", "-de_novo_otu", "-id", mid, "-coverage", mcov] + extra, threads=1)
+        m = re.search(r"num_yid_ycov: (\d+)\s+num_yid_ncov: (\d+)\s+num_nid_ycov: (\d+)\s+num_denovo: (\d+)", r["stdout"])
+        h, _, _ = hostio.read_fastx(os.path.join(r["out_dir"], "aligned_denovo.fq"))
+        log = ora.parse_log(r["log"])
+        res[case] = dict(args=extra, min_id=float(mid), min_cov=float(mcov), counts=[int(x) for x in m.groups()],
+                         denovo_reads=sorted(hostio.seq_id(x) for x in h), minimal_score=log["minimal_score"],
+                         total_denovo=int(re.search(r"de novo clustering = (\d+)", r["log"]).group(1)))
+        print(case, res[case]["counts"], len(res[case]["denovo_reads"]), res[case]["total_denovo"])
+    with open(os.path.join(HERE, "denovo.json"), "w") as f:
+        json.dump(res, f, indent=0)
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "denovo":
+        return make_denovo()
     if not ora.have_reference_binary():
         sys.exit("oracle/_ref/sortmerna_ref missing: make -C oracle -f Makefile.ref")
     rng = np.random.default_rng(SEED)
@@ -213,6 +244,7 @@ def main():
             with open(src, "rb") as fi, gzip.open(os.path.join(idx_dir, fn + ".gz"), "wb", compresslevel=9) as fo:
                 fo.write(fi.read())
     make_t0(tmp)
+    make_denovo()
     shutil.rmtree(tmp, ignore_errors=True)
     print("sizes:", {fn: os.path.getsize(os.path.join(idx_dir, fn)) for fn in os.listdir(idx_dir)})
 

@@ -56,3 +56,26 @@ def assert_same_results(a, b, what=""):
             cx = a["cigar"][int(x["cigar_off"]):int(x["cigar_off"]) + int(x["cigar_len"])]
             cy = b["cigar"][int(y["cigar_off"]):int(y["cigar_off"]) + int(y["cigar_len"])]
             assert np.array_equal(cx, cy), f"{what}: read {r} alignment {k} cigar {cx} vs {cy}"
+
+
+def blast_rows(golden, exp, out, stats):
+    """BLAST rows of a result dict the way the reference printed them for this golden case (report_blast.cpp:99-365)."""
+    from sortmerna_b200 import hostio
+    b = golden["batch"]
+    tot = int(np.diff(b.off.astype(np.int64)).sum())
+    gum = list(zip(exp["log"]["lambda_"], exp["log"]["K"]))
+    evp = [hostio.evalue_params(st, k, tot, b.n) for st, (_, k) in zip(golden["stats"], gum)]
+    return hostio.format_blast_rows(b, golden["refs"], out["res"], out["alns"], out["cigar"], out["slots"], stats, gum, evp)
+
+
+def assert_blast_rows_equal(ours, theirs, evalue_rtol=1.2e-2):
+    """Every column identical except the E-value (column 11), which the reference computes from the full-precision Gumbel
+    lambda/K while the goldens only hold the 6 digits of aligned.log (exp(-lambda*S) moves by ~1e-4 relative) and prints with 3
+    significant digits: tolerance = one unit of the last printed digit (1.2e-2 relative)."""
+    a, b = sorted(ours), sorted(theirs)
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        fx, fy = x.split("\t"), y.split("\t")
+        assert fx[:10] == fy[:10] and fx[11:] == fy[11:], (x, y)
+        ex, ey = float(fx[10]), float(fy[10])
+        assert abs(ex - ey) <= evalue_rtol * max(abs(ey), 1e-300) + 1e-300, (x, y)

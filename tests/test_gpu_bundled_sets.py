@@ -24,12 +24,15 @@ def _need(*paths):
             pytest.skip(f"{p} not staged (tools/stage_data.py)")
 
 
-def _run_case(fastas, idx_dir, read_files, ref_extra, threads):
+def _run_case(fastas, idx_dir, read_files, ref_extra, threads, **native_kw):
+    """The reference runs on the index ITS OWN builder makes (<idx_dir>_ref); the GPU path runs on the index smr_build_index
+    makes (<idx_dir>) -- so the comparison also covers the native index builder at full database size."""
     from oracle import ora
     from tools import stage_data
-    idx_dir, _ = stage_data.ensure_indexes(fastas, idx_dir, extra=tuple(ref_extra))   # index-build options (-max_pos) == run options here
+    ref_idx, _ = stage_data.ensure_indexes(fastas, idx_dir + "_ref", extra=tuple(ref_extra), builder="reference")   # index-build options (-max_pos) == run options here
+    idx_dir, _ = stage_data.ensure_indexes(fastas, idx_dir, **native_kw)
     with tempfile.TemporaryDirectory(prefix="smr_sets_") as d:
-        r = ora.run_reference(fastas, read_files, os.path.join(d, "w"), extra=["-sam", "-fastx", "-other"] + list(ref_extra), threads=threads, idx_dir=idx_dir)
+        r = ora.run_reference(fastas, read_files, os.path.join(d, "w"), extra=["-sam", "-fastx", "-other"] + list(ref_extra), threads=threads, idx_dir=ref_idx)
         log = ora.parse_log(r["log"])
         sam = ora.read_sam_rows(os.path.join(r["out_dir"], "aligned.sam"))
     pre = hostio.find_index_prefixes(idx_dir)
@@ -67,7 +70,7 @@ def test_set2_amplicon_vs_bac16s_id85():
     reads = [os.path.join(CACHE, "sets", "set2_environmental_study_550_amplicon.fasta")]
     fastas = [os.path.join(CACHE, "sets", "silva-bac-16s-database-id85.fasta")]
     _need(*reads, *fastas)
-    log, sam, rows, got, batch = _run_case(fastas, os.path.join(CACHE, "idx_set2"), reads, ["-max_pos", "250"], threads=os.cpu_count() or 8)
+    log, sam, rows, got, batch = _run_case(fastas, os.path.join(CACHE, "idx_set2"), reads, ["-max_pos", "250"], threads=os.cpu_count() or 8, max_pos=250)
     assert (log["passing"], log["failing"]) == (99999, 1)            # scripts/t3.jinja:30-32
     assert int(got["res"]["is_hit"].sum()) == 99999
     assert sorted(rows) == sorted(sam)

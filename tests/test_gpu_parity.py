@@ -5,8 +5,8 @@ import os
 import numpy as np
 import pytest
 
-from conftest import case_names, load_case
-from helpers import assert_same_results, params_kwargs_from_args, strip_seq
+from conftest import case_names, load_case, load_denovo
+from helpers import assert_blast_rows_equal, assert_same_results, blast_rows, params_kwargs_from_args, strip_seq
 from sortmerna_b200 import api, hostio
 
 pytestmark = pytest.mark.gpu
@@ -128,6 +128,45 @@ def test_align_matches_oracle_and_reference(aligner, golden, oracle_indexes, cas
     if case != "default":
         rows = strip_seq(rows)
     assert sorted(rows) == sorted(exp["sam"])
+    aligner.set_params(api.default_params())
+
+
+@pytest.mark.parametrize("case", ["default", "best3", "scores", "nobest2", "rev_only"])
+def test_report_arithmetic_on_gpu(aligner, golden, case):
+    """smr_aln_stats (calc_miss_gap_match computed by the traceback kernel) == the host restatement for every stored
+    alignment, and the BLAST rows built from it == the rows the reference binary printed."""
+    exp = load_case(case)
+    kw = params_kwargs_from_args(exp["args"])
+    aligner.set_params(api.default_params(**kw))
+    for k in range(2):
+        aligner.set_minimal_score(k, exp["log"]["minimal_score"][k])
+    b = golden["batch"]
+    got = aligner.align(b.cat, b.off, with_stats=True)
+    want = hostio.host_aln_stats(b, golden["refs"], got["res"], got["alns"], got["cigar"], got["slots"])
+    slots = got["slots"]
+    live = np.zeros(b.n * slots, bool)
+    for r in range(b.n):
+        live[r * slots:r * slots + int(got["res"]["n_align"][r])] = True
+    assert live.sum() > 0
+    for f in ("n_miss", "n_gap", "n_match", "n_match_denovo"):
+        assert np.array_equal(got["stats"][f][live], want[f][live]), f
+    assert_blast_rows_equal(blast_rows(golden, exp, got, got["stats"]), exp["blast"])
+    aligner.set_params(api.default_params())
+
+
+@pytest.mark.parametrize("case", ["default", "best3", "rev_only", "loose"])
+def test_denovo_classification_on_gpu(aligner, golden, case):
+    """denovo_stats counters / aligned_denovo read set from the GPU's smr_aln_stats == what the reference binary reported."""
+    dn = load_denovo()[case]
+    aligner.set_params(api.default_params(**params_kwargs_from_args(dn["args"])))
+    for k in range(2):
+        aligner.set_minimal_score(k, dn["minimal_score"][k])
+    b = golden["batch"]
+    got = aligner.align(b.cat, b.off, with_stats=True)
+    cls = hostio.denovo_classes(got["res"], got["alns"], got["slots"], got["stats"], dn["min_id"], dn["min_cov"])
+    assert cls.sum(axis=0).tolist() == dn["counts"]
+    ids = sorted(hostio.seq_id(b.headers[r]) for r in np.nonzero(hostio.is_denovo_read(cls))[0])
+    assert ids == dn["denovo_reads"]
     aligner.set_params(api.default_params())
 
 

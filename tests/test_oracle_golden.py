@@ -7,8 +7,8 @@ import os
 import numpy as np
 import pytest
 
-from conftest import case_names, load_case
-from helpers import params_kwargs_from_args, strip_seq
+from conftest import case_names, load_case, load_denovo
+from helpers import assert_blast_rows_equal, blast_rows, params_kwargs_from_args, strip_seq
 from oracle import ora
 from sortmerna_b200 import hostio
 
@@ -39,6 +39,29 @@ def test_oracle_matches_reference_sam(golden, oracle_indexes, case):
     # aligned.log "Coverage by database" (summary.cpp:160-170), %.2f of matched/total
     cov = [round(100.0 * int(m) / golden["batch"].n, 2) for m in out["matched"]]
     assert cov == pytest.approx(exp["log"]["coverage"], abs=0.011)
+
+
+@pytest.mark.parametrize("case", case_names())
+def test_report_arithmetic_matches_reference_blast(golden, oracle_indexes, case):
+    """calc_miss_gap_match / %id / %cov / bitscore / E-value / clipped CIGAR restated in hostio reproduce the reference's BLAST rows."""
+    exp, prm, out = run_oracle(golden, oracle_indexes, case)
+    st = hostio.host_aln_stats(golden["batch"], golden["refs"], out["res"], out["alns"], out["cigar"], out["slots"])
+    assert_blast_rows_equal(blast_rows(golden, exp, out, st), exp["blast"])
+
+
+@pytest.mark.parametrize("case", ["default", "best3", "rev_only", "loose"])
+def test_denovo_classification_matches_reference(golden, oracle_indexes, case):
+    """denovo_stats counters and the aligned_denovo read set (-otu_map -de_novo_otu -id X -coverage Y) from the host restatement."""
+    dn = load_denovo()[case]
+    prm = ora.default_params(**params_kwargs_from_args(dn["args"]))
+    b = golden["batch"]
+    out = ora.align(oracle_indexes, [0, 1], [0, 0], 2, golden["refs"], dn["minimal_score"], [18, 9, 3, 18, 9, 3], prm, b, nthreads=2)
+    st = hostio.host_aln_stats(b, golden["refs"], out["res"], out["alns"], out["cigar"], out["slots"])
+    cls = hostio.denovo_classes(out["res"], out["alns"], out["slots"], st, dn["min_id"], dn["min_cov"])
+    assert cls.sum(axis=0).tolist() == dn["counts"]
+    assert int(cls[:, 3].sum()) == dn["total_denovo"]
+    ids = sorted(hostio.seq_id(b.headers[r]) for r in np.nonzero(hostio.is_denovo_read(cls))[0])
+    assert ids == dn["denovo_reads"]
 
 
 def test_oracle_thread_invariance(golden, oracle_indexes):

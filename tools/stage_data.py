@@ -4,8 +4,9 @@ travels to the GPU box with the gpurun snapshot, like the built .so files):
 
   data_cache/rRNA_databases/*.fasta   copies of /root/reference/data/rRNA_databases (inputs, not code)
   data_cache/sets/...                 the bundled read sets used by BASELINE.json configs 2 and 4
-  data_cache/idx/                     the reference's own index of each database, built by the
-                                      unmodified reference (oracle/_ref/sortmerna_ref -index 1)
+  data_cache/idx/                     the index of each database in the reference's on-disk format, built by
+                                      smr_build_index (our builder; tests/test_index_builder.py proves the files equal the
+                                      reference builder's up to the arbitrary id numbering)
 
 `ensure_indexes()` is also what bench.py calls on the GPU box when data_cache/idx is incomplete
 (the FASTA files travel, the 1.1 GB of index files need not).
@@ -59,8 +60,17 @@ def _have_index(idx_dir, fasta):
                              for s in (".kmer_0.dat", ".bursttrie_0.dat", ".pos_0.dat", ".stats"))
 
 
+def build_index_native(fasta, idx_dir, **kw):
+    """smr_build_index (sortmerna_b200/csrc/smr_build.cpp): our own builder, same files as the reference's."""
+    from sortmerna_b200 import api
+    os.makedirs(idx_dir, exist_ok=True)
+    t0 = time.time()
+    api.build_index(fasta, os.path.join(idx_dir, os.path.splitext(os.path.basename(fasta))[0]), **kw)
+    return time.time() - t0
+
+
 def build_index(fasta, idx_dir, extra=()):
-    """Run the reference's index builder (indexdb.cpp:1119-2095) for one database."""
+    """Run the reference's index builder (indexdb.cpp:1119-2095) for one database (tests / cross-checks only)."""
     os.makedirs(idx_dir, exist_ok=True)
     wd = os.path.join(CACHE, "_work", os.path.basename(fasta) + f".{os.getpid()}")
     shutil.rmtree(wd, ignore_errors=True)
@@ -77,16 +87,21 @@ def build_index(fasta, idx_dir, extra=()):
     return time.time() - t0
 
 
-def ensure_indexes(fastas, idx_dir=None, workers=8, extra=()):
-    """Build whatever is missing, databases in parallel (the builder itself is single-threaded)."""
+def ensure_indexes(fastas, idx_dir=None, workers=8, extra=(), builder="native", **kw):
+    """Build whatever is missing, databases in parallel.  builder="native": smr_build_index (kw: max_pos, interval, lnwin, max_mb);
+    builder="reference": the unmodified reference binary with the CLI arguments in `extra` (cross-checks only)."""
     idx_dir = idx_dir or os.path.join(CACHE, "idx")
     todo = [f for f in fastas if not _have_index(idx_dir, f)]
     times = {}
     if todo:
-        if not os.path.exists(REF_BIN):
-            raise RuntimeError("oracle/_ref/sortmerna_ref is missing (build it with oracle/Makefile.ref where /root/reference exists)")
+        if builder == "reference":
+            if not os.path.exists(REF_BIN):
+                raise RuntimeError("oracle/_ref/sortmerna_ref is missing (build it with oracle/Makefile.ref where /root/reference exists)")
+            fn = lambda f: build_index(f, idx_dir, extra)
+        else:
+            fn = lambda f: build_index_native(f, idx_dir, **kw)
         with ThreadPoolExecutor(max_workers=workers) as ex:
-            for f, t in zip(todo, ex.map(lambda f: build_index(f, idx_dir, extra), todo)):
+            for f, t in zip(todo, ex.map(fn, todo)):
                 times[os.path.basename(f)] = round(t, 1)
     return idx_dir, times
 
@@ -96,5 +111,5 @@ if __name__ == "__main__":
     t0 = time.time()
     d, times = ensure_indexes([db_path(n) for n in DBS])
     print("index dir", d, "built", times, "wall", round(time.time() - t0, 1), "s")
-    ensure_indexes([os.path.join(CACHE, "sets", "silva-bac-16s-database-id85.fasta")], os.path.join(CACHE, "idx_set2"), extra=("-max_pos", "250"))
+    ensure_indexes([os.path.join(CACHE, "sets", "silva-bac-16s-database-id85.fasta")], os.path.join(CACHE, "idx_set2"), max_pos=250)
     subprocess.run(["du", "-sh", os.path.join(CACHE, "idx"), CACHE])
