@@ -69,10 +69,11 @@ typedef struct {
  * format -- the files Index::load (index.cpp:143-357), Refstats::load (refstats.cpp:103-190) and smr_load_index_part read.
  * Content is that of the reference's builder (same windows, alphabet map, burst tries, counts, position lists, part split);
  * only the arbitrary numbering of the unique L-mers differs (order of first occurrence instead of a CMPH hash value).
- * lnwin = -L (18), interval = -interval (1), max_pos = -max_pos (10000; 0 = all), max_mb = -m (3072).
+ * lnwin = -L (18), interval = -interval (1), max_pos = -max_pos (10000; 0 = all), max_mb = -m (3072); threads: 2*threads
+ * workers build the tries of disjoint 9-mer classes (0 = cores/8 clamped to 1..8); the files do not depend on it.
  * report6 (optional): parts, sequences, windows, unique L-mers, trie nodes, bytes written.  err: message buffer. */
 int smr_build_index(const char* fasta_path, const char* out_prefix, uint32_t lnwin, uint32_t interval, uint32_t max_pos,
-                    double max_mb, uint64_t* report6, char* err, size_t err_cap);
+                    double max_mb, uint32_t threads, uint64_t* report6, char* err, size_t err_cap);
 
 /* Report-side arithmetic of one stored alignment = Read::calc_miss_gap_match (src/sortmerna/read.cpp:547-589), computed on the
  * GPU from the CIGAR it has just produced: what %id / %cov / NM:i / BLAST columns 3,5,6 are derived from. */

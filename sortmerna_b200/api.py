@@ -85,15 +85,16 @@ def _ptr(a):
     return C.c_void_p(a.ctypes.data)
 
 
-def build_index(fasta: str, out_prefix: str, lnwin: int = 18, interval: int = 1, max_pos: int = 10000, max_mb: float = 3072.0) -> dict:
+def build_index(fasta: str, out_prefix: str, lnwin: int = 18, interval: int = 1, max_pos: int = 10000, max_mb: float = 3072.0,
+                threads: int = 0) -> dict:
     """smr_build_index: the native stand-in for the reference's `build_index` (indexdb.cpp:1119-2095).  Host code only (no GPU
     needed); writes <out_prefix>.{kmer,bursttrie,pos}_P.dat + .stats.  Defaults = the reference's (-L 18 -interval 1 -max_pos 10000 -m 3072)."""
     L = load_library()
-    L.smr_build_index.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.POINTER(C.c_uint64),
+    L.smr_build_index.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32, C.POINTER(C.c_uint64),
                                   C.c_char_p, C.c_size_t]
     rep = (C.c_uint64 * 6)()
     err = C.create_string_buffer(1024)
-    rc = L.smr_build_index(os.fsencode(fasta), os.fsencode(out_prefix), lnwin, interval, max_pos, float(max_mb), rep, err, len(err))
+    rc = L.smr_build_index(os.fsencode(fasta), os.fsencode(out_prefix), lnwin, interval, max_pos, float(max_mb), threads, rep, err, len(err))
     if rc != 0:
         raise SmrError(f"smr_build_index({fasta}): {err.value.decode(errors='replace')}")
     return dict(zip(("parts", "numseq", "windows", "unique_lmers", "trie_nodes", "bytes_written"), (int(x) for x in rep)))

@@ -18,6 +18,7 @@
 #include <deque>
 #include <exception>
 #include <fstream>
+#include <thread>
 
 namespace smr {
 namespace {
@@ -190,6 +191,9 @@ std::string build_index_files(const std::string& fasta, const std::string& prefi
   const uint32_t limit = 1u << L;
   const uint32_t mask32 = limit - 1;
   const uint32_t burst_depth = pread - half - 3;
+  uint32_t nthreads = opt.threads;
+  if (nthreads == 0) { const uint32_t hw = std::thread::hardware_concurrency(); nthreads = hw / 8 < 1 ? 1 : (hw / 8 > 8 ? 8 : hw / 8); }
+  if (nthreads > 64) nthreads = 64;
   struct PartStat { uint64_t start_part, seq_part_size; uint32_t numseq_part, pad; };
   std::vector<PartStat> parts;
   BuildReport report;
@@ -214,39 +218,87 @@ std::string build_index_files(const std::string& fasta, const std::string& prefi
       if (next >= recs.size()) break;   // only oversized sequences were left
       return "no index was created, all of your sequences are too large to be indexed with the current memory limit";
     }
-    TriePool tp;
+    // Mini tries are independent per 9-mer, and forward / reverse tries are independent of each other apart from the ids:
+    // worker t of T owns the 9-mers k with k % T == t, once for the forward and once for the reverse tries (2T threads).
+    // Forward workers number new L-mers locally (made global by a per-worker base afterwards -- still a bijection onto
+    // [0,N)); reverse workers store the window index of the inserting window and take that window's id at the end.
+    const uint32_t T = nthreads;
+    std::vector<TriePool> poolF(T), poolR(T);
+    std::vector<uint32_t> localN(T, 0);
     std::vector<uint32_t> rootF(limit, kNoneB), rootR(limit, kNoneB), count(limit, 0);
-    std::vector<bool> by_forward(limit, false);
-    std::vector<uint32_t> win_id;
-    uint32_t next_id = 0, unused = 0;
     size_t total_win = 0;
     for (size_t m : members) total_win += (recs[m].seq.size() - pread + opt.interval) / opt.interval;
-    win_id.reserve(total_win);
-    for (size_t m : members) {
-      const uint8_t* s = recs[m].seq.data();
-      const uint32_t len = (uint32_t)recs[m].seq.size();
-      const uint32_t numwin = (len - pread + opt.interval) / opt.interval;
-      uint32_t kf = 0, kr = 0;
-      for (uint32_t j = 0; j < half; ++j) { kf = (kf << 2) | s[j]; kr = (kr << 2) | s[half + 1 + j]; }
-      uint32_t pos = 0;
-      for (uint32_t j = 0; j < numwin; ++j) {
-        // 9-mer occurrence counts (indexdb.cpp:1457-1464)
+    if (total_win >= 0xFFFFFFFFull) return "more than 2^32 windows in one index part";
+    std::vector<uint32_t> win_id(total_win);
+    std::vector<uint8_t> win_owner(total_win);
+    // fn(w, kf, kr, tf): every window of the part in scan order; tf = pointer to character `half` of the window
+    auto scan = [&](auto&& fn) {
+      size_t w = 0;
+      for (size_t m : members) {
+        const uint8_t* s = recs[m].seq.data();
+        const uint32_t len = (uint32_t)recs[m].seq.size();
+        const uint32_t numwin = (len - pread + opt.interval) / opt.interval;
+        uint32_t kf = 0, kr = 0;
+        for (uint32_t j = 0; j < half; ++j) { kf = (kf << 2) | s[j]; kr = (kr << 2) | s[half + 1 + j]; }
+        uint32_t pos = 0;
+        for (uint32_t j = 0; j < numwin; ++j, ++w) {
+          fn(w, kf, kr, s + pos + half);
+          if (j != numwin - 1)
+            for (uint32_t sh = 0; sh < opt.interval; ++sh) {
+              kf = ((kf << 2) & mask32) | s[pos + half];
+              kr = ((kr << 2) & mask32) | s[pos + half + 1 + half];
+              ++pos;
+            }
+        }
+      }
+    };
+    {
+      std::vector<std::thread> pool;
+      for (uint32_t t = 0; t < T; ++t) {
+        pool.emplace_back([&, t]() {     // forward (L+1)-mers: prefix 9-mer -> tail s[pos+half .. pos+L]
+          TriePool& tp = poolF[t];
+          uint32_t next_id = 0;
+          scan([&](size_t w, uint32_t kf, uint32_t, const uint8_t* tf) {
+            if (kf % T != t) return;
+            win_id[w] = trie_add(tp, rootF[kf], [tf](uint32_t k) -> uint32_t { return tf[k]; }, half + 1, burst_depth, kNoneB, next_id);
+            win_owner[w] = (uint8_t)t;
+          });
+          localN[t] = next_id;
+        });
+        pool.emplace_back([&, t]() {     // reverse (L+1)-mers: suffix 9-mer s[pos+half+1 .. pos+L] -> tail s[pos+half], .., s[pos]
+          TriePool& tp = poolR[t];
+          uint32_t unused = 0;
+          scan([&](size_t w, uint32_t, uint32_t kr, const uint8_t* tf) {
+            if (kr % T != t) return;
+            trie_add(tp, rootR[kr], [tf](uint32_t k) -> uint32_t { return *(tf - k); }, half + 1, burst_depth, (uint32_t)w, unused);
+          });
+        });
+      }
+      // 9-mer occurrence counts (indexdb.cpp:1457-1464): order dependent ("already counted by the forward window"), sequential
+      std::vector<bool> by_forward(limit, false);
+      scan([&](size_t, uint32_t kf, uint32_t kr, const uint8_t*) {
         count[kf]++;
         by_forward[kf] = true;
         if (!by_forward[kr]) count[kr]++;
-        // forward (L+1)-mer: prefix 9-mer -> tail s[pos+half .. pos+L]
-        const uint8_t* tf = s + pos + half;
-        const uint32_t id = trie_add(tp, rootF[kf], [tf](uint32_t k) -> uint32_t { return tf[k]; }, half + 1, burst_depth, kNoneB, next_id);
-        // reverse (L+1)-mer: suffix 9-mer s[pos+half+1 .. pos+L] -> tail s[pos+half], s[pos+half-1], .., s[pos]
-        trie_add(tp, rootR[kr], [tf](uint32_t k) -> uint32_t { return *(tf - k); }, half + 1, burst_depth, id, unused);
-        win_id.push_back(id);
-        if (j != numwin - 1)
-          for (uint32_t sh = 0; sh < opt.interval; ++sh) {
-            kf = ((kf << 2) & mask32) | s[pos + half];
-            kr = ((kr << 2) & mask32) | s[pos + half + 1 + half];
-            ++pos;
-          }
-      }
+      });
+      for (auto& th : pool) th.join();
+    }
+    std::vector<uint32_t> base(T + 1, 0);
+    for (uint32_t t = 0; t < T; ++t) base[t + 1] = base[t] + localN[t];
+    const uint32_t next_id = base[T];
+    {
+      std::vector<std::thread> pool;
+      for (uint32_t t = 0; t < T; ++t)
+        pool.emplace_back([&, t]() {
+          for (auto& b : poolF[t].buckets) for (BEntry& e : b) e.id += base[t];
+          const size_t lo = total_win * t / T, hi = total_win * (t + 1) / T;
+          for (size_t w = lo; w < hi; ++w) win_id[w] += base[win_owner[w]];
+        });
+      for (auto& th : pool) th.join();
+      pool.clear();
+      for (uint32_t t = 0; t < T; ++t)
+        pool.emplace_back([&, t]() { for (auto& b : poolR[t].buckets) for (BEntry& e : b) e.id = win_id[e.id]; });
+      for (auto& th : pool) th.join();
     }
     // positions (add_kmer_to_table, indexdb.cpp:318-348): scan order, at most max_pos per id (0 = all)
     std::vector<uint32_t> psize(next_id, 0);
@@ -283,23 +335,43 @@ std::string build_index_files(const std::string& fasta, const std::string& prefi
     // files
     const std::string ps = std::to_string(part_num);
     if (!write_file(prefix + ".kmer_" + ps + ".dat", count.data(), (size_t)limit * 4, err)) return err;
-    std::vector<uint8_t> stream;
-    stream.reserve((size_t)limit * 8 + tp.nodes.size() * 4 + (size_t)total_win * 20);
-    for (uint32_t i = 0; i < limit; ++i) {
-      const uint32_t sz[2] = {rootF[i] != kNoneB ? trie_bytes(tp, rootF[i]) : 0u, rootR[i] != kNoneB ? trie_bytes(tp, rootR[i]) : 0u};
-      const size_t at = stream.size();
-      stream.resize(at + 8);
-      memcpy(&stream[at], sz, 8);
-      if (rootF[i] != kNoneB) trie_stream(tp, rootF[i], stream);
-      if (rootR[i] != kNoneB) trie_stream(tp, rootR[i], stream);
+    // .bursttrie: 9-mers in order; T contiguous ranges are streamed in parallel and written back to back
+    std::vector<std::vector<uint8_t>> streams(T);
+    {
+      std::vector<std::thread> pool;
+      for (uint32_t t = 0; t < T; ++t)
+        pool.emplace_back([&, t]() {
+          std::vector<uint8_t>& stream = streams[t];
+          const uint32_t lo = (uint32_t)((uint64_t)limit * t / T), hi = (uint32_t)((uint64_t)limit * (t + 1) / T);
+          for (uint32_t i = lo; i < hi; ++i) {
+            const TriePool& pf = poolF[i % T];
+            const TriePool& pr = poolR[i % T];
+            const uint32_t sz[2] = {rootF[i] != kNoneB ? trie_bytes(pf, rootF[i]) : 0u, rootR[i] != kNoneB ? trie_bytes(pr, rootR[i]) : 0u};
+            const size_t at = stream.size();
+            stream.resize(at + 8);
+            memcpy(&stream[at], sz, 8);
+            if (rootF[i] != kNoneB) trie_stream(pf, rootF[i], stream);
+            if (rootR[i] != kNoneB) trie_stream(pr, rootR[i], stream);
+          }
+        });
+      for (auto& th : pool) th.join();
     }
-    if (!write_file(prefix + ".bursttrie_" + ps + ".dat", stream.data(), stream.size(), err)) return err;
+    size_t stream_bytes = 0, trie_nodes = 0;
+    for (uint32_t t = 0; t < T; ++t) { stream_bytes += streams[t].size(); trie_nodes += poolF[t].nodes.size() + poolR[t].nodes.size(); }
+    {
+      const std::string path = prefix + ".bursttrie_" + ps + ".dat";
+      FILE* f = fopen(path.c_str(), "wb");
+      if (!f) return "cannot open " + path + " for writing: " + strerror(errno);
+      bool ok = true;
+      for (uint32_t t = 0; t < T && ok; ++t) ok = streams[t].empty() || fwrite(streams[t].data(), 1, streams[t].size(), f) == streams[t].size();
+      if (fclose(f) != 0 || !ok) return "short write to " + path;
+    }
     if (!write_file(prefix + ".pos_" + ps + ".dat", posbuf.data(), posbuf.size() * 4, err)) return err;
     parts.push_back(PartStat{start_part, seq_part_size, (uint32_t)members.size(), 0});
     report.unique_lmers += next_id;
     report.windows += total_win;
-    report.trie_nodes += tp.nodes.size();
-    report.bytes_written += (uint64_t)limit * 4 + stream.size() + posbuf.size() * 4;
+    report.trie_nodes += trie_nodes;
+    report.bytes_written += (uint64_t)limit * 4 + stream_bytes + posbuf.size() * 4;
     ++part_num;
     first = next;
   }
@@ -341,10 +413,10 @@ std::string build_index_files(const std::string& fasta, const std::string& prefi
 
 // C ABI (include/smr_b200.h)
 extern "C" int smr_build_index(const char* fasta_path, const char* out_prefix, uint32_t lnwin, uint32_t interval, uint32_t max_pos,
-                               double max_mb, uint64_t* report6, char* err, size_t err_cap) {
+                               double max_mb, uint32_t threads, uint64_t* report6, char* err, size_t err_cap) {
   if (!fasta_path || !out_prefix) return 2;   // SMR_ERR_ARG
   smr::BuildOptions o;
-  o.lnwin = lnwin; o.interval = interval; o.max_pos = max_pos; o.max_mb = max_mb;
+  o.lnwin = lnwin; o.interval = interval; o.max_pos = max_pos; o.max_mb = max_mb; o.threads = threads;
   smr::BuildReport rep;
   std::string e;
   try {

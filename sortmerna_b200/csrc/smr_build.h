@@ -11,6 +11,7 @@ struct BuildOptions {
   uint32_t interval = 1;    // -interval (options.hpp:588)
   uint32_t max_pos = 10000; // -max_pos  (options.hpp:589); 0 = keep every position
   double max_mb = 3072;     // -m        (options.hpp:586): estimated MB per index part
+  uint32_t threads = 0;     // T: 2T worker threads (forward / reverse tries of the 9-mers k % T == t); 0 = cores / 8, 1..8
 };
 
 struct BuildReport {
