@@ -25,6 +25,9 @@ struct Part {
 struct DevBuf {
   void* p = nullptr; size_t cap = 0;
 };
+struct PinBuf {   // grow-only pinned host staging (page-locked once; pageable vectors cost a page-fault pass + a bounce copy per batch)
+  void* p = nullptr; size_t cap = 0;
+};
 
 }  // namespace
 
@@ -49,6 +52,7 @@ struct smr_ctx {
   size_t hits_stride = 0; uint32_t cnt_stride = 0;
   DevBuf lis_arena, lis_epochs, final_arena, lane_hits, tb_arena, tb_jobs, aln_stats;
   smr_aln_stats* host_stats = nullptr;   // optional output of the report arithmetic
+  PinBuf h_state, h_flags, h_hitdb, h_outaln, h_stats, h_cigar, h_off32, h_pkoff;
   uint32_t tb_threads = 0, tb_cap_w = 0, tb_cap_cig = 0; size_t tb_cap_dir = 0, tb_stride = 0;
   uint32_t lis_warps = 0, final_warps = 0;
   size_t lis_stride = 0, final_stride = 0;
@@ -83,6 +87,15 @@ int ensure(smr_ctx* ctx, DevBuf& b, size_t bytes) {
   return SMR_OK;
 }
 void release(DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+int ensure_pinned(smr_ctx* ctx, PinBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return SMR_OK;
+  if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+  const size_t want = bytes + bytes / 8 + 256;
+  CK(cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+  b.cap = want;
+  return SMR_OK;
+}
+void release(PinBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
 
 template <class T>
 int upload_vec(smr_ctx* ctx, Part& pt, const std::vector<T>& v, const T** out) {
@@ -168,7 +181,8 @@ int upload_batch_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_
   cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1);
   CK(cudaEventRecord(e0, ctx->stream));
   std::vector<uint32_t>& off32 = ctx->off32; off32.resize(nreads + 1);
-  std::vector<uint32_t> pkoff(nreads + 1);
+  { int prc; if ((prc = ensure_pinned(ctx, ctx->h_pkoff, (size_t)(nreads + 1) * 4))) return prc; if ((prc = ensure_pinned(ctx, ctx->h_off32, (size_t)(nreads + 1) * 4))) return prc; }
+  uint32_t* pkoff = (uint32_t*)ctx->h_pkoff.p;
   uint32_t max_len = 0; uint64_t w = 0;
   for (uint32_t r = 0; r <= nreads; ++r) {
     off32[r] = (uint32_t)(seq_off[r] - seq_off[0]);
@@ -202,8 +216,9 @@ int upload_batch_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_
   if ((rc = ensure(ctx, ctx->scalars, 64))) return rc;
   if ((rc = ensure(ctx, ctx->counters, (size_t)(dcCount + 64) * 8))) return rc;
   CK(cudaMemcpyAsync(ctx->seq04.p, seq_cat + seq_off[0], total, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->seq_off.p, off32.data(), (size_t)(nreads + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->pk_off.p, pkoff.data(), (size_t)(nreads + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  memcpy(ctx->h_off32.p, off32.data(), (size_t)(nreads + 1) * 4);
+  CK(cudaMemcpyAsync(ctx->seq_off.p, ctx->h_off32.p, (size_t)(nreads + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->pk_off.p, pkoff, (size_t)(nreads + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(ctx->pk03.p, 0, (size_t)(w + 4) * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->pk03alt.p, 0, (size_t)(w + 4) * 4, ctx->stream));
   // hit regions are per chunk
@@ -362,22 +377,32 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
   const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
   cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1);
   CK(cudaEventRecord(e0, ctx->stream));
-  std::vector<ReadState> st(n); std::vector<uint32_t> fl(n); std::vector<uint16_t> hdb(n);
-  std::vector<OutAln> oa((size_t)n * slots);
-  std::vector<AlnStats> ast;
-  if (ctx->host_stats) { ast.resize((size_t)n * slots); CK(cudaMemcpyAsync(ast.data(), ctx->aln_stats.p, ast.size() * sizeof(AlnStats), cudaMemcpyDeviceToHost, ctx->stream)); }
+  int prc;
+  if ((prc = ensure_pinned(ctx, ctx->h_state, (size_t)n * sizeof(ReadState)))) return prc;
+  if ((prc = ensure_pinned(ctx, ctx->h_flags, (size_t)n * 4))) return prc;
+  if ((prc = ensure_pinned(ctx, ctx->h_hitdb, (size_t)n * 2))) return prc;
+  if ((prc = ensure_pinned(ctx, ctx->h_outaln, (size_t)n * slots * sizeof(OutAln)))) return prc;
+  const ReadState* st = (const ReadState*)ctx->h_state.p; const uint32_t* fl = (const uint32_t*)ctx->h_flags.p;
+  const uint16_t* hdb = (const uint16_t*)ctx->h_hitdb.p; const OutAln* oa = (const OutAln*)ctx->h_outaln.p;
+  const AlnStats* ast = nullptr;
+  if (ctx->host_stats) {
+    if ((prc = ensure_pinned(ctx, ctx->h_stats, (size_t)n * slots * sizeof(AlnStats)))) return prc;
+    ast = (const AlnStats*)ctx->h_stats.p;
+    CK(cudaMemcpyAsync(ctx->h_stats.p, ctx->aln_stats.p, (size_t)n * slots * sizeof(AlnStats), cudaMemcpyDeviceToHost, ctx->stream));
+  }
   unsigned long long used = 0;
   std::vector<unsigned long long> cnt(dcCount + 64);
-  CK(cudaMemcpyAsync(st.data(), ctx->state.p, (size_t)n * sizeof(ReadState), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(fl.data(), ctx->flags.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(hdb.data(), ctx->hit_db.p, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(oa.data(), ctx->out_aln.p, (size_t)n * slots * sizeof(OutAln), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_state.p, ctx->state.p, (size_t)n * sizeof(ReadState), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_flags.p, ctx->flags.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_hitdb.p, ctx->hit_db.p, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_outaln.p, ctx->out_aln.p, (size_t)n * slots * sizeof(OutAln), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(&used, scalars_of(ctx).cigar_used, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(cnt.data(), ctx->counters.p, cnt.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   used = std::min<unsigned long long>(used, ctx->cigar_cap_dev);
-  std::vector<uint32_t> cig(used);
-  if (used) CK(cudaMemcpy(cig.data(), ctx->cigar_pool.p, used * 4, cudaMemcpyDeviceToHost));
+  if ((prc = ensure_pinned(ctx, ctx->h_cigar, (size_t)used * 4 + 16))) return prc;
+  const uint32_t* cig = (const uint32_t*)ctx->h_cigar.p;
+  if (used) CK(cudaMemcpyAsync(ctx->h_cigar.p, ctx->cigar_pool.p, used * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaEventRecord(e1, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->t_d2h = ms;
@@ -396,7 +421,7 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
       if (k >= s.n_align) continue;
       const OutAln& d = oa[(size_t)r * slots + k];
       if (out.cigar_used + d.cigar_len > out.cigar_cap) { ctx->err = "cigar pool too small"; return SMR_ERR_CAPACITY; }
-      memcpy(out.cigar_pool + out.cigar_used, cig.data() + d.cigar_off, (size_t)d.cigar_len * 4);
+      memcpy(out.cigar_pool + out.cigar_used, cig + d.cigar_off, (size_t)d.cigar_len * 4);
       a.cigar_off = (uint32_t)out.cigar_used; a.cigar_len = d.cigar_len; out.cigar_used += d.cigar_len;
       a.ref_num = d.ref_num; a.ref_begin1 = d.ref_begin1; a.ref_end1 = d.ref_end1; a.read_begin1 = d.read_begin1; a.read_end1 = d.read_end1;
       a.readlen = d.readlen; a.score1 = d.score1; a.part = d.part; a.index_num = d.index_num; a.strand = d.strand;
@@ -483,6 +508,8 @@ void smr_destroy(smr_ctx* ctx) {
                     &ctx->hit_db, &ctx->aln_work, &ctx->out_aln, &ctx->hits, &ctx->cost, &ctx->bins, &ctx->scalars, &ctx->counters, &ctx->cigar_pool,
                     &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs, &ctx->aln_stats};
   for (DevBuf* b : bufs) release(*b);
+  PinBuf* pins[] = {&ctx->h_state, &ctx->h_flags, &ctx->h_hitdb, &ctx->h_outaln, &ctx->h_stats, &ctx->h_cigar, &ctx->h_off32, &ctx->h_pkoff};
+  for (PinBuf* b : pins) release(*b);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
