@@ -29,6 +29,10 @@ struct SeqView {
   __device__ __forceinline__ SeqView reversed_prefix(int32_t end) const { return SeqView{base, start + end * step, -step, comp}; }
 };
 
+#ifndef SMR_SW_VARIANT
+#define SMR_SW_VARIANT 3
+#endif
+
 struct SwScore { int32_t match, mismatch, sN, go, ge, one; };  // one == 1 at run time (keeps IMADs on the fma pipe)
 struct SwEnd { int32_t score, ref, read; };
 
@@ -165,6 +169,7 @@ __device__ int32_t sw_score_warp(const int32_t* __restrict__ s_prof, const uint8
   const int32_t* prow = s_prof + lane;
   const int32_t nsteps = n + 31;
   const int32_t nge = -sc.ge, ngo = -sc.go, one = sc.one;
+  const int32_t nz = lane ? sc.one : 0; (void)nz;
   // software pipeline: the substitution scores of the next column are fetched while this one is computed
   int32_t sc_cur[R];
   {
@@ -172,6 +177,7 @@ __device__ int32_t sw_score_warp(const int32_t* __restrict__ s_prof, const uint8
 #pragma unroll
     for (int r = 0; r < R; ++r) sc_cur[r] = pt[r * 32];
   }
+#pragma unroll 2
   for (int32_t ts = 0; ts < nsteps; ++ts) {
     int32_t sc_next[R];
     {
@@ -180,8 +186,33 @@ __device__ int32_t sw_score_warp(const int32_t* __restrict__ s_prof, const uint8
       for (int r = 0; r < R; ++r) sc_next[r] = pt[r * 32];
     }
     int32_t upH = __shfl_up_sync(kFull, outH, 1), upF = __shfl_up_sync(kFull, outF, 1);
+#if SMR_SW_VARIANT == 3
+    upH *= nz; upF *= nz;          // row -1 is all zeros; a multiply (fma pipe) instead of a select (alu pipe)
+#else
     if (lane == 0) { upH = 0; upF = 0; }
+#endif
     int32_t X[R], Xgo[R], F[R + 1];
+#if SMR_SW_VARIANT == 3
+    // 4 ALU-pipe ops + 1 IMAD per cell.  F is carried as G = F + go (outF / upF hold G):
+    //   X = max(diag + s, E, 0);  G' = max(G - ge, X)  [= F' + go, F' = max(F - ge, X - go)];  H = max(X, G - go);  E' = max(E - ge, H - go)
+    // the boundary G = 0 stands for F = -go, which like every negative F can never win against X >= 0
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int32_t diag = r == 0 ? diagH : Hp[r - 1];
+      X[r] = __viaddmax_s32_relu(diag, sc_cur[r], E[r]);
+    }
+    diagH = upH;
+    F[0] = upF;
+#pragma unroll
+    for (int r = 0; r < R; ++r) F[r + 1] = __viaddmax_s32(F[r], nge, X[r]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int32_t h = __viaddmax_s32(F[r], ngo, X[r]);
+      E[r] = __viaddmax_s32(E[r], nge, h * one + ngo);
+      Hp[r] = h;
+    }
+    (void)Xgo;
+#elif SMR_SW_VARIANT == 0
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int32_t diag = r == 0 ? diagH : Hp[r - 1];
@@ -198,6 +229,43 @@ __device__ int32_t sw_score_warp(const int32_t* __restrict__ s_prof, const uint8
       E[r] = __vimax3_s32(E[r] * one + nge, Xgo[r], F[r] * one + ngo);
       Hp[r] = h;
     }
+#elif SMR_SW_VARIANT == 1
+    // 4 ALU-pipe ops + 2 IMAD per cell; the vertical F chain is one VIADDMNMX per row:
+    //   X = max(diag + s, E, 0);  F' = max(F - ge, X - go)  (F - go < F - ge never wins);  H = max(X, F);  E' = max(E - ge, H - go)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int32_t diag = r == 0 ? diagH : Hp[r - 1];
+      X[r] = __viaddmax_s32_relu(diag, sc_cur[r], E[r]);
+      Xgo[r] = X[r] * one + ngo;
+    }
+    diagH = upH;
+    F[0] = upF;
+#pragma unroll
+    for (int r = 0; r < R; ++r) F[r + 1] = __viaddmax_s32(F[r], nge, Xgo[r]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int32_t h = max(X[r], F[r]);
+      E[r] = __viaddmax_s32(E[r], nge, h * one + ngo);
+      Hp[r] = h;
+    }
+#else
+    // 4 ALU-pipe ops + 1 IMAD per cell; the vertical chain is VIMNMX.RELU -> IMAD -> VIADDMNMX per row
+    F[0] = upF;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int32_t diag = r == 0 ? diagH : Hp[r - 1];
+      X[r] = __viaddmax_s32(diag, sc_cur[r], E[r]);
+    }
+    diagH = upH;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int32_t h = __vimax_s32_relu(X[r], F[r]);
+      Xgo[r] = h * one + ngo;
+      F[r + 1] = __viaddmax_s32(F[r], nge, Xgo[r]);
+      E[r] = __viaddmax_s32(E[r], nge, Xgo[r]);
+      Hp[r] = h;
+    }
+#endif
     if (FIND) {
       if (found == 0x7FFFFFFF) {
         int32_t rr = -1;
