@@ -339,11 +339,12 @@ def main():
     step_ms = float(np.sum(dev_ms))          # CUDA events on the library's stream, summed over the K steps
     # ---- end to end through the public call: pinned host buffers in, host results out, every step ----
     al.align(cats[0][: min(n, 1 << 16) * READ_LEN], off[: min(n, 1 << 16) + 1])  # warm the host path
+    al.align(cats[0], off, reuse_outputs=True)                                    # first touch of the reusable result buffers
     barrier()
     t0 = time.perf_counter()
     e2e_steps = args.steps
     for s_i in range(e2e_steps):
-        res_e = al.align(cats[s_i], off)
+        res_e = al.align(cats[s_i], off, reuse_outputs=True)
     barrier()
     e2e_s = time.perf_counter() - t0
     h2d = int(cats[0].nbytes + off.nbytes)

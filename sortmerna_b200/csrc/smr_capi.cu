@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "smr_final.cuh"
@@ -53,6 +54,7 @@ struct smr_ctx {
   DevBuf lis_arena, lis_epochs, final_arena, lane_hits, tb_arena, tb_jobs, aln_stats;
   smr_aln_stats* host_stats = nullptr;   // optional output of the report arithmetic
   PinBuf h_state, h_flags, h_hitdb, h_outaln, h_stats, h_cigar, h_off32, h_pkoff;
+  std::vector<uint64_t> h_coff;
   uint32_t tb_threads = 0, tb_cap_w = 0, tb_cap_cig = 0; size_t tb_cap_dir = 0, tb_stride = 0;
   uint32_t lis_warps = 0, final_warps = 0;
   size_t lis_stride = 0, final_stride = 0;
@@ -407,31 +409,53 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
   CK(cudaStreamSynchronize(ctx->stream));
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->t_d2h = ms;
   int rc = SMR_OK;
+  // pass 1 (sequential, cheap): flagged reads, cigar offsets in the caller's pool (running sum in read order), counters
+  std::vector<uint64_t>& coff = ctx->h_coff; coff.resize((size_t)n + 1);
+  uint64_t run = out.cigar_used;
   for (uint32_t r = 0; r < n; ++r) {
-    const uint32_t dst = map ? map[r] : r;
+    coff[r] = run;
     if (fl[r] & kErrTrace) { ctx->err = "trace back error (ssw.c:707 is fatal in the reference too)"; rc = SMR_ERR_INDEX; }
     if (fl[r]) { flagged.push_back(r); for (int bit = 0; bit < 6; ++bit) if (fl[r] & (1u << bit)) ctx->flag_hist[bit]++; continue; }
-    smr_read_result& o = out.results[dst];
     const ReadState& s = st[r];
-    o.lastIndex = s.lastIndex; o.lastPart = s.lastPart; o.hit_seeds = s.hit_seeds; o.min_index = s.min_index; o.max_index = s.max_index;
-    o.n_align = s.n_align; o.max_SW_count = s.max_SW_count; o.is_done = s.is_done; o.is_hit = s.is_hit;
-    for (uint32_t k = 0; k < slots; ++k) {
-      smr_aln& a = out.alns[(size_t)dst * slots + k];
-      memset(&a, 0, sizeof(a));
-      if (k >= s.n_align) continue;
-      const OutAln& d = oa[(size_t)r * slots + k];
-      if (out.cigar_used + d.cigar_len > out.cigar_cap) { ctx->err = "cigar pool too small"; return SMR_ERR_CAPACITY; }
-      memcpy(out.cigar_pool + out.cigar_used, cig + d.cigar_off, (size_t)d.cigar_len * 4);
-      a.cigar_off = (uint32_t)out.cigar_used; a.cigar_len = d.cigar_len; out.cigar_used += d.cigar_len;
-      a.ref_num = d.ref_num; a.ref_begin1 = d.ref_begin1; a.ref_end1 = d.ref_end1; a.read_begin1 = d.read_begin1; a.read_end1 = d.read_end1;
-      a.readlen = d.readlen; a.score1 = d.score1; a.part = d.part; a.index_num = d.index_num; a.strand = d.strand;
-      if (ctx->host_stats) { const AlnStats& st2 = ast[(size_t)r * slots + k]; ctx->host_stats[(size_t)dst * slots + k] = smr_aln_stats{st2.n_miss, st2.n_gap, st2.n_match, st2.n_match_denovo}; }
-    }
+    for (uint32_t k = 0; k < slots && k < s.n_align; ++k) run += oa[(size_t)r * slots + k].cigar_len;
     if (s.is_hit && out.counters) {
       if (out.n_counters > SMR_CNT_NUM_ALIGNED) out.counters[SMR_CNT_NUM_ALIGNED]++;
       const uint32_t ci = SMR_CNT_FIXED + hdb[r];
       if (hdb[r] != 0xFFFF && ci < out.n_counters) out.counters[ci]++;
     }
+  }
+  coff[n] = run;
+  if (run > out.cigar_cap) { ctx->err = "cigar pool too small"; return SMR_ERR_CAPACITY; }
+  out.cigar_used = run;
+  // pass 2: results, alignments and cigars of disjoint read ranges, by a few host threads for large batches
+  auto pack = [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t r = lo; r < hi; ++r) {
+      if (fl[r]) continue;
+      const uint32_t dst = map ? map[r] : r;
+      smr_read_result& o = out.results[dst];
+      const ReadState& s = st[r];
+      o.lastIndex = s.lastIndex; o.lastPart = s.lastPart; o.hit_seeds = s.hit_seeds; o.min_index = s.min_index; o.max_index = s.max_index;
+      o.n_align = s.n_align; o.max_SW_count = s.max_SW_count; o.is_done = s.is_done; o.is_hit = s.is_hit;
+      uint64_t at = coff[r];
+      for (uint32_t k = 0; k < slots; ++k) {
+        smr_aln& a = out.alns[(size_t)dst * slots + k];
+        memset(&a, 0, sizeof(a));
+        if (k >= s.n_align) continue;
+        const OutAln& d = oa[(size_t)r * slots + k];
+        memcpy(out.cigar_pool + at, cig + d.cigar_off, (size_t)d.cigar_len * 4);
+        a.cigar_off = (uint32_t)at; a.cigar_len = d.cigar_len; at += d.cigar_len;
+        a.ref_num = d.ref_num; a.ref_begin1 = d.ref_begin1; a.ref_end1 = d.ref_end1; a.read_begin1 = d.read_begin1; a.read_end1 = d.read_end1;
+        a.readlen = d.readlen; a.score1 = d.score1; a.part = d.part; a.index_num = d.index_num; a.strand = d.strand;
+        if (ctx->host_stats) { const AlnStats& st2 = ast[(size_t)r * slots + k]; ctx->host_stats[(size_t)dst * slots + k] = smr_aln_stats{st2.n_miss, st2.n_gap, st2.n_match, st2.n_match_denovo}; }
+      }
+    }
+  };
+  const uint32_t nthr = n >= (1u << 16) ? std::min<uint32_t>(8, std::max<uint32_t>(1, std::thread::hardware_concurrency() / 2)) : 1;
+  if (nthr <= 1) pack(0, n);
+  else {
+    std::vector<std::thread> pool;
+    for (uint32_t t = 0; t < nthr; ++t) pool.emplace_back(pack, (uint32_t)((uint64_t)n * t / nthr), (uint32_t)((uint64_t)n * (t + 1) / nthr));
+    for (auto& th : pool) th.join();
   }
   if (out.counters) {
     static const int mapc[][2] = {{SMR_CNT_NUM_SHORT, dcNumShort}, {SMR_CNT_SW_CALLS, dcSwCalls}, {SMR_CNT_SW_CELLS, dcSwCells},

@@ -90,10 +90,13 @@ __device__ void warp_sort_u64(unsigned long long* a, uint32_t n_pow2) {
   }
 }
 // ascending sort of one 64-bit key per lane (pad with ~0ull), entirely in registers
-__device__ __forceinline__ unsigned long long warp_sort32_u64(unsigned long long key) {
+// `n` (warp-uniform) = number of real keys: only the first next_pow2(n) lanes need to end up sorted, which takes the
+// merge stages up to that block size only (3 of the 15 stages for n <= 4)
+__device__ __forceinline__ unsigned long long warp_sort32_u64(unsigned long long key, const unsigned n = 32) {
   const unsigned lane = lane_id();
 #pragma unroll
   for (unsigned k = 2; k <= 32; k <<= 1) {
+    if ((k >> 1) >= n) break;
 #pragma unroll
     for (unsigned j = k >> 1; j > 0; j >>= 1) {
       const unsigned long long other = __shfl_xor_sync(kFull, key, j);
@@ -239,7 +242,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
       key = ((unsigned long long)(0xFFFFFu - c) << 32) | seq;
       E.ar.bitmap[seq >> 5] = 0; E.ar.summary[seq >> 10] = 0;
     }
-    key = warp_sort32_u64(key);
+    key = warp_sort32_u64(key, ncand);
     E.ar.grp[lane] = key;
     E.ar.cand[lane] = key;   // (kept for the cursor clean-up; grp is the working group buffer)
   } else {
@@ -411,7 +414,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
     if (np <= 32u) {
       unsigned long long key = lane < np ? P[lane] : ~0ull;
       __syncwarp();
-      key = warp_sort32_u64(key);
+      key = warp_sort32_u64(key, np);
       if (lane < np) P[lane] = key;
       __syncwarp();
     } else {
