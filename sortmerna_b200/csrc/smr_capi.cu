@@ -166,7 +166,7 @@ int setup_arenas(smr_ctx* ctx) {
   ctx->tb_threads = (uint32_t)ctx->sm_count * 1024u;
   ctx->tb_cap_w = 2 * 32 * ctx->scale + 8;                       // band widths up to 32*scale
   ctx->tb_cap_cig = 128 * ctx->scale;
-  ctx->tb_cap_dir = (size_t)12288 * ctx->scale;                  // (2*band+1) * readLen * 3 bytes
+  ctx->tb_cap_dir = (size_t)32768 * ctx->scale;                  // (2*band+1) * readLen * 3 bytes: band 32 at 150 nt
   ctx->tb_stride = ((size_t)ctx->tb_cap_w * 12 + (size_t)ctx->tb_cap_cig * 4 + ctx->tb_cap_dir + 255) & ~(size_t)255;
   while (ctx->tb_threads > 4096 && ctx->tb_stride * ctx->tb_threads > budget) ctx->tb_threads /= 2;
   if (int rc = ensure(ctx, ctx->tb_arena, ctx->tb_stride * ctx->tb_threads)) return rc;
