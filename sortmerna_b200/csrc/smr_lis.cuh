@@ -196,15 +196,21 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
     }
     const uint32_t incl = warp_incl_scan_u32(s_l), tot = __shfl_sync(kFull, incl, 31), excl = incl - s_l;
     E.n_pos_entries += tot;
-    for (uint32_t e0 = 0; e0 < tot; e0 += 32) {
+    // entry e of the concatenated position lists of these 32 hits -> its reference number (0xFFFFFFFF past the end)
+    auto fetch_seq = [&](const uint32_t e0) -> uint32_t {
       const uint32_t e = e0 + lane;
-      const bool act = e < tot;
       uint32_t lo = 0;                       // owner = first lane whose inclusive sum exceeds e
 #pragma unroll
       for (int stp = 16; stp > 0; stp >>= 1) { const uint32_t v = __shfl_sync(kFull, incl, lo + stp - 1); if (v <= e) lo += stp; }
       lo = min(lo, 31u);
       const uint32_t o_own = __shfl_sync(kFull, o_l, lo), ex_own = __shfl_sync(kFull, excl, lo);
-      const uint32_t seq = act ? __ldg(&ix.pos[o_own + (e - ex_own)]).y : 0xFFFFFFFFu;
+      return e < tot ? __ldg(&ix.pos[o_own + (e - ex_own)]).y : 0xFFFFFFFFu;
+    };
+    uint32_t seq_next = tot ? fetch_seq(0) : 0xFFFFFFFFu;
+    for (uint32_t e0 = 0; e0 < tot; e0 += 32) {
+      const uint32_t seq = seq_next;
+      if (e0 + 32 < tot) seq_next = fetch_seq(e0 + 32);   // in flight while this round's histogram words are read
+      const bool act = seq != 0xFFFFFFFFu;
       const unsigned grp = __match_any_sync(kFull, seq);
       bool trans = false;
       if (act && (unsigned)(__ffs(grp) - 1) == lane && seq < E.ar.hist_cap) {
@@ -304,19 +310,26 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
           if (hit_selected(hv, rc, s0, s1, s2)) { o_l = __ldg(ix.pos_off + hv.x); s_l = __ldg(ix.pos_off + hv.x + 1) - o_l; w_l = hv.y & kWinMask; }
         }
         const uint32_t incl = warp_incl_scan_u32(s_l), tot = __shfl_sync(kFull, incl, 31), excl = incl - s_l;
-        for (uint32_t e0 = 0; e0 < tot; e0 += 32) {
+        uint32_t w_cur = 0, w_nxt = 0;
+        auto fetch_pos = [&](const uint32_t e0, uint32_t& w_own) -> uint2 {
           const uint32_t e = e0 + lane;
           uint32_t lo = 0;
 #pragma unroll
           for (int stp = 16; stp > 0; stp >>= 1) { const uint32_t v = __shfl_sync(kFull, incl, lo + stp - 1); if (v <= e) lo += stp; }
           lo = min(lo, 31u);
-          const uint32_t o_own = __shfl_sync(kFull, o_l, lo), ex_own = __shfl_sync(kFull, excl, lo), w_own = __shfl_sync(kFull, w_l, lo);
-          if (e < tot) {
-            const uint2 ps = __ldg(&ix.pos[o_own + (e - ex_own)]);
-            if (ps.y < E.ar.hist_cap && (E.ar.hist[ps.y] & 0x80000000u)) {
-              const uint32_t slot = atomicAdd(&E.ar.hist[ps.y], 1u) & 0x7FFFFFFFu;
-              E.ar.pall[slot] = ((unsigned long long)ps.x << 32) | w_own;
-            }
+          const uint32_t o_own = __shfl_sync(kFull, o_l, lo), ex_own = __shfl_sync(kFull, excl, lo);
+          w_own = __shfl_sync(kFull, w_l, lo);
+          return e < tot ? __ldg(&ix.pos[o_own + (e - ex_own)]) : make_uint2(0u, 0xFFFFFFFFu);
+        };
+        uint2 ps_next = tot ? fetch_pos(0, w_nxt) : make_uint2(0u, 0xFFFFFFFFu);
+        for (uint32_t e0 = 0; e0 < tot; e0 += 32) {
+          const uint2 ps = ps_next; w_cur = w_nxt;
+          if (e0 + 32 < tot) ps_next = fetch_pos(e0 + 32, w_nxt);
+          if (ps.y < E.ar.hist_cap) {
+            // ONE round trip: the add returns the cursor when bit 31 is set; on the word of a non-candidate (an epoch-tagged
+            // count below num_seeds that nothing reads again in this epoch) the extra count is harmless
+            const uint32_t old = atomicAdd(&E.ar.hist[ps.y], 1u);
+            if (old & 0x80000000u) E.ar.pall[old & 0x7FFFFFFFu] = ((unsigned long long)ps.x << 32) | w_cur;
           }
         }
       }
@@ -378,6 +391,8 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
     prev_occur = max_occur; first_cand = false;
 
     long long tc0 = clock64();
+    // start of the reference and of its successor: requested now, needed only after the pairs are gathered and sorted
+    const uint64_t ref_base = __ldg(ix.ref_off + max_ref), ref_next = __ldg(ix.ref_off + max_ref + 1);
     // gather (refpos, readpos) pairs of this reference (:181-201)
     const uint32_t np = max_occur;
     unsigned long long* P; uint32_t* lb; uint32_t* lp;
@@ -441,7 +456,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
         if (lis_len >= (uint32_t)o.min_lis) {                                               // :261
           const uint32_t lcs_ref_start = (uint32_t)(P[f + lis_first] >> 32), lcs_que_start = (uint32_t)P[f + lis_first];
           uint64_t head = 0, tail = 0, ars = 0, aqs = 0, alen = 0;
-          const uint64_t reflen = __ldg(ix.ref_off + max_ref + 1) - __ldg(ix.ref_off + max_ref);
+          const uint64_t reflen = ref_next - ref_base;
           const uint32_t edges = o.edges_is_percent ? (uint32_t)((o.edges / 100.0) * (double)rlen) : (uint32_t)o.edges;  // :278-282
           const uint64_t em1 = (uint64_t)(uint32_t)(edges - 1u);
           if (lcs_ref_start < lcs_que_start) {                                              // :288-330
@@ -465,7 +480,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
           SeqView q;
           if (!rc.reversed) q = SeqView{B.seq04 + rc.seq_base, (int32_t)aqs, 1, false};
           else q = SeqView{B.seq04 + rc.seq_base, (int32_t)(rc.len - 1 - aqs), -1, true};
-          const SeqView t{ix.refseq + __ldg(ix.ref_off + max_ref), (int32_t)win_start, 1, false};
+          const SeqView t{ix.refseq + ref_base, (int32_t)win_start, 1, false};
           { const long long t2 = clock64(); E.cyc[3] += (unsigned long long)(t2 - tc0); tc0 = t2; }
           int32_t sw = 0;
           if (qlen > 0 && alen > 0 && (uint32_t)alen <= E.ar.row_cap) sw = sw_score(q, qlen, t, (int32_t)alen, sc, E.s_ref, E.s_prof, E.ar.rowH, E.ar.rowF);
