@@ -240,6 +240,14 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library chatter) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -262,7 +270,7 @@ def main():
                 vals.append(v); secs.append(t)
         v = float(np.mean(vals))
         desc = f"{sample} synthetic 150 bp reads per step vs the 8 databases, alignment loops only (index loading excluded), -threads {cores}"
-        print(json.dumps({
+        emit(({
             "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16/u8 (SSE2)", "data": "synthetic", "impl": "reference",
@@ -422,14 +430,14 @@ def main():
         "counters": counters,
         "setup_s": setup_s, "index_build_s": built,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # reported baseline: rank 0 at N = 1 only
         sample = args.cpu_sample or int(min(100_000, max(5_000, 1_000 * cores)))
         v, t, total, _ = run_reference_sample(fastas, reference_index_dir(fastas), first_reads[:sample], cores)
         out["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference",
                                "sample": f"first {sample} reads of the same synthetic workload vs the 8 databases, reference CPU build "
                                          f"(oracle/_ref/sortmerna_ref -threads {cores}), alignment loops {t:.1f} s (index loading excluded; "
                                          f"'Done alignment' incl. loading {total:.1f} s)"}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
