@@ -274,7 +274,8 @@ def main():
             "metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1000.0 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16/u8 (SSE2)", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "10 M synthetic 150 bp Illumina reads vs all 8 data/rRNA_databases refs (bounded sample per step)",
+            "config": {"workload": "10 M synthetic 150 bp Illumina reads vs all 8 data/rRNA_databases refs, 1xB200",
+                       "sampled": "each step is a bounded sample of that workload (reads_per_step reads, same generator)",
                        "reads_per_step": sample, "read_len": READ_LEN, "databases": 8},
             "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": desc},
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
