@@ -145,6 +145,20 @@ int smr_align_batch(smr_ctx*, const uint8_t* seq_cat, const uint64_t* seq_off, u
  * indexing as alns[]; nullptr = do not compute).  Host buffer of nreads * max(1,num_alignments) entries. */
 int smr_set_stats_buffer(smr_ctx*, smr_aln_stats* stats);
 
+/* Input decode on the device: `text` = the bytes of an uncompressed FASTA or FASTQ file (or a record-aligned
+ * piece of one).  Replaces, for the reads of this batch, the record split of Readfeed (src/sortmerna/readfeed.cpp:683-770),
+ * Read::Read(readstr) (read.cpp:141-176) and the nt_table encoding of Read::init (read.cpp:264-288, common.hpp:68-77):
+ * the text is copied to the device once and newline indexing, record split and 0-4 encoding run there; the decoded batch
+ * becomes the resident batch (as after smr_upload_batch): follow with smr_run_resident / smr_download_results.
+ * FASTQ: 4 lines per record; FASTA: '>' header + any number of sequence lines; CR LF tolerated; a missing final newline is
+ * fine; trailing blank lines are ignored.  *nreads = records found. */
+int smr_upload_fastx(smr_ctx*, const char* text, uint64_t nbytes, uint32_t* nreads);
+
+/* Where the resident reads are: header_text_off[r] = offset of record r's header line in the text given to
+ * smr_upload_fastx (for Read::getSeqId / report writers; nullptr = skip; only after smr_upload_fastx), read_off[0..nreads] =
+ * offsets into the concatenated 0-4 codes, seq04 (optional) = those codes (seq_cap bytes available). */
+int smr_resident_layout(smr_ctx*, uint64_t* header_text_off, uint64_t* read_off, uint8_t* seq04, uint64_t seq_cap);
+
 /* Same work with the batch already resident: upload once, run many times (bench `value` leg). */
 int smr_upload_batch(smr_ctx*, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads);
 int smr_run_resident(smr_ctx*);                       /* all kernels of one pass over the resident batch */

@@ -25,7 +25,7 @@ STATUS = {0: "SMR_OK", 1: "SMR_ERR_CUDA", 2: "SMR_ERR_ARG", 3: "SMR_ERR_INDEX", 
 SYMBOLS = ["smr_init", "smr_destroy", "smr_last_error", "smr_device_count", "smr_load_index_part",
            "smr_set_minimal_score", "smr_set_params", "smr_index_info", "smr_align_batch", "smr_upload_batch",
            "smr_run_resident", "smr_download_results", "smr_last_timings", "smr_debug_seed_windows", "smr_debug_ssw",
-           "smr_debug_dpx_peak", "smr_set_stats_buffer", "smr_build_index"]
+           "smr_debug_dpx_peak", "smr_set_stats_buffer", "smr_build_index", "smr_upload_fastx", "smr_resident_layout"]
 
 CNT_NAMES = ("num_aligned", "num_short", "sw_calls", "sw_cells", "windows", "trie_nodes", "buckets",
              "bucket_entries", "pos_entries", "lis_calls", "dbg_max_read_cycles", "dbg_sum_read_cycles", "dbg_lis_kernel_cycles",
@@ -210,6 +210,29 @@ class Aligner:
         self._n_resident = off.size - 1
         self._check(self.L.smr_upload_batch(self.h, _ptr(cat), _ptr(off), C.c_uint32(off.size - 1)), "smr_upload_batch")
 
+    def upload_fastx(self, text: bytes) -> int:
+        """smr_upload_fastx: the bytes of an uncompressed FASTA / FASTQ file; record split and 0-4 encoding run on the device.
+        Returns the number of reads; continue with run_resident() / download()."""
+        n = C.c_uint32(0)
+        buf = np.frombuffer(text, dtype=np.uint8)
+        self._check(self.L.smr_upload_fastx(self.h, _ptr(buf), C.c_uint64(buf.size), C.byref(n)), "smr_upload_fastx")
+        self._n_resident = int(n.value)
+        return self._n_resident
+
+    def resident_layout(self, with_headers: bool = True, with_seq: bool = True):
+        """smr_resident_layout: (header offsets in the uploaded text, read offsets, concatenated 0-4 codes) of the resident batch."""
+        n = self._n_resident
+        hdr = np.zeros(n, np.uint64) if with_headers else None
+        off = np.zeros(n + 1, np.uint64)
+        self._check(self.L.smr_resident_layout(self.h, _ptr(hdr) if with_headers and n else C.c_void_p(0), _ptr(off), C.c_void_p(0), C.c_uint64(0)),
+                    "smr_resident_layout")
+        seq = None
+        if with_seq:
+            seq = np.zeros(int(off[n]), np.uint8)
+            if seq.size:
+                self._check(self.L.smr_resident_layout(self.h, C.c_void_p(0), C.c_void_p(0), _ptr(seq), C.c_uint64(seq.size)), "smr_resident_layout")
+        return hdr, off, seq
+
     def run_resident(self):
         self._check(self.L.smr_run_resident(self.h), "smr_run_resident")
 
@@ -226,7 +249,7 @@ class Aligner:
         out = np.zeros(8, np.float64)
         self.L.smr_last_timings(self.h, _ptr(out))
         return dict(total_ms=out[0], seed_ms=out[1], lis_ms=out[2], final_ms=out[3], h2d_ms=out[4], d2h_ms=out[5],
-                    launches=int(out[6]))
+                    launches=int(out[6]), decode_ms=out[7])
 
     def dpx_peak(self) -> float:
         """measured dependent-free DPX thread-ops/s (1e9/s) on this device"""

@@ -10,6 +10,7 @@
 #include <thread>
 #include <vector>
 
+#include "smr_decode.cuh"
 #include "smr_final.cuh"
 #include "smr_index.h"
 
@@ -55,6 +56,9 @@ struct smr_ctx {
   smr_aln_stats* host_stats = nullptr;   // optional output of the report arithmetic
   PinBuf h_state, h_flags, h_hitdb, h_outaln, h_stats, h_cigar, h_off32, h_pkoff;
   std::vector<uint64_t> h_coff;
+  DevBuf d_text, d_cnt, d_scal, d_nl, d_hdr, d_sb, d_rec, d_spos, d_hdroff, scan_sums;   // input decode (smr_decode.cuh)
+  bool device_only_reads = false;   // the resident batch was decoded on the device: no host copy of the sequences yet
+  double t_decode = 0;
   uint32_t tb_threads = 0, tb_cap_w = 0, tb_cap_cig = 0; size_t tb_cap_dir = 0, tb_stride = 0;
   uint32_t lis_warps = 0, final_warps = 0;
   size_t lis_stride = 0, final_stride = 0;
@@ -176,6 +180,8 @@ int setup_arenas(smr_ctx* ctx) {
   return SMR_OK;
 }
 
+int finish_upload(smr_ctx* ctx, uint32_t nreads, uint64_t w);
+
 int upload_batch_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads, bool keep_host) {
   if (nreads == 0) { ctx->nreads = 0; return SMR_OK; }
   const uint64_t total = seq_off[nreads] - seq_off[0];
@@ -207,6 +213,24 @@ int upload_batch_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_
   if ((rc = ensure(ctx, ctx->seq04, total + 64))) return rc;
   if ((rc = ensure(ctx, ctx->seq_off, (size_t)(nreads + 1) * 4))) return rc;
   if ((rc = ensure(ctx, ctx->pk_off, (size_t)(nreads + 1) * 4))) return rc;
+  CK(cudaMemcpyAsync(ctx->seq04.p, seq_cat + seq_off[0], total, cudaMemcpyHostToDevice, ctx->stream));
+  memcpy(ctx->h_off32.p, off32.data(), (size_t)(nreads + 1) * 4);
+  CK(cudaMemcpyAsync(ctx->seq_off.p, ctx->h_off32.p, (size_t)(nreads + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->pk_off.p, pkoff, (size_t)(nreads + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->device_only_reads = false;
+  if ((rc = finish_upload(ctx, nreads, w))) return rc;
+  CK(cudaEventRecord(e1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));   // off32/pkoff are stack-owned
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->t_h2d = ms;
+  return SMR_OK;
+}
+
+// the part of an upload that does not depend on where the reads came from: seq04 / seq_off / pk_off are on the device,
+// ctx->off32 (host) holds the offsets; sizes the per-batch buffers and 2-bit packs the reads
+int finish_upload(smr_ctx* ctx, uint32_t nreads, uint64_t w) {
+  const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
+  const std::vector<uint32_t>& off32 = ctx->off32;
+  int rc;
   if ((rc = ensure(ctx, ctx->pk03, (size_t)(w + 4) * 4))) return rc;
   if ((rc = ensure(ctx, ctx->pk03alt, (size_t)(w + 4) * 4))) return rc;
   if ((rc = ensure(ctx, ctx->has_n, nreads))) return rc;
@@ -217,10 +241,6 @@ int upload_batch_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_
   if ((rc = ensure(ctx, ctx->out_aln, (size_t)nreads * slots * sizeof(OutAln)))) return rc;
   if ((rc = ensure(ctx, ctx->scalars, 64))) return rc;
   if ((rc = ensure(ctx, ctx->counters, (size_t)(dcCount + 64) * 8))) return rc;
-  CK(cudaMemcpyAsync(ctx->seq04.p, seq_cat + seq_off[0], total, cudaMemcpyHostToDevice, ctx->stream));
-  memcpy(ctx->h_off32.p, off32.data(), (size_t)(nreads + 1) * 4);
-  CK(cudaMemcpyAsync(ctx->seq_off.p, ctx->h_off32.p, (size_t)(nreads + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->pk_off.p, pkoff, (size_t)(nreads + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(ctx->pk03.p, 0, (size_t)(w + 4) * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->pk03alt.p, 0, (size_t)(w + 4) * 4, ctx->stream));
   // hit regions are per chunk
@@ -243,9 +263,91 @@ int upload_batch_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_
   b.pk_off = (const uint32_t*)ctx->pk_off.p;
   pack_reads_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(b, (uint32_t*)ctx->pk03.p, (uint32_t*)ctx->pk03alt.p, (uint8_t*)ctx->has_n.p);
   CK(cudaGetLastError());
+  return SMR_OK;
+}
+
+// exclusive scan of n u32 on the device (out may alias in); total (optional, device pointer) receives the sum
+int device_scan(smr_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* total_dev) {
+  const uint32_t ntiles = (uint32_t)((n + kScanTile - 1) / kScanTile);
+  int rc;
+  if ((rc = ensure(ctx, ctx->scan_sums, (size_t)std::max<uint32_t>(ntiles, 1) * 4))) return rc;
+  if (ntiles == 0) { if (total_dev) CK(cudaMemsetAsync(total_dev, 0, 4, ctx->stream)); return SMR_OK; }
+  scan_tile_sums_kernel<<<ntiles, kScanThreads, 0, ctx->stream>>>(in, n, (uint32_t*)ctx->scan_sums.p);
+  scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>((uint32_t*)ctx->scan_sums.p, ntiles, total_dev);
+  scan_apply_kernel<<<ntiles, kScanThreads, 0, ctx->stream>>>(in, n, (const uint32_t*)ctx->scan_sums.p, out);
+  CK(cudaGetLastError());
+  return SMR_OK;
+}
+
+// FASTA / FASTQ text -> resident batch (smr_decode.cuh)
+int upload_fastx_impl(smr_ctx* ctx, const char* text, uint64_t nbytes, uint32_t* nreads_out) {
+  *nreads_out = 0;
+  ctx->nreads = 0;
+  if (nbytes == 0) return SMR_OK;
+  if (nbytes >= ((uint64_t)1 << 36)) { ctx->err = "text batch too large: split it"; return SMR_ERR_ARG; }
+  const uint32_t fmt = text[0] == '@' ? kFmtFastq : kFmtFasta;
+  if (text[0] != '@' && text[0] != '>') { ctx->err = "reads text must start with '@' (FASTQ) or '>' (FASTA)"; return SMR_ERR_ARG; }
+  cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1), e2 = get_event(ctx, 2);
+  int rc;
+  CK(cudaEventRecord(e0, ctx->stream));
+  if ((rc = ensure(ctx, ctx->d_text, nbytes + 64))) return rc;
+  CK(cudaMemcpyAsync(ctx->d_text.p, text, nbytes, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaEventRecord(e1, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));   // off32/pkoff are stack-owned
+  const uint8_t* dt = (const uint8_t*)ctx->d_text.p;
+  const uint64_t nchunks = nbytes / 32 + 1;
+  if ((rc = ensure(ctx, ctx->d_cnt, nchunks * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->d_scal, 64))) return rc;
+  uint32_t* scal = (uint32_t*)ctx->d_scal.p;   // [0] nlines [1] nrec [2] total nt [3] err [4] words [5] max_len
+  CK(cudaMemsetAsync(scal, 0, 64, ctx->stream));
+  const int grid = ctx->sm_count * 8;
+  count_newlines_kernel<<<grid, 256, 0, ctx->stream>>>(dt, nbytes, (uint32_t*)ctx->d_cnt.p, nchunks);
+  if ((rc = device_scan(ctx, (const uint32_t*)ctx->d_cnt.p, (uint32_t*)ctx->d_cnt.p, nchunks, scal + 0))) return rc;
+  uint32_t h[8];
+  CK(cudaMemcpyAsync(h, scal, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const uint32_t nlines = h[0];
+  if (nlines == 0) return SMR_OK;
+  if ((rc = ensure(ctx, ctx->d_nl, (size_t)nlines * 8))) return rc;
+  if ((rc = ensure(ctx, ctx->d_hdr, (size_t)nlines * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->d_sb, (size_t)nlines * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->d_rec, (size_t)nlines * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->d_spos, (size_t)nlines * 4))) return rc;
+  write_newlines_kernel<<<grid, 256, 0, ctx->stream>>>(dt, nbytes, (const uint32_t*)ctx->d_cnt.p, nchunks, (uint64_t*)ctx->d_nl.p);
+  line_info_kernel<<<grid, 256, 0, ctx->stream>>>(dt, (const uint64_t*)ctx->d_nl.p, nlines, fmt, (uint32_t*)ctx->d_hdr.p, (uint32_t*)ctx->d_sb.p, scal + 3);
+  if ((rc = device_scan(ctx, (const uint32_t*)ctx->d_hdr.p, (uint32_t*)ctx->d_rec.p, nlines, scal + 1))) return rc;
+  if ((rc = device_scan(ctx, (const uint32_t*)ctx->d_sb.p, (uint32_t*)ctx->d_spos.p, nlines, scal + 2))) return rc;
+  CK(cudaMemcpyAsync(h, scal, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const uint32_t nreads = h[1], total = h[2], err = h[3];
+  if (err) { ctx->err = err & kDecBadHeader ? "reads text: a record does not start with its header character" : "reads text: FASTQ separator line '+' missing"; return SMR_ERR_ARG; }
+  if (total >= 0xF0000000u) { ctx->err = "batch larger than 2^32 nucleotides: split it"; return SMR_ERR_ARG; }
+  if (nreads == 0) return SMR_OK;
+  if ((rc = ensure(ctx, ctx->seq04, (size_t)total + 64))) return rc;
+  if ((rc = ensure(ctx, ctx->seq_off, (size_t)(nreads + 1) * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->pk_off, (size_t)(nreads + 1) * 4))) return rc;
+  if ((rc = ensure(ctx, ctx->d_hdroff, (size_t)nreads * 8))) return rc;
+  scatter_lines_kernel<<<grid, 256, 0, ctx->stream>>>(dt, (const uint64_t*)ctx->d_nl.p, nlines, (const uint32_t*)ctx->d_hdr.p, (const uint32_t*)ctx->d_rec.p,
+                                                       (const uint32_t*)ctx->d_sb.p, (const uint32_t*)ctx->d_spos.p, (uint8_t*)ctx->seq04.p,
+                                                       (uint32_t*)ctx->seq_off.p, (uint64_t*)ctx->d_hdroff.p);
+  CK(cudaMemcpyAsync((uint32_t*)ctx->seq_off.p + nreads, scal + 2, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  // packed-word offsets and the longest read (what upload_batch_impl computes on the host)
+  if ((rc = ensure(ctx, ctx->d_cnt, (size_t)(nreads + 1) * 4))) return rc;
+  record_words_kernel<<<grid, 256, 0, ctx->stream>>>((const uint32_t*)ctx->seq_off.p, nreads, (uint32_t*)ctx->d_cnt.p, scal + 5);
+  if ((rc = device_scan(ctx, (const uint32_t*)ctx->d_cnt.p, (uint32_t*)ctx->pk_off.p, (uint64_t)nreads + 1, scal + 4))) return rc;
+  ctx->off32.resize((size_t)nreads + 1);
+  if ((rc = ensure_pinned(ctx, ctx->h_off32, (size_t)(nreads + 1) * 4))) return rc;
+  CK(cudaMemcpyAsync(ctx->h_off32.p, ctx->seq_off.p, (size_t)(nreads + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h, scal, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaEventRecord(e2, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(ctx->off32.data(), ctx->h_off32.p, (size_t)(nreads + 1) * 4);
+  ctx->nreads = nreads; ctx->total_nt = total; ctx->max_len = h[5];
+  ctx->h_seq.clear(); ctx->h_off.clear(); ctx->device_only_reads = true;
+  if ((rc = finish_upload(ctx, nreads, h[4]))) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->t_h2d = ms;
+  cudaEventElapsedTime(&ms, e1, e2); ctx->t_decode = ms;
+  *nreads_out = nreads;
   return SMR_OK;
 }
 
@@ -530,7 +632,8 @@ void smr_destroy(smr_ctx* ctx) {
   for (auto& pt : ctx->parts) for (void* p : pt.owned) cudaFree(p);
   DevBuf* bufs[] = {&ctx->seq04, &ctx->seq_off, &ctx->pk03, &ctx->pk03alt, &ctx->pk_off, &ctx->has_n, &ctx->hit_cnt, &ctx->flags, &ctx->state,
                     &ctx->hit_db, &ctx->aln_work, &ctx->out_aln, &ctx->hits, &ctx->cost, &ctx->bins, &ctx->scalars, &ctx->counters, &ctx->cigar_pool,
-                    &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs, &ctx->aln_stats};
+                    &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs, &ctx->aln_stats,
+                    &ctx->d_text, &ctx->d_cnt, &ctx->d_scal, &ctx->d_nl, &ctx->d_hdr, &ctx->d_sb, &ctx->d_rec, &ctx->d_spos, &ctx->d_hdroff, &ctx->scan_sums};
   for (DevBuf* b : bufs) release(*b);
   PinBuf* pins[] = {&ctx->h_state, &ctx->h_flags, &ctx->h_hitdb, &ctx->h_outaln, &ctx->h_stats, &ctx->h_cigar, &ctx->h_off32, &ctx->h_pkoff};
   for (PinBuf* b : pins) release(*b);
@@ -629,6 +732,29 @@ int smr_upload_batch(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_o
   return upload_batch_impl(ctx, seq_cat, seq_off, nreads, true);
 }
 
+int smr_upload_fastx(smr_ctx* ctx, const char* text, uint64_t nbytes, uint32_t* nreads) {
+  if (!ctx || (!text && nbytes) || !nreads) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ctx->scale = 1;
+  return upload_fastx_impl(ctx, text, nbytes, nreads);
+}
+
+int smr_resident_layout(smr_ctx* ctx, uint64_t* header_text_off, uint64_t* read_off, uint8_t* seq04, uint64_t seq_cap) {
+  if (!ctx) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const uint32_t n = ctx->nreads;
+  if (read_off) for (uint32_t r = 0; r <= n; ++r) read_off[r] = n ? ctx->off32[r] : 0;
+  if (header_text_off && n) {
+    if (!ctx->device_only_reads) { ctx->err = "the resident batch was not uploaded as text"; return SMR_ERR_ARG; }
+    CK(cudaMemcpy(header_text_off, ctx->d_hdroff.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  }
+  if (seq04 && n) {
+    if (seq_cap < ctx->total_nt) { ctx->err = "sequence buffer too small"; return SMR_ERR_CAPACITY; }
+    CK(cudaMemcpy(seq04, ctx->seq04.p, ctx->total_nt, cudaMemcpyDeviceToHost));
+  }
+  return SMR_OK;
+}
+
 int smr_run_resident(smr_ctx* ctx) {
   if (!ctx) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
@@ -650,6 +776,11 @@ int smr_download_results(smr_ctx* ctx, smr_read_result* results, smr_aln* alns, 
     if (getenv("SMR_VERBOSE")) fprintf(stderr, "[smr] %zu reads overflowed their scratch (resident batch): retrying with scale 8 (causes so far: lane %llu region %llu pairs %llu trace %llu cigar %llu err %llu)\n", flagged.size(),
       (unsigned long long)ctx->flag_hist[0], (unsigned long long)ctx->flag_hist[1], (unsigned long long)ctx->flag_hist[2], (unsigned long long)ctx->flag_hist[3], (unsigned long long)ctx->flag_hist[4], (unsigned long long)ctx->flag_hist[5]);
     // redo the overflowed reads from the retained host copy with larger scratch
+    if (ctx->device_only_reads) {   // decoded on the device: fetch the sequences now (only when a retry is needed)
+      ctx->h_seq.resize(ctx->total_nt);
+      CK(cudaMemcpy(ctx->h_seq.data(), ctx->seq04.p, ctx->total_nt, cudaMemcpyDeviceToHost));
+      ctx->h_off.assign(ctx->off32.begin(), ctx->off32.end());
+    }
     std::vector<uint8_t> hs; std::vector<uint64_t> ho;
     hs.swap(ctx->h_seq); ho.swap(ctx->h_off);
     std::vector<uint8_t> sseq; std::vector<uint64_t> soff(1, 0);
@@ -668,7 +799,7 @@ int smr_download_results(smr_ctx* ctx, smr_read_result* results, smr_aln* alns, 
 int smr_last_timings(const smr_ctx* ctx, double out[8]) {
   if (!ctx || !out) return SMR_ERR_ARG;
   out[0] = ctx->t_total; out[1] = ctx->t_seed; out[2] = ctx->t_lis; out[3] = ctx->t_final; out[4] = ctx->t_h2d; out[5] = ctx->t_d2h;
-  out[6] = (double)ctx->n_launch; out[7] = 0;
+  out[6] = (double)ctx->n_launch; out[7] = ctx->t_decode;
   return SMR_OK;
 }
 
