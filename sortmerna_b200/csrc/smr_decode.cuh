@@ -104,10 +104,21 @@ __global__ void count_newlines_kernel(const uint8_t* __restrict__ text, uint64_t
 __global__ void write_newlines_kernel(const uint8_t* __restrict__ text, uint64_t n, const uint32_t* __restrict__ first, uint64_t nchunks,
                                       uint64_t* __restrict__ nl_pos) {
   for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t b0 = c * 32, b1 = b0 + 32 < n ? b0 + 32 : n;
+    const uint64_t b0 = c * 32;
     uint32_t k = first[c];
-    for (uint64_t i = b0; i < b1; ++i) if (text[i] == '\n') nl_pos[k++] = i;
-    if (b0 + 32 > n && n > 0 && text[n - 1] != '\n') nl_pos[k] = n;
+    if (b0 + 32 <= n) {
+      const uint4 a = __ldg((const uint4*)(text + b0)), b = __ldg((const uint4*)(text + b0 + 16));
+      const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t x = w[i] ^ 0x0A0A0A0Au;
+        uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 in every byte that is '\n'
+        while (z) { const uint32_t bit = __ffs(z) - 1; z &= z - 1; nl_pos[k++] = b0 + 4 * i + (bit >> 3); }
+      }
+    } else {
+      for (uint64_t i = b0; i < n; ++i) if (text[i] == '\n') nl_pos[k++] = i;
+      if (n > 0 && text[n - 1] != '\n') nl_pos[k] = n;
+    }
   }
 }
 
