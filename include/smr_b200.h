@@ -75,6 +75,16 @@ typedef struct {
 int smr_build_index(const char* fasta_path, const char* out_prefix, uint32_t lnwin, uint32_t interval, uint32_t max_pos,
                     double max_mb, uint32_t threads, uint64_t* report6, char* err, size_t err_cap);
 
+/* KVDB blob writer (host code): for every read of a batch the byte string Read::toBinString() would store
+ * under its id (src/sortmerna/read.cpp:429-462; alignment_struct2::toString read.cpp:79-101; s_align2::toString
+ * include/ssw.hpp:106-140), written straight from the result buffers, so Read::load_db (read.cpp:467-539) reads back what the
+ * CPU path would have stored.  Reads without a stored alignment get an empty blob (read.cpp:431-432).
+ * num_alignments = opts.num_alignments; denovo4 (optional) = per read {c_yid_ycov, n_yid_ncov, n_nid_ycov, n_denovo}
+ * (zero while aligning; set by denovo_stats).  blob_off[0..nreads] receives the offsets; call with out == nullptr to size. */
+int smr_pack_kvdb_blobs(const smr_read_result* results, const smr_aln* alns, const uint32_t* cigar_pool, uint32_t nreads,
+                        uint32_t slots, int32_t num_alignments, const uint32_t* denovo4, uint8_t* out, uint64_t out_cap,
+                        uint64_t* blob_off);
+
 /* Report-side arithmetic of one stored alignment = Read::calc_miss_gap_match (src/sortmerna/read.cpp:547-589), computed on the
  * GPU from the CIGAR it has just produced: what %id / %cov / NM:i / BLAST columns 3,5,6 are derived from. */
 typedef struct {

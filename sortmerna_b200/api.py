@@ -25,7 +25,7 @@ STATUS = {0: "SMR_OK", 1: "SMR_ERR_CUDA", 2: "SMR_ERR_ARG", 3: "SMR_ERR_INDEX", 
 SYMBOLS = ["smr_init", "smr_destroy", "smr_last_error", "smr_device_count", "smr_load_index_part",
            "smr_set_minimal_score", "smr_set_params", "smr_index_info", "smr_align_batch", "smr_upload_batch",
            "smr_run_resident", "smr_download_results", "smr_last_timings", "smr_debug_seed_windows", "smr_debug_ssw",
-           "smr_debug_dpx_peak", "smr_set_stats_buffer", "smr_build_index", "smr_upload_fastx", "smr_resident_layout"]
+           "smr_debug_dpx_peak", "smr_set_stats_buffer", "smr_build_index", "smr_upload_fastx", "smr_resident_layout", "smr_pack_kvdb_blobs"]
 
 CNT_NAMES = ("num_aligned", "num_short", "sw_calls", "sw_cells", "windows", "trie_nodes", "buckets",
              "bucket_entries", "pos_entries", "lis_calls", "dbg_max_read_cycles", "dbg_sum_read_cycles", "dbg_lis_kernel_cycles",
@@ -98,6 +98,26 @@ def build_index(fasta: str, out_prefix: str, lnwin: int = 18, interval: int = 1,
     if rc != 0:
         raise SmrError(f"smr_build_index({fasta}): {err.value.decode(errors='replace')}")
     return dict(zip(("parts", "numseq", "windows", "unique_lmers", "trie_nodes", "bytes_written"), (int(x) for x in rep)))
+
+
+def pack_kvdb_blobs(out: dict, num_alignments: int, denovo: np.ndarray | None = None):
+    """smr_pack_kvdb_blobs: Read::toBinString() of every read of a result dict (align() / download() / the oracle's), as
+    (blob bytes, offsets[nreads+1]).  denovo: optional (nreads, 4) uint32 counters of hostio.denovo_classes."""
+    L = load_library()
+    res, alns, cig, slots = out["res"], out["alns"], np.ascontiguousarray(out["cigar"], np.uint32), int(out["slots"])
+    n = res.shape[0]
+    off = np.zeros(n + 1, np.uint64)
+    dn = np.ascontiguousarray(denovo, np.uint32) if denovo is not None else None
+    args = [_ptr(res), _ptr(alns), _ptr(cig) if cig.size else C.c_void_p(0), C.c_uint32(n), C.c_uint32(slots), C.c_int32(num_alignments),
+            _ptr(dn) if dn is not None else C.c_void_p(0)]
+    rc = L.smr_pack_kvdb_blobs(*args, C.c_void_p(0), C.c_uint64(0), _ptr(off))
+    if rc != 0:
+        raise SmrError(f"smr_pack_kvdb_blobs: {STATUS.get(rc, rc)}")
+    buf = np.zeros(int(off[n]), np.uint8)
+    rc = L.smr_pack_kvdb_blobs(*args, _ptr(buf) if buf.size else C.c_void_p(0), C.c_uint64(buf.size), _ptr(off))
+    if rc != 0:
+        raise SmrError(f"smr_pack_kvdb_blobs: {STATUS.get(rc, rc)}")
+    return buf, off
 
 
 class SmrError(RuntimeError):
