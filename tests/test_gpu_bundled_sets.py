@@ -74,3 +74,24 @@ def test_set2_amplicon_vs_bac16s_id85():
     assert (log["passing"], log["failing"]) == (99999, 1)            # scripts/t3.jinja:30-32
     assert int(got["res"]["is_hit"].sum()) == 99999
     assert sorted(rows) == sorted(sam)
+
+
+def test_bench_workload_sample_vs_reference():
+    """The synthetic workload bench.py measures (BASELINE configs 3/5: 150 nt reads at 1 % / 10 % error + random, vs the 8
+    databases): 20,000 reads from bench.gen_reads through the GPU path and through the unmodified reference ON THE SAME BOX --
+    every SAM row and the pass/fail totals identical."""
+    import bench
+    from oracle import ora
+    from tools import stage_data
+    fastas = [stage_data.db_path(n) for n in stage_data.DBS]
+    _need(*fastas)
+    refs = [hostio.load_references(f) for f in fastas]
+    reads = bench.gen_reads(bench.DbPool(refs), 20000, bench.GEN_SEED + 4242)
+    with tempfile.TemporaryDirectory(prefix="smr_wl_") as d:
+        fq = os.path.join(d, "wl.fq")
+        bench.write_fastq(fq, reads)
+        log, sam, rows, got, batch = _run_case(fastas, os.path.join(CACHE, "idx"), [fq], [], threads=os.cpu_count() or 8)
+    assert log["passing"] + log["failing"] == 20000
+    assert int(got["res"]["is_hit"].sum()) == log["passing"]
+    assert 0.5 < log["passing"] / 20000 < 0.8          # two thirds of the workload derive from the databases
+    assert sorted(rows) == sorted(sam)
