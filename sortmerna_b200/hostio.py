@@ -127,6 +127,23 @@ def load_references(path: str) -> References:
     return References(path, [seq_id(x) for x in h], encode_nt(b"".join(s)), off)
 
 
+def split_by_parts(refs: "References", stats: "IndexStats") -> list:
+    """The references of each index part (References::load reads [start_part, start_part + seq_part_size) of the FASTA,
+    references.cpp:55-154): `ref_num` of an alignment is relative to its part."""
+    out, first = [], 0
+    for (_, _, nseq) in stats.parts:
+        off = refs.off[first:first + nseq + 1]
+        out.append(References(refs.path, refs.ids[first:first + nseq], refs.cat[int(off[0]):int(off[-1])], (off - off[0]).astype(np.uint64)))
+        first += nseq
+    return out
+
+
+def _refs_of(refs_by_index, al):
+    """refs_by_index[index_num] is a References (single-part index) or the list split_by_parts returns"""
+    refs = refs_by_index[int(al["index_num"])]
+    return refs[int(al["part"])] if isinstance(refs, (list, tuple)) else refs
+
+
 @dataclass
 class IndexStats:
     """Contents of <prefix>.stats (refstats.cpp:129-190; writer indexdb.cpp:2020-2080)."""
@@ -227,7 +244,7 @@ def format_blast_rows(batch: "ReadBatch", refs_by_index: list, results, alns, ci
             end_mask = rlen - int(al["read_end1"]) - 1
             if end_mask > 0:
                 cs += f"{end_mask}S"
-            refs = refs_by_index[idx]
+            refs = _refs_of(refs_by_index, al)
             rows.append("\t".join([name, refs.ids[int(al["ref_num"])], _g3(pid * 100), str(int(al["read_end1"]) - int(al["read_begin1"]) + 1),
                                    str(miss), str(gap), str(int(al["read_begin1"]) + 1), str(int(al["read_end1"]) + 1),
                                    str(int(al["ref_begin1"]) + 1), str(int(al["ref_end1"]) + 1), _g3(evalue), str(bitscore), cs,
@@ -242,7 +259,7 @@ def host_aln_stats(batch: "ReadBatch", refs_by_index: list, results, alns, cigar
         enc = batch.cat[int(batch.off[r]):int(batch.off[r + 1])]
         for a in range(int(results["n_align"][r])):
             al = alns[r * slots + a]
-            refs = refs_by_index[int(al["index_num"])]
+            refs = _refs_of(refs_by_index, al)
             e04 = enc if bool(al["strand"]) else np.where(enc < 4, 3 - enc, 4)[::-1]
             rseq = refs.cat[int(refs.off[int(al["ref_num"])]):int(refs.off[int(al["ref_num"]) + 1])]
             cig = cigar_pool[int(al["cigar_off"]):int(al["cigar_off"]) + int(al["cigar_len"])]
@@ -325,7 +342,7 @@ def format_sam_rows(batch: ReadBatch, refs_by_index: list, results, alns, cigar_
         name = seq_id(batch.headers[r])
         for a in range(na):
             al = alns[r * slots + a]
-            refs = refs_by_index[int(al["index_num"])]
+            refs = _refs_of(refs_by_index, al)
             cig = cigar_pool[int(al["cigar_off"]):int(al["cigar_off"]) + int(al["cigar_len"])]
             strand = bool(al["strand"])
             cs = ""

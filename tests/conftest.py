@@ -54,8 +54,28 @@ def load_denovo():
         return json.load(f)
 
 
+MULTIPART_CASES = ("parts",)   # golden cases whose index LAYOUT differs (tests/golden/make_golden.py EXTRA_INDEX_CASES)
+
+
 def case_names():
-    return sorted(d[5:] for d in os.listdir(GOLDEN) if d.startswith("case_"))
+    return sorted(d[5:] for d in os.listdir(GOLDEN) if d.startswith("case_") and d[5:] not in MULTIPART_CASES)
+
+
+@pytest.fixture(scope="session")
+def golden_parts():
+    """The two golden database slices indexed in 3 parts each (smr_build_index with -m 0.5, proven equal to the reference's
+    builder in tests/test_index_builder.py), with the per-part references."""
+    from sortmerna_b200 import api, hostio
+    d = tempfile.mkdtemp(prefix="smr_idx_parts_")
+    out = []
+    for name in ("db_arc.fasta", "db_bac.fasta"):
+        fasta = os.path.join(GOLDEN, name)
+        prefix = os.path.join(d, name)
+        api.build_index(fasta, prefix, max_mb=0.5)
+        st = hostio.parse_stats(prefix)
+        out.append(dict(prefix=prefix, stats=st, part_refs=hostio.split_by_parts(hostio.load_references(fasta), st)))
+    yield out
+    shutil.rmtree(d, ignore_errors=True)
 
 
 @pytest.fixture(scope="session")

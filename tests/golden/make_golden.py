@@ -45,6 +45,28 @@ CASES = {
     "edges_pct": ["-edges", "10%"],
     "seeds3": ["-num_seeds", "3"],
 }
+# index-build options that change the index LAYOUT (not the alignment parameters): the reference builds its own index for these
+EXTRA_INDEX_CASES = {
+    # 9.5e-6 "MB" per window (indexdb.cpp:1381): both database slices split into 3 index parts -- the per-part loop of align()
+    # (processor.cpp:196-262), part-relative ref_num, Read::best re-initialised per part
+    "parts": ["-m", "0.5"],
+}
+
+
+def make_extra_index_cases():
+    arc_p, bac_p, reads_p = (os.path.join(HERE, f) for f in ("db_arc.fasta", "db_bac.fasta", "reads_mix.fq"))
+    tmp = tempfile.mkdtemp(prefix="smr_golden_x_")
+    for case, extra in EXTRA_INDEX_CASES.items():
+        r = ora.run_reference([arc_p, bac_p], reads_p, os.path.join(tmp, case), extra=["-sam", "-blast", "1 cigar qcov qstrand", "-fastx", "-other"] + extra, threads=1)
+        log = ora.parse_log(r["log"])
+        sam = ["\t".join(f[:9] + ["*", "*"] + f[11:]) for f in (ln.split("\t") for ln in ora.read_sam_rows(os.path.join(r["out_dir"], "aligned.sam")))]
+        blast = [ln.rstrip("\n") for ln in open(os.path.join(r["out_dir"], "aligned.blast"))]
+        nparts = [hostio.parse_stats(p).num_parts for p in hostio.find_index_prefixes(r["idx_dir"]).values()]
+        os.makedirs(os.path.join(HERE, "case_" + case), exist_ok=True)
+        with open(os.path.join(HERE, "case_" + case, "expected.json"), "w") as f:
+            json.dump(dict(args=extra, log=log, sam=sam, blast=blast, num_parts=sorted(nparts)), f, indent=0)
+        print(case, "passing", log["passing"], "sam rows", len(sam), "parts", nparts)
+    shutil.rmtree(tmp, ignore_errors=True)
 
 
 def take_fasta(src, dst, nseq, skip=0, min_len=0):
@@ -202,6 +224,8 @@ def make_denovo():
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "denovo":
         return make_denovo()
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        return make_extra_index_cases()
     if not ora.have_reference_binary():
         sys.exit("oracle/_ref/sortmerna_ref missing: make -C oracle -f Makefile.ref")
     rng = np.random.default_rng(SEED)
@@ -245,6 +269,7 @@ def main():
                 fo.write(fi.read())
     make_t0(tmp)
     make_denovo()
+    make_extra_index_cases()
     shutil.rmtree(tmp, ignore_errors=True)
     print("sizes:", {fn: os.path.getsize(os.path.join(idx_dir, fn)) for fn in os.listdir(idx_dir)})
 

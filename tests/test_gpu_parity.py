@@ -170,6 +170,31 @@ def test_denovo_classification_on_gpu(aligner, golden, case):
     aligner.set_params(api.default_params())
 
 
+def test_multipart_index(golden, golden_parts):
+    """3 index parts per database resident at once: identical per-read state / alignments to the oracle's per-part loop and
+    identical SAM rows to the reference's `-m 0.5` run (tests/golden/case_parts)."""
+    ora = _ora()
+    exp = load_case("parts")
+    al = api.Aligner(0)
+    al.set_params(api.default_params())
+    oix, inum, parts, refs, ms = [], [], [], [], []
+    for k, g in enumerate(golden_parts):
+        for p in range(g["stats"].num_parts):
+            al.load_index_part(k, p, g["prefix"], g["part_refs"][p], exp["log"]["minimal_score"][k], (18, 9, 3), g["stats"].lnwin)
+            oix.append(ora.OracleIndex(g["prefix"], p, g["stats"].lnwin)); inum.append(k); parts.append(p)
+            refs.append(g["part_refs"][p]); ms.append(exp["log"]["minimal_score"][k])
+    b = golden["batch"]
+    got = al.align(b.cat, b.off)
+    want = ora.align(oix, inum, parts, 2, refs, ms, [18, 9, 3] * len(oix), ora.default_params(), b, nthreads=4)
+    assert_same_results(got, want, "multipart")
+    assert got["matched"].tolist() == want["matched"].tolist()
+    by_index = [g["part_refs"] for g in golden_parts]
+    rows = strip_seq(hostio.format_sam_rows(b, by_index, got["res"], got["alns"], got["cigar"], got["slots"]))
+    assert sorted(rows) == sorted(exp["sam"])
+    assert got["counters"]["num_aligned"] == exp["log"]["passing"]
+    al.close()
+
+
 def test_resident_path_equals_host_path(aligner, golden):
     exp = load_case("default")
     for k in range(2):

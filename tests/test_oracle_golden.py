@@ -64,6 +64,29 @@ def test_denovo_classification_matches_reference(golden, oracle_indexes, case):
     assert ids == dn["denovo_reads"]
 
 
+def test_oracle_multipart_index_matches_reference(golden, golden_parts):
+    """Index split into 3 parts per database (-m 0.5): the per-part loop of align() (processor.cpp:196-262) -- part-relative
+    ref_num, Read::best re-initialised per part, stored state carried across parts -- against the reference's own run."""
+    exp = load_case("parts")
+    assert [g["stats"].num_parts for g in golden_parts] == exp["num_parts"] == [3, 3]
+    oix, inum, parts, refs, ms = [], [], [], [], []
+    for k, g in enumerate(golden_parts):
+        for p in range(g["stats"].num_parts):
+            oix.append(ora.OracleIndex(g["prefix"], p, g["stats"].lnwin)); inum.append(k); parts.append(p)
+            refs.append(g["part_refs"][p]); ms.append(exp["log"]["minimal_score"][k])
+    out = ora.align(oix, inum, parts, 2, refs, ms, [18, 9, 3] * len(oix), ora.default_params(), golden["batch"], nthreads=2)
+    by_index = [g["part_refs"] for g in golden_parts]
+    rows = strip_seq(hostio.format_sam_rows(golden["batch"], by_index, out["res"], out["alns"], out["cigar"], out["slots"]))
+    assert sorted(rows) == sorted(exp["sam"])
+    assert int(out["res"]["is_hit"].sum()) == exp["log"]["passing"]
+    st = hostio.host_aln_stats(golden["batch"], by_index, out["res"], out["alns"], out["cigar"], out["slots"])
+    b = golden["batch"]
+    tot = int(np.diff(b.off.astype(np.int64)).sum())
+    gum = list(zip(exp["log"]["lambda_"], exp["log"]["K"]))
+    evp = [hostio.evalue_params(g["stats"], k, tot, b.n) for g, (_, k) in zip(golden_parts, gum)]
+    assert_blast_rows_equal(hostio.format_blast_rows(b, by_index, out["res"], out["alns"], out["cigar"], out["slots"], st, gum, evp), exp["blast"])
+
+
 def test_oracle_thread_invariance(golden, oracle_indexes):
     _, _, a = run_oracle(golden, oracle_indexes, "default", nthreads=1)
     _, _, b = run_oracle(golden, oracle_indexes, "default", nthreads=4)
