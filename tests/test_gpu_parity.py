@@ -170,6 +170,28 @@ def test_denovo_classification_on_gpu(aligner, golden, case):
     aligner.set_params(api.default_params())
 
 
+def test_batch_of_several_chunks(golden, monkeypatch):
+    """A batch larger than the per-launch chunk (1 M reads in production; 200 here via SMR_CHUNK_READS): the chunk loop of
+    run_impl must give the results of the single-chunk run."""
+    exp = load_case("best3")
+    b = golden["batch"]
+
+    def run():
+        al = api.Aligner(0)
+        al.set_params(api.default_params(num_alignments=3))
+        for k in range(2):
+            al.load_index_part(k, 0, golden["prefixes"][k], golden["refs"][k], exp["log"]["minimal_score"][k], (18, 9, 3), golden["stats"][k].lnwin)
+        out = al.align(b.cat, b.off, with_stats=True)
+        al.close()
+        return out
+
+    one = run()
+    monkeypatch.setenv("SMR_CHUNK_READS", "200")
+    many = run()
+    assert_same_results(many, one, "4 chunks vs 1")
+    assert np.array_equal(many["stats"], one["stats"]) and many["matched"].tolist() == one["matched"].tolist()
+
+
 def test_multipart_index(golden, golden_parts):
     """3 index parts per database resident at once: identical per-read state / alignments to the oracle's per-part loop and
     identical SAM rows to the reference's `-m 0.5` run (tests/golden/case_parts)."""
