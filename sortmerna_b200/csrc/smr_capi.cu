@@ -152,13 +152,10 @@ int setup_arenas(smr_ctx* ctx) {
   const size_t budget = (size_t)8 << 30;
   while (ctx->lis_warps > 64 && ctx->lis_stride * ctx->lis_warps > budget) ctx->lis_warps /= 2;
   if (int rc = ensure(ctx, ctx->lis_arena, ctx->lis_stride * ctx->lis_warps)) return rc;
-  const size_t old_cap = ctx->lis_epochs.cap;
   if (int rc = ensure(ctx, ctx->lis_epochs, (size_t)ctx->lis_warps * 4)) return rc;
-  // histogram epochs start at 0 over a zeroed histogram
-  if (ctx->lis_epochs.cap != old_cap || true) {
-    CK(cudaMemsetAsync(ctx->lis_arena.p, 0, ctx->lis_stride * ctx->lis_warps, ctx->stream));
-    CK(cudaMemsetAsync(ctx->lis_epochs.p, 0, (size_t)ctx->lis_warps * 4, ctx->stream));
-  }
+  // histogram epochs start at 0 over a zeroed histogram (every run: the arena layout depends on the scale of the run)
+  CK(cudaMemsetAsync(ctx->lis_arena.p, 0, ctx->lis_stride * ctx->lis_warps, ctx->stream));
+  CK(cudaMemsetAsync(ctx->lis_epochs.p, 0, (size_t)ctx->lis_warps * 4, ctx->stream));
   ctx->cap_w = 2 * 256 * ctx->scale + 8;          // band widths up to 256*scale
   ctx->cap_cig = 2 * (ctx->max_len + 64) + 16;
   ctx->cap_dir = (size_t)65536 * ctx->scale + (size_t)ctx->max_len * 9 * 3 + 64;
@@ -351,7 +348,7 @@ int upload_fastx_impl(smr_ctx* ctx, const char* text, uint64_t nbytes, uint32_t*
   return SMR_OK;
 }
 
-DevBatch make_batch(smr_ctx* ctx, uint32_t c0, uint32_t n, const std::vector<uint32_t>& /*unused*/) {
+DevBatch make_batch(smr_ctx* ctx, uint32_t c0, uint32_t n) {
   DevBatch b{};
   b.nreads = n; b.r0 = c0;
   b.seq04 = (const uint8_t*)ctx->seq04.p; b.seq_off = (const uint32_t*)ctx->seq_off.p;
@@ -399,7 +396,7 @@ int run_impl(smr_ctx* ctx) {
   cudaEvent_t eb = get_event(ctx, evi++); CK(cudaEventRecord(eb, ctx->stream));
   for (uint32_t c0 = 0; c0 < nreads; c0 += ctx->chunk_reads) {
     const uint32_t n = std::min(ctx->chunk_reads, nreads - c0);
-    DevBatch b = make_batch(ctx, c0, n, {});
+    DevBatch b = make_batch(ctx, c0, n);
     b.seq_base0 = ctx->off32[c0];
     CK(cudaMemsetAsync(sc.work_n, 0, 8, ctx->stream));   // (unused word) + lis_next
     CK(cudaMemsetAsync(b.cost, 0, (size_t)n * 4, ctx->stream));
@@ -786,11 +783,10 @@ int smr_download_results(smr_ctx* ctx, smr_read_result* results, smr_aln* alns, 
     hs.swap(ctx->h_seq); ho.swap(ctx->h_off);
     std::vector<uint8_t> sseq; std::vector<uint64_t> soff(1, 0);
     for (uint32_t r : flagged) { sseq.insert(sseq.end(), hs.begin() + ho[r], hs.begin() + ho[r + 1]); soff.push_back(sseq.size()); }
-    const uint32_t keep_n = ctx->nreads;
     ctx->scale = 8;
     rc = align_impl(ctx, sseq.data(), soff.data(), (uint32_t)flagged.size(), out, flagged.data(), 1);
     ctx->scale = 1;
-    (void)keep_n;   // the resident batch was replaced by the retry batch: upload again before the next smr_run_resident
+    // the resident batch was replaced by the retry batch: upload again before the next smr_run_resident
     ctx->nreads = 0;
   }
   if (cigar_used) *cigar_used = out.cigar_used;
