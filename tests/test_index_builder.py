@@ -134,3 +134,53 @@ def test_reference_binary_gives_golden_output_on_native_index():
         assert [ln.rstrip("\n") for ln in open(os.path.join(r["out_dir"], "aligned.blast"))] == exp["blast"]
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+@need_ref
+@pytest.mark.parametrize("seed", range(12))
+def test_native_index_fuzz_against_reference_builder(checker, seed):
+    """Random FASTA files (IUPAC / lower-case / odd letters, wrapped lines, blanks inside lines, repeats that fill buckets past
+    the burst threshold, sequences of the minimum length 19, tabs and blanks in headers) and random build options:
+    smr_build_index == the reference's builder up to the id numbering."""
+    import numpy as np
+    rng = np.random.default_rng(1000 + seed)
+    d = tempfile.mkdtemp(prefix="smr_bi_fz_")
+    try:
+        alpha = list("ACGT" * 12 + "NRYKMSWBDHVXacgtnu")
+        nseq = int(rng.integers(1, 40))
+        base = "".join(rng.choice(list("ACGT"), 400))
+        recs = []
+        for i in range(nseq):
+            kind = rng.integers(0, 4)
+            if kind == 0:
+                s = "".join(rng.choice(alpha, int(rng.integers(19, 600))))
+            elif kind == 1:   # near copies: many 19-mers share 9-mer prefixes -> buckets burst
+                s = list(base[int(rng.integers(0, 50)):])
+                for _ in range(int(rng.integers(0, 30))):
+                    s[int(rng.integers(len(s)))] = "ACGT"[int(rng.integers(4))]
+                s = "".join(s)
+            elif kind == 2:   # low complexity
+                s = ("ACGT"[int(rng.integers(4))] * int(rng.integers(19, 200))) + "".join(rng.choice(list("AC"), int(rng.integers(0, 100))))
+            else:
+                s = "".join(rng.choice(list("ACGT"), 19))
+            recs.append((f">s{i}\tdesc {i} x", s))
+        wrap = int(rng.choice([0, 60, 7]))
+        fasta = os.path.join(d, f"fz{seed}.fasta")
+        with open(fasta, "w") as f:
+            for h, s in recs:
+                f.write(h + "\n")
+                if wrap:
+                    f.write("\n".join(s[k:k + wrap] for k in range(0, len(s), wrap)) + "\n")
+                else:
+                    f.write(s + "\n")
+        opt = [dict(), dict(max_pos=2), dict(interval=3), dict(max_mb=0.002), dict(max_pos=0, interval=2)][int(rng.integers(5))]
+        ref_extra = []
+        for k, flag in (("max_pos", "-max_pos"), ("interval", "-interval"), ("max_mb", "-m")):
+            if k in opt:
+                ref_extra += [flag, str(opt[k])]
+        os.makedirs(os.path.join(d, "ref"))
+        ref_prefix = reference_build(fasta, os.path.join(d, "ref"), ref_extra)
+        api.build_index(fasta, os.path.join(d, "x"), threads=int(rng.integers(1, 4)), **opt)
+        equiv(checker, ref_prefix, os.path.join(d, "x"))
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
