@@ -16,7 +16,7 @@ REF_BIN = os.path.join(ROOT, "oracle", "_ref", "sortmerna_ref")
 
 
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/sortmerna_ref not built")
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("SMR_FUZZ_SEEDS", "12"))))
 def test_oracle_equals_reference_on_random_cases(seed):
     from oracle import ora
     d = tempfile.mkdtemp(prefix="smr_fz_")
@@ -27,6 +27,8 @@ def test_oracle_equals_reference_on_random_cases(seed):
         except RuntimeError as e:
             if "Sls::error" in str(e) or "ALP" in str(e):
                 pytest.skip("scoring set outside the reference's Gumbel tables")
+            if "[validate:" in str(e):
+                pytest.skip("option combination refused by the reference's own validation")
             raise
         log = ora.parse_log(r["log"])
         sam = strip_seq(ora.read_sam_rows(os.path.join(r["out_dir"], "aligned.sam")))
