@@ -1,0 +1,59 @@
+"""The reference-side binding (integration/align_gpu.cpp): the UNMODIFIED reference host program -- CLI, Readfeed, Refstats,
+KVDB, summary, report writers -- linked with the binding in place of its align() must write the files the reference writes:
+aligned.sam, aligned.blast, aligned.fq, other.fq byte for byte, aligned.log apart from time stamps.
+On a box without a GPU the C ABI behind the binding is the oracle-backed stand-in oracle/capi_oracle_mock.cpp (TEST ONLY), which
+checks the binding itself (feed order incl. paired files, KVDB keys / blobs, counters, index and reference hand-over);
+tests/test_gpu_integration.py runs the same comparison with the product library on the GPU."""
+import os
+import shutil
+import tempfile
+
+import pytest
+
+from conftest import GOLDEN
+from integration_common import REF_DIR, assert_same_outputs, run_host
+from sortmerna_b200 import hostio
+
+need = pytest.mark.skipif(not (os.path.exists(os.path.join(REF_DIR, "sortmerna_ref")) and os.path.exists(os.path.join(REF_DIR, "sortmerna_gpu_mock"))),
+                          reason="oracle/_ref host binaries not built (oracle/Makefile.ref)")
+REPORTS = ["-sam", "-blast", "1 cigar qcov qstrand", "-fastx", "-other"]
+
+
+@need
+@pytest.mark.parametrize("extra", [[], ["-num_alignments", "3"], ["-no-best", "-num_alignments", "2"], ["-F"], ["-otu_map", "-de_novo_otu", "-id", "0.97", "-coverage", "0.97"]],
+                         ids=["default", "best3", "nobest2", "fwd", "denovo"])
+def test_host_program_with_binding_writes_reference_outputs(extra):
+    d = tempfile.mkdtemp(prefix="smr_integ_")
+    try:
+        reads = [os.path.join(GOLDEN, "reads_mix.fq")]
+        ref, _ = run_host("sortmerna_ref", os.path.join(d, "ref"), reads, REPORTS + extra)
+        got, log = run_host("sortmerna_gpu_mock", os.path.join(d, "got"), reads, REPORTS + extra)
+        assert "Starting alignment (libsmr_b200)" in log
+        assert_same_outputs(got, ref)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+@need
+@pytest.mark.parametrize("threads", [1, 4])
+def test_paired_files(threads):
+    """Two reads files (paired, -paired_in): the binding follows the reference's alternating feed order (processor.cpp:104-160).
+    Inputs avoid the reference's file-switch quirk (see integration/align_gpu.cpp): no read shorter than the seed and
+    -num_alignments 3, so that no read is is_done before the second index pass."""
+    d = tempfile.mkdtemp(prefix="smr_integ_")
+    try:
+        h, s, q = hostio.read_fastx(os.path.join(GOLDEN, "reads_mix.fq"))
+        keep = [i for i in range(len(h)) if len(s[i]) >= 18][:600]
+        paths = []
+        for k in (0, 1):
+            p = os.path.join(d, f"r{k + 1}.fq")
+            with open(p, "w") as f:
+                for i in keep[k * 300:k * 300 + 300]:
+                    f.write(f"{h[i]}\n{s[i].decode()}\n+\n{q[i].decode()}\n")
+            paths.append(p)
+        extra = REPORTS + ["-paired_in", "-num_alignments", "3"]
+        ref, _ = run_host("sortmerna_ref", os.path.join(d, "ref"), paths, extra, threads=threads)
+        got, _ = run_host("sortmerna_gpu_mock", os.path.join(d, "got"), paths, extra, threads=threads)
+        assert_same_outputs(got, ref)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
