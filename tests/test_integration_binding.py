@@ -20,8 +20,9 @@ REPORTS = ["-sam", "-blast", "1 cigar qcov qstrand", "-fastx", "-other"]
 
 
 @need
-@pytest.mark.parametrize("extra", [[], ["-num_alignments", "3"], ["-no-best", "-num_alignments", "2"], ["-F"], ["-otu_map", "-de_novo_otu", "-id", "0.97", "-coverage", "0.97"]],
-                         ids=["default", "best3", "nobest2", "fwd", "denovo"])
+@pytest.mark.parametrize("extra", [[], ["-num_alignments", "3"], ["-no-best", "-num_alignments", "2"], ["-F"], ["-otu_map", "-de_novo_otu", "-id", "0.97", "-coverage", "0.97"],
+                                   ["-m", "0.5"], ["-match", "2", "-mismatch", "-4", "-gap_open", "6", "-gap_ext", "3", "-N", "-2", "-edges", "10%"]],
+                         ids=["default", "best3", "nobest2", "fwd", "denovo", "parts", "scores_edges"])
 def test_host_program_with_binding_writes_reference_outputs(extra):
     d = tempfile.mkdtemp(prefix="smr_integ_")
     try:
