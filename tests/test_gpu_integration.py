@@ -27,3 +27,11 @@ def test_reference_host_with_gpu_library(extra):
         assert_same_outputs(got, ref)
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_reference_t9_golden_sam_rows_on_gpu():
+    """scripts/test.jinja t9 (exact SAM rows, forward + reverse-complement reference) through the drop-in host program"""
+    from test_integration_binding import T9_ROWS, run_t9
+    if not os.path.exists(os.path.join(REF_DIR, "sortmerna_gpu")):
+        pytest.skip("oracle/_ref/sortmerna_gpu not built")
+    assert run_t9("sortmerna_gpu") == T9_ROWS

@@ -58,3 +58,34 @@ def test_paired_files(threads):
         assert_same_outputs(got, ref)
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+T9_ROWS = [   # scripts/test.jinja:447-476 (t9 "test_output_all_alignments_f_rc"): the reference's own golden SAM rows
+    ["GQ099317.1.1325_157_453_0:0:0_0:0:0_99/1", "0", "GQ099317.1.1325_157_453_0:0:0_0:0:0_99/1", "1", "255", "101M", "*", "0", "0",
+     "GCTGGCACGGAGTTAGCCGGGGCTTATAAATGGTACCGTCATTGATTCTTCCCATTCTTTCGAAGTTTACATCCCGAGGGACTTCATCCTTCACGCGGCGT", "*", "AS:i:202", "NM:i:0"],
+    ["GQ099317.1.1325_157_453_0:0:0_0:0:0_99/1", "16", "GQ099317.1.1325_157_453_0:0:0_0:0:0_99/1", "102", "255", "101M", "*", "0", "0",
+     "ACGCCGCGTGAAGGATGAAGTCCCTCGGGATGTAAACTTCGAAAGAATGGGAAGAATCAATGACGGTACCATTTATAAGCCCCGGCTAACTCCGTGCCAGC", "*", "AS:i:202", "NM:i:0"],
+]
+
+
+def run_t9(binary):
+    """the reference's t9: one read against a reference file holding a sequence and its reverse complement.  The original asks
+    for `-num_alignments 0` (all alignments), which the GPU path does not implement; `-no-best -num_alignments 2` stores the same
+    two alignments (checked against the reference binary with its original arguments in the build container)."""
+    import subprocess
+    d = tempfile.mkdtemp(prefix="smr_t9_")
+    try:
+        t9 = os.path.join(GOLDEN, "t9")
+        cmd = [os.path.join(REF_DIR, binary), "-ref", os.path.join(t9, "ref_GQ099317_forward_and_rc.fasta"), "-reads", os.path.join(t9, "illumina_GQ099317.fasta"),
+               "-no-best", "-num_alignments", "2", "-mismatch", "-3", "-sam", "-workdir", d, "-threads", "1", "-task", "4"]
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout[-2000:]
+        return [ln.rstrip("\n").split("\t") for ln in open(os.path.join(d, "out", "aligned.sam")) if not ln.startswith("@")]
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+@need
+def test_reference_t9_golden_sam_rows():
+    assert run_t9("sortmerna_gpu_mock") == T9_ROWS
+    assert run_t9("sortmerna_ref") == T9_ROWS
