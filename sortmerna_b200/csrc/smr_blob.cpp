@@ -8,6 +8,7 @@
 //   u16 max_SW_count; i32 num_alignments; u32 hit_seeds; u64 alignment_bytes;
 //   alignment = u32 min_index, max_index; u64 n; n x ( u64 bytes; u64 ncigar; u32 cigar[ncigar]; u32 ref_num;
 //               i32 ref_begin1, ref_end1, read_begin1, read_end1; u32 readlen; u16 score1, part, index_num; u8 strand )
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <thread>
