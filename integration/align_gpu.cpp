@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <fstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.hpp"
@@ -48,8 +49,13 @@ void align(Readfeed& readfeed, Readstats& readstats, Index& /*index: the library
 {
   INFO("==== Starting alignment (libsmr_b200) ====");
   if (opts.num_alignments == 0) { ERR("'-num_alignments 0' is not supported by the GPU path"); exit(EXIT_FAILURE); }
-  smr_ctx* ctx = nullptr;
-  if (smr_init(0, &ctx) != SMR_OK) { ERR("no usable CUDA device: the GPU alignment path has no CPU fallback"); exit(EXIT_FAILURE); }
+  // one context per GPU (SMR_GPUS, default 1; never more than the devices present): reads shard by record, every GPU holds the
+  // whole index, the only cross-GPU state are the Readstats counters (summed below) -- SURVEY 8(e)
+  int ngpu = 1;
+  if (const char* e = getenv("SMR_GPUS")) ngpu = std::max(1, std::min(atoi(e), smr_device_count()));
+  std::vector<smr_ctx*> ctxs((size_t)ngpu, nullptr);
+  for (int g = 0; g < ngpu; ++g)
+    if (smr_init(g, &ctxs[g]) != SMR_OK) { ERR("no usable CUDA device ", g, ": the GPU alignment path has no CPU fallback"); exit(EXIT_FAILURE); }
 
   Refstats refstats(opts, readstats);            // unchanged: .stats, Gumbel parameters, minimal_score (refstats.cpp:103-276)
   References refs;
@@ -59,9 +65,9 @@ void align(Readfeed& readfeed, Readstats& readstats, Index& /*index: the library
   p.num_alignments = (int32_t)opts.num_alignments; p.is_best = opts.is_best ? 1 : 0;
   p.is_forward = opts.is_forward ? 1 : 0; p.is_reverse = opts.is_reverse ? 1 : 0; p.is_full_search = opts.is_full_search ? 1 : 0;
   p.minoccur = (int32_t)opts.minoccur;
-  if (smr_set_params(ctx, &p) != SMR_OK) die(ctx, "smr_set_params");
+  for (smr_ctx* ctx : ctxs) if (smr_set_params(ctx, &p) != SMR_OK) die(ctx, "smr_set_params");
 
-  // every (index, part) becomes resident once (the reference loads / unloads them one at a time, processor.cpp:216-262)
+  // every (index, part) becomes resident once per GPU (the reference loads / unloads them one at a time, processor.cpp:216-262)
   for (size_t i = 0; i < opts.indexfiles.size(); ++i)
     for (uint16_t part = 0; part < refstats.num_index_parts[i]; ++part) {
       const std::string pfx = opts.indexfiles[i].second, sfx = "_" + std::to_string(part) + ".dat";
@@ -70,34 +76,52 @@ void align(Readfeed& readfeed, Readstats& readstats, Index& /*index: the library
       std::string cat; std::vector<uint64_t> off(1, 0);
       for (auto& r : refs.buffer) { cat += r.sequence; off.push_back(cat.size()); }
       const uint32_t skip[3] = {opts.skiplengths[i][0], opts.skiplengths[i][1], opts.skiplengths[i][2]};
-      if (smr_load_index_part(ctx, (uint32_t)i, part, kmer.data(), kmer.size(), trie.data(), trie.size(), pos.data(), pos.size(),
-                              (const uint8_t*)cat.data(), off.data(), (uint32_t)refs.buffer.size(), refstats.lnwin[i], refstats.minimal_score[i], skip) != SMR_OK)
-        die(ctx, "smr_load_index_part");
+      for (smr_ctx* ctx : ctxs)
+        if (smr_load_index_part(ctx, (uint32_t)i, part, kmer.data(), kmer.size(), trie.data(), trie.size(), pos.data(), pos.size(),
+                                (const uint8_t*)cat.data(), off.data(), (uint32_t)refs.buffer.size(), refstats.lnwin[i], refstats.minimal_score[i], skip) != SMR_OK)
+          die(ctx, "smr_load_index_part");
       refs.unload();
     }
 
-  // batches of reads from the unchanged Readfeed; read ids ("<file>_<n>") stay the KVDB keys
+  // batches of reads from the unchanged Readfeed; read ids ("<file>_<n>") stay the KVDB keys.  Up to one batch per GPU is in
+  // flight; results are stored in batch order.
   const uint32_t slots = (uint32_t)std::max<int32_t>(1, (int32_t)opts.num_alignments);
   const size_t nrefs = opts.indexfiles.size();
-  std::vector<std::string> ids; std::string seqcat; std::vector<uint64_t> off(1, 0);
+  uint32_t batch_reads = 1u << 20;
+  if (const char* e = getenv("SMR_BATCH_READS")) batch_reads = (uint32_t)std::max(1, atoi(e));
+  struct Batch {
+    std::vector<std::string> ids; std::string seqcat; std::vector<uint64_t> off{0};
+    std::vector<smr_read_result> res; std::vector<smr_aln> alns; std::vector<uint32_t> cigars; uint64_t used = 0; std::vector<uint64_t> cnt;
+    std::string blobs; std::vector<uint64_t> boff;
+  };
+  std::vector<Batch> pending;
+  pending.emplace_back();
   std::vector<uint64_t> total(SMR_CNT_FIXED + nrefs, 0);
-  auto flush = [&]() {
-    const uint32_t n = (uint32_t)ids.size();
-    if (n == 0) return;
-    std::vector<smr_read_result> res(n); std::vector<smr_aln> alns((size_t)n * slots);
-    std::vector<uint32_t> cigars((size_t)64 * n * slots + 4096); uint64_t used = 0;
-    std::vector<uint64_t> cnt(SMR_CNT_FIXED + nrefs, 0);
-    if (smr_align_batch(ctx, (const uint8_t*)seqcat.data(), off.data(), n, res.data(), alns.data(), cigars.data(), cigars.size(), &used,
-                        cnt.data(), (uint32_t)cnt.size()) != SMR_OK) die(ctx, "smr_align_batch");
-    std::vector<uint64_t> boff((size_t)n + 1);
-    smr_pack_kvdb_blobs(res.data(), alns.data(), cigars.data(), n, slots, (int32_t)opts.num_alignments, nullptr, nullptr, 0, boff.data());
-    std::string blobs(boff[n], '\0');
-    if (smr_pack_kvdb_blobs(res.data(), alns.data(), cigars.data(), n, slots, (int32_t)opts.num_alignments, nullptr, (uint8_t*)&blobs[0], blobs.size(), boff.data()) != SMR_OK)
-      die(ctx, "smr_pack_kvdb_blobs");
-    for (uint32_t r = 0; r < n; ++r)
-      if (boff[r + 1] > boff[r]) kvdb.put(ids[r], blobs.substr(boff[r], boff[r + 1] - boff[r]));   // == kvdb.put(read.id, read.toBinString())
-    for (size_t k = 0; k < cnt.size(); ++k) total[k] += cnt[k];
-    ids.clear(); seqcat.clear(); off.assign(1, 0);
+  auto run_batch = [&](smr_ctx* ctx, Batch& b) {
+    const uint32_t n = (uint32_t)b.ids.size();
+    b.res.resize(n); b.alns.resize((size_t)n * slots); b.cigars.resize((size_t)64 * n * slots + 4096); b.cnt.assign(SMR_CNT_FIXED + nrefs, 0);
+    if (smr_align_batch(ctx, (const uint8_t*)b.seqcat.data(), b.off.data(), n, b.res.data(), b.alns.data(), b.cigars.data(), b.cigars.size(), &b.used,
+                        b.cnt.data(), (uint32_t)b.cnt.size()) != SMR_OK) die(ctx, "smr_align_batch");
+    b.boff.resize((size_t)n + 1);
+    smr_pack_kvdb_blobs(b.res.data(), b.alns.data(), b.cigars.data(), n, slots, (int32_t)opts.num_alignments, nullptr, nullptr, 0, b.boff.data());
+    b.blobs.assign(b.boff[n], '\0');
+    if (smr_pack_kvdb_blobs(b.res.data(), b.alns.data(), b.cigars.data(), n, slots, (int32_t)opts.num_alignments, nullptr, (uint8_t*)&b.blobs[0], b.blobs.size(),
+                            b.boff.data()) != SMR_OK) die(ctx, "smr_pack_kvdb_blobs");
+  };
+  auto flush = [&]() {                       // run the pending batches (one per GPU, concurrently), then store their results in order
+    if (pending.back().ids.empty()) pending.pop_back();
+    if (pending.empty()) { pending.emplace_back(); return; }
+    std::vector<std::thread> workers;
+    for (size_t k = 1; k < pending.size(); ++k) workers.emplace_back(run_batch, ctxs[k], std::ref(pending[k]));
+    run_batch(ctxs[0], pending[0]);
+    for (auto& t : workers) t.join();
+    for (Batch& b : pending) {
+      for (uint32_t r = 0; r < (uint32_t)b.ids.size(); ++r)
+        if (b.boff[r + 1] > b.boff[r]) kvdb.put(b.ids[r], b.blobs.substr(b.boff[r], b.boff[r + 1] - b.boff[r]));   // == kvdb.put(read.id, read.toBinString())
+      for (size_t k = 0; k < b.cnt.size(); ++k) total[k] += b.cnt[k];
+    }
+    pending.clear();
+    pending.emplace_back();
   };
 
   readfeed.init_reading();
@@ -108,10 +132,11 @@ void align(Readfeed& readfeed, Readstats& readstats, Index& /*index: the library
       Read read(readstr);
       read.init(opts);
       if (!read.isEmpty && read.isValid) {                         // too-short reads go along: the library counts them (num_short) and never aligns them
-        ids.push_back(read.id);
-        for (char c : read.sequence) seqcat.push_back((char)nt_table[(int)((unsigned char)c & 0x7F)]);   // 0..3, 4 = ambiguous (common.hpp:68-77)
-        off.push_back(seqcat.size());
-        if (ids.size() == (1u << 20)) flush();
+        Batch& b = pending.back();
+        b.ids.push_back(read.id);
+        for (char c : read.sequence) b.seqcat.push_back((char)nt_table[(int)((unsigned char)c & 0x7F)]);   // 0..3, 4 = ambiguous (common.hpp:68-77)
+        b.off.push_back(b.seqcat.size());
+        if (b.ids.size() == batch_reads) { if ((int)pending.size() == ngpu) flush(); else pending.emplace_back(); }
       }
       readstr.resize(0);
       // Known deviation (paired files only): the reference `continue`s past its file switch for a read it does not process in
@@ -128,7 +153,7 @@ void align(Readfeed& readfeed, Readstats& readstats, Index& /*index: the library
   readstats.num_aligned.store(total[SMR_CNT_NUM_ALIGNED], std::memory_order_relaxed);
   readstats.num_short.store(total[SMR_CNT_NUM_SHORT], std::memory_order_relaxed);
   for (size_t i = 0; i < nrefs; ++i) readstats.reads_matched_per_db[i] += total[SMR_CNT_FIXED + i];
-  smr_destroy(ctx);
+  for (smr_ctx* ctx : ctxs) smr_destroy(ctx);
   INFO("==== Done alignment (libsmr_b200) ====\n");
 
   readstats.set_is_set_aligned_id_cov();

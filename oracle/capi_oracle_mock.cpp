@@ -24,6 +24,8 @@ struct smr_ctx {
 
 extern "C" {
 
+int smr_device_count(void) { const char* e = getenv("SMR_MOCK_DEVICES"); return e ? atoi(e) : 1; }
+
 int smr_init(int, smr_ctx** out) {
   smr_ctx* c = new smr_ctx;
   char tmpl[] = "/tmp/smr_mock_XXXXXX";

@@ -60,6 +60,22 @@ def test_paired_files(threads):
         shutil.rmtree(d, ignore_errors=True)
 
 
+@need
+def test_two_gpus_small_batches(monkeypatch):
+    """SMR_GPUS=2: one context per GPU, batches dispatched concurrently, results stored in batch order, counters summed -- with
+    100-read batches so that several rounds of two batches each happen (the stand-in reports two devices)."""
+    d = tempfile.mkdtemp(prefix="smr_integ_")
+    try:
+        reads = [os.path.join(GOLDEN, "reads_mix.fq")]
+        extra = REPORTS + ["-num_alignments", "3"]
+        ref, _ = run_host("sortmerna_ref", os.path.join(d, "ref"), reads, extra)
+        monkeypatch.setenv("SMR_GPUS", "2"); monkeypatch.setenv("SMR_MOCK_DEVICES", "2"); monkeypatch.setenv("SMR_BATCH_READS", "100")
+        got, _ = run_host("sortmerna_gpu_mock", os.path.join(d, "got"), reads, extra)
+        assert_same_outputs(got, ref)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 T9_ROWS = [   # scripts/test.jinja:447-476 (t9 "test_output_all_alignments_f_rc"): the reference's own golden SAM rows
     ["GQ099317.1.1325_157_453_0:0:0_0:0:0_99/1", "0", "GQ099317.1.1325_157_453_0:0:0_0:0:0_99/1", "1", "255", "101M", "*", "0", "0",
      "GCTGGCACGGAGTTAGCCGGGGCTTATAAATGGTACCGTCATTGATTCTTCCCATTCTTTCGAAGTTTACATCCCGAGGGACTTCATCCTTCACGCGGCGT", "*", "AS:i:202", "NM:i:0"],
