@@ -43,7 +43,7 @@ struct smr_ctx {
   uint32_t n_index_files = 0;
   int sm_count = 148;
   uint32_t chunk_reads = 1u << 20;
-  uint32_t lis_ctas_per_sm = 4;   // persistent CTAs of the candidate kernel per SM (matches its __launch_bounds__)
+  uint32_t lis_ctas_per_sm = 2;   // persistent CTAs of the candidate kernel per SM (matches its __launch_bounds__)
 
   // resident batch
   uint32_t nreads = 0; uint64_t total_nt = 0; uint32_t max_len = 0;
@@ -52,7 +52,7 @@ struct smr_ctx {
   DevBuf seq04, seq_off, pk03, pk03alt, pk_off, has_n, hit_cnt, flags, state, hit_db, aln_work, out_aln;
   DevBuf hits, cost, bins, scalars, counters, cigar_pool, parts_dev;
   size_t hits_stride = 0; uint32_t cnt_stride = 0;
-  DevBuf lis_arena, lis_epochs, final_arena, lane_hits, tb_arena, tb_jobs, aln_stats;
+  DevBuf lis_arena, lis_epochs, lis_queue, lis_done, lis_rows, final_arena, lane_hits, tb_arena, tb_jobs, aln_stats;
   smr_aln_stats* host_stats = nullptr;   // optional output of the report arithmetic
   PinBuf h_state, h_flags, h_hitdb, h_outaln, h_stats, h_cigar, h_off32, h_pkoff;
   std::vector<uint64_t> h_coff;
@@ -62,7 +62,8 @@ struct smr_ctx {
   uint32_t tb_threads = 0, tb_cap_w = 0, tb_cap_cig = 0; size_t tb_cap_dir = 0, tb_stride = 0;
   uint32_t lis_warps = 0, final_warps = 0;
   size_t lis_stride = 0, final_stride = 0;
-  uint32_t hist_cap = 0, cand_cap = 0, pair_cap = 0, row_cap = 0, pall_cap = 0, cap_w = 0, cap_cig = 0; size_t cap_dir = 0;
+  uint32_t hist_cap = 0, cand_cap = 0, pair_cap = 0, row_cap = 0, pall_cap = 0, task_cap = 0, cap_w = 0, cap_cig = 0; size_t cap_dir = 0;
+  uint32_t lis_ctas = 0;
   uint32_t lane_hits_cap = 0, lane_hits_warps = 0;
   uint64_t cigar_cap_dev = 0;
   uint32_t scale = 1;         // scratch scale of the current run (1 = fast path)
@@ -131,11 +132,11 @@ cudaEvent_t get_event(smr_ctx* ctx, size_t i) {
   return ctx->ev[i];
 }
 
-// scalars block layout (u32): [0]=work_n [1]=lis work_next [2]=final work_next ; cigar_used (u64) at byte 16
-struct Scalars { uint32_t* work_n; uint32_t* lis_next; uint32_t* fin_next; unsigned long long* cigar_used; };
+// scalars block layout (u32): [0]=work_n [1]=lis work_next [2]=final work_next ; cigar_used (u64) at byte 16 ; task queue cursors at 32..
+struct Scalars { uint32_t* work_n; uint32_t* lis_next; uint32_t* fin_next; unsigned long long* cigar_used; uint32_t* q_head; uint32_t* q_tail; uint32_t* planners_done; };
 Scalars scalars_of(smr_ctx* ctx) {
   uint8_t* p = (uint8_t*)ctx->scalars.p;
-  return Scalars{(uint32_t*)p, (uint32_t*)(p + 4), (uint32_t*)(p + 8), (unsigned long long*)(p + 16)};
+  return Scalars{(uint32_t*)p, (uint32_t*)(p + 4), (uint32_t*)(p + 8), (unsigned long long*)(p + 16), (uint32_t*)(p + 128), (uint32_t*)(p + 256), (uint32_t*)(p + 384)};
 }
 
 int setup_arenas(smr_ctx* ctx) {
@@ -144,15 +145,26 @@ int setup_arenas(smr_ctx* ctx) {
   ctx->hist_cap = max_nref;
   ctx->cand_cap = std::max(64u, max_nref);
   ctx->pair_cap = pow2_ge(4096u * ctx->scale);
-  ctx->row_cap = ctx->max_len + 2 * 64 + 64;
-  ctx->lis_warps = (uint32_t)ctx->sm_count * ctx->lis_ctas_per_sm * kLisWarpsPerCta;
+  ctx->task_cap = 2 * ctx->pair_cap;
+  // SW windows are at most read length + 2 * edges columns (alignment.cpp:272-357; edges may be a percentage of the read)
+  const uint32_t edges = ctx->prm.edges_is_percent ? (uint32_t)((ctx->prm.edges / 100.0) * (double)ctx->max_len) : (uint32_t)std::max(0, ctx->prm.edges);
+  ctx->row_cap = ctx->max_len + 2 * edges + 2 * 64 + 64;
+  // planner and scorer warps wait for each other: EVERY CTA of the grid must be resident at once
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lis_kernel, kLisWarpsPerCta * 32, 0));
+  if (occ < 1) { ctx->err = "lis_kernel does not fit on an SM"; return SMR_ERR_CUDA; }
+  ctx->lis_ctas = (uint32_t)ctx->sm_count * std::min<uint32_t>(ctx->lis_ctas_per_sm, (uint32_t)occ);
+  ctx->lis_warps = ctx->lis_ctas * kPlannerWarps;   // planner warps (each owns an arena)
   ctx->pall_cap = 32768u * ctx->scale;
-  ctx->lis_stride = lis_arena_bytes(ctx->hist_cap, ctx->cand_cap, ctx->pair_cap, ctx->row_cap, ctx->pall_cap);
-  // keep the arena total under ~8 GB: fewer persistent warps for huge reference sets
+  ctx->lis_stride = lis_arena_bytes(ctx->hist_cap, ctx->cand_cap, ctx->pair_cap, ctx->task_cap, ctx->pall_cap);
+  // keep the arena total under ~8 GB: fewer persistent CTAs for huge reference sets
   const size_t budget = (size_t)8 << 30;
-  while (ctx->lis_warps > 64 && ctx->lis_stride * ctx->lis_warps > budget) ctx->lis_warps /= 2;
+  while (ctx->lis_ctas > 16 && ctx->lis_stride * ctx->lis_warps > budget) { ctx->lis_ctas /= 2; ctx->lis_warps = ctx->lis_ctas * kPlannerWarps; }
   if (int rc = ensure(ctx, ctx->lis_arena, ctx->lis_stride * ctx->lis_warps)) return rc;
   if (int rc = ensure(ctx, ctx->lis_epochs, (size_t)ctx->lis_warps * 4)) return rc;
+  if (int rc = ensure(ctx, ctx->lis_queue, (size_t)kQueueCap * sizeof(QSlot) + 64)) return rc;
+  if (int rc = ensure(ctx, ctx->lis_done, (size_t)ctx->lis_warps * 4 + 64)) return rc;
+  if (int rc = ensure(ctx, ctx->lis_rows, (size_t)ctx->lis_ctas * kScorerWarps * 2 * ctx->row_cap * 4)) return rc;
   // histogram epochs start at 0 over a zeroed histogram (every run: the arena layout depends on the scale of the run)
   CK(cudaMemsetAsync(ctx->lis_arena.p, 0, ctx->lis_stride * ctx->lis_warps, ctx->stream));
   CK(cudaMemsetAsync(ctx->lis_epochs.p, 0, (size_t)ctx->lis_warps * 4, ctx->stream));
@@ -236,7 +248,7 @@ int finish_upload(smr_ctx* ctx, uint32_t nreads, uint64_t w) {
   if ((rc = ensure(ctx, ctx->hit_db, (size_t)nreads * 2))) return rc;
   if ((rc = ensure(ctx, ctx->aln_work, (size_t)nreads * slots * sizeof(AlnWork)))) return rc;
   if ((rc = ensure(ctx, ctx->out_aln, (size_t)nreads * slots * sizeof(OutAln)))) return rc;
-  if ((rc = ensure(ctx, ctx->scalars, 64))) return rc;
+  if ((rc = ensure(ctx, ctx->scalars, 512))) return rc;
   if ((rc = ensure(ctx, ctx->counters, (size_t)(dcCount + 64) * 8))) return rc;
   CK(cudaMemsetAsync(ctx->pk03.p, 0, (size_t)(w + 4) * 4, ctx->stream));
   CK(cudaMemsetAsync(ctx->pk03alt.p, 0, (size_t)(w + 4) * 4, ctx->stream));
@@ -385,7 +397,7 @@ int run_impl(smr_ctx* ctx) {
   ctx->cigar_cap_dev = (uint64_t)nreads * slots * 24 * ctx->scale + 4096;
   if ((rc = ensure(ctx, ctx->cigar_pool, ctx->cigar_cap_dev * 4))) return rc;
   const Scalars sc = scalars_of(ctx);
-  CK(cudaMemsetAsync(ctx->scalars.p, 0, 64, ctx->stream));
+  CK(cudaMemsetAsync(ctx->scalars.p, 0, 512, ctx->stream));
   CK(cudaMemsetAsync(ctx->counters.p, 0, (size_t)(dcCount + 64) * 8, ctx->stream));
   CK(cudaMemsetAsync(ctx->state.p, 0, (size_t)nreads * sizeof(ReadState), ctx->stream));
   CK(cudaMemsetAsync(ctx->flags.p, 0, (size_t)nreads * 4, ctx->stream));
@@ -417,9 +429,14 @@ int run_impl(smr_ctx* ctx) {
       LisGlobals lg{};
       lg.arena_base = (uint8_t*)ctx->lis_arena.p; lg.arena_stride = ctx->lis_stride;
       lg.hist_cap = ctx->hist_cap; lg.cand_cap = ctx->cand_cap; lg.pair_cap = ctx->pair_cap; lg.row_cap = ctx->row_cap; lg.pall_cap = ctx->pall_cap;
+      lg.task_cap = ctx->task_cap;
       lg.epochs = (uint32_t*)ctx->lis_epochs.p; lg.aln_work = (AlnWork*)ctx->aln_work.p; lg.slots = slots; lg.work_next = sc.lis_next;
       lg.parts = (const DevIndex*)ctx->parts_dev.p; lg.nparts = (uint32_t)hp.size();
-      lis_kernel<<<ctx->lis_warps / kLisWarpsPerCta, kLisWarpsPerCta * 32, 0, ctx->stream>>>(b, dp, lg);
+      lg.ring = (QSlot*)ctx->lis_queue.p; lg.done = (uint32_t*)ctx->lis_done.p; lg.score_rows = (int32_t*)ctx->lis_rows.p;
+      lg.q_head = sc.q_head; lg.q_tail = sc.q_tail; lg.planners_done = sc.planners_done;
+      lis_reset_kernel<<<kQueueCap / 256, 256, 0, ctx->stream>>>(lg, ctx->lis_warps);
+      CK(cudaGetLastError());
+      lis_kernel<<<ctx->lis_ctas, kLisWarpsPerCta * 32, 0, ctx->stream>>>(b, dp, lg);
       CK(cudaGetLastError());
       CK(cudaEventRecord(s2, ctx->stream));
       spans.push_back({evi - 3, 0});
@@ -561,7 +578,8 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
                                   {SMR_CNT_WINDOWS, dcWindows}, {SMR_CNT_TRIE_NODES, dcNodes}, {SMR_CNT_BUCKETS, dcBuckets},
                                   {SMR_CNT_BUCKET_ENTRIES, dcEntries}, {SMR_CNT_POS_ENTRIES, dcPosEntries}, {SMR_CNT_LIS_CALLS, dcLisCalls},
                                   {10, dcMaxReadCycles}, {11, dcSumReadCycles}, {12, dcLisKernelCycles},
-                                  {13, dcCycVote}, {14, dcCycOrder}, {15, dcCycGroup}, {16, dcCycPrep}, {17, dcCycSwSetup}, {18, dcCycSwLoop}, {19, dcCycBook}};
+                                  {13, dcCycVote}, {14, dcCycOrder}, {15, dcCycGroup}, {16, dcCycPlan}, {17, dcCycWait}, {18, dcCycReplay}, {19, dcSpecCalls},
+                                  {20, dcSpecCells}, {21, dcSpecPairs}, {22, dcSlowPairs}};
     for (auto& m : mapc) if ((uint32_t)m[0] < out.n_counters) out.counters[m[0]] += cnt[m[1]];
   }
   return rc;
@@ -630,7 +648,7 @@ void smr_destroy(smr_ctx* ctx) {
   for (auto& pt : ctx->parts) for (void* p : pt.owned) cudaFree(p);
   DevBuf* bufs[] = {&ctx->seq04, &ctx->seq_off, &ctx->pk03, &ctx->pk03alt, &ctx->pk_off, &ctx->has_n, &ctx->hit_cnt, &ctx->flags, &ctx->state,
                     &ctx->hit_db, &ctx->aln_work, &ctx->out_aln, &ctx->hits, &ctx->cost, &ctx->bins, &ctx->scalars, &ctx->counters, &ctx->cigar_pool,
-                    &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs, &ctx->aln_stats,
+                    &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->lis_queue, &ctx->lis_done, &ctx->lis_rows, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs, &ctx->aln_stats,
                     &ctx->d_text, &ctx->d_cnt, &ctx->d_scal, &ctx->d_nl, &ctx->d_hdr, &ctx->d_sb, &ctx->d_rec, &ctx->d_spos, &ctx->d_hdroff, &ctx->scan_sums};
   for (DevBuf* b : bufs) release(*b);
   PinBuf* pins[] = {&ctx->h_state, &ctx->h_flags, &ctx->h_hitdb, &ctx->h_outaln, &ctx->h_stats, &ctx->h_cigar, &ctx->h_off32, &ctx->h_pkoff};

@@ -15,14 +15,56 @@
 //   * the deque `match_set` is a [front, next) index range over the sorted pairs (:205-238, 486-506);
 //   * ssw_align's reverse pass and CIGAR are deferred to the finalize kernel: accept / replace / stop
 //     decisions only need score1 (:388-469).
+//
+// Warp specialisation.  The kernel's warps have two roles:
+//   * PLANNER warps own reads.  For each compute_lis_alignment call they vote, order and group as above, then walk the
+//     candidates in the reference's order WITHOUT scoring: every (candidate, sliding-window step) that would reach
+//     ssw_align becomes a task record (window, query segment).  Which steps reach it is score-independent -- the
+//     (it, f) trajectory of the deque only depends on the pairs (:231-238, 486-506) -- except for heuristic 1 (:243-246),
+//     the `best` countdown (:165-169) and the stop rules (:462-469), which the REPLAY applies afterwards to the table of
+//     scores, in order, exactly as the reference would have.  Batches are sized so that little is scored in vain: a batch
+//     never reaches the level drop at which the countdown could stop the call, tasks behind a successful alignment of
+//     the same candidate (skipped by heuristic 1) are only submitted when their lead task failed, and batches grow
+//     geometrically so that a perfect-score stop wastes at most what was useful.
+//   * SCORER warps drain a global multi-producer/multi-consumer queue of task PAIRS and score two tasks per pass with
+//     the packed 16-bit DPX kernel (smr_sw.cuh), whoever the read belongs to: a read with thousands of candidates is
+//     scored by the whole GPU instead of by its one warp (round 1: the heaviest read occupied one warp for 310 of the
+//     376 ms), and the integer-pipe loop never waits on the memory-latency phases of voting and grouping.
 #pragma once
 #include "smr_seed.cuh"
 #include "smr_sw.cuh"
 
 namespace smr {
 
-constexpr int kLisWarpsPerCta = 4;
+constexpr int kScorerWarps = 4;    // warps 0..3 of a CTA score, one per SM sub-partition
+constexpr int kPlannerWarps = 4;   // warps 4..7 plan
+constexpr int kLisWarpsPerCta = kScorerWarps + kPlannerWarps;
 constexpr int kPairsShared = 128;  // pairs / LIS arrays kept in shared memory up to this many
+constexpr uint32_t kQueueCap = 1u << 20;         // task-pair ring (slots)
+constexpr uint32_t kNoTask = 0xFFFFFFu;
+constexpr uint32_t kPoison = 0xFFFFu;             // planner id of the shutdown entries
+constexpr uint32_t kBatchCandCap = 4096;          // candidates per batch
+
+// one Smith-Waterman call the reference would make (alignment.cpp:365-381), as the scorers see it
+struct SwTask {
+  uint32_t ref_abs;     // first window column in parts[part].refseq
+  uint32_t q_abs;       // query element 0 in seq04 (reverse strand: last base of the segment, walked backwards, complemented)
+  uint32_t alen, qlen;  // window columns, query rows
+  uint32_t meta;        // part slot | reversed << 16
+  uint32_t score;       // OUT (scorer): ssw score
+  uint32_t pad0, pad1;
+};
+// ... and as the replay sees it
+struct PlanTask {
+  uint32_t max_ref, win_start, aqs;
+  uint32_t cf;          // candidate (relative to the batch) | flags << 24
+  uint32_t lead;        // index of the unconditional task that decides whether this (conditional) one is needed
+};
+constexpr uint32_t kTfPush = 1u;     // the step pushed new pairs into the window (alignment.cpp:231-238)
+constexpr uint32_t kTfUncond = 2u;   // not skippable by heuristic 1 whatever the earlier scores are
+constexpr uint32_t kTfReset = 4u;    // a step without a task but with a push lies between the previous task and this one
+
+struct QSlot { uint32_t seq, planner, ta, tb; };   // one queue entry = up to two tasks of one planner (tb == kNoTask: one)
 
 struct LisArena {            // per-warp scratch in HBM
   uint32_t* hist;            // [hist_cap] epoch<<20 | count, indexed by reference number
@@ -34,14 +76,21 @@ struct LisArena {            // per-warp scratch in HBM
   uint32_t* summary;         // [ceil(hist_cap/1024)] non-zero words of bitmap
   unsigned long long* pairs; // [pair_cap] (power of two) refpos<<32 | readpos
   uint32_t* lis_b; uint32_t* lis_p;  // [pair_cap]
-  int32_t* rowH; int32_t* rowF;      // [row_cap]
-  uint32_t hist_cap, cand_cap, pair_cap, row_cap;
+  SwTask* tasks; PlanTask* ptasks;   // [task_cap]
+  uint32_t* sel;                     // [task_cap] task indices of the round being submitted
+  uint32_t* cfirst;                  // [kBatchCandCap + 1] first task of each candidate of the batch | reset-at-end << 31
+  uint32_t hist_cap, cand_cap, pair_cap, task_cap;
 };
 
 struct LisGlobals {
-  uint8_t* arena_base; size_t arena_stride;   // per-warp arena
-  uint32_t hist_cap, cand_cap, pair_cap, row_cap, pall_cap;
-  uint32_t* epochs;                            // [total warps]
+  uint8_t* arena_base; size_t arena_stride;   // per-planner arena
+  uint32_t hist_cap, cand_cap, pair_cap, row_cap, pall_cap, task_cap;
+  uint32_t* epochs;                            // [planners]
+  QSlot* ring;                                 // [kQueueCap]
+  uint32_t* q_head; uint32_t* q_tail;          // consumer / producer cursors
+  uint32_t* planners_done;                     // planners that ran out of reads
+  uint32_t* done;                              // [planners] tasks scored so far for each planner
+  int32_t* score_rows;                         // [scorers][2 * row_cap] scratch of the s32 row-block fallback
   AlnWork* aln_work;                           // [nreads * slots]
   uint32_t slots;
   uint32_t* work_next;                         // [1] persistent-loop cursor
@@ -51,24 +100,27 @@ struct LisGlobals {
 __device__ __forceinline__ LisArena carve_arena(const LisGlobals& g, uint32_t warp) {
   LisArena a;
   uint8_t* p = g.arena_base + (size_t)warp * g.arena_stride;
-  a.hist_cap = g.hist_cap; a.cand_cap = g.cand_cap; a.pair_cap = g.pair_cap; a.row_cap = g.row_cap;
+  a.hist_cap = g.hist_cap; a.cand_cap = g.cand_cap; a.pair_cap = g.pair_cap; a.task_cap = g.task_cap;
   a.cand = (unsigned long long*)p; p += (size_t)g.cand_cap * 8;
   a.grp = (unsigned long long*)p; p += (size_t)g.cand_cap * 8;
   a.pairs = (unsigned long long*)p; p += (size_t)g.pair_cap * 8;
   a.hist = (uint32_t*)p; p += (size_t)g.hist_cap * 4;
   a.lis_b = (uint32_t*)p; p += (size_t)g.pair_cap * 4;
   a.lis_p = (uint32_t*)p; p += (size_t)g.pair_cap * 4;
-  a.rowH = (int32_t*)p; p += (size_t)g.row_cap * 4;
-  a.rowF = (int32_t*)p; p += (size_t)g.row_cap * 4;
+  a.sel = (uint32_t*)p; p += (size_t)g.task_cap * 4;
+  a.cfirst = (uint32_t*)p; p += (size_t)(kBatchCandCap + 1) * 4;
   a.bitmap = (uint32_t*)p; p += (size_t)((g.hist_cap + 31) / 32) * 4;
   a.summary = (uint32_t*)p; p += (size_t)((g.hist_cap + 1023) / 1024) * 4;
-  p = (uint8_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-  a.pall = (unsigned long long*)p; a.pall_cap = g.pall_cap;
+  p = (uint8_t*)(((uintptr_t)p + 31) & ~(uintptr_t)31);
+  a.pall = (unsigned long long*)p; a.pall_cap = g.pall_cap; p += (size_t)g.pall_cap * 8;
+  a.tasks = (SwTask*)p; p += (size_t)g.task_cap * sizeof(SwTask);
+  a.ptasks = (PlanTask*)p;
   return a;
 }
-__host__ __device__ inline size_t lis_arena_bytes(uint32_t hist_cap, uint32_t cand_cap, uint32_t pair_cap, uint32_t row_cap, uint32_t pall_cap) {
-  size_t b = (size_t)cand_cap * 16 + (size_t)pair_cap * 8 + (size_t)hist_cap * 4 + (size_t)pair_cap * 8 + (size_t)row_cap * 8 +
-             (size_t)((hist_cap + 31) / 32) * 4 + (size_t)((hist_cap + 1023) / 1024) * 4 + 64 + (size_t)pall_cap * 8;
+__host__ __device__ inline size_t lis_arena_bytes(uint32_t hist_cap, uint32_t cand_cap, uint32_t pair_cap, uint32_t task_cap, uint32_t pall_cap) {
+  size_t b = (size_t)cand_cap * 16 + (size_t)pair_cap * 8 + (size_t)hist_cap * 4 + (size_t)pair_cap * 8 + (size_t)task_cap * 4 +
+             (size_t)(kBatchCandCap + 1) * 4 + (size_t)((hist_cap + 31) / 32) * 4 + (size_t)((hist_cap + 1023) / 1024) * 4 + 64 +
+             (size_t)pall_cap * 8 + (size_t)task_cap * (sizeof(SwTask) + sizeof(PlanTask));
   return (b + 255) & ~(size_t)255;
 }
 
@@ -159,12 +211,40 @@ struct PassEnv {
   const DevIndex* ix; const DevBatch* b; const DevParams* prm; const LisGlobals* g;
   LisArena ar; uint32_t* epoch_ptr; uint32_t epoch;
   unsigned long long* s_pairs; uint32_t* s_b; uint32_t* s_p;   // shared-memory fast buffers (kPairsShared)
-  uint8_t* s_ref;                                               // staged reference window (kRefStage + 64)
-  int32_t* s_prof;                                              // query profile (kProfWords)
   const uint2* hits; uint32_t nh;                               // hit region of (current part, current read)
-  unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls;
-  unsigned long long cyc[8];                                    // warp cycles per phase: vote, order, group, prep, sw setup, sw loop, book
+  uint32_t planner;                                             // ordinal of this planner warp
+  uint32_t submitted;                                           // tasks handed to the scorers so far (g.done[planner] catches up)
+  unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls, n_spec_calls, n_spec_cells;
+  unsigned long long cyc[8];                                    // warp cycles per phase: vote, order, group, plan, wait, replay
 };
+
+// ---- the task queue (bounded MPMC ring, per-slot sequence numbers) ----
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
+
+// hands the tasks sel[0 .. nsel) of this planner to the scorers, two per queue entry, and waits for their scores
+__device__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
+  if (nsel == 0) return;
+  const LisGlobals& g = *E.g;
+  const unsigned lane = lane_id();
+  const uint32_t npairs = (nsel + 1) >> 1;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(g.q_tail, npairs);
+  base = __shfl_sync(kFull, base, 0);
+  for (uint32_t i = lane; i < npairs; i += 32) {
+    const uint32_t idx = base + i;
+    QSlot* sl = g.ring + (idx & (kQueueCap - 1));
+    while (ld_volatile_u32(&sl->seq) != idx) __nanosleep(64);        // the consumer of the previous lap has left the slot
+    const uint32_t ta = E.ar.sel[2 * i], tb = (2 * i + 1 < nsel) ? E.ar.sel[2 * i + 1] : kNoTask;
+    sl->planner = E.planner; sl->ta = ta; sl->tb = tb;
+  }
+  __threadfence();      // task records + entries before the sequence numbers that publish them
+  __syncwarp();
+  for (uint32_t i = lane; i < npairs; i += 32) { const uint32_t idx = base + i; st_volatile_u32(&g.ring[idx & (kQueueCap - 1)].seq, idx + 1); }
+  E.submitted += nsel;
+  if (lane == 0) { while (ld_volatile_u32(g.done + E.planner) != E.submitted) __nanosleep(128); __threadfence(); }
+  __syncwarp();
+}
 
 __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score, const uint32_t ncand, const bool by_level,
                                uint32_t level, const bool grouped);
@@ -347,21 +427,143 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   }
 }
 
-// candidates in order (alignment.cpp:150-508); returns through rc.flags on scratch overflow
-__device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score, const uint32_t ncand, const bool by_level,
-                               uint32_t level, const bool grouped) {
+// One candidate reference of a batch (alignment.cpp:171-507 without the ssw_align call): gathers and sorts its pairs, slides
+// the window and appends one task per step that would reach ssw_align.  Returns false on scratch overflow (rc.flags set).
+__device__ bool plan_candidate(PassEnv& E, ReadCtx& rc, const unsigned long long ck, const uint32_t cand_rel, uint32_t& ntask, const bool grouped) {
   const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
   const unsigned lane = lane_id();
   const uint32_t s0 = ix.skip[0], s1 = ix.skip[1], s2 = ix.skip[2];
   const uint2* hits = E.hits;
   const uint32_t nh = E.nh;
-  // ---- 3. candidates in order (alignment.cpp:150-508) ----
-  bool is_aligned = false, is_search_candidates = true, first_cand = true, stop_all = false;
-  uint32_t prev_occur = 0;
   const uint64_t rlen = rc.len, lnwin = ix.lnwin;
+  const uint32_t max_ref = (uint32_t)ck, max_occur = 0xFFFFFu - (uint32_t)(ck >> 32);
+  // start of the reference and of its successor: requested now, needed only after the pairs are gathered and sorted
+  const uint64_t ref_base = __ldg(ix.ref_off + max_ref), ref_next = __ldg(ix.ref_off + max_ref + 1);
+  // gather (refpos, readpos) pairs of this reference (:181-201)
+  const uint32_t np = max_occur;
+  unsigned long long* P; uint32_t* lb; uint32_t* lp;
+  if (np <= (uint32_t)kPairsShared) { P = E.s_pairs; lb = E.s_b; lp = E.s_p; }
+  else if (np <= E.ar.pair_cap) { P = E.ar.pairs; lb = E.ar.lis_b; lp = E.ar.lis_p; }
+  else { rc.flags |= kOvfPairs; return false; }
+  if (ntask + np > E.ar.task_cap) { rc.flags |= kOvfPairs; return false; }   // at most one task per pair
+  uint32_t filled = 0;
+  if (grouped) {   // the pairs of this reference were grouped by the one-pass scatter
+    const uint32_t seg_end = E.ar.hist[max_ref] & 0x7FFFFFFFu, seg = seg_end - np;
+    for (uint32_t i = lane; i < np; i += 32) P[i] = E.ar.pall[seg + i];
+    filled = np;
+  } else
+  for (uint32_t h0 = 0; h0 < nh; h0 += 32) {
+    const uint32_t h = h0 + lane;
+    uint32_t first = 0, cnt = 0, win = 0;
+    if (h < nh) {
+      const uint2 hv = hits[h];
+      if (hit_selected(hv, rc, s0, s1, s2)) {
+        win = hv.y & kWinMask;
+        uint32_t lo = __ldg(ix.pos_off + hv.x), hi = __ldg(ix.pos_off + hv.x + 1);
+        const uint32_t end = hi;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&ix.pos[mid]).y < max_ref) lo = mid + 1; else hi = mid; }
+        first = lo;
+        while (first + cnt < end && __ldg(&ix.pos[first + cnt]).y == max_ref) ++cnt;
+      }
+    }
+    const uint32_t incl = warp_incl_scan_u32(cnt), tot = __shfl_sync(kFull, incl, 31);
+    uint32_t w = filled + incl - cnt;
+    for (uint32_t c = 0; c < cnt; ++c, ++w) if (w < np) P[w] = ((unsigned long long)__ldg(&ix.pos[first + c]).x << 32) | win;
+    filled += tot;
+  }
+  __syncwarp();
+  if (filled != np) { rc.flags |= kErrTrace; return false; }   // internal consistency: votes == gathered pairs
+  if (np <= 32u) {
+    unsigned long long key = lane < np ? P[lane] : ~0ull;
+    __syncwarp();
+    key = warp_sort32_u64(key, np);
+    if (lane < np) P[lane] = key;
+    __syncwarp();
+  } else {
+    const uint32_t np2 = next_pow2(np);
+    for (uint32_t i = np + lane; i < np2; i += 32) P[i] = ~0ull;
+    __syncwarp();
+    warp_sort_u64(P, np2);
+  }
+  // sliding window over the sorted pairs (:205-507); the trajectory of (it, f) does not depend on any score
+  const uint64_t reflen = ref_next - ref_base;
+  const uint32_t edges = o.edges_is_percent ? (uint32_t)((o.edges / 100.0) * (double)rlen) : (uint32_t)o.edges;  // :278-282
+  const uint64_t em1 = (uint64_t)(uint32_t)(edges - 1u);
+  uint32_t it = 0, f = 0;
+  uint32_t begin_ref = (uint32_t)(P[0] >> 32), begin_read = (uint32_t)P[0];
+  bool reset = false;            // a push step without a task since the previous task of this candidate
+  uint32_t lead = kNoTask;       // the last unconditional task of this candidate
+  while (it != np) {
+    const uint64_t end_ref_max = (uint64_t)begin_ref + rlen - begin_read - lnwin + 1;     // :231
+    bool push = false;
+    while (it != np && (uint64_t)(uint32_t)(P[it] >> 32) <= end_ref_max) { ++it; push = true; }
+    bool task = false;
+    if ((it - f) >= (uint32_t)o.num_seeds) {
+      // find_lis is sequential: lane 0 runs it, the result is broadcast
+      uint32_t lis_first = 0, lis_len = 0;
+      if (lane == 0) lis_len = find_lis_dev(P + f, it - f, lb, lp, lis_first);
+      lis_len = __shfl_sync(kFull, lis_len, 0); lis_first = __shfl_sync(kFull, lis_first, 0);
+      if (lis_len >= (uint32_t)o.min_lis) {                                               // :261
+        const uint32_t lcs_ref_start = (uint32_t)(P[f + lis_first] >> 32), lcs_que_start = (uint32_t)P[f + lis_first];
+        uint64_t head = 0, tail = 0, ars = 0, aqs = 0, alen = 0;
+        if (lcs_ref_start < lcs_que_start) {                                              // :288-330
+          aqs = lcs_que_start - lcs_ref_start;
+          if (reflen < rlen) {
+            if (aqs > (rlen - reflen)) alen = reflen - (aqs - (rlen - reflen)); else alen = reflen;
+          } else {
+            tail = reflen - ars - rlen; if (tail > em1) tail = edges;
+            alen = rlen + head + tail - aqs;
+          }
+        } else {                                                                          // :331-357
+          ars = lcs_ref_start - lcs_que_start;
+          if (ars > em1) head = edges;
+          if (ars + rlen > reflen) { tail = 0; alen = reflen - ars - head; }
+          else { tail = reflen - ars - rlen; if (tail > em1) tail = edges; alen = rlen + head + tail; }
+        }
+        const int32_t qlen = (int32_t)(alen - head - tail);
+        const uint32_t win_start = (uint32_t)(ars - head);
+        const uint32_t fl = (push ? kTfPush : 0u) | ((push || reset) ? kTfUncond : 0u) | (reset ? kTfReset : 0u);
+        if (lane == 0) {
+          SwTask t;
+          t.ref_abs = (uint32_t)ref_base + win_start;
+          t.q_abs = rc.reversed ? rc.seq_base + (rc.len - 1u - (uint32_t)aqs) : rc.seq_base + (uint32_t)aqs;   // query = current strand, 0-4 alphabet (:360-366)
+          t.alen = (uint32_t)alen; t.qlen = qlen > 0 ? (uint32_t)qlen : 0u;
+          t.meta = ix.slot | (rc.reversed ? 0x10000u : 0u);
+          t.score = 0; t.pad0 = 0; t.pad1 = 0;
+          E.ar.tasks[ntask] = t;
+          PlanTask pt;
+          pt.max_ref = max_ref; pt.win_start = win_start; pt.aqs = (uint32_t)aqs; pt.cf = cand_rel | (fl << 24);
+          pt.lead = (fl & kTfUncond) ? ntask : lead;
+          E.ar.ptasks[ntask] = pt;
+        }
+        if (fl & kTfUncond) lead = ntask;
+        ++ntask;
+        task = true; reset = false;
+      }
+    }
+    if (!task && push) reset = true;
+    // pop (:486-506)
+    if (it > f) ++f;
+    if (it == f) {
+      if (it != np) { begin_ref = (uint32_t)(P[it] >> 32); begin_read = (uint32_t)P[it]; } else break;
+    } else { begin_ref = (uint32_t)(P[f] >> 32); begin_read = (uint32_t)P[f]; }
+  }
+  if (lane == 0) E.ar.cfirst[cand_rel + 1] = ntask | (reset ? 0x80000000u : 0u);   // end of this candidate's tasks | "ends on a reset"
+  __syncwarp();
+  return true;
+}
+
+// candidates in order (alignment.cpp:150-508), in batches: plan -> score (by the scorer warps) -> replay.
+// Returns through rc.flags on scratch overflow.
+__device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score, const uint32_t ncand, const bool by_level,
+                               uint32_t level, const bool grouped) {
+  const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
+  const unsigned lane = lane_id();
+  bool is_aligned = false, first_cand = true, stop_all = false, searching = true;
+  uint32_t prev_occur = 0;
   const uint32_t N = (uint32_t)o.num_alignments;
   AlnWork* slots = E.g->aln_work + (size_t)rc.r * E.g->slots;
-  const SwScore sc{o.match, o.mismatch, o.score_N, o.gap_open, o.gap_ext, o.one};
+  uint32_t cap = 8;   // unconditional tasks per batch; doubles per batch (a perfect-score stop wastes at most what was useful)
 
   for (;;) {
     // the next group: everything (sorted) for small lists, else the members of the current count level
@@ -383,117 +585,104 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
       for (int o2 = 16; o2 > 0; o2 >>= 1) next_level = max(next_level, __shfl_xor_sync(kFull, next_level, o2));
       __syncwarp();
     }
-  for (uint32_t k = 0; k < ngrp && is_search_candidates; ++k) {
-    const unsigned long long ck = E.ar.grp[k];
-    const uint32_t max_ref = (uint32_t)ck, max_occur = 0xFFFFFu - (uint32_t)(ck >> 32);
-    if (max_occur < (uint32_t)o.num_seeds) { stop_all = true; break; }                       // :158
-    if (is_aligned && o.min_lis > 0 && !first_cand && max_occur < prev_occur) { --rc.best; if (rc.best < 1) { stop_all = true; break; } }  // :165-169
-    prev_occur = max_occur; first_cand = false;
-
-    long long tc0 = clock64();
-    // start of the reference and of its successor: requested now, needed only after the pairs are gathered and sorted
-    const uint64_t ref_base = __ldg(ix.ref_off + max_ref), ref_next = __ldg(ix.ref_off + max_ref + 1);
-    // gather (refpos, readpos) pairs of this reference (:181-201)
-    const uint32_t np = max_occur;
-    unsigned long long* P; uint32_t* lb; uint32_t* lp;
-    if (np <= (uint32_t)kPairsShared) { P = E.s_pairs; lb = E.s_b; lp = E.s_p; }
-    else if (np <= E.ar.pair_cap) { P = E.ar.pairs; lb = E.ar.lis_b; lp = E.ar.lis_p; }
-    else { rc.flags |= kOvfPairs; return; }
-    uint32_t filled = 0;
-    if (grouped) {   // the pairs of this reference were grouped by the one-pass scatter
-      const uint32_t seg_end = E.ar.hist[max_ref] & 0x7FFFFFFFu, seg = seg_end - np;
-      for (uint32_t i = lane; i < np; i += 32) P[i] = E.ar.pall[seg + i];
-      filled = np;
-    } else
-    for (uint32_t h0 = 0; h0 < nh; h0 += 32) {
-      const uint32_t h = h0 + lane;
-      uint32_t first = 0, cnt = 0, win = 0;
-      if (h < nh) {
-        const uint2 hv = hits[h];
-        if (hit_selected(hv, rc, s0, s1, s2)) {
-          win = hv.y & kWinMask;
-          uint32_t lo = __ldg(ix.pos_off + hv.x), hi = __ldg(ix.pos_off + hv.x + 1);
-          const uint32_t end = hi;
-          while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&ix.pos[mid]).y < max_ref) lo = mid + 1; else hi = mid; }
-          first = lo;
-          while (first + cnt < end && __ldg(&ix.pos[first + cnt]).y == max_ref) ++cnt;
-        }
+    uint32_t k = 0;
+    while (k < ngrp && searching) {
+      long long tc0 = clock64();
+      // ---- entry of the batch's first candidate (:158-169): decided now, with the scores known so far ----
+      {
+        const uint32_t occ = 0xFFFFFu - (uint32_t)(E.ar.grp[k] >> 32);
+        if (occ < (uint32_t)o.num_seeds) { stop_all = true; break; }                                                                    // :158
+        if (is_aligned && o.min_lis > 0 && !first_cand && occ < prev_occur) { --rc.best; if (rc.best < 1) { stop_all = true; break; } }   // :165-169
+        prev_occur = occ; first_cand = false;
       }
-      const uint32_t incl = warp_incl_scan_u32(cnt), tot = __shfl_sync(kFull, incl, 31);
-      uint32_t w = filled + incl - cnt;
-      for (uint32_t c = 0; c < cnt; ++c, ++w) if (w < np) P[w] = ((unsigned long long)__ldg(&ix.pos[first + c]).x << 32) | win;
-      filled += tot;
-    }
-    __syncwarp();
-    if (filled != np) { rc.flags |= kErrTrace; return; }   // internal consistency: votes == gathered pairs
-    if (np <= 32u) {
-      unsigned long long key = lane < np ? P[lane] : ~0ull;
+      // ---- plan: candidates k .. k2.  The batch ends before the level drop at which the countdown of `best` could end the
+      //      call (so nothing behind a possible stop is scored), when it holds `cap` unconditional tasks, or when full ----
+      const uint32_t budget = o.min_lis > 0 ? (uint32_t)max(rc.best, 1) : 0xFFFFFFFFu;
+      // without `best`, the call ends at the N-th accepted alignment (:466-468): speculate on no more than are still wanted
+      const uint32_t cap_now = (N > 0 && !o.is_best) ? min(cap, 2u * (N > rc.n_align ? N - rc.n_align : 1u)) : cap;
+      uint32_t ntask = 0, nuncond = 0, drops = 0, k2 = k, lvl_prev = prev_occur;
+      if (lane == 0) E.ar.cfirst[0] = 0;
+      for (; k2 < ngrp && (k2 - k) < kBatchCandCap; ++k2) {
+        const unsigned long long ck = E.ar.grp[k2];
+        const uint32_t occ = 0xFFFFFu - (uint32_t)(ck >> 32);
+        if (k2 > k) {
+          if (occ < lvl_prev && ++drops >= budget) break;
+          if (nuncond >= cap_now) break;
+          if (occ < (uint32_t)o.num_seeds) break;     // the call ends there (:158), decided at the next batch entry
+          if (ntask + occ > E.ar.task_cap) break;     // at most one task per pair: the next candidate might not fit
+        }
+        lvl_prev = occ;
+        const uint32_t before = ntask;
+        if (!plan_candidate(E, rc, ck, k2 - k, ntask, grouped)) return;
+        // unconditional tasks of this candidate
+        uint32_t nu = 0;
+        for (uint32_t t = before + lane; t < ntask; t += 32) nu += ((E.ar.ptasks[t].cf >> 24) & kTfUncond) ? 1u : 0u;
+        nuncond += warp_sum_u32(nu);
+      }
       __syncwarp();
-      key = warp_sort32_u64(key, np);
-      if (lane < np) P[lane] = key;
+      { const long long t2 = clock64(); E.cyc[3] += (unsigned long long)(t2 - tc0); tc0 = t2; }
+      // ---- score, round A: the unconditional tasks ----
+      uint32_t nsel = 0;
+      for (uint32_t t0 = 0; t0 < ntask; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        const bool pick = t < ntask && ((E.ar.ptasks[t].cf >> 24) & kTfUncond);
+        const unsigned pm = __ballot_sync(kFull, pick);
+        if (pick) E.ar.sel[nsel + __popc(pm & ((1u << lane) - 1))] = t;
+        nsel += __popc(pm);
+      }
       __syncwarp();
-    } else {
-      const uint32_t np2 = next_pow2(np);
-      for (uint32_t i = np + lane; i < np2; i += 32) P[i] = ~0ull;
-      __syncwarp();
-      warp_sort_u64(P, np2);
-    }
-
-    // sliding window over the sorted pairs (:205-507)
-    uint32_t it = 0, f = 0;
-    uint32_t begin_ref = (uint32_t)(P[0] >> 32), begin_read = (uint32_t)P[0];
-    while (it != np && is_search_candidates) {
-      const uint64_t end_ref_max = (uint64_t)begin_ref + rlen - begin_read - lnwin + 1;     // :231
-      bool push = false;
-      while (it != np && (uint64_t)(uint32_t)(P[it] >> 32) <= end_ref_max) { ++it; push = true; }
-      bool skip = false;
-      if (!push && is_aligned) skip = true; else is_aligned = false;                        // heuristic 1 (:244-245)
-      if (!skip && (it - f) >= (uint32_t)o.num_seeds) {
-        // find_lis is sequential: lane 0 runs it, the result is broadcast
-        uint32_t lis_first = 0, lis_len = 0;
-        if (lane == 0) lis_len = find_lis_dev(P + f, it - f, lb, lp, lis_first);
-        lis_len = __shfl_sync(kFull, lis_len, 0); lis_first = __shfl_sync(kFull, lis_first, 0);
-        if (lis_len >= (uint32_t)o.min_lis) {                                               // :261
-          const uint32_t lcs_ref_start = (uint32_t)(P[f + lis_first] >> 32), lcs_que_start = (uint32_t)P[f + lis_first];
-          uint64_t head = 0, tail = 0, ars = 0, aqs = 0, alen = 0;
-          const uint64_t reflen = ref_next - ref_base;
-          const uint32_t edges = o.edges_is_percent ? (uint32_t)((o.edges / 100.0) * (double)rlen) : (uint32_t)o.edges;  // :278-282
-          const uint64_t em1 = (uint64_t)(uint32_t)(edges - 1u);
-          if (lcs_ref_start < lcs_que_start) {                                              // :288-330
-            aqs = lcs_que_start - lcs_ref_start;
-            if (reflen < rlen) {
-              if (aqs > (rlen - reflen)) alen = reflen - (aqs - (rlen - reflen)); else alen = reflen;
-            } else {
-              tail = reflen - ars - rlen; if (tail > em1) tail = edges;
-              alen = rlen + head + tail - aqs;
-            }
-          } else {                                                                          // :331-357
-            ars = lcs_ref_start - lcs_que_start;
-            if (ars > em1) head = edges;
-            if (ars + rlen > reflen) { tail = 0; alen = reflen - ars - head; }
-            else { tail = reflen - ars - rlen; if (tail > em1) tail = edges; alen = rlen + head + tail; }
+      submit_and_wait(E, nsel);
+      E.n_spec_calls += nsel;
+      // ---- round B: tasks heuristic 1 would skip after a successful lead (:243-246) are needed when the lead failed ----
+      if (nsel < ntask) {
+        uint32_t nsel2 = 0;
+        for (uint32_t t0 = 0; t0 < ntask; t0 += 32) {
+          const uint32_t t = t0 + lane;
+          bool pick = false;
+          if (t < ntask) {
+            const PlanTask pt = E.ar.ptasks[t];
+            if (!((pt.cf >> 24) & kTfUncond)) pick = (__ldcg(&E.ar.tasks[pt.lead].score) & 0xFFFFu) <= ix.minimal_score;
           }
+          const unsigned pm = __ballot_sync(kFull, pick);
+          if (pick) E.ar.sel[nsel2 + __popc(pm & ((1u << lane) - 1))] = t | 0x80000000u;
+          nsel2 += __popc(pm);
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < nsel2; i += 32) { const uint32_t t = E.ar.sel[i] & 0x7FFFFFFFu; E.ar.sel[i] = t; E.ar.ptasks[t].cf |= (8u << 24); }   // scored
+        __syncwarp();
+        submit_and_wait(E, nsel2);
+        E.n_spec_calls += nsel2;
+      }
+      { const long long t2 = clock64(); E.cyc[4] += (unsigned long long)(t2 - tc0); tc0 = t2; }
+      // ---- replay: the reference's decisions over the scores, in order ----
+      for (uint32_t c = 0; c < k2 - k && searching; ++c) {
+        if (c > 0) {   // entry of a later candidate of the batch (:158-169); the countdown cannot reach 0 inside a batch
+          const uint32_t occ = 0xFFFFFu - (uint32_t)(E.ar.grp[k + c] >> 32);
+          if (is_aligned && o.min_lis > 0 && occ < prev_occur) { --rc.best; if (rc.best < 1) { stop_all = true; searching = false; break; } }
+          prev_occur = occ;
+        }
+        is_aligned = false;   // the first step of a candidate always pushes: `else is_aligned = false` (:245)
+        const uint32_t t_lo = E.ar.cfirst[c] & 0x7FFFFFFFu, t_hi_w = E.ar.cfirst[c + 1];
+        const uint32_t t_hi = t_hi_w & 0x7FFFFFFFu;
+        for (uint32_t t = t_lo; t < t_hi && searching; ++t) {
+          const PlanTask pt = E.ar.ptasks[t];
+          const uint32_t fl = pt.cf >> 24;
+          if (fl & kTfReset) is_aligned = false;
+          if (!(fl & kTfPush) && is_aligned) continue;                                      // heuristic 1 (:244-245)
+          is_aligned = false;
+          if (!(fl & (kTfUncond | 8u))) { rc.flags |= kErrTrace; return; }                  // internal consistency: a needed task was not scored
+          const SwTask tk = E.ar.tasks[t];
+          const uint32_t sw = __ldcg(&E.ar.tasks[t].score);
           if (rc.hasn) rc.form04 = true;                                                    // flip34 before SSW (:360-361)
-          const int32_t qlen = (int32_t)(alen - head - tail);
-          const uint32_t win_start = (uint32_t)(ars - head);
-          // query = current strand in the 0-4 alphabet, starting at aqs
-          SeqView q;
-          if (!rc.reversed) q = SeqView{B.seq04 + rc.seq_base, (int32_t)aqs, 1, false};
-          else q = SeqView{B.seq04 + rc.seq_base, (int32_t)(rc.len - 1 - aqs), -1, true};
-          const SeqView t{ix.refseq + ref_base, (int32_t)win_start, 1, false};
-          { const long long t2 = clock64(); E.cyc[3] += (unsigned long long)(t2 - tc0); tc0 = t2; }
-          int32_t sw = 0;
-          if (qlen > 0 && alen > 0 && (uint32_t)alen <= E.ar.row_cap) sw = sw_score(q, qlen, t, (int32_t)alen, sc, E.s_ref, E.s_prof, E.ar.rowH, E.ar.rowF);
-          { const long long t2 = clock64(); E.cyc[5] += (unsigned long long)(t2 - tc0); tc0 = t2; }
-          E.n_sw_calls++; E.n_sw_cells += (unsigned long long)alen * (unsigned long long)(qlen > 0 ? qlen : 0);
-          const uint32_t score1 = (uint32_t)sw & 0xFFFFu;                                   // s_align.score1 is uint16
+          E.n_sw_calls++; E.n_sw_cells += (unsigned long long)tk.alen * (unsigned long long)tk.qlen;
+          const uint32_t score1 = sw & 0xFFFFu;                                             // s_align.score1 is uint16
           is_aligned = score1 > ix.minimal_score;                                           // :388
           if (is_aligned) {
             if (score1 == max_SW_score) ++rc.max_SW_count;                                  // :391
             AlnWork a;
-            a.ref_num = max_ref; a.win_ref_start = win_start; a.win_len = (uint32_t)alen; a.q_start = (uint32_t)aqs; a.q_len = (uint32_t)qlen;
+            a.ref_num = pt.max_ref; a.win_ref_start = pt.win_start; a.win_len = tk.alen; a.q_start = pt.aqs; a.q_len = tk.qlen;
             a.score1 = (uint16_t)score1; a.part = (uint16_t)ix.part; a.index_num = (uint16_t)ix.index_num;
-            a.strand = rc.reversed ? 0 : 1; a.idx_slot = (uint16_t)ix.slot;
+            a.strand = rc.reversed ? 0 : 1; a.idx_slot = (uint16_t)ix.slot; a.pad0 = 0;
             if (!rc.is_hit) {                                                               // :411-416
               rc.is_hit = true;   // readstats.num_aligned / reads_matched_per_db are summed from hit_db at download time
               if (lane == 0) B.hit_db[rc.r] = (uint16_t)ix.index_num;
@@ -520,23 +709,20 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
             }
             __syncwarp();
             if (N > 0) {                                                                    // :462-469
-              if (o.is_best) { if (N == rc.max_SW_count) is_search_candidates = false; }
-              else if (N == rc.n_align) is_search_candidates = false;
+              if (o.is_best) { if (N == rc.max_SW_count) searching = false; }
+              else if (N == rc.n_align) searching = false;
             }
             search = false;                                                                 // :472
           }
         }
+        if (searching && (t_hi_w & 0x80000000u)) is_aligned = false;
       }
-      // pop (:486-506)
-      if (it > f) ++f;
-      if (it == f) {
-        if (it != np) { begin_ref = (uint32_t)(P[it] >> 32); begin_read = (uint32_t)P[it]; } else break;
-      } else { begin_ref = (uint32_t)(P[f] >> 32); begin_read = (uint32_t)P[f]; }
+      { const long long t2 = clock64(); E.cyc[5] += (unsigned long long)(t2 - tc0); }
+      k = k2;
+      cap = min(cap * 2u, 2048u);
+      __syncwarp();
     }
-    { const long long t2 = clock64(); E.cyc[6] += (unsigned long long)(t2 - tc0); }
-    __syncwarp();
-  }
-    if (!by_level || stop_all || !is_search_candidates) break;
+    if (!by_level || stop_all || !searching) break;
     level = next_level;
   }
 }
@@ -587,32 +773,112 @@ __device__ void traverse_dev(PassEnv& E, ReadCtx& rc, const bool is_last_strand)
   } else if (ix.is_last && is_last_strand && rc.n_align > 0) rc.is_done = true;
 }
 
-// The candidate kernel: persistent warps drain the chunk's reads heaviest-first; each read is taken
+// ---- scorer role: pop task pairs, score them with the packed kernel, report ----
+__device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGlobals& g, uint8_t* s_ref, uint32_t* s_prof, const uint32_t scorer) {
+  const unsigned lane = lane_id();
+  const SwScore sc{prm.match, prm.mismatch, prm.score_N, prm.gap_open, prm.gap_ext, prm.one};
+  int32_t* rowH = g.score_rows + (size_t)scorer * 2 * g.row_cap; int32_t* rowF = rowH + g.row_cap;
+  // identity of the query profile resident in each half: (q_abs, qlen | rev << 31, R)
+  uint32_t keyq[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, keym[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}; int keyR = 0;
+  unsigned long long n_pairs = 0, n_cells = 0, n_slow = 0;
+  for (;;) {
+    uint32_t h = 0;
+    if (lane == 0) {
+      h = atomicAdd(g.q_head, 1u);
+      const QSlot* sl = g.ring + (h & (kQueueCap - 1));
+      while (ld_volatile_u32(&sl->seq) != h + 1u) __nanosleep(96);
+      __threadfence();
+    }
+    h = __shfl_sync(kFull, h, 0);
+    QSlot* sl = g.ring + (h & (kQueueCap - 1));
+    const uint32_t planner = __ldcg(&sl->planner), ta = __ldcg(&sl->ta), tb = __ldcg(&sl->tb);
+    if (lane == 0) st_volatile_u32(&sl->seq, h + kQueueCap);   // slot free for the next lap (after the payload was read)
+    if (planner == kPoison) break;
+    SwTask* tasks = (SwTask*)0;
+    {
+      // the task arrays live in the planner's arena
+      LisArena ar = carve_arena(g, planner);
+      tasks = ar.tasks;
+    }
+    const uint4 da = __ldcg((const uint4*)(tasks + ta));
+    const uint32_t ma = __ldcg(&tasks[ta].meta);
+    uint4 db = make_uint4(0, 0, 0, 0); uint32_t mb = 0;
+    const bool two = tb != kNoTask;
+    if (two) { db = __ldcg((const uint4*)(tasks + tb)); mb = __ldcg(&tasks[tb].meta); }
+    PairProblem A, Bp;
+    {
+      const bool rev = (ma >> 16) & 1u;
+      A.q = SeqView{b.seq04, (int32_t)da.y, rev ? -1 : 1, rev}; A.m = (int32_t)da.w;
+      A.t = SeqView{g.parts[ma & 0xFFFFu].refseq, (int32_t)da.x, 1, false}; A.n = (int32_t)da.z;
+    }
+    if (two) {
+      const bool rev = (mb >> 16) & 1u;
+      Bp.q = SeqView{b.seq04, (int32_t)db.y, rev ? -1 : 1, rev}; Bp.m = (int32_t)db.w;
+      Bp.t = SeqView{g.parts[mb & 0xFFFFu].refseq, (int32_t)db.x, 1, false}; Bp.n = (int32_t)db.z;
+    } else { Bp = A; Bp.m = 0; Bp.n = 0; }
+    uint32_t sa = 0, sb = 0;
+    const bool oka = A.m > 0 && A.n > 0 && sw_pair_ok(A.m, A.n, sc), okb = !two || Bp.m <= 0 || Bp.n <= 0 || sw_pair_ok(Bp.m, Bp.n, sc);
+    if (oka && okb) {
+      const int R = pair_rows(max(A.m, Bp.m));
+      const uint32_t kqa = da.y, kma = da.w | ((ma & 0x10000u) << 15), kqb = two ? db.y : 0xFFFFFFFEu, kmb = two ? (db.w | ((mb & 0x10000u) << 15)) : 0u;
+      const bool buildA = !(R == keyR && keyq[0] == kqa && keym[0] == kma), buildB = !(R == keyR && keyq[1] == kqb && keym[1] == kmb);
+      const uint32_t r2 = sw_pair(A, Bp, R, buildA, buildB, sc, s_ref, s_prof);
+      keyR = R; keyq[0] = kqa; keym[0] = kma; keyq[1] = kqb; keym[1] = kmb;
+      sa = r2 & 0xFFFFu; sb = r2 >> 16;
+    } else {
+      // shapes or scoring schemes outside the 16-bit kernel: the s32 wavefront (row blocks for long queries)
+      keyR = 0;
+      if (A.m > 0 && A.n > 0 && (uint32_t)A.n <= g.row_cap) sa = (uint32_t)sw_forward_any(A.q, A.m, A.t, A.n, sc, rowH, rowF).score;
+      if (two && Bp.m > 0 && Bp.n > 0 && (uint32_t)Bp.n <= g.row_cap) sb = (uint32_t)sw_forward_any(Bp.q, Bp.m, Bp.t, Bp.n, sc, rowH, rowF).score;
+      ++n_slow;
+    }
+    ++n_pairs; n_cells += (unsigned long long)da.z * da.w + (unsigned long long)db.z * db.w;
+    if (lane == 0) {
+      tasks[ta].score = sa;
+      if (two) tasks[tb].score = sb;
+      __threadfence();
+      atomicAdd(g.done + planner, two ? 2u : 1u);
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    atomicAdd(&b.counters[dcSpecCells], n_cells); atomicAdd(&b.counters[dcSpecPairs], n_pairs); atomicAdd(&b.counters[dcSlowPairs], n_slow);
+  }
+}
+
+// The candidate kernel.  Planner warps drain the chunk's reads heaviest-first; each read is taken
 // through every loaded (index, part) in --ref order -- the reference's index-major loop
 // (processor.cpp:219-277) run read-major, with the KVDB carry-over of read.cpp:429-539 kept in
-// DevBatch::state between parts (equivalent because reads are independent).
-__global__ void __launch_bounds__(kLisWarpsPerCta * 32, 4)
+// DevBatch::state between parts (equivalent because reads are independent).  Scorer warps
+// run scorer_loop until the last planner has published the shutdown entries.
+__global__ void __launch_bounds__(kLisWarpsPerCta * 32, 2)
 lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
-  __shared__ unsigned long long s_pairs[kLisWarpsPerCta][kPairsShared];
-  __shared__ uint32_t s_b[kLisWarpsPerCta][kPairsShared];
-  __shared__ uint32_t s_p[kLisWarpsPerCta][kPairsShared];
-  __shared__ __align__(16) uint8_t s_ref[kLisWarpsPerCta][kRefStage + 64];
-  __shared__ int32_t s_prof[kLisWarpsPerCta][kProfWords];
+  __shared__ unsigned long long s_pairs[kPlannerWarps][kPairsShared];
+  __shared__ uint32_t s_b[kPlannerWarps][kPairsShared];
+  __shared__ uint32_t s_p[kPlannerWarps][kPairsShared];
+  __shared__ __align__(16) uint8_t s_ref[kScorerWarps][2 * (kRefStage + 64)];
+  __shared__ uint32_t s_prof[kScorerWarps][2 * kPairProfWords];
   __shared__ uint32_t s_bin_start[kCostBins + 1];
   const unsigned lane = lane_id();
-  const uint32_t wic = threadIdx.x >> 5, warp = blockIdx.x * kLisWarpsPerCta + wic;
+  const uint32_t wic = threadIdx.x >> 5;
   if (threadIdx.x == 0) {   // bins are drained from the heaviest (highest log2 cost) down
     uint32_t acc = 0;
     for (int k = 0; k < kCostBins; ++k) { s_bin_start[k] = acc; acc += b.bin_count[kCostBins - 1 - k]; }
     s_bin_start[kCostBins] = acc;
   }
   __syncthreads();
+  if (wic < (uint32_t)kScorerWarps) {
+    scorer_loop(b, prm, g, s_ref[wic], s_prof[wic], blockIdx.x * kScorerWarps + wic);
+    return;
+  }
+  const uint32_t pw = wic - kScorerWarps, planner = blockIdx.x * kPlannerWarps + pw;
   PassEnv E;
   E.b = &b; E.prm = &prm; E.g = &g;
-  E.ar = carve_arena(g, warp);
-  E.epoch_ptr = g.epochs + warp; E.epoch = *E.epoch_ptr;
-  E.s_pairs = s_pairs[wic]; E.s_b = s_b[wic]; E.s_p = s_p[wic]; E.s_ref = s_ref[wic]; E.s_prof = s_prof[wic];
-  E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = 0;
+  E.ar = carve_arena(g, planner);
+  E.planner = planner; E.submitted = 0;
+  E.epoch_ptr = g.epochs + planner; E.epoch = *E.epoch_ptr;
+  E.s_pairs = s_pairs[pw]; E.s_b = s_b[pw]; E.s_p = s_p[pw];
+  E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = E.n_spec_calls = E.n_spec_cells = 0;
   for (int i = 0; i < 8; ++i) E.cyc[i] = 0;
   const uint32_t nwork = s_bin_start[kCostBins];
   unsigned long long t_max = 0, t_sum = 0; const long long t_k0 = clock64();
@@ -665,10 +931,32 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     *E.epoch_ptr = E.epoch;
     atomicAdd(&b.counters[dcSwCalls], E.n_sw_calls); atomicAdd(&b.counters[dcSwCells], E.n_sw_cells);
     atomicAdd(&b.counters[dcPosEntries], E.n_pos_entries); atomicAdd(&b.counters[dcLisCalls], E.n_lis_calls);
-    for (int i = 0; i < 7; ++i) atomicAdd(&b.counters[dcCycVote + i], E.cyc[i]);
+    atomicAdd(&b.counters[dcSpecCalls], E.n_spec_calls);
+    for (int i = 0; i < 6; ++i) atomicAdd(&b.counters[dcCycVote + i], E.cyc[i]);
     atomicMax(&b.counters[dcMaxReadCycles], t_max); atomicAdd(&b.counters[dcSumReadCycles], t_sum);
     atomicMax(&b.counters[dcLisKernelCycles], (unsigned long long)(clock64() - t_k0));
+    // the last planner out shuts the scorers down: one entry each
+    const uint32_t nplanners = gridDim.x * kPlannerWarps, nscorers = gridDim.x * kScorerWarps;
+    if (atomicAdd(g.planners_done, 1u) + 1u == nplanners) {
+      const uint32_t base = atomicAdd(g.q_tail, nscorers);
+      for (uint32_t i = 0; i < nscorers; ++i) {
+        const uint32_t idx = base + i;
+        QSlot* sl = g.ring + (idx & (kQueueCap - 1));
+        while (ld_volatile_u32(&sl->seq) != idx) __nanosleep(64);
+        sl->planner = kPoison; sl->ta = kNoTask; sl->tb = kNoTask;
+        __threadfence();
+        st_volatile_u32(&sl->seq, idx + 1);
+      }
+    }
   }
+}
+
+// queue / counter reset before every lis_kernel launch
+__global__ void lis_reset_kernel(LisGlobals g, uint32_t nplanners) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kQueueCap) { QSlot s; s.seq = i; s.planner = 0; s.ta = 0; s.tb = 0; g.ring[i] = s; }
+  if (i < nplanners) g.done[i] = 0;
+  if (i == 0) { *g.q_head = 0; *g.q_tail = 0; *g.planners_done = 0; }
 }
 
 }  // namespace smr

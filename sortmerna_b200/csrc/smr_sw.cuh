@@ -371,6 +371,165 @@ __device__ SwEnd sw_locate(const SeqView q, const int32_t m, const SeqView t, co
 }
 
 // ---------------------------------------------------------------------------------------------
+// Packed score pass: TWO independent (query, window) problems per warp pass, problem A in the low and
+// problem B in the high 16 bits of every register (the exact 16-bit path of the reference is the word
+// kernel sw_sse2_word, ssw.c:399-575; packing two ALIGNMENTS rather than two cells of one alignment keeps
+// the vertical F chain of a lane's rows intact).  Same wavefront as sw_score_warp, cell update with the
+// DPX 16x2 forms:
+//   X = max(diag + s, E, 0)         VIADDMNMX.S16x2.RELU
+//   G' = max(G - ge, X)             VIADDMNMX.S16x2      (G = F + go, as in sw_score_warp variant 3)
+//   H = max(G - go, X)              VIADDMNMX.S16x2
+//   E' = max(E - ge, H - go)        VIADD.16x2 + VIADDMNMX.S16x2
+//   best = max(best, H, H')         VIMNMX3.S16x2 per two rows
+// = 5.5 ALU-pipe instructions per PAIR of cells (the s32 loop issues 4.9 per cell).
+// Valid while every score fits 15 bits: m * match <= kPairMaxScore (checked by sw_pair_ok).
+// Query profile per problem: prof[tb][rp][lane] = s(row 2rp, tb) | s(row 2rp+1, tb) << 16 (rows of the lane's strip), so
+// one LDS per problem serves two rows and a PRMT per row merges the two problems' scores into one register.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPairProfWords = kProfTables * 4 * 32;   // per problem: 6 tables x (R <= 8 -> 4 row pairs) x 32 lanes
+constexpr int32_t kPairMaxScore = 32000;
+constexpr int32_t kPairDead = -32000;                  // substitution score of rows past the query end
+
+__device__ __forceinline__ bool sw_pair_ok(const int32_t m, const int32_t n, const SwScore sc) {
+  return m <= 256 && n <= kRefStage && sc.mismatch < 0 && sc.mismatch > -1024 && sc.go > 0 && sc.go < 1024 && sc.sN < 0 && sc.sN > -1024 &&
+         sc.ge <= sc.go && sc.ge >= 0 && sc.match >= 0 && m * sc.match <= kPairMaxScore;
+}
+
+__device__ __forceinline__ uint32_t pack16(const int32_t lo, const int32_t hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+
+template <int R>
+__device__ uint32_t sw_pair_warp(const uint32_t* __restrict__ profA, const uint32_t* __restrict__ profB, const uint8_t* __restrict__ refA,
+                                 const uint8_t* __restrict__ refB, const int32_t nmax, const SwScore sc) {
+  constexpr int RP = (R + 1) / 2;
+  const int lane = (int)lane_id();
+  uint32_t Hp[R], E[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { Hp[r] = 0; E[r] = 0; }
+  uint32_t diagH = 0, outH = 0, outF = 0, best = 0;
+  const uint8_t* cpA = refA + 32 - lane;
+  const uint8_t* cpB = refB + 32 - lane;
+  const uint32_t* pA = profA + lane;
+  const uint32_t* pB = profB + lane;
+  const int32_t nsteps = nmax + 31;
+  const uint32_t nge2 = pack16(-sc.ge, -sc.ge), ngo2 = pack16(-sc.go, -sc.go);
+  const uint32_t nz = lane ? (uint32_t)sc.one : 0u;
+  uint32_t sc_cur[R];
+  {
+    const uint32_t* ta = pA + (int32_t)cpA[0] * (RP * 32);
+    const uint32_t* tb = pB + (int32_t)cpB[0] * (RP * 32);
+#pragma unroll
+    for (int rp = 0; rp < RP; ++rp) {
+      const uint32_t wa = ta[rp * 32], wb = tb[rp * 32];
+      sc_cur[2 * rp] = __byte_perm(wa, wb, 0x5410);
+      if (2 * rp + 1 < R) sc_cur[2 * rp + 1] = __byte_perm(wa, wb, 0x7632);
+    }
+  }
+#pragma unroll 2
+  for (int32_t ts = 0; ts < nsteps; ++ts) {
+    uint32_t sc_next[R];
+    {
+      const uint32_t* ta = pA + (int32_t)cpA[ts + 1] * (RP * 32);   // [nsteps] is still inside the trailing sentinels
+      const uint32_t* tb = pB + (int32_t)cpB[ts + 1] * (RP * 32);
+#pragma unroll
+      for (int rp = 0; rp < RP; ++rp) {
+        const uint32_t wa = ta[rp * 32], wb = tb[rp * 32];
+        sc_next[2 * rp] = __byte_perm(wa, wb, 0x5410);
+        if (2 * rp + 1 < R) sc_next[2 * rp + 1] = __byte_perm(wa, wb, 0x7632);
+      }
+    }
+    const uint32_t upH = __shfl_up_sync(kFull, outH, 1) * nz, upF = __shfl_up_sync(kFull, outF, 1) * nz;   // row -1 is all zeros
+    uint32_t X[R], F[R + 1];
+#pragma unroll
+    for (int r = 0; r < R; ++r) X[r] = __viaddmax_s16x2_relu(r == 0 ? diagH : Hp[r - 1], sc_cur[r], E[r]);
+    diagH = upH;
+    F[0] = upF;
+#pragma unroll
+    for (int r = 0; r < R; ++r) F[r + 1] = __viaddmax_s16x2(F[r], nge2, X[r]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint32_t h = __viaddmax_s16x2(F[r], ngo2, X[r]);
+      E[r] = __viaddmax_s16x2(E[r], nge2, __vadd2(h, ngo2));
+      Hp[r] = h;
+    }
+#pragma unroll
+    for (int r = 0; r + 1 < R; r += 2) best = __vimax3_s16x2(best, Hp[r], Hp[r + 1]);
+    if (R & 1) best = __vmaxs2(best, Hp[R - 1]);
+    outH = Hp[R - 1]; outF = F[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) sc_cur[r] = sc_next[r];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(kFull, best, o));
+  return best;
+}
+
+// query profile of one problem for the packed pass (R rows per lane, m real rows)
+template <int R>
+__device__ __forceinline__ void pair_profile(const SeqView q, const int32_t m, const SwScore sc, uint32_t* __restrict__ prof) {
+  constexpr int RP = (R + 1) / 2;
+  const int lane = (int)lane_id();
+  uint32_t c[2 * RP];
+#pragma unroll
+  for (int r = 0; r < 2 * RP; ++r) { const int32_t i = lane * R + r; c[r] = (r < R && i < m) ? q.at(i) : 7u; }
+#pragma unroll
+  for (int rp = 0; rp < RP; ++rp) {
+    const uint32_t c0 = c[2 * rp], c1 = c[2 * rp + 1];
+    const int32_t mis0 = c0 == 7u ? kPairDead : (c0 >= 4u ? sc.sN : sc.mismatch), mis1 = c1 == 7u ? kPairDead : (c1 >= 4u ? sc.sN : sc.mismatch);
+#pragma unroll
+    for (int tb = 0; tb < 4; ++tb) prof[(tb * RP + rp) * 32 + lane] = pack16(c0 == (uint32_t)tb ? sc.match : mis0, c1 == (uint32_t)tb ? sc.match : mis1);
+    prof[(4 * RP + rp) * 32 + lane] = pack16(c0 == 7u ? kPairDead : sc.sN, c1 == 7u ? kPairDead : sc.sN);   // reference N
+    prof[(5 * RP + rp) * 32 + lane] = pack16(mis0, mis1);                                                   // outside the window: never a match
+  }
+}
+
+// window of `n` columns staged with 32 sentinel columns in front and sentinels up to column nstage + 32 behind
+__device__ __forceinline__ void stage_window_pair(const SeqView t, const int32_t n, const int32_t nstage, uint8_t* __restrict__ s_ref) {
+  const int lane = (int)lane_id();
+  constexpr int K = (kRefStage + 64) / 32;
+  uint32_t v[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int32_t j = lane + 32 * k - 32;
+    v[k] = (j >= 0 && j < n && lane + 32 * k < nstage + 64) ? min(t.at(j), 4u) : 5u;
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) if (lane + 32 * k < nstage + 64) s_ref[lane + 32 * k] = (uint8_t)v[k];
+}
+
+struct PairProblem { SeqView q; int32_t m; SeqView t; int32_t n; };
+
+// scores of two problems (B may be empty: m == 0, n == 0) -> score A | score B << 16.  s_ref: 2 x (kRefStage + 64) bytes,
+// s_prof: 2 x kPairProfWords words of this warp.  keyA/keyB: caller-kept identity of the profile resident in each half
+// (a batch of one read reuses its query many times), 0 = none.
+template <int R>
+__device__ __noinline__ uint32_t sw_pair_run(const PairProblem A, const PairProblem B, const bool buildA, const bool buildB, const SwScore sc,
+                                             uint8_t* __restrict__ s_ref, uint32_t* __restrict__ s_prof) {
+  const int32_t nmax = max(A.n, B.n);
+  __syncwarp();
+  stage_window_pair(A.t, A.n, nmax, s_ref);
+  stage_window_pair(B.t, B.n, nmax, s_ref + kRefStage + 64);
+  if (buildA) pair_profile<R>(A.q, A.m, sc, s_prof);
+  if (buildB) pair_profile<R>(B.q, B.m, sc, s_prof + kPairProfWords);
+  __syncwarp();
+  return sw_pair_warp<R>(s_prof, s_prof + kPairProfWords, s_ref, s_ref + kRefStage + 64, nmax, sc);
+}
+
+__device__ __forceinline__ int pair_rows(const int32_t m) { return m <= 32 ? 1 : m <= 64 ? 2 : m <= 96 ? 3 : m <= 128 ? 4 : m <= 160 ? 5 : m <= 192 ? 6 : 8; }
+
+__device__ uint32_t sw_pair(const PairProblem A, const PairProblem B, const int R, const bool buildA, const bool buildB, const SwScore sc,
+                            uint8_t* s_ref, uint32_t* s_prof) {
+  switch (R) {
+    case 1: return sw_pair_run<1>(A, B, buildA, buildB, sc, s_ref, s_prof);
+    case 2: return sw_pair_run<2>(A, B, buildA, buildB, sc, s_ref, s_prof);
+    case 3: return sw_pair_run<3>(A, B, buildA, buildB, sc, s_ref, s_prof);
+    case 4: return sw_pair_run<4>(A, B, buildA, buildB, sc, s_ref, s_prof);
+    case 5: return sw_pair_run<5>(A, B, buildA, buildB, sc, s_ref, s_prof);
+    case 6: return sw_pair_run<6>(A, B, buildA, buildB, sc, s_ref, s_prof);
+    default: return sw_pair_run<8>(A, B, buildA, buildB, sc, s_ref, s_prof);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // banded_sw (ssw.c:577-773) -- executed by ONE lane; band coordinates as set_u / set_d (:70,:73)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int32_t band_u(int32_t w, int32_t i, int32_t j) { int32_t x = i - w; x = x > 0 ? x : 0; return j - x + 1; }
