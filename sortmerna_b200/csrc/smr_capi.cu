@@ -43,7 +43,7 @@ struct smr_ctx {
   uint32_t n_index_files = 0;
   int sm_count = 148;
   uint32_t chunk_reads = 1u << 20;
-  uint32_t lis_ctas_per_sm = 2;   // persistent CTAs of the candidate kernel per SM (matches its __launch_bounds__)
+  uint32_t lis_ctas_per_sm = kLisMinCtas;   // persistent CTAs of the candidate kernel per SM (matches its __launch_bounds__)
 
   // resident batch
   uint32_t nreads = 0; uint64_t total_nt = 0; uint32_t max_len = 0;
@@ -151,7 +151,8 @@ int setup_arenas(smr_ctx* ctx) {
   ctx->row_cap = ctx->max_len + 2 * edges + 2 * 64 + 64;
   // planner and scorer warps wait for each other: EVERY CTA of the grid must be resident at once
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lis_kernel, kLisWarpsPerCta * 32, 0));
+  CK(cudaFuncSetAttribute(lis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLisSmemBytes));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lis_kernel, kLisWarpsPerCta * 32, kLisSmemBytes));
   if (occ < 1) { ctx->err = "lis_kernel does not fit on an SM"; return SMR_ERR_CUDA; }
   ctx->lis_ctas = (uint32_t)ctx->sm_count * std::min<uint32_t>(ctx->lis_ctas_per_sm, (uint32_t)occ);
   ctx->lis_warps = ctx->lis_ctas * kPlannerWarps;   // planner warps (each owns an arena)
@@ -436,7 +437,7 @@ int run_impl(smr_ctx* ctx) {
       lg.q_head = sc.q_head; lg.q_tail = sc.q_tail; lg.planners_done = sc.planners_done;
       lis_reset_kernel<<<kQueueCap / 256, 256, 0, ctx->stream>>>(lg, ctx->lis_warps);
       CK(cudaGetLastError());
-      lis_kernel<<<ctx->lis_ctas, kLisWarpsPerCta * 32, 0, ctx->stream>>>(b, dp, lg);
+      lis_kernel<<<ctx->lis_ctas, kLisWarpsPerCta * 32, kLisSmemBytes, ctx->stream>>>(b, dp, lg);
       CK(cudaGetLastError());
       CK(cudaEventRecord(s2, ctx->stream));
       spans.push_back({evi - 3, 0});
@@ -579,7 +580,7 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
                                   {SMR_CNT_BUCKET_ENTRIES, dcEntries}, {SMR_CNT_POS_ENTRIES, dcPosEntries}, {SMR_CNT_LIS_CALLS, dcLisCalls},
                                   {10, dcMaxReadCycles}, {11, dcSumReadCycles}, {12, dcLisKernelCycles},
                                   {13, dcCycVote}, {14, dcCycOrder}, {15, dcCycGroup}, {16, dcCycPlan}, {17, dcCycWait}, {18, dcCycReplay}, {19, dcSpecCalls},
-                                  {20, dcSpecCells}, {21, dcSpecPairs}, {22, dcSlowPairs}};
+                                  {20, dcSpecCells}, {21, dcSpecPairs}, {22, dcSlowPairs}, {23, dcScWait}, {24, dcScLoad}, {25, dcScSw}, {26, dcScPub}};
     for (auto& m : mapc) if ((uint32_t)m[0] < out.n_counters) out.counters[m[0]] += cnt[m[1]];
   }
   return rc;

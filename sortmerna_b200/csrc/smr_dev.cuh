@@ -70,7 +70,8 @@ constexpr uint32_t kErrTrace = 32u;     // "Trace back error" (ssw.c:707) -- fat
 // instrumentation counters (device side, u64), same order as SMR_CNT_* after the first two
 enum DevCnt { dcNumAligned = 0, dcNumShort, dcSwCalls, dcSwCells, dcWindows, dcNodes, dcBuckets, dcEntries, dcPosEntries,
               dcLisCalls, dcMaxReadCycles, dcSumReadCycles, dcLisKernelCycles,
-              dcCycVote, dcCycOrder, dcCycGroup, dcCycPlan, dcCycWait, dcCycReplay, dcSpecCalls, dcSpecCells, dcSpecPairs, dcSlowPairs, dcCount = 32 };
+              dcCycVote, dcCycOrder, dcCycGroup, dcCycPlan, dcCycWait, dcCycReplay, dcSpecCalls, dcSpecCells, dcSpecPairs, dcSlowPairs,
+              dcScWait, dcScLoad, dcScSw, dcScPub, dcCount = 32 };
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 

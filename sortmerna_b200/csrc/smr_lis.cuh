@@ -36,8 +36,21 @@
 
 namespace smr {
 
-constexpr int kScorerWarps = 4;    // warps 0..3 of a CTA score, one per SM sub-partition
-constexpr int kPlannerWarps = 4;   // warps 4..7 plan
+#ifndef SMR_SCORER_WARPS
+#define SMR_SCORER_WARPS 8
+#endif
+#ifndef SMR_PLANNER_WARPS
+#define SMR_PLANNER_WARPS 8
+#endif
+#ifndef SMR_LIS_MIN_CTAS
+#define SMR_LIS_MIN_CTAS 2
+#endif
+constexpr int kScorerWarps = SMR_SCORER_WARPS;     // the first warps of a CTA score (one per SM sub-partition with 4)
+constexpr int kPlannerWarps = SMR_PLANNER_WARPS;   // the others plan
+constexpr int kLisMinCtas = SMR_LIS_MIN_CTAS;      // CTAs per SM the register budget is set for
+constexpr int kScorerSmem = 2 * kPairProfWords * 4 + 2 * (kRefStage + 64);   // two query profiles + two staged windows
+constexpr int kPlannerSmem = 128 * 16;                                        // kPairsShared pairs + LIS arrays
+constexpr int kLisSmemBytes = kScorerWarps * kScorerSmem + kPlannerWarps * kPlannerSmem;
 constexpr int kLisWarpsPerCta = kScorerWarps + kPlannerWarps;
 constexpr int kPairsShared = 128;  // pairs / LIS arrays kept in shared memory up to this many
 constexpr uint32_t kQueueCap = 1u << 20;         // task-pair ring (slots)
@@ -78,7 +91,7 @@ struct LisArena {            // per-warp scratch in HBM
   uint32_t* lis_b; uint32_t* lis_p;  // [pair_cap]
   SwTask* tasks; PlanTask* ptasks;   // [task_cap]
   uint32_t* sel;                     // [task_cap] task indices of the round being submitted
-  uint32_t* cfirst;                  // [kBatchCandCap + 1] first task of each candidate of the batch | reset-at-end << 31
+  uint32_t* cfirst;                  // [3][kBatchCandCap] per candidate of the batch: first task; count | big << 30 | ends-on-reset << 31; uncond mask
   uint32_t hist_cap, cand_cap, pair_cap, task_cap;
 };
 
@@ -108,7 +121,7 @@ __device__ __forceinline__ LisArena carve_arena(const LisGlobals& g, uint32_t wa
   a.lis_b = (uint32_t*)p; p += (size_t)g.pair_cap * 4;
   a.lis_p = (uint32_t*)p; p += (size_t)g.pair_cap * 4;
   a.sel = (uint32_t*)p; p += (size_t)g.task_cap * 4;
-  a.cfirst = (uint32_t*)p; p += (size_t)(kBatchCandCap + 1) * 4;
+  a.cfirst = (uint32_t*)p; p += (size_t)kBatchCandCap * 3 * 4;
   a.bitmap = (uint32_t*)p; p += (size_t)((g.hist_cap + 31) / 32) * 4;
   a.summary = (uint32_t*)p; p += (size_t)((g.hist_cap + 1023) / 1024) * 4;
   p = (uint8_t*)(((uintptr_t)p + 31) & ~(uintptr_t)31);
@@ -119,13 +132,13 @@ __device__ __forceinline__ LisArena carve_arena(const LisGlobals& g, uint32_t wa
 }
 __host__ __device__ inline size_t lis_arena_bytes(uint32_t hist_cap, uint32_t cand_cap, uint32_t pair_cap, uint32_t task_cap, uint32_t pall_cap) {
   size_t b = (size_t)cand_cap * 16 + (size_t)pair_cap * 8 + (size_t)hist_cap * 4 + (size_t)pair_cap * 8 + (size_t)task_cap * 4 +
-             (size_t)(kBatchCandCap + 1) * 4 + (size_t)((hist_cap + 31) / 32) * 4 + (size_t)((hist_cap + 1023) / 1024) * 4 + 64 +
+             (size_t)kBatchCandCap * 3 * 4 + (size_t)((hist_cap + 31) / 32) * 4 + (size_t)((hist_cap + 1023) / 1024) * 4 + 64 +
              (size_t)pall_cap * 8 + (size_t)task_cap * (sizeof(SwTask) + sizeof(PlanTask));
   return (b + 255) & ~(size_t)255;
 }
 
 // ---- warp bitonic sort of 64-bit keys, ascending; n_pow2 = power of two >= n, tail padded by the caller ----
-__device__ void warp_sort_u64(unsigned long long* a, uint32_t n_pow2) {
+__device__ __noinline__ void warp_sort_u64(unsigned long long* a, uint32_t n_pow2) {
   const unsigned lane = lane_id();
   for (uint32_t k = 2; k <= n_pow2; k <<= 1) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
@@ -144,7 +157,7 @@ __device__ void warp_sort_u64(unsigned long long* a, uint32_t n_pow2) {
 // ascending sort of one 64-bit key per lane (pad with ~0ull), entirely in registers
 // `n` (warp-uniform) = number of real keys: only the first next_pow2(n) lanes need to end up sorted, which takes the
 // merge stages up to that block size only (3 of the 15 stages for n <= 4)
-__device__ __forceinline__ unsigned long long warp_sort32_u64(unsigned long long key, const unsigned n = 32) {
+__device__ __noinline__ unsigned long long warp_sort32_u64(unsigned long long key, const unsigned n = 32) {
   const unsigned lane = lane_id();
 #pragma unroll
   for (unsigned k = 2; k <= 32; k <<= 1) {
@@ -223,7 +236,7 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return 
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
 
 // hands the tasks sel[0 .. nsel) of this planner to the scorers, two per queue entry, and waits for their scores
-__device__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
+__device__ __noinline__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
   if (nsel == 0) return;
   const LisGlobals& g = *E.g;
   const unsigned lane = lane_id();
@@ -427,25 +440,95 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   }
 }
 
-// One candidate reference of a batch (alignment.cpp:171-507 without the ssw_align call): gathers and sorts its pairs, slides
-// the window and appends one task per step that would reach ssw_align.  Returns false on scratch overflow (rc.flags set).
-__device__ bool plan_candidate(PassEnv& E, ReadCtx& rc, const unsigned long long ck, const uint32_t cand_rel, uint32_t& ntask, const bool grouped) {
-  const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
+constexpr int kLanePairs = 32;    // candidates with up to this many pairs are planned by ONE lane (32 candidates per warp step)
+
+struct CandPlan { uint32_t cnt, umask, nuncond; bool reset; };   // tasks of a candidate; umask: bit j = task j is unconditional (j < 32)
+
+// The sliding window of one candidate over its SORTED pairs (alignment.cpp:205-507 without the ssw_align call), by ONE thread:
+// one task per step that would reach ssw_align, written to tasks[toff ..].  The trajectory of (it, f) does not depend on any score.
+__device__ __noinline__ void plan_slide_thread(const PassEnv& E, const ReadCtx& rc, const unsigned long long* __restrict__ P, const uint32_t np, uint32_t* lb, uint32_t* lp,
+                                  const uint32_t max_ref, const uint64_t ref_base, const uint64_t reflen, const uint32_t cand_rel, const uint32_t toff,
+                                  CandPlan& out) {
+  const DevIndex& ix = *E.ix; const DevParams& o = *E.prm;
+  const uint64_t rlen = rc.len, lnwin = ix.lnwin;
+  const uint32_t edges = o.edges_is_percent ? (uint32_t)((o.edges / 100.0) * (double)rlen) : (uint32_t)o.edges;  // :278-282
+  const uint64_t em1 = (uint64_t)(uint32_t)(edges - 1u);
+  uint32_t it = 0, f = 0, cnt = 0, umask = 0, nunc = 0;
+  uint32_t begin_ref = (uint32_t)(P[0] >> 32), begin_read = (uint32_t)P[0];
+  bool reset = false;            // a push step without a task since the previous task of this candidate
+  uint32_t lead = kNoTask;       // the last unconditional task of this candidate
+  while (it != np) {
+    const uint64_t end_ref_max = (uint64_t)begin_ref + rlen - begin_read - lnwin + 1;     // :231
+    bool push = false;
+    while (it != np && (uint64_t)(uint32_t)(P[it] >> 32) <= end_ref_max) { ++it; push = true; }
+    bool task = false;
+    if ((it - f) >= (uint32_t)o.num_seeds) {
+      uint32_t lis_first = 0;
+      const uint32_t lis_len = find_lis_dev(P + f, it - f, lb, lp, lis_first);
+      if (lis_len >= (uint32_t)o.min_lis) {                                               // :261
+        const uint32_t lcs_ref_start = (uint32_t)(P[f + lis_first] >> 32), lcs_que_start = (uint32_t)P[f + lis_first];
+        uint64_t head = 0, tail = 0, ars = 0, aqs = 0, alen = 0;
+        if (lcs_ref_start < lcs_que_start) {                                              // :288-330
+          aqs = lcs_que_start - lcs_ref_start;
+          if (reflen < rlen) {
+            if (aqs > (rlen - reflen)) alen = reflen - (aqs - (rlen - reflen)); else alen = reflen;
+          } else {
+            tail = reflen - ars - rlen; if (tail > em1) tail = edges;
+            alen = rlen + head + tail - aqs;
+          }
+        } else {                                                                          // :331-357
+          ars = lcs_ref_start - lcs_que_start;
+          if (ars > em1) head = edges;
+          if (ars + rlen > reflen) { tail = 0; alen = reflen - ars - head; }
+          else { tail = reflen - ars - rlen; if (tail > em1) tail = edges; alen = rlen + head + tail; }
+        }
+        const int32_t qlen = (int32_t)(alen - head - tail);
+        const uint32_t win_start = (uint32_t)(ars - head);
+        const bool unc = push || reset;
+        const uint32_t fl = (push ? kTfPush : 0u) | (unc ? kTfUncond : 0u) | (reset ? kTfReset : 0u);
+        const uint32_t ti = toff + cnt;
+        SwTask t;
+        t.ref_abs = (uint32_t)ref_base + win_start;
+        t.q_abs = rc.reversed ? rc.seq_base + (rc.len - 1u - (uint32_t)aqs) : rc.seq_base + (uint32_t)aqs;   // query = current strand, 0-4 alphabet (:360-366)
+        t.alen = (uint32_t)alen; t.qlen = qlen > 0 ? (uint32_t)qlen : 0u;
+        t.meta = ix.slot | (rc.reversed ? 0x10000u : 0u);
+        t.score = 0; t.pad0 = 0; t.pad1 = 0;
+        E.ar.tasks[ti] = t;
+        PlanTask pt;
+        pt.max_ref = max_ref; pt.win_start = win_start; pt.aqs = (uint32_t)aqs; pt.cf = cand_rel | (fl << 24);
+        pt.lead = unc ? ti : lead;
+        E.ar.ptasks[ti] = pt;
+        if (unc) { lead = ti; ++nunc; if (cnt < 32u) umask |= 1u << cnt; }
+        ++cnt;
+        task = true; reset = false;
+      }
+    }
+    if (!task && push) reset = true;
+    // pop (:486-506)
+    if (it > f) ++f;
+    if (it == f) {
+      if (it != np) { begin_ref = (uint32_t)(P[it] >> 32); begin_read = (uint32_t)P[it]; } else break;
+    } else { begin_ref = (uint32_t)(P[f] >> 32); begin_read = (uint32_t)P[f]; }
+  }
+  out.cnt = cnt; out.umask = umask; out.nuncond = nunc; out.reset = reset;
+}
+
+// A candidate with more than kLanePairs pairs (or whose pairs were not grouped by the scatter): the warp gathers and sorts the
+// pairs (alignment.cpp:181-201), lane 0 slides.  Returns false on scratch overflow (rc.flags set).
+__device__ __noinline__ bool plan_candidate_warp(PassEnv& E, ReadCtx& rc, const unsigned long long ck, const uint32_t cand_rel, const uint32_t toff, const bool grouped,
+                                    CandPlan& out) {
+  const DevIndex& ix = *E.ix;
   const unsigned lane = lane_id();
   const uint32_t s0 = ix.skip[0], s1 = ix.skip[1], s2 = ix.skip[2];
   const uint2* hits = E.hits;
   const uint32_t nh = E.nh;
-  const uint64_t rlen = rc.len, lnwin = ix.lnwin;
   const uint32_t max_ref = (uint32_t)ck, max_occur = 0xFFFFFu - (uint32_t)(ck >> 32);
-  // start of the reference and of its successor: requested now, needed only after the pairs are gathered and sorted
   const uint64_t ref_base = __ldg(ix.ref_off + max_ref), ref_next = __ldg(ix.ref_off + max_ref + 1);
-  // gather (refpos, readpos) pairs of this reference (:181-201)
   const uint32_t np = max_occur;
   unsigned long long* P; uint32_t* lb; uint32_t* lp;
   if (np <= (uint32_t)kPairsShared) { P = E.s_pairs; lb = E.s_b; lp = E.s_p; }
   else if (np <= E.ar.pair_cap) { P = E.ar.pairs; lb = E.ar.lis_b; lp = E.ar.lis_p; }
   else { rc.flags |= kOvfPairs; return false; }
-  if (ntask + np > E.ar.task_cap) { rc.flags |= kOvfPairs; return false; }   // at most one task per pair
   uint32_t filled = 0;
   if (grouped) {   // the pairs of this reference were grouped by the one-pass scatter
     const uint32_t seg_end = E.ar.hist[max_ref] & 0x7FFFFFFFu, seg = seg_end - np;
@@ -485,70 +568,10 @@ __device__ bool plan_candidate(PassEnv& E, ReadCtx& rc, const unsigned long long
     __syncwarp();
     warp_sort_u64(P, np2);
   }
-  // sliding window over the sorted pairs (:205-507); the trajectory of (it, f) does not depend on any score
-  const uint64_t reflen = ref_next - ref_base;
-  const uint32_t edges = o.edges_is_percent ? (uint32_t)((o.edges / 100.0) * (double)rlen) : (uint32_t)o.edges;  // :278-282
-  const uint64_t em1 = (uint64_t)(uint32_t)(edges - 1u);
-  uint32_t it = 0, f = 0;
-  uint32_t begin_ref = (uint32_t)(P[0] >> 32), begin_read = (uint32_t)P[0];
-  bool reset = false;            // a push step without a task since the previous task of this candidate
-  uint32_t lead = kNoTask;       // the last unconditional task of this candidate
-  while (it != np) {
-    const uint64_t end_ref_max = (uint64_t)begin_ref + rlen - begin_read - lnwin + 1;     // :231
-    bool push = false;
-    while (it != np && (uint64_t)(uint32_t)(P[it] >> 32) <= end_ref_max) { ++it; push = true; }
-    bool task = false;
-    if ((it - f) >= (uint32_t)o.num_seeds) {
-      // find_lis is sequential: lane 0 runs it, the result is broadcast
-      uint32_t lis_first = 0, lis_len = 0;
-      if (lane == 0) lis_len = find_lis_dev(P + f, it - f, lb, lp, lis_first);
-      lis_len = __shfl_sync(kFull, lis_len, 0); lis_first = __shfl_sync(kFull, lis_first, 0);
-      if (lis_len >= (uint32_t)o.min_lis) {                                               // :261
-        const uint32_t lcs_ref_start = (uint32_t)(P[f + lis_first] >> 32), lcs_que_start = (uint32_t)P[f + lis_first];
-        uint64_t head = 0, tail = 0, ars = 0, aqs = 0, alen = 0;
-        if (lcs_ref_start < lcs_que_start) {                                              // :288-330
-          aqs = lcs_que_start - lcs_ref_start;
-          if (reflen < rlen) {
-            if (aqs > (rlen - reflen)) alen = reflen - (aqs - (rlen - reflen)); else alen = reflen;
-          } else {
-            tail = reflen - ars - rlen; if (tail > em1) tail = edges;
-            alen = rlen + head + tail - aqs;
-          }
-        } else {                                                                          // :331-357
-          ars = lcs_ref_start - lcs_que_start;
-          if (ars > em1) head = edges;
-          if (ars + rlen > reflen) { tail = 0; alen = reflen - ars - head; }
-          else { tail = reflen - ars - rlen; if (tail > em1) tail = edges; alen = rlen + head + tail; }
-        }
-        const int32_t qlen = (int32_t)(alen - head - tail);
-        const uint32_t win_start = (uint32_t)(ars - head);
-        const uint32_t fl = (push ? kTfPush : 0u) | ((push || reset) ? kTfUncond : 0u) | (reset ? kTfReset : 0u);
-        if (lane == 0) {
-          SwTask t;
-          t.ref_abs = (uint32_t)ref_base + win_start;
-          t.q_abs = rc.reversed ? rc.seq_base + (rc.len - 1u - (uint32_t)aqs) : rc.seq_base + (uint32_t)aqs;   // query = current strand, 0-4 alphabet (:360-366)
-          t.alen = (uint32_t)alen; t.qlen = qlen > 0 ? (uint32_t)qlen : 0u;
-          t.meta = ix.slot | (rc.reversed ? 0x10000u : 0u);
-          t.score = 0; t.pad0 = 0; t.pad1 = 0;
-          E.ar.tasks[ntask] = t;
-          PlanTask pt;
-          pt.max_ref = max_ref; pt.win_start = win_start; pt.aqs = (uint32_t)aqs; pt.cf = cand_rel | (fl << 24);
-          pt.lead = (fl & kTfUncond) ? ntask : lead;
-          E.ar.ptasks[ntask] = pt;
-        }
-        if (fl & kTfUncond) lead = ntask;
-        ++ntask;
-        task = true; reset = false;
-      }
-    }
-    if (!task && push) reset = true;
-    // pop (:486-506)
-    if (it > f) ++f;
-    if (it == f) {
-      if (it != np) { begin_ref = (uint32_t)(P[it] >> 32); begin_read = (uint32_t)P[it]; } else break;
-    } else { begin_ref = (uint32_t)(P[f] >> 32); begin_read = (uint32_t)P[f]; }
-  }
-  if (lane == 0) E.ar.cfirst[cand_rel + 1] = ntask | (reset ? 0x80000000u : 0u);   // end of this candidate's tasks | "ends on a reset"
+  CandPlan cp{0, 0, 0, false};
+  if (lane == 0) plan_slide_thread(E, rc, P, np, lb, lp, max_ref, ref_base, ref_next - ref_base, cand_rel, toff, cp);
+  out.cnt = __shfl_sync(kFull, cp.cnt, 0); out.umask = __shfl_sync(kFull, cp.umask, 0); out.nuncond = __shfl_sync(kFull, cp.nuncond, 0);
+  out.reset = __shfl_sync(kFull, cp.reset ? 1u : 0u, 0) != 0;
   __syncwarp();
   return true;
 }
@@ -559,11 +582,13 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
                                uint32_t level, const bool grouped) {
   const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
   const unsigned lane = lane_id();
+  const unsigned lt = (1u << lane) - 1u;
   bool is_aligned = false, first_cand = true, stop_all = false, searching = true;
   uint32_t prev_occur = 0;
   const uint32_t N = (uint32_t)o.num_alignments;
   AlnWork* slots = E.g->aln_work + (size_t)rc.r * E.g->slots;
-  uint32_t cap = 8;   // unconditional tasks per batch; doubles per batch (a perfect-score stop wastes at most what was useful)
+  uint32_t cap = 8;   // candidates per batch; doubles per batch (a perfect-score stop wastes at most what was useful)
+  uint32_t* cfirst = E.ar.cfirst; uint32_t* ccnt = cfirst + kBatchCandCap; uint32_t* cumask = ccnt + kBatchCandCap;
 
   for (;;) {
     // the next group: everything (sorted) for small lists, else the members of the current count level
@@ -577,7 +602,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
         if (i < ncand) { key = E.ar.cand[i]; c = 0xFFFFFu - (uint32_t)(key >> 32); }
         const bool pick = i < ncand && c == level;
         const unsigned pm = __ballot_sync(kFull, pick);
-        if (pick) E.ar.grp[ngrp + __popc(pm & ((1u << lane) - 1))] = key;
+        if (pick) E.ar.grp[ngrp + __popc(pm & lt)] = key;
         ngrp += __popc(pm);
         if (i < ncand && c < level) next_level = max(next_level, c);
       }
@@ -595,131 +620,212 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
         if (is_aligned && o.min_lis > 0 && !first_cand && occ < prev_occur) { --rc.best; if (rc.best < 1) { stop_all = true; break; } }   // :165-169
         prev_occur = occ; first_cand = false;
       }
-      // ---- plan: candidates k .. k2.  The batch ends before the level drop at which the countdown of `best` could end the
-      //      call (so nothing behind a possible stop is scored), when it holds `cap` unconditional tasks, or when full ----
+      // ---- extent of the batch: candidates k .. k + nb.  It ends before the level drop at which the countdown of `best` could
+      //      end the call (so nothing behind a possible stop is scored), at `cap` candidates, or when the task array is full ----
       const uint32_t budget = o.min_lis > 0 ? (uint32_t)max(rc.best, 1) : 0xFFFFFFFFu;
       // without `best`, the call ends at the N-th accepted alignment (:466-468): speculate on no more than are still wanted
-      const uint32_t cap_now = (N > 0 && !o.is_best) ? min(cap, 2u * (N > rc.n_align ? N - rc.n_align : 1u)) : cap;
-      uint32_t ntask = 0, nuncond = 0, drops = 0, k2 = k, lvl_prev = prev_occur;
-      if (lane == 0) E.ar.cfirst[0] = 0;
-      for (; k2 < ngrp && (k2 - k) < kBatchCandCap; ++k2) {
-        const unsigned long long ck = E.ar.grp[k2];
-        const uint32_t occ = 0xFFFFFu - (uint32_t)(ck >> 32);
-        if (k2 > k) {
-          if (occ < lvl_prev && ++drops >= budget) break;
-          if (nuncond >= cap_now) break;
-          if (occ < (uint32_t)o.num_seeds) break;     // the call ends there (:158), decided at the next batch entry
-          if (ntask + occ > E.ar.task_cap) break;     // at most one task per pair: the next candidate might not fit
+      const uint32_t cap_now = min((N > 0 && !o.is_best) ? min(cap, 2u * (N > rc.n_align ? N - rc.n_align : 1u)) : cap, (uint32_t)kBatchCandCap);
+      uint32_t nb = 0;
+      {
+        uint32_t drops = 0, tsum = 0, prev = prev_occur; bool ended = false;
+        for (uint32_t c0 = 0; !ended; c0 += 32) {
+          const uint32_t c = c0 + lane;
+          const bool in = k + c < ngrp && c < cap_now;
+          const uint32_t occ = in ? 0xFFFFFu - (uint32_t)(E.ar.grp[k + c] >> 32) : 0u;
+          uint32_t up = __shfl_up_sync(kFull, occ, 1); if (lane == 0) up = prev;
+          const uint32_t d = (in && occ < up) ? 1u : 0u;
+          const uint32_t dincl = drops + warp_incl_scan_u32(d), tincl = tsum + warp_incl_scan_u32(occ);
+          // candidate c belongs to the batch unless: out of range, a drop that exhausts the budget, the call's end (:158), or no room
+          const bool stop = !in || (c > 0 && (dincl >= budget || occ < (uint32_t)o.num_seeds || tincl > E.ar.task_cap));
+          const unsigned sm = __ballot_sync(kFull, stop);
+          if (sm) { nb = c0 + (uint32_t)(__ffs(sm) - 1); ended = true; }
+          else { drops = __shfl_sync(kFull, dincl, 31); tsum = __shfl_sync(kFull, tincl, 31); prev = __shfl_sync(kFull, occ, 31); }
         }
-        lvl_prev = occ;
-        const uint32_t before = ntask;
-        if (!plan_candidate(E, rc, ck, k2 - k, ntask, grouped)) return;
-        // unconditional tasks of this candidate
-        uint32_t nu = 0;
-        for (uint32_t t = before + lane; t < ntask; t += 32) nu += ((E.ar.ptasks[t].cf >> 24) & kTfUncond) ? 1u : 0u;
-        nuncond += warp_sum_u32(nu);
+      }
+      if (nb == 0) { rc.flags |= kErrTrace; return; }   // (the first candidate always belongs: its pairs fit, np <= pair_cap is checked below)
+      // ---- plan: one candidate per lane (its few pairs in thread-local arrays); candidates with many pairs by the whole warp ----
+      uint32_t tbase = 0, nselA = 0, ncond = 0;
+      for (uint32_t c0 = 0; c0 < nb; c0 += 32) {
+        const uint32_t c = c0 + lane;
+        const bool valid = c < nb;
+        const unsigned long long ck = valid ? E.ar.grp[k + c] : 0ull;
+        const uint32_t max_ref = (uint32_t)ck, np = valid ? 0xFFFFFu - (uint32_t)(ck >> 32) : 0u;
+        const uint32_t incl = warp_incl_scan_u32(np), toff = tbase + incl - np;
+        const bool small = valid && grouped && np <= (uint32_t)kLanePairs;
+        CandPlan cp{0, 0, 0, false};
+        if (small) {
+          const uint64_t ref_base = __ldg(ix.ref_off + max_ref), ref_next = __ldg(ix.ref_off + max_ref + 1);
+          const uint32_t seg = (E.ar.hist[max_ref] & 0x7FFFFFFFu) - np;
+          unsigned long long P[kLanePairs]; uint32_t lb[kLanePairs], lp[kLanePairs];
+          for (uint32_t i = 0; i < np; ++i) {    // insertion sort while loading (refpos asc, readpos asc: alignment.cpp:197-201)
+            const unsigned long long v = E.ar.pall[seg + i];
+            uint32_t j = i;
+            while (j > 0 && P[j - 1] > v) { P[j] = P[j - 1]; --j; }
+            P[j] = v;
+          }
+          plan_slide_thread(E, rc, P, np, lb, lp, max_ref, ref_base, ref_next - ref_base, c, toff, cp);
+        }
+        unsigned big = __ballot_sync(kFull, valid && !small);
+        while (big) {
+          const int L = __ffs(big) - 1; big &= big - 1;
+          const unsigned long long ckL = __shfl_sync(kFull, ck, L);
+          const uint32_t toffL = __shfl_sync(kFull, toff, L);
+          CandPlan cb{0, 0, 0, false};
+          if (!plan_candidate_warp(E, rc, ckL, c0 + (uint32_t)L, toffL, grouped, cb)) return;
+          if ((int)lane == L) { cp = cb; cp.umask = 0; }
+          // its unconditional tasks go to round A now (they may be more than 32: no mask)
+          for (uint32_t t0 = 0; t0 < cb.cnt; t0 += 32) {
+            const uint32_t t = t0 + lane;
+            const bool pick = t < cb.cnt && ((E.ar.ptasks[toffL + t].cf >> 24) & kTfUncond);
+            const unsigned pm = __ballot_sync(kFull, pick);
+            if (pick) E.ar.sel[nselA + __popc(pm & lt)] = toffL + t;
+            nselA += __popc(pm);
+          }
+        }
+        if (valid) { cfirst[c] = toff; ccnt[c] = cp.cnt | (cp.reset ? 0x80000000u : 0u) | (small ? 0u : 0x40000000u); cumask[c] = cp.umask; }
+        // round A entries of the lane-planned candidates
+        {
+          const uint32_t nu = small ? (uint32_t)__popc(cp.umask) : 0u;
+          const uint32_t ui = warp_incl_scan_u32(nu);
+          uint32_t w = nselA + ui - nu, m = small ? cp.umask : 0u;
+          while (m) { const uint32_t j = (uint32_t)__ffs(m) - 1u; m &= m - 1u; E.ar.sel[w++] = toff + j; }
+          nselA += __shfl_sync(kFull, ui, 31);
+        }
+        ncond += warp_sum_u32(valid ? cp.cnt - cp.nuncond : 0u);
+        tbase += __shfl_sync(kFull, incl, 31);
       }
       __syncwarp();
       { const long long t2 = clock64(); E.cyc[3] += (unsigned long long)(t2 - tc0); tc0 = t2; }
       // ---- score, round A: the unconditional tasks ----
-      uint32_t nsel = 0;
-      for (uint32_t t0 = 0; t0 < ntask; t0 += 32) {
-        const uint32_t t = t0 + lane;
-        const bool pick = t < ntask && ((E.ar.ptasks[t].cf >> 24) & kTfUncond);
-        const unsigned pm = __ballot_sync(kFull, pick);
-        if (pick) E.ar.sel[nsel + __popc(pm & ((1u << lane) - 1))] = t;
-        nsel += __popc(pm);
-      }
-      __syncwarp();
-      submit_and_wait(E, nsel);
-      E.n_spec_calls += nsel;
+      submit_and_wait(E, nselA);
+      E.n_spec_calls += nselA;
       // ---- round B: tasks heuristic 1 would skip after a successful lead (:243-246) are needed when the lead failed ----
-      if (nsel < ntask) {
-        uint32_t nsel2 = 0;
-        for (uint32_t t0 = 0; t0 < ntask; t0 += 32) {
-          const uint32_t t = t0 + lane;
-          bool pick = false;
-          if (t < ntask) {
-            const PlanTask pt = E.ar.ptasks[t];
-            if (!((pt.cf >> 24) & kTfUncond)) pick = (__ldcg(&E.ar.tasks[pt.lead].score) & 0xFFFFu) <= ix.minimal_score;
+      if (ncond) {
+        uint32_t nselB = 0;
+        for (uint32_t c0 = 0; c0 < nb; c0 += 32) {
+          const uint32_t c = c0 + lane;
+          const bool valid = c < nb;
+          const uint32_t toff = valid ? cfirst[c] : 0u, cw = valid ? ccnt[c] : 0u, cnt = cw & 0x3FFFFFFFu;
+          const bool bigc = (cw & 0x40000000u) != 0;
+          uint32_t bmask = 0;
+          if (valid && !bigc && cnt) {
+            uint32_t m = cumask[c];
+            while (m) {
+              const uint32_t j = (uint32_t)__ffs(m) - 1u; m &= m - 1u;
+              const uint32_t jn = m ? (uint32_t)__ffs(m) - 1u : cnt;        // next unconditional task (or the end)
+              if (jn > j + 1 && (__ldcg(&E.ar.tasks[toff + j].score) & 0xFFFFu) <= ix.minimal_score) bmask |= ((jn < 32u ? (1u << jn) : 0u) - 1u) & ~((2u << j) - 1u);
+            }
           }
-          const unsigned pm = __ballot_sync(kFull, pick);
-          if (pick) E.ar.sel[nsel2 + __popc(pm & ((1u << lane) - 1))] = t | 0x80000000u;
-          nsel2 += __popc(pm);
+          const uint32_t nbm = (uint32_t)__popc(bmask), bi = warp_incl_scan_u32(nbm);
+          uint32_t w = nselB + bi - nbm;
+          while (bmask) { const uint32_t j = (uint32_t)__ffs(bmask) - 1u; bmask &= bmask - 1u; E.ar.sel[w++] = toff + j; }
+          nselB += __shfl_sync(kFull, bi, 31);
+          unsigned big = __ballot_sync(kFull, valid && bigc && cnt);
+          while (big) {
+            const int L = __ffs(big) - 1; big &= big - 1;
+            const uint32_t toffL = __shfl_sync(kFull, toff, L), cntL = __shfl_sync(kFull, cnt, L);
+            for (uint32_t t0 = 0; t0 < cntL; t0 += 32) {
+              const uint32_t t = t0 + lane;
+              bool pick = false;
+              if (t < cntL) {
+                const PlanTask pt = E.ar.ptasks[toffL + t];
+                if (!((pt.cf >> 24) & kTfUncond)) pick = (__ldcg(&E.ar.tasks[pt.lead].score) & 0xFFFFu) <= ix.minimal_score;
+              }
+              const unsigned pm = __ballot_sync(kFull, pick);
+              if (pick) E.ar.sel[nselB + __popc(pm & lt)] = toffL + t;
+              nselB += __popc(pm);
+            }
+          }
         }
         __syncwarp();
-        for (uint32_t i = lane; i < nsel2; i += 32) { const uint32_t t = E.ar.sel[i] & 0x7FFFFFFFu; E.ar.sel[i] = t; E.ar.ptasks[t].cf |= (8u << 24); }   // scored
-        __syncwarp();
-        submit_and_wait(E, nsel2);
-        E.n_spec_calls += nsel2;
+        submit_and_wait(E, nselB);
+        E.n_spec_calls += nselB;
       }
       { const long long t2 = clock64(); E.cyc[4] += (unsigned long long)(t2 - tc0); tc0 = t2; }
       // ---- replay: the reference's decisions over the scores, in order ----
-      for (uint32_t c = 0; c < k2 - k && searching; ++c) {
-        if (c > 0) {   // entry of a later candidate of the batch (:158-169); the countdown cannot reach 0 inside a batch
-          const uint32_t occ = 0xFFFFFu - (uint32_t)(E.ar.grp[k + c] >> 32);
-          if (is_aligned && o.min_lis > 0 && occ < prev_occur) { --rc.best; if (rc.best < 1) { stop_all = true; searching = false; break; } }
-          prev_occur = occ;
-        }
-        is_aligned = false;   // the first step of a candidate always pushes: `else is_aligned = false` (:245)
-        const uint32_t t_lo = E.ar.cfirst[c] & 0x7FFFFFFFu, t_hi_w = E.ar.cfirst[c + 1];
-        const uint32_t t_hi = t_hi_w & 0x7FFFFFFFu;
-        for (uint32_t t = t_lo; t < t_hi && searching; ++t) {
-          const PlanTask pt = E.ar.ptasks[t];
-          const uint32_t fl = pt.cf >> 24;
-          if (fl & kTfReset) is_aligned = false;
-          if (!(fl & kTfPush) && is_aligned) continue;                                      // heuristic 1 (:244-245)
-          is_aligned = false;
-          if (!(fl & (kTfUncond | 8u))) { rc.flags |= kErrTrace; return; }                  // internal consistency: a needed task was not scored
-          const SwTask tk = E.ar.tasks[t];
-          const uint32_t sw = __ldcg(&E.ar.tasks[t].score);
-          if (rc.hasn) rc.form04 = true;                                                    // flip34 before SSW (:360-361)
-          E.n_sw_calls++; E.n_sw_cells += (unsigned long long)tk.alen * (unsigned long long)tk.qlen;
-          const uint32_t score1 = sw & 0xFFFFu;                                             // s_align.score1 is uint16
-          is_aligned = score1 > ix.minimal_score;                                           // :388
-          if (is_aligned) {
-            if (score1 == max_SW_score) ++rc.max_SW_count;                                  // :391
-            AlnWork a;
-            a.ref_num = pt.max_ref; a.win_ref_start = pt.win_start; a.win_len = tk.alen; a.q_start = pt.aqs; a.q_len = tk.qlen;
-            a.score1 = (uint16_t)score1; a.part = (uint16_t)ix.part; a.index_num = (uint16_t)ix.index_num;
-            a.strand = rc.reversed ? 0 : 1; a.idx_slot = (uint16_t)ix.slot; a.pad0 = 0;
-            if (!rc.is_hit) {                                                               // :411-416
-              rc.is_hit = true;   // readstats.num_aligned / reads_matched_per_db are summed from hit_db at download time
-              if (lane == 0) B.hit_db[rc.r] = (uint16_t)ix.index_num;
-            }
-            if (N == 0 || !o.is_best || (o.is_best && rc.n_align < N)) {                    // :420-424
-              if (rc.n_align < E.g->slots) { if (lane == 0) slots[rc.n_align] = a; rc.n_align++; rc.is_new_hit = true; }
-            } else if (o.is_best && rc.n_align == N && slots[rc.min_index].score1 < score1) {  // :425-459
-              if (N > 1 && rc.max_index == 0 && rc.min_index == 0) {
-                uint32_t mn = 0, mx = 0, mns = slots[0].score1, mxs = slots[0].score1;      // findMinIndex / findMaxIndex (:533-561)
-                for (uint32_t i2 = 0; i2 < rc.n_align; ++i2) { const uint32_t s = slots[i2].score1; if (s < mns) { mns = s; mn = i2; } if (s > mxs) { mxs = s; mx = i2; } }
-                rc.min_index = mn; rc.max_index = mx;
-              }
-              const uint32_t mn = rc.min_index, mx = rc.max_index;
-              __syncwarp();
-              if (lane == 0) slots[mn] = a;
-              __syncwarp();
-              rc.is_new_hit = true;
-              if (score1 > slots[mx].score1 && rc.n_align > 1) {
-                rc.max_index = mn;
-                uint32_t m2 = 0, ms = slots[0].score1;
-                for (uint32_t i2 = 0; i2 < rc.n_align; ++i2) { const uint32_t s = slots[i2].score1; if (s < ms) { ms = s; m2 = i2; } }
-                rc.min_index = m2;
-              }
-            }
-            __syncwarp();
-            if (N > 0) {                                                                    // :462-469
-              if (o.is_best) { if (N == rc.max_SW_count) searching = false; }
-              else if (N == rc.n_align) searching = false;
-            }
-            search = false;                                                                 // :472
+      for (uint32_t c0 = 0; c0 < nb && searching; c0 += 32) {
+        // this chunk's candidates: (first task, count, flags, votes), one per lane
+        const uint32_t cl = c0 + lane;
+        const uint32_t v_toff = cl < nb ? cfirst[cl] : 0u, v_cw = cl < nb ? ccnt[cl] : 0u;
+        const uint32_t v_occ = cl < nb ? 0xFFFFFu - (uint32_t)(E.ar.grp[k + cl] >> 32) : 0u;
+        const uint32_t cend = min(32u, nb - c0);
+        for (uint32_t ci = 0; ci < cend && searching; ++ci) {
+          const uint32_t c = c0 + ci;
+          const uint32_t toff = __shfl_sync(kFull, v_toff, ci), cw = __shfl_sync(kFull, v_cw, ci), occ = __shfl_sync(kFull, v_occ, ci);
+          const uint32_t cnt = cw & 0x3FFFFFFFu;
+          if (c > 0) {   // entry of a later candidate of the batch (:158-169); the countdown cannot reach 0 inside a batch
+            if (is_aligned && o.min_lis > 0 && occ < prev_occur) { --rc.best; if (rc.best < 1) { stop_all = true; searching = false; break; } }
+            prev_occur = occ;
           }
+          is_aligned = false;   // the first step of a candidate always pushes: `else is_aligned = false` (:245)
+          for (uint32_t t0 = 0; t0 < cnt && searching; t0 += 32) {
+            // this chunk's tasks: flags, score, cells, one per lane
+            const uint32_t tl = toff + t0 + lane;
+            uint32_t v_fl = 0, v_sc = 0, v_alen = 0, v_qlen = 0;
+            if (t0 + lane < cnt) {
+              v_fl = E.ar.ptasks[tl].cf >> 24;
+              const uint4 w0 = __ldcg((const uint4*)&E.ar.tasks[tl]);
+              v_alen = w0.z; v_qlen = w0.w; v_sc = __ldcg(&E.ar.tasks[tl].score);
+            }
+            const uint32_t tend = min(32u, cnt - t0);
+            for (uint32_t ti = 0; ti < tend && searching; ++ti) {
+              const uint32_t fl = __shfl_sync(kFull, v_fl, ti);
+              if (fl & kTfReset) is_aligned = false;
+              if (!(fl & kTfPush) && is_aligned) continue;                                      // heuristic 1 (:244-245)
+              is_aligned = false;
+              const uint32_t sw = __shfl_sync(kFull, v_sc, ti), alen = __shfl_sync(kFull, v_alen, ti), qlen = __shfl_sync(kFull, v_qlen, ti);
+              const uint32_t t = toff + t0 + ti;
+              if (rc.hasn) rc.form04 = true;                                                    // flip34 before SSW (:360-361)
+              E.n_sw_calls++; E.n_sw_cells += (unsigned long long)alen * (unsigned long long)qlen;
+              const uint32_t score1 = sw & 0xFFFFu;                                             // s_align.score1 is uint16
+              is_aligned = score1 > ix.minimal_score;                                           // :388
+              if (is_aligned) {
+                const PlanTask pt = E.ar.ptasks[t];
+                if (!(fl & kTfUncond) && (__ldcg(&E.ar.tasks[pt.lead].score) & 0xFFFFu) > ix.minimal_score) { rc.flags |= kErrTrace; return; }   // consistency: it was scored
+                if (score1 == max_SW_score) ++rc.max_SW_count;                                  // :391
+                AlnWork a;
+                a.ref_num = pt.max_ref; a.win_ref_start = pt.win_start; a.win_len = alen; a.q_start = pt.aqs; a.q_len = qlen;
+                a.score1 = (uint16_t)score1; a.part = (uint16_t)ix.part; a.index_num = (uint16_t)ix.index_num;
+                a.strand = rc.reversed ? 0 : 1; a.idx_slot = (uint16_t)ix.slot; a.pad0 = 0;
+                if (!rc.is_hit) {                                                               // :411-416
+                  rc.is_hit = true;   // readstats.num_aligned / reads_matched_per_db are summed from hit_db at download time
+                  if (lane == 0) B.hit_db[rc.r] = (uint16_t)ix.index_num;
+                }
+                if (N == 0 || !o.is_best || (o.is_best && rc.n_align < N)) {                    // :420-424
+                  if (rc.n_align < E.g->slots) { if (lane == 0) slots[rc.n_align] = a; rc.n_align++; rc.is_new_hit = true; }
+                } else if (o.is_best && rc.n_align == N && slots[rc.min_index].score1 < score1) {  // :425-459
+                  if (N > 1 && rc.max_index == 0 && rc.min_index == 0) {
+                    uint32_t mn = 0, mx = 0, mns = slots[0].score1, mxs = slots[0].score1;      // findMinIndex / findMaxIndex (:533-561)
+                    for (uint32_t i2 = 0; i2 < rc.n_align; ++i2) { const uint32_t s = slots[i2].score1; if (s < mns) { mns = s; mn = i2; } if (s > mxs) { mxs = s; mx = i2; } }
+                    rc.min_index = mn; rc.max_index = mx;
+                  }
+                  const uint32_t mn = rc.min_index, mx = rc.max_index;
+                  __syncwarp();
+                  if (lane == 0) slots[mn] = a;
+                  __syncwarp();
+                  rc.is_new_hit = true;
+                  if (score1 > slots[mx].score1 && rc.n_align > 1) {
+                    rc.max_index = mn;
+                    uint32_t m2 = 0, ms = slots[0].score1;
+                    for (uint32_t i2 = 0; i2 < rc.n_align; ++i2) { const uint32_t s = slots[i2].score1; if (s < ms) { ms = s; m2 = i2; } }
+                    rc.min_index = m2;
+                  }
+                }
+                __syncwarp();
+                if (N > 0) {                                                                    // :462-469
+                  if (o.is_best) { if (N == rc.max_SW_count) searching = false; }
+                  else if (N == rc.n_align) searching = false;
+                }
+                search = false;                                                                 // :472
+              }
+            }
+          }
+          if (searching && (cw & 0x80000000u)) is_aligned = false;
         }
-        if (searching && (t_hi_w & 0x80000000u)) is_aligned = false;
       }
       { const long long t2 = clock64(); E.cyc[5] += (unsigned long long)(t2 - tc0); }
-      k = k2;
-      cap = min(cap * 2u, 2048u);
+      k += nb;
+      cap = min(cap * 2u, (uint32_t)kBatchCandCap);
       __syncwarp();
     }
     if (!by_level || stop_all || !searching) break;
@@ -780,9 +886,10 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
   int32_t* rowH = g.score_rows + (size_t)scorer * 2 * g.row_cap; int32_t* rowF = rowH + g.row_cap;
   // identity of the query profile resident in each half: (q_abs, qlen | rev << 31, R)
   uint32_t keyq[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, keym[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}; int keyR = 0;
-  unsigned long long n_pairs = 0, n_cells = 0, n_slow = 0;
+  unsigned long long n_pairs = 0, n_cells = 0, n_slow = 0, cy_wait = 0, cy_load = 0, cy_sw = 0, cy_pub = 0;
   for (;;) {
     uint32_t h = 0;
+    long long tq = clock64();
     if (lane == 0) {
       h = atomicAdd(g.q_head, 1u);
       const QSlot* sl = g.ring + (h & (kQueueCap - 1));
@@ -790,6 +897,7 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
       __threadfence();
     }
     h = __shfl_sync(kFull, h, 0);
+    { const long long t2 = clock64(); cy_wait += (unsigned long long)(t2 - tq); tq = t2; }
     QSlot* sl = g.ring + (h & (kQueueCap - 1));
     const uint32_t planner = __ldcg(&sl->planner), ta = __ldcg(&sl->ta), tb = __ldcg(&sl->tb);
     if (lane == 0) st_volatile_u32(&sl->seq, h + kQueueCap);   // slot free for the next lap (after the payload was read)
@@ -809,14 +917,15 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
     {
       const bool rev = (ma >> 16) & 1u;
       A.q = SeqView{b.seq04, (int32_t)da.y, rev ? -1 : 1, rev}; A.m = (int32_t)da.w;
-      A.t = SeqView{g.parts[ma & 0xFFFFu].refseq, (int32_t)da.x, 1, false}; A.n = (int32_t)da.z;
+      A.t = g.parts[ma & 0xFFFFu].refseq + da.x; A.n = (int32_t)da.z;
     }
     if (two) {
       const bool rev = (mb >> 16) & 1u;
       Bp.q = SeqView{b.seq04, (int32_t)db.y, rev ? -1 : 1, rev}; Bp.m = (int32_t)db.w;
-      Bp.t = SeqView{g.parts[mb & 0xFFFFu].refseq, (int32_t)db.x, 1, false}; Bp.n = (int32_t)db.z;
+      Bp.t = g.parts[mb & 0xFFFFu].refseq + db.x; Bp.n = (int32_t)db.z;
     } else { Bp = A; Bp.m = 0; Bp.n = 0; }
     uint32_t sa = 0, sb = 0;
+    { const long long t2 = clock64(); cy_load += (unsigned long long)(t2 - tq); tq = t2; }
     const bool oka = A.m > 0 && A.n > 0 && sw_pair_ok(A.m, A.n, sc), okb = !two || Bp.m <= 0 || Bp.n <= 0 || sw_pair_ok(Bp.m, Bp.n, sc);
     if (oka && okb) {
       const int R = pair_rows(max(A.m, Bp.m));
@@ -828,11 +937,12 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
     } else {
       // shapes or scoring schemes outside the 16-bit kernel: the s32 wavefront (row blocks for long queries)
       keyR = 0;
-      if (A.m > 0 && A.n > 0 && (uint32_t)A.n <= g.row_cap) sa = (uint32_t)sw_forward_any(A.q, A.m, A.t, A.n, sc, rowH, rowF).score;
-      if (two && Bp.m > 0 && Bp.n > 0 && (uint32_t)Bp.n <= g.row_cap) sb = (uint32_t)sw_forward_any(Bp.q, Bp.m, Bp.t, Bp.n, sc, rowH, rowF).score;
+      if (A.m > 0 && A.n > 0 && (uint32_t)A.n <= g.row_cap) sa = (uint32_t)sw_forward_any(A.q, A.m, SeqView{A.t, 0, 1, false}, A.n, sc, rowH, rowF).score;
+      if (two && Bp.m > 0 && Bp.n > 0 && (uint32_t)Bp.n <= g.row_cap) sb = (uint32_t)sw_forward_any(Bp.q, Bp.m, SeqView{Bp.t, 0, 1, false}, Bp.n, sc, rowH, rowF).score;
       ++n_slow;
     }
     ++n_pairs; n_cells += (unsigned long long)da.z * da.w + (unsigned long long)db.z * db.w;
+    { const long long t2 = clock64(); cy_sw += (unsigned long long)(t2 - tq); tq = t2; }
     if (lane == 0) {
       tasks[ta].score = sa;
       if (two) tasks[tb].score = sb;
@@ -840,9 +950,11 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
       atomicAdd(g.done + planner, two ? 2u : 1u);
     }
     __syncwarp();
+    { const long long t2 = clock64(); cy_pub += (unsigned long long)(t2 - tq); }
   }
   if (lane == 0) {
     atomicAdd(&b.counters[dcSpecCells], n_cells); atomicAdd(&b.counters[dcSpecPairs], n_pairs); atomicAdd(&b.counters[dcSlowPairs], n_slow);
+    atomicAdd(&b.counters[dcScWait], cy_wait); atomicAdd(&b.counters[dcScLoad], cy_load); atomicAdd(&b.counters[dcScSw], cy_sw); atomicAdd(&b.counters[dcScPub], cy_pub);
   }
 }
 
@@ -851,13 +963,9 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
 // (processor.cpp:219-277) run read-major, with the KVDB carry-over of read.cpp:429-539 kept in
 // DevBatch::state between parts (equivalent because reads are independent).  Scorer warps
 // run scorer_loop until the last planner has published the shutdown entries.
-__global__ void __launch_bounds__(kLisWarpsPerCta * 32, 2)
+__global__ void __launch_bounds__(kLisWarpsPerCta * 32, kLisMinCtas)
 lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
-  __shared__ unsigned long long s_pairs[kPlannerWarps][kPairsShared];
-  __shared__ uint32_t s_b[kPlannerWarps][kPairsShared];
-  __shared__ uint32_t s_p[kPlannerWarps][kPairsShared];
-  __shared__ __align__(16) uint8_t s_ref[kScorerWarps][2 * (kRefStage + 64)];
-  __shared__ uint32_t s_prof[kScorerWarps][2 * kPairProfWords];
+  extern __shared__ __align__(16) uint8_t lis_smem[];     // kLisSmemBytes: scorer warps first, then planner warps
   __shared__ uint32_t s_bin_start[kCostBins + 1];
   const unsigned lane = lane_id();
   const uint32_t wic = threadIdx.x >> 5;
@@ -868,7 +976,8 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   }
   __syncthreads();
   if (wic < (uint32_t)kScorerWarps) {
-    scorer_loop(b, prm, g, s_ref[wic], s_prof[wic], blockIdx.x * kScorerWarps + wic);
+    uint8_t* sm = lis_smem + (size_t)wic * kScorerSmem;
+    scorer_loop(b, prm, g, sm + 2 * kPairProfWords * 4, (uint32_t*)sm, blockIdx.x * kScorerWarps + wic);
     return;
   }
   const uint32_t pw = wic - kScorerWarps, planner = blockIdx.x * kPlannerWarps + pw;
@@ -877,7 +986,10 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   E.ar = carve_arena(g, planner);
   E.planner = planner; E.submitted = 0;
   E.epoch_ptr = g.epochs + planner; E.epoch = *E.epoch_ptr;
-  E.s_pairs = s_pairs[pw]; E.s_b = s_b[pw]; E.s_p = s_p[pw];
+  {
+    uint8_t* sm = lis_smem + (size_t)kScorerWarps * kScorerSmem + (size_t)pw * kPlannerSmem;
+    E.s_pairs = (unsigned long long*)sm; E.s_b = (uint32_t*)(sm + kPairsShared * 8); E.s_p = E.s_b + kPairsShared;
+  }
   E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = E.n_spec_calls = E.n_spec_cells = 0;
   for (int i = 0; i < 8; ++i) E.cyc[i] = 0;
   const uint32_t nwork = s_bin_start[kCostBins];

@@ -386,7 +386,7 @@ __device__ SwEnd sw_locate(const SeqView q, const int32_t m, const SeqView t, co
 // Query profile per problem: prof[tb][rp][lane] = s(row 2rp, tb) | s(row 2rp+1, tb) << 16 (rows of the lane's strip), so
 // one LDS per problem serves two rows and a PRMT per row merges the two problems' scores into one register.
 // ---------------------------------------------------------------------------------------------
-constexpr int kPairProfWords = kProfTables * 4 * 32;   // per problem: 6 tables x (R <= 8 -> 4 row pairs) x 32 lanes
+constexpr int kPairProfWords = kProfTables * 4 * 32;   // per problem: 6 tables x 4 row pairs (R <= 8) x 32 lanes
 constexpr int32_t kPairMaxScore = 32000;
 constexpr int32_t kPairDead = -32000;                  // substitution score of rows past the query end
 
@@ -397,9 +397,11 @@ __device__ __forceinline__ bool sw_pair_ok(const int32_t m, const int32_t n, con
 
 __device__ __forceinline__ uint32_t pack16(const int32_t lo, const int32_t hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 
+constexpr int kPairRP = 4;   // row pairs per lane in the profile layout (fixed: one layout for every R <= 8)
+
 template <int R>
-__device__ uint32_t sw_pair_warp(const uint32_t* __restrict__ profA, const uint32_t* __restrict__ profB, const uint8_t* __restrict__ refA,
-                                 const uint8_t* __restrict__ refB, const int32_t nmax, const SwScore sc) {
+__device__ __noinline__ uint32_t sw_pair_warp(const uint32_t* __restrict__ profA, const uint32_t* __restrict__ profB, const uint8_t* __restrict__ refA,
+                                              const uint8_t* __restrict__ refB, const int32_t nmax, const SwScore sc) {
   constexpr int RP = (R + 1) / 2;
   const int lane = (int)lane_id();
   uint32_t Hp[R], E[R];
@@ -413,10 +415,11 @@ __device__ uint32_t sw_pair_warp(const uint32_t* __restrict__ profA, const uint3
   const int32_t nsteps = nmax + 31;
   const uint32_t nge2 = pack16(-sc.ge, -sc.ge), ngo2 = pack16(-sc.go, -sc.go);
   const uint32_t nz = lane ? (uint32_t)sc.one : 0u;
+  // software pipeline, two deep: the column letters are fetched two steps ahead, the substitution scores one step ahead
   uint32_t sc_cur[R];
   {
-    const uint32_t* ta = pA + (int32_t)cpA[0] * (RP * 32);
-    const uint32_t* tb = pB + (int32_t)cpB[0] * (RP * 32);
+    const uint32_t* ta = pA + (int32_t)cpA[0] * (kPairRP * 32);
+    const uint32_t* tb = pB + (int32_t)cpB[0] * (kPairRP * 32);
 #pragma unroll
     for (int rp = 0; rp < RP; ++rp) {
       const uint32_t wa = ta[rp * 32], wb = tb[rp * 32];
@@ -424,12 +427,14 @@ __device__ uint32_t sw_pair_warp(const uint32_t* __restrict__ profA, const uint3
       if (2 * rp + 1 < R) sc_cur[2 * rp + 1] = __byte_perm(wa, wb, 0x7632);
     }
   }
+  int32_t ia = (int32_t)cpA[1] * (kPairRP * 32), ib = (int32_t)cpB[1] * (kPairRP * 32);
 #pragma unroll 2
   for (int32_t ts = 0; ts < nsteps; ++ts) {
     uint32_t sc_next[R];
     {
-      const uint32_t* ta = pA + (int32_t)cpA[ts + 1] * (RP * 32);   // [nsteps] is still inside the trailing sentinels
-      const uint32_t* tb = pB + (int32_t)cpB[ts + 1] * (RP * 32);
+      const uint32_t* ta = pA + ia;
+      const uint32_t* tb = pB + ib;
+      ia = (int32_t)cpA[ts + 2] * (kPairRP * 32); ib = (int32_t)cpB[ts + 2] * (kPairRP * 32);   // [nsteps + 1] is still inside the trailing sentinels
 #pragma unroll
       for (int rp = 0; rp < RP; ++rp) {
         const uint32_t wa = ta[rp * 32], wb = tb[rp * 32];
@@ -463,69 +468,66 @@ __device__ uint32_t sw_pair_warp(const uint32_t* __restrict__ profA, const uint3
   return best;
 }
 
-// query profile of one problem for the packed pass (R rows per lane, m real rows)
-template <int R>
-__device__ __forceinline__ void pair_profile(const SeqView q, const int32_t m, const SwScore sc, uint32_t* __restrict__ prof) {
-  constexpr int RP = (R + 1) / 2;
+// query profile of one problem for the packed pass: R rows per lane (run-time), m real rows; one copy of this code serves every R
+__device__ __noinline__ void pair_profile(const SeqView q, const int32_t m, const int R, const SwScore sc, uint32_t* __restrict__ prof) {
   const int lane = (int)lane_id();
-  uint32_t c[2 * RP];
+  uint32_t c[2 * kPairRP];
 #pragma unroll
-  for (int r = 0; r < 2 * RP; ++r) { const int32_t i = lane * R + r; c[r] = (r < R && i < m) ? q.at(i) : 7u; }
+  for (int r = 0; r < 2 * kPairRP; ++r) { const int32_t i = lane * R + r; c[r] = (r < R && i < m) ? q.at(i) : 7u; }
 #pragma unroll
-  for (int rp = 0; rp < RP; ++rp) {
+  for (int rp = 0; rp < kPairRP; ++rp) {
     const uint32_t c0 = c[2 * rp], c1 = c[2 * rp + 1];
     const int32_t mis0 = c0 == 7u ? kPairDead : (c0 >= 4u ? sc.sN : sc.mismatch), mis1 = c1 == 7u ? kPairDead : (c1 >= 4u ? sc.sN : sc.mismatch);
 #pragma unroll
-    for (int tb = 0; tb < 4; ++tb) prof[(tb * RP + rp) * 32 + lane] = pack16(c0 == (uint32_t)tb ? sc.match : mis0, c1 == (uint32_t)tb ? sc.match : mis1);
-    prof[(4 * RP + rp) * 32 + lane] = pack16(c0 == 7u ? kPairDead : sc.sN, c1 == 7u ? kPairDead : sc.sN);   // reference N
-    prof[(5 * RP + rp) * 32 + lane] = pack16(mis0, mis1);                                                   // outside the window: never a match
+    for (int tb = 0; tb < 4; ++tb) prof[(tb * kPairRP + rp) * 32 + lane] = pack16(c0 == (uint32_t)tb ? sc.match : mis0, c1 == (uint32_t)tb ? sc.match : mis1);
+    prof[(4 * kPairRP + rp) * 32 + lane] = pack16(c0 == 7u ? kPairDead : sc.sN, c1 == 7u ? kPairDead : sc.sN);   // reference N
+    prof[(5 * kPairRP + rp) * 32 + lane] = pack16(mis0, mis1);                                                   // outside the window: never a match
   }
 }
 
-// window of `n` columns staged with 32 sentinel columns in front and sentinels up to column nstage + 32 behind
-__device__ __forceinline__ void stage_window_pair(const SeqView t, const int32_t n, const int32_t nstage, uint8_t* __restrict__ s_ref) {
+// windows of two problems (forward reference bytes, 0..4) staged with 32 sentinel columns in front and sentinels up to column
+// nstage + 32 behind.  All loads of a lane are issued before the first store: one memory latency per pair of windows.
+__device__ __noinline__ void pair_stage(const uint8_t* __restrict__ ga, const int32_t na, const uint8_t* __restrict__ gb, const int32_t nb, const int32_t nstage,
+                                        uint8_t* __restrict__ s_ref) {
   const int lane = (int)lane_id();
   constexpr int K = (kRefStage + 64) / 32;
-  uint32_t v[K];
+  uint32_t va[K], vb[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const int32_t j = lane + 32 * k - 32;
-    v[k] = (j >= 0 && j < n && lane + 32 * k < nstage + 64) ? min(t.at(j), 4u) : 5u;
+    const bool in = lane + 32 * k < nstage + 64;
+    va[k] = (j >= 0 && j < na && in) ? min((uint32_t)__ldg(ga + j), 4u) : 5u;
+    vb[k] = (j >= 0 && j < nb && in) ? min((uint32_t)__ldg(gb + j), 4u) : 5u;
   }
 #pragma unroll
-  for (int k = 0; k < K; ++k) if (lane + 32 * k < nstage + 64) s_ref[lane + 32 * k] = (uint8_t)v[k];
+  for (int k = 0; k < K; ++k) if (lane + 32 * k < nstage + 64) { s_ref[lane + 32 * k] = (uint8_t)va[k]; s_ref[kRefStage + 64 + lane + 32 * k] = (uint8_t)vb[k]; }
 }
 
-struct PairProblem { SeqView q; int32_t m; SeqView t; int32_t n; };
-
-// scores of two problems (B may be empty: m == 0, n == 0) -> score A | score B << 16.  s_ref: 2 x (kRefStage + 64) bytes,
-// s_prof: 2 x kPairProfWords words of this warp.  keyA/keyB: caller-kept identity of the profile resident in each half
-// (a batch of one read reuses its query many times), 0 = none.
-template <int R>
-__device__ __noinline__ uint32_t sw_pair_run(const PairProblem A, const PairProblem B, const bool buildA, const bool buildB, const SwScore sc,
-                                             uint8_t* __restrict__ s_ref, uint32_t* __restrict__ s_prof) {
-  const int32_t nmax = max(A.n, B.n);
-  __syncwarp();
-  stage_window_pair(A.t, A.n, nmax, s_ref);
-  stage_window_pair(B.t, B.n, nmax, s_ref + kRefStage + 64);
-  if (buildA) pair_profile<R>(A.q, A.m, sc, s_prof);
-  if (buildB) pair_profile<R>(B.q, B.m, sc, s_prof + kPairProfWords);
-  __syncwarp();
-  return sw_pair_warp<R>(s_prof, s_prof + kPairProfWords, s_ref, s_ref + kRefStage + 64, nmax, sc);
-}
+struct PairProblem { SeqView q; int32_t m; const uint8_t* t; int32_t n; };   // t: first window column (forward reference bytes)
 
 __device__ __forceinline__ int pair_rows(const int32_t m) { return m <= 32 ? 1 : m <= 64 ? 2 : m <= 96 ? 3 : m <= 128 ? 4 : m <= 160 ? 5 : m <= 192 ? 6 : 8; }
 
+// scores of two problems (B may be empty: m == 0, n == 0) -> score A | score B << 16.  s_ref: 2 x (kRefStage + 64) bytes,
+// s_prof: 2 x kPairProfWords words of this warp.  buildA / buildB: the profile of that half is not the resident one
+// (a batch of one read reuses its query many times).
 __device__ uint32_t sw_pair(const PairProblem A, const PairProblem B, const int R, const bool buildA, const bool buildB, const SwScore sc,
                             uint8_t* s_ref, uint32_t* s_prof) {
+  const int32_t nmax = max(A.n, B.n);
+  __syncwarp();
+  pair_stage(A.t, A.n, B.t, B.n, nmax, s_ref);
+  if (buildA) pair_profile(A.q, A.m, R, sc, s_prof);
+  if (buildB) pair_profile(B.q, B.m, R, sc, s_prof + kPairProfWords);
+  __syncwarp();
+  const uint32_t* pa = s_prof; const uint32_t* pb = s_prof + kPairProfWords;
+  const uint8_t* ra = s_ref; const uint8_t* rb = s_ref + kRefStage + 64;
   switch (R) {
-    case 1: return sw_pair_run<1>(A, B, buildA, buildB, sc, s_ref, s_prof);
-    case 2: return sw_pair_run<2>(A, B, buildA, buildB, sc, s_ref, s_prof);
-    case 3: return sw_pair_run<3>(A, B, buildA, buildB, sc, s_ref, s_prof);
-    case 4: return sw_pair_run<4>(A, B, buildA, buildB, sc, s_ref, s_prof);
-    case 5: return sw_pair_run<5>(A, B, buildA, buildB, sc, s_ref, s_prof);
-    case 6: return sw_pair_run<6>(A, B, buildA, buildB, sc, s_ref, s_prof);
-    default: return sw_pair_run<8>(A, B, buildA, buildB, sc, s_ref, s_prof);
+    case 1: return sw_pair_warp<1>(pa, pb, ra, rb, nmax, sc);
+    case 2: return sw_pair_warp<2>(pa, pb, ra, rb, nmax, sc);
+    case 3: return sw_pair_warp<3>(pa, pb, ra, rb, nmax, sc);
+    case 4: return sw_pair_warp<4>(pa, pb, ra, rb, nmax, sc);
+    case 5: return sw_pair_warp<5>(pa, pb, ra, rb, nmax, sc);
+    case 6: return sw_pair_warp<6>(pa, pb, ra, rb, nmax, sc);
+    default: return sw_pair_warp<8>(pa, pb, ra, rb, nmax, sc);
   }
 }
 
