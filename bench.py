@@ -222,6 +222,36 @@ def run_reference_sample(fastas, idx_dir, reads, threads):
     return reads.shape[0] / t, t, total, log
 
 
+def host_cores():
+    """Threads the reference CPU arm may really use: the affinity mask AND the cgroup CPU quota (os.cpu_count() ignores both).
+    Returns (threads to use, description)."""
+    ncpu = os.cpu_count() or 1
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = ncpu
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:                      # cgroup v2: "<quota> <period>" or "max <period>"
+            q, per = f.read().split()[:2]
+            if q != "max":
+                quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    eff = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    try:
+        load = os.getloadavg()[0]
+    except Exception:
+        load = float("nan")
+    return eff, dict(os_cpu_count=ncpu, affinity=aff, cgroup_quota=quota, threads_used=eff, loadavg_1m=load)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -251,7 +281,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cores = os.cpu_count() or 1
+    cores, core_info = host_cores()
 
     if args.impl == "reference":
         if rank != 0:
@@ -259,7 +289,9 @@ def main():
         fastas, _, _, refs, _, _ = load_databases(native_index=False)
         idx_dir = reference_index_dir(fastas)
         pool = DbPool(refs)
-        sample = args.cpu_sample or int(min(40_000, max(4_000, 300 * cores)))   # ~5 s of reference CPU time per step
+        # ~10 s of reference CPU time per step (about 230 reads/s per core on this workload): large enough that thread start-up
+        # and the skew between the reference's static per-thread splits do not dominate (round 1: 300 reads per thread did)
+        sample = args.cpu_sample or int(min(400_000, max(20_000, 2_300 * cores)))
         vals, secs = [], []
         for s in range(args.warmup + args.steps):
             if s < args.warmup and s > 0:
@@ -277,7 +309,8 @@ def main():
             "config": {"workload": "10 M synthetic 150 bp Illumina reads vs all 8 data/rRNA_databases refs, 1xB200",
                        "sampled": "each step is a bounded sample of that workload (reads_per_step reads, same generator)",
                        "reads_per_step": sample, "read_len": READ_LEN, "databases": 8},
-            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": desc},
+            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference", "sample": desc, "host": core_info,
+                             "per_step": [float(x) for x in vals]},
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
@@ -432,9 +465,9 @@ def main():
         "setup_s": setup_s, "index_build_s": built,
     }
     if not args.no_cpu_baseline and world == 1:   # reported baseline: rank 0 at N = 1 only
-        sample = args.cpu_sample or int(min(100_000, max(5_000, 1_000 * cores)))
+        sample = min(n, args.cpu_sample or int(min(400_000, max(20_000, 2_300 * cores))))
         v, t, total, _ = run_reference_sample(fastas, reference_index_dir(fastas), first_reads[:sample], cores)
-        out["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference",
+        out["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": cores, "kind": "reference", "host": core_info,
                                "sample": f"first {sample} reads of the same synthetic workload vs the 8 databases, reference CPU build "
                                          f"(oracle/_ref/sortmerna_ref -threads {cores}), alignment loops {t:.1f} s (index loading excluded; "
                                          f"'Done alignment' incl. loading {total:.1f} s)"}

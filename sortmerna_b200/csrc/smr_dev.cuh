@@ -71,7 +71,7 @@ constexpr uint32_t kErrTrace = 32u;     // "Trace back error" (ssw.c:707) -- fat
 enum DevCnt { dcNumAligned = 0, dcNumShort, dcSwCalls, dcSwCells, dcWindows, dcNodes, dcBuckets, dcEntries, dcPosEntries,
               dcLisCalls, dcMaxReadCycles, dcSumReadCycles, dcLisKernelCycles,
               dcCycVote, dcCycOrder, dcCycGroup, dcCycPlan, dcCycWait, dcCycReplay, dcSpecCalls, dcSpecCells, dcSpecPairs, dcSlowPairs,
-              dcScWait, dcScLoad, dcScSw, dcScPub, dcCount = 32 };
+              dcScWait, dcScLoad, dcScSw, dcScPub, dcRoundsA, dcRoundsB, dcCount = 32 };
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 

@@ -40,18 +40,38 @@ namespace smr {
 #define SMR_SCORER_WARPS 8
 #endif
 #ifndef SMR_PLANNER_WARPS
-#define SMR_PLANNER_WARPS 8
+#define SMR_PLANNER_WARPS 7
 #endif
 #ifndef SMR_LIS_MIN_CTAS
 #define SMR_LIS_MIN_CTAS 2
 #endif
-constexpr int kScorerWarps = SMR_SCORER_WARPS;     // the first warps of a CTA score (one per SM sub-partition with 4)
+constexpr int kScorerWarps = SMR_SCORER_WARPS;     // the first warps of a CTA score
+constexpr int kFetcherWarps = 1;                   // then one warp that pops the task queue and stages the scorers' inputs (TMA bulk copies)
 constexpr int kPlannerWarps = SMR_PLANNER_WARPS;   // the others plan
 constexpr int kLisMinCtas = SMR_LIS_MIN_CTAS;      // CTAs per SM the register budget is set for
-constexpr int kScorerSmem = 2 * kPairProfWords * 4 + 2 * (kRefStage + 64);   // two query profiles + two staged windows
-constexpr int kPlannerSmem = 128 * 16;                                        // kPairsShared pairs + LIS arrays
+constexpr int kLisWarpsPerCta = kScorerWarps + kFetcherWarps + kPlannerWarps;
+static_assert(2 * kScorerWarps <= 32, "one fetcher lane per (scorer, slot)");
+
+// A scorer's input slot (two per scorer: one is filled while the other is scored).  The fetcher lane writes the header, arms
+// the mbarrier with the byte count and issues the bulk copies; the scorer waits on the mbarrier's phase.
+constexpr int kWinOff = 48;                         // bulk destination inside win[]: 32 sentinel columns + 15 bytes of alignment slack fit in front
+constexpr int kWinBuf = kWinOff + kRefStage + 64;   // 560: 16-byte aligned copy of <= 448 + 30 bytes, then sentinels up to column nmax + 32
+constexpr int kQBuf = 288;                          // 16-byte aligned copy of <= 256 + 30 query bytes
+struct __align__(16) ScSlot {
+  uint8_t win[2][kWinBuf];
+  uint8_t q[2][kQBuf];
+  uint32_t planner, ta, tb, slow;     // slow: outside the packed kernel's range -> nothing staged, s32 fallback from global memory
+  uint32_t mA, nA, woffA, qoffA;      // rows, columns, index of column 0 in win[0], index of query element 0 in q[0]
+  uint32_t mB, nB, woffB, qoffB;
+  uint32_t metaA, metaB, qabsA, qabsB;
+  uint32_t refA, refB, pad0, pad1;
+  unsigned long long bar;             // mbarrier: 1 arrival (the fetcher lane) + the bulk copies' bytes
+  volatile uint32_t freed;            // slots of this buffer the scorer has finished with
+  uint32_t pad2;
+};
+constexpr int kScorerSmem = 2 * kPairProfWords * 4 + 2 * (int)sizeof(ScSlot);   // two query profiles + two input slots
+constexpr int kPlannerSmem = 128 * 16;                                          // kPairsShared pairs + LIS arrays
 constexpr int kLisSmemBytes = kScorerWarps * kScorerSmem + kPlannerWarps * kPlannerSmem;
-constexpr int kLisWarpsPerCta = kScorerWarps + kPlannerWarps;
 constexpr int kPairsShared = 128;  // pairs / LIS arrays kept in shared memory up to this many
 constexpr uint32_t kQueueCap = 1u << 20;         // task-pair ring (slots)
 constexpr uint32_t kNoTask = 0xFFFFFFu;
@@ -227,7 +247,7 @@ struct PassEnv {
   const uint2* hits; uint32_t nh;                               // hit region of (current part, current read)
   uint32_t planner;                                             // ordinal of this planner warp
   uint32_t submitted;                                           // tasks handed to the scorers so far (g.done[planner] catches up)
-  unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls, n_spec_calls, n_spec_cells;
+  unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls, n_spec_calls, n_spec_cells /* rounds A */, n_rounds_b;
   unsigned long long cyc[8];                                    // warp cycles per phase: vote, order, group, plan, wait, replay
 };
 
@@ -698,7 +718,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
       { const long long t2 = clock64(); E.cyc[3] += (unsigned long long)(t2 - tc0); tc0 = t2; }
       // ---- score, round A: the unconditional tasks ----
       submit_and_wait(E, nselA);
-      E.n_spec_calls += nselA;
+      E.n_spec_calls += nselA; E.n_spec_cells += nselA ? 1 : 0;
       // ---- round B: tasks heuristic 1 would skip after a successful lead (:243-246) are needed when the lead failed ----
       if (ncond) {
         uint32_t nselB = 0;
@@ -739,7 +759,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
         }
         __syncwarp();
         submit_and_wait(E, nselB);
-        E.n_spec_calls += nselB;
+        E.n_spec_calls += nselB; E.n_rounds_b += nselB ? 1 : 0;
       }
       { const long long t2 = clock64(); E.cyc[4] += (unsigned long long)(t2 - tc0); tc0 = t2; }
       // ---- replay: the reference's decisions over the scores, in order ----
@@ -749,7 +769,34 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
         const uint32_t v_toff = cl < nb ? cfirst[cl] : 0u, v_cw = cl < nb ? ccnt[cl] : 0u;
         const uint32_t v_occ = cl < nb ? 0xFFFFFu - (uint32_t)(E.ar.grp[k + cl] >> 32) : 0u;
         const uint32_t cend = min(32u, nb - c0);
-        for (uint32_t ci = 0; ci < cend && searching; ++ci) {
+        // fast path: candidates none of whose tasks aligned change nothing but the call counters (every task of such a candidate was
+        // scored and consumed: heuristic 1 only skips behind a success) -- one candidate per lane; the sequential replay starts at
+        // the first candidate of the chunk that holds a success
+        uint32_t ci0 = 0;
+        {
+          const uint32_t cntl = v_cw & 0x3FFFFFFFu;
+          bool succ = cl < nb && (v_cw & 0x40000000u) != 0 && cntl > 0;   // (many-pair candidates take the sequential path)
+          unsigned long long cells = 0;
+          if (cl < nb && !(v_cw & 0x40000000u)) {
+            for (uint32_t j = 0; j < cntl; ++j) {
+              const uint4 w0 = __ldcg((const uint4*)&E.ar.tasks[v_toff + j]);
+              if ((__ldcg(&E.ar.tasks[v_toff + j].score) & 0xFFFFu) > ix.minimal_score) { succ = true; break; }
+              cells += (unsigned long long)w0.z * (unsigned long long)w0.w;
+            }
+          }
+          const unsigned sm = __ballot_sync(kFull, succ);
+          ci0 = sm ? (uint32_t)(__ffs(sm) - 1) : cend;
+          const bool mine = lane < ci0 && cl < nb;
+          const uint32_t ncons = warp_sum_u32(mine ? cntl : 0u);
+          E.n_sw_calls += ncons; E.n_sw_cells += warp_sum_u64(mine ? cells : 0ull);
+          if (ncons && rc.hasn) rc.form04 = true;                                               // flip34 before SSW (:360-361)
+          if (ci0 > 0) {
+            // entry of the chunk's first candidate (:165-169) with the state the previous chunk left; behind it nothing is aligned
+            if (c0 > 0 && is_aligned && o.min_lis > 0 && __shfl_sync(kFull, v_occ, 0) < prev_occur) --rc.best;   // (cannot reach 0 inside a batch)
+            is_aligned = false; prev_occur = __shfl_sync(kFull, v_occ, ci0 - 1);
+          }
+        }
+        for (uint32_t ci = ci0; ci < cend && searching; ++ci) {
           const uint32_t c = c0 + ci;
           const uint32_t toff = __shfl_sync(kFull, v_toff, ci), cw = __shfl_sync(kFull, v_cw, ci), occ = __shfl_sync(kFull, v_occ, ci);
           const uint32_t cnt = cw & 0x3FFFFFFFu;
@@ -879,71 +926,129 @@ __device__ void traverse_dev(PassEnv& E, ReadCtx& rc, const bool is_last_strand)
   } else if (ix.is_last && is_last_strand && rc.n_align > 0) rc.is_done = true;
 }
 
-// ---- scorer role: pop task pairs, score them with the packed kernel, report ----
-__device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGlobals& g, uint8_t* s_ref, uint32_t* s_prof, const uint32_t scorer) {
+// ---- fetcher role: one lane per (scorer, slot) pops task pairs from the queue and stages their inputs ----
+__device__ void fetcher_loop(const DevBatch& b, const DevParams& prm, const LisGlobals& g, uint8_t* scorer_smem) {
   const unsigned lane = lane_id();
   const SwScore sc{prm.match, prm.mismatch, prm.score_N, prm.gap_open, prm.gap_ext, prm.one};
+  const bool mine = lane < 2u * kScorerWarps;
+  ScSlot* sl = (ScSlot*)(scorer_smem + (size_t)(lane >> 1) * kScorerSmem + 2 * kPairProfWords * 4) + (lane & 1u);
+  uint32_t filled = 0, h = 0;
+  bool have = false, done = !mine;
+  for (;;) {
+    bool progress = false;
+    if (!done) {
+      if (!have && sl->freed == filled) { h = atomicAdd(g.q_head, 1u); have = true; }
+      if (have) {
+        QSlot* qs = g.ring + (h & (kQueueCap - 1));
+        if (ld_volatile_u32(&qs->seq) == h + 1u) {
+          __threadfence();
+          const uint32_t planner = __ldcg(&qs->planner), ta = __ldcg(&qs->ta), tb = __ldcg(&qs->tb);
+          st_volatile_u32(&qs->seq, h + kQueueCap);   // slot free for the next lap (after the payload was read)
+          have = false; progress = true;
+          sl->planner = planner; sl->ta = ta; sl->tb = tb;
+          if (planner == kPoison) { mbar_arrive(&sl->bar); done = true; }
+          else {
+            const SwTask* tasks = carve_arena(g, planner).tasks;
+            const uint4 da = __ldcg((const uint4*)(tasks + ta));
+            const uint32_t ma = __ldcg(&tasks[ta].meta);
+            const bool two = tb != kNoTask;
+            uint4 db = make_uint4(0, 0, 0, 0); uint32_t mb = 0;
+            if (two) { db = __ldcg((const uint4*)(tasks + tb)); mb = __ldcg(&tasks[tb].meta); }
+            const bool oka = da.w > 0 && da.z > 0 && sw_pair_ok((int32_t)da.w, (int32_t)da.z, sc);
+            const bool okb = !two || db.w == 0 || db.z == 0 || sw_pair_ok((int32_t)db.w, (int32_t)db.z, sc);
+            const bool fast = oka && okb;
+            const bool liveb = two && db.w > 0 && db.z > 0;
+            sl->slow = fast ? 0u : 1u;
+            sl->mA = da.w; sl->nA = da.z; sl->metaA = ma; sl->qabsA = da.y; sl->refA = da.x;
+            sl->mB = two ? db.w : 0u; sl->nB = two ? db.z : 0u; sl->metaB = mb; sl->qabsB = db.y; sl->refB = db.x;
+            if (!fast) mbar_arrive(&sl->bar);
+            else {
+              // 16-byte aligned supersets of [ref_abs, ref_abs + n) and of the query segment (minus strand: it ends at q_abs)
+              const uint8_t* ra = g.parts[ma & 0xFFFFu].refseq;
+              const uint32_t wa0 = da.x & ~15u, wab = ((da.x & 15u) + da.z + 15u) & ~15u;
+              const uint32_t qsa = (ma & 0x10000u) ? da.y - (da.w - 1u) : da.y, qa0 = qsa & ~15u, qab = ((qsa & 15u) + da.w + 15u) & ~15u;
+              sl->woffA = kWinOff + (da.x & 15u); sl->qoffA = (ma & 0x10000u) ? (qsa & 15u) + da.w - 1u : (qsa & 15u);
+              uint32_t wb0 = 0, wbb = 0, qb0 = 0, qbb = 0; const uint8_t* rb = ra;
+              if (liveb) {
+                rb = g.parts[mb & 0xFFFFu].refseq;
+                wb0 = db.x & ~15u; wbb = ((db.x & 15u) + db.z + 15u) & ~15u;
+                const uint32_t qsb = (mb & 0x10000u) ? db.y - (db.w - 1u) : db.y;
+                qb0 = qsb & ~15u; qbb = ((qsb & 15u) + db.w + 15u) & ~15u;
+                sl->woffB = kWinOff + (db.x & 15u); sl->qoffB = (mb & 0x10000u) ? (qsb & 15u) + db.w - 1u : (qsb & 15u);
+              } else { sl->woffB = kWinOff; sl->qoffB = 0; sl->mB = 0; sl->nB = 0; }
+              mbar_arrive_expect_tx(&sl->bar, wab + qab + wbb + qbb);
+              bulk_g2s(sl->win[0] + kWinOff, ra + wa0, wab, &sl->bar);
+              bulk_g2s(sl->q[0], b.seq04 + qa0, qab, &sl->bar);
+              if (liveb) { bulk_g2s(sl->win[1] + kWinOff, rb + wb0, wbb, &sl->bar); bulk_g2s(sl->q[1], b.seq04 + qb0, qbb, &sl->bar); }
+            }
+            ++filled;
+          }
+        }
+      }
+    }
+    if (__all_sync(kFull, done)) break;
+    if (!__any_sync(kFull, progress)) __nanosleep(64);
+  }
+}
+
+// ---- scorer role: take a staged task pair, score it with the packed kernel, report ----
+__device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGlobals& g, uint8_t* sm, const uint32_t scorer) {
+  const unsigned lane = lane_id();
+  const SwScore sc{prm.match, prm.mismatch, prm.score_N, prm.gap_open, prm.gap_ext, prm.one};
+  uint32_t* s_prof = (uint32_t*)sm;
+  ScSlot* slots = (ScSlot*)(sm + 2 * kPairProfWords * 4);
   int32_t* rowH = g.score_rows + (size_t)scorer * 2 * g.row_cap; int32_t* rowF = rowH + g.row_cap;
   // identity of the query profile resident in each half: (q_abs, qlen | rev << 31, R)
   uint32_t keyq[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, keym[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}; int keyR = 0;
+  uint32_t par[2] = {0, 0}, nfreed[2] = {0, 0}, exited = 0;
   unsigned long long n_pairs = 0, n_cells = 0, n_slow = 0, cy_wait = 0, cy_load = 0, cy_sw = 0, cy_pub = 0;
   for (;;) {
-    uint32_t h = 0;
     long long tq = clock64();
-    if (lane == 0) {
-      h = atomicAdd(g.q_head, 1u);
-      const QSlot* sl = g.ring + (h & (kQueueCap - 1));
-      while (ld_volatile_u32(&sl->seq) != h + 1u) __nanosleep(96);
-      __threadfence();
+    int k = -1;
+    for (;;) {
+      if (!(exited & 1u) && mbar_try_wait(&slots[0].bar, par[0])) { k = 0; break; }
+      if (!(exited & 2u) && mbar_try_wait(&slots[1].bar, par[1])) { k = 1; break; }
+      __nanosleep(32);
     }
-    h = __shfl_sync(kFull, h, 0);
+    par[k] ^= 1u;
+    ScSlot& S = slots[k];
     { const long long t2 = clock64(); cy_wait += (unsigned long long)(t2 - tq); tq = t2; }
-    QSlot* sl = g.ring + (h & (kQueueCap - 1));
-    const uint32_t planner = __ldcg(&sl->planner), ta = __ldcg(&sl->ta), tb = __ldcg(&sl->tb);
-    if (lane == 0) st_volatile_u32(&sl->seq, h + kQueueCap);   // slot free for the next lap (after the payload was read)
-    if (planner == kPoison) break;
-    SwTask* tasks = (SwTask*)0;
-    {
-      // the task arrays live in the planner's arena
-      LisArena ar = carve_arena(g, planner);
-      tasks = ar.tasks;
-    }
-    const uint4 da = __ldcg((const uint4*)(tasks + ta));
-    const uint32_t ma = __ldcg(&tasks[ta].meta);
-    uint4 db = make_uint4(0, 0, 0, 0); uint32_t mb = 0;
+    const uint32_t planner = S.planner;
+    if (planner == kPoison) { exited |= 1u << k; if (exited == 3u) break; continue; }
+    const uint32_t ta = S.ta, tb = S.tb;
     const bool two = tb != kNoTask;
-    if (two) { db = __ldcg((const uint4*)(tasks + tb)); mb = __ldcg(&tasks[tb].meta); }
-    PairProblem A, Bp;
-    {
-      const bool rev = (ma >> 16) & 1u;
-      A.q = SeqView{b.seq04, (int32_t)da.y, rev ? -1 : 1, rev}; A.m = (int32_t)da.w;
-      A.t = g.parts[ma & 0xFFFFu].refseq + da.x; A.n = (int32_t)da.z;
-    }
-    if (two) {
-      const bool rev = (mb >> 16) & 1u;
-      Bp.q = SeqView{b.seq04, (int32_t)db.y, rev ? -1 : 1, rev}; Bp.m = (int32_t)db.w;
-      Bp.t = g.parts[mb & 0xFFFFu].refseq + db.x; Bp.n = (int32_t)db.z;
-    } else { Bp = A; Bp.m = 0; Bp.n = 0; }
+    const int32_t mA = (int32_t)S.mA, nA = (int32_t)S.nA, mB = (int32_t)S.mB, nB = (int32_t)S.nB;
     uint32_t sa = 0, sb = 0;
-    { const long long t2 = clock64(); cy_load += (unsigned long long)(t2 - tq); tq = t2; }
-    const bool oka = A.m > 0 && A.n > 0 && sw_pair_ok(A.m, A.n, sc), okb = !two || Bp.m <= 0 || Bp.n <= 0 || sw_pair_ok(Bp.m, Bp.n, sc);
-    if (oka && okb) {
-      const int R = pair_rows(max(A.m, Bp.m));
-      const uint32_t kqa = da.y, kma = da.w | ((ma & 0x10000u) << 15), kqb = two ? db.y : 0xFFFFFFFEu, kmb = two ? (db.w | ((mb & 0x10000u) << 15)) : 0u;
-      const bool buildA = !(R == keyR && keyq[0] == kqa && keym[0] == kma), buildB = !(R == keyR && keyq[1] == kqb && keym[1] == kmb);
-      const uint32_t r2 = sw_pair(A, Bp, R, buildA, buildB, sc, s_ref, s_prof);
+    if (!S.slow) {
+      const int R = pair_rows(max(mA, mB));
+      const int32_t nmax = max(nA, nB);
+      uint8_t* wa = S.win[0] + S.woffA; uint8_t* wb = S.win[1] + S.woffB;
+      pair_sentinels(wa, nA, nmax);
+      pair_sentinels(wb, nB, nmax);
+      const uint32_t kqa = S.qabsA, kma = (uint32_t)mA | ((S.metaA & 0x10000u) << 15), kqb = mB ? S.qabsB : 0xFFFFFFFEu, kmb = mB ? ((uint32_t)mB | ((S.metaB & 0x10000u) << 15)) : 0u;
+      if (!(R == keyR && keyq[0] == kqa && keym[0] == kma)) { const bool rev = (S.metaA & 0x10000u) != 0; pair_profile(S.q[0] + S.qoffA, rev ? -1 : 1, rev, mA, R, sc, s_prof); }
+      if (!(R == keyR && keyq[1] == kqb && keym[1] == kmb)) { const bool rev = (S.metaB & 0x10000u) != 0; pair_profile(S.q[1] + S.qoffB, rev ? -1 : 1, rev, mB, R, sc, s_prof + kPairProfWords); }
       keyR = R; keyq[0] = kqa; keym[0] = kma; keyq[1] = kqb; keym[1] = kmb;
+      __syncwarp();
+      { const long long t2 = clock64(); cy_load += (unsigned long long)(t2 - tq); tq = t2; }
+      const uint32_t r2 = sw_pair_dispatch(R, s_prof, s_prof + kPairProfWords, wa, wb, nmax, sc);
       sa = r2 & 0xFFFFu; sb = r2 >> 16;
     } else {
-      // shapes or scoring schemes outside the 16-bit kernel: the s32 wavefront (row blocks for long queries)
+      // shapes or scoring schemes outside the 16-bit kernel: the s32 wavefront (row blocks for long queries), from global memory
       keyR = 0;
-      if (A.m > 0 && A.n > 0 && (uint32_t)A.n <= g.row_cap) sa = (uint32_t)sw_forward_any(A.q, A.m, SeqView{A.t, 0, 1, false}, A.n, sc, rowH, rowF).score;
-      if (two && Bp.m > 0 && Bp.n > 0 && (uint32_t)Bp.n <= g.row_cap) sb = (uint32_t)sw_forward_any(Bp.q, Bp.m, SeqView{Bp.t, 0, 1, false}, Bp.n, sc, rowH, rowF).score;
+      const bool reva = (S.metaA & 0x10000u) != 0, revb = (S.metaB & 0x10000u) != 0;
+      if (mA > 0 && nA > 0 && (uint32_t)nA <= g.row_cap)
+        sa = (uint32_t)sw_forward_any(SeqView{b.seq04, (int32_t)S.qabsA, reva ? -1 : 1, reva}, mA, SeqView{g.parts[S.metaA & 0xFFFFu].refseq, (int32_t)S.refA, 1, false}, nA, sc, rowH, rowF).score;
+      if (two && mB > 0 && nB > 0 && (uint32_t)nB <= g.row_cap)
+        sb = (uint32_t)sw_forward_any(SeqView{b.seq04, (int32_t)S.qabsB, revb ? -1 : 1, revb}, mB, SeqView{g.parts[S.metaB & 0xFFFFu].refseq, (int32_t)S.refB, 1, false}, nB, sc, rowH, rowF).score;
       ++n_slow;
     }
-    ++n_pairs; n_cells += (unsigned long long)da.z * da.w + (unsigned long long)db.z * db.w;
+    ++n_pairs; n_cells += (unsigned long long)nA * mA + (unsigned long long)nB * mB;
     { const long long t2 = clock64(); cy_sw += (unsigned long long)(t2 - tq); tq = t2; }
+    __syncwarp();
     if (lane == 0) {
+      S.freed = ++nfreed[k];                       // the fetcher may refill this slot
+      SwTask* tasks = carve_arena(g, planner).tasks;
       tasks[ta].score = sa;
       if (two) tasks[tb].score = sb;
       __threadfence();
@@ -974,13 +1079,15 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     for (int k = 0; k < kCostBins; ++k) { s_bin_start[k] = acc; acc += b.bin_count[kCostBins - 1 - k]; }
     s_bin_start[kCostBins] = acc;
   }
-  __syncthreads();
-  if (wic < (uint32_t)kScorerWarps) {
-    uint8_t* sm = lis_smem + (size_t)wic * kScorerSmem;
-    scorer_loop(b, prm, g, sm + 2 * kPairProfWords * 4, (uint32_t*)sm, blockIdx.x * kScorerWarps + wic);
-    return;
+  if (threadIdx.x < 2u * kScorerWarps) {   // the input slots' mbarriers and hand-back counters
+    ScSlot* sl = (ScSlot*)(lis_smem + (size_t)(threadIdx.x >> 1) * kScorerSmem + 2 * kPairProfWords * 4) + (threadIdx.x & 1u);
+    mbar_init(&sl->bar, 1); sl->freed = 0;
   }
-  const uint32_t pw = wic - kScorerWarps, planner = blockIdx.x * kPlannerWarps + pw;
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  if (wic < (uint32_t)kScorerWarps) { scorer_loop(b, prm, g, lis_smem + (size_t)wic * kScorerSmem, blockIdx.x * kScorerWarps + wic); return; }
+  if (wic == (uint32_t)kScorerWarps) { fetcher_loop(b, prm, g, lis_smem); return; }
+  const uint32_t pw = wic - kScorerWarps - kFetcherWarps, planner = blockIdx.x * kPlannerWarps + pw;
   PassEnv E;
   E.b = &b; E.prm = &prm; E.g = &g;
   E.ar = carve_arena(g, planner);
@@ -990,7 +1097,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     uint8_t* sm = lis_smem + (size_t)kScorerWarps * kScorerSmem + (size_t)pw * kPlannerSmem;
     E.s_pairs = (unsigned long long*)sm; E.s_b = (uint32_t*)(sm + kPairsShared * 8); E.s_p = E.s_b + kPairsShared;
   }
-  E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = E.n_spec_calls = E.n_spec_cells = 0;
+  E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = E.n_spec_calls = E.n_spec_cells = E.n_rounds_b = 0;
   for (int i = 0; i < 8; ++i) E.cyc[i] = 0;
   const uint32_t nwork = s_bin_start[kCostBins];
   unsigned long long t_max = 0, t_sum = 0; const long long t_k0 = clock64();
@@ -1043,12 +1150,12 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     *E.epoch_ptr = E.epoch;
     atomicAdd(&b.counters[dcSwCalls], E.n_sw_calls); atomicAdd(&b.counters[dcSwCells], E.n_sw_cells);
     atomicAdd(&b.counters[dcPosEntries], E.n_pos_entries); atomicAdd(&b.counters[dcLisCalls], E.n_lis_calls);
-    atomicAdd(&b.counters[dcSpecCalls], E.n_spec_calls);
+    atomicAdd(&b.counters[dcSpecCalls], E.n_spec_calls); atomicAdd(&b.counters[dcRoundsA], E.n_spec_cells); atomicAdd(&b.counters[dcRoundsB], E.n_rounds_b);
     for (int i = 0; i < 6; ++i) atomicAdd(&b.counters[dcCycVote + i], E.cyc[i]);
     atomicMax(&b.counters[dcMaxReadCycles], t_max); atomicAdd(&b.counters[dcSumReadCycles], t_sum);
     atomicMax(&b.counters[dcLisKernelCycles], (unsigned long long)(clock64() - t_k0));
     // the last planner out shuts the scorers down: one entry each
-    const uint32_t nplanners = gridDim.x * kPlannerWarps, nscorers = gridDim.x * kScorerWarps;
+    const uint32_t nplanners = gridDim.x * kPlannerWarps, nscorers = gridDim.x * kScorerWarps * 2;   // one shutdown entry per fetcher lane
     if (atomicAdd(g.planners_done, 1u) + 1u == nplanners) {
       const uint32_t base = atomicAdd(g.q_tail, nscorers);
       for (uint32_t i = 0; i < nscorers; ++i) {

@@ -407,13 +407,13 @@ __device__ __noinline__ uint32_t sw_pair_warp(const uint32_t* __restrict__ profA
   uint32_t Hp[R], E[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) { Hp[r] = 0; E[r] = 0; }
-  uint32_t diagH = 0, outH = 0, outF = 0, best = 0;
+  uint32_t diagH = 0, upH = 0, upF = 0, best = 0;
   const uint8_t* cpA = refA + 32 - lane;
   const uint8_t* cpB = refB + 32 - lane;
   const uint32_t* pA = profA + lane;
   const uint32_t* pB = profB + lane;
   const int32_t nsteps = nmax + 31;
-  const uint32_t nge2 = pack16(-sc.ge, -sc.ge), ngo2 = pack16(-sc.go, -sc.go);
+  const uint32_t nge2 = pack16(-sc.ge, -sc.ge), ngo2 = pack16(-sc.go, -sc.go), n2ge2 = pack16(-2 * sc.ge, -2 * sc.ge);
   const uint32_t nz = lane ? (uint32_t)sc.one : 0u;
   // software pipeline, two deep: the column letters are fetched two steps ahead, the substitution scores one step ahead
   uint32_t sc_cur[R];
@@ -442,24 +442,37 @@ __device__ __noinline__ uint32_t sw_pair_warp(const uint32_t* __restrict__ profA
         if (2 * rp + 1 < R) sc_next[2 * rp + 1] = __byte_perm(wa, wb, 0x7632);
       }
     }
-    const uint32_t upH = __shfl_up_sync(kFull, outH, 1) * nz, upF = __shfl_up_sync(kFull, outF, 1) * nz;   // row -1 is all zeros
+    // the boundary values of this step were requested (shuffled) right after the F chain of the previous step, so that the
+    // shuffle latency (30 cycles) runs under the H / E updates of the other rows instead of heading the step's critical path:
+    // a dependent VIADDMNMX.S16x2 issues every 8.4 cycles, the loop-carried chain is IMAD + R of them
     uint32_t X[R], F[R + 1];
 #pragma unroll
     for (int r = 0; r < R; ++r) X[r] = __viaddmax_s16x2_relu(r == 0 ? diagH : Hp[r - 1], sc_cur[r], E[r]);
     diagH = upH;
     F[0] = upF;
+    // vertical chain F[r+1] = max(F[r] - ge, X[r]) with a look-ahead of two rows: A = max(X[r] - ge, X[r+1]) does not depend on F, so
+    // F[r+2] = max(F[r] - 2 ge, A) and the loop-carried chain is ceil(R/2)+ dependent instructions (8.4 cycles each) instead of R
 #pragma unroll
-    for (int r = 0; r < R; ++r) F[r + 1] = __viaddmax_s16x2(F[r], nge2, X[r]);
+    for (int r = 0; r + 1 < R; r += 2) {
+      const uint32_t A = __viaddmax_s16x2(X[r], nge2, X[r + 1]);
+      F[r + 1] = __viaddmax_s16x2(F[r], nge2, X[r]);
+      F[r + 2] = __viaddmax_s16x2(F[r], n2ge2, A);
+    }
+    if (R & 1) F[R] = __viaddmax_s16x2(F[R - 1], nge2, X[R - 1]);
+    const uint32_t hl = __viaddmax_s16x2(F[R - 1], ngo2, X[R - 1]);
+    const uint32_t rawH = __shfl_up_sync(kFull, hl, 1), rawF = __shfl_up_sync(kFull, F[R], 1);
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < R - 1; ++r) {
       const uint32_t h = __viaddmax_s16x2(F[r], ngo2, X[r]);
       E[r] = __viaddmax_s16x2(E[r], nge2, __vadd2(h, ngo2));
       Hp[r] = h;
     }
+    E[R - 1] = __viaddmax_s16x2(E[R - 1], nge2, __vadd2(hl, ngo2));
+    Hp[R - 1] = hl;
+    upH = rawH * nz; upF = rawF * nz;   // row -1 is all zeros (consumed at the top of the next step)
 #pragma unroll
     for (int r = 0; r + 1 < R; r += 2) best = __vimax3_s16x2(best, Hp[r], Hp[r + 1]);
     if (R & 1) best = __vmaxs2(best, Hp[R - 1]);
-    outH = Hp[R - 1]; outF = F[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) sc_cur[r] = sc_next[r];
   }
@@ -468,15 +481,16 @@ __device__ __noinline__ uint32_t sw_pair_warp(const uint32_t* __restrict__ profA
   return best;
 }
 
-// query profile of one problem for the packed pass: R rows per lane (run-time), m real rows; one copy of this code serves every R
-__device__ __noinline__ void pair_profile(const SeqView q, const int32_t m, const int R, const SwScore sc, uint32_t* __restrict__ prof) {
+// query profile of one problem for the packed pass: R rows per lane (run-time), m real rows; one copy of this code serves every R.
+// qb: the query bytes (0..4) staged in shared memory by the bulk copy; element i = qb[i * step], complemented on the minus strand.
+__device__ __noinline__ void pair_profile(const uint8_t* __restrict__ qb, const int32_t step, const bool comp, const int32_t m, const int R, const SwScore sc,
+                                          uint32_t* __restrict__ prof) {
   const int lane = (int)lane_id();
-  uint32_t c[2 * kPairRP];
-#pragma unroll
-  for (int r = 0; r < 2 * kPairRP; ++r) { const int32_t i = lane * R + r; c[r] = (r < R && i < m) ? q.at(i) : 7u; }
-#pragma unroll
+#pragma unroll 1
   for (int rp = 0; rp < kPairRP; ++rp) {
-    const uint32_t c0 = c[2 * rp], c1 = c[2 * rp + 1];
+    const int32_t r0 = 2 * rp, i0 = lane * R + r0;
+    uint32_t c0 = (r0 < R && i0 < m) ? (uint32_t)qb[i0 * step] : 7u, c1 = (r0 + 1 < R && i0 + 1 < m) ? (uint32_t)qb[(i0 + 1) * step] : 7u;
+    if (comp) { if (c0 < 4u) c0 = 3u - c0; if (c1 < 4u) c1 = 3u - c1; }
     const int32_t mis0 = c0 == 7u ? kPairDead : (c0 >= 4u ? sc.sN : sc.mismatch), mis1 = c1 == 7u ? kPairDead : (c1 >= 4u ? sc.sN : sc.mismatch);
 #pragma unroll
     for (int tb = 0; tb < 4; ++tb) prof[(tb * kPairRP + rp) * 32 + lane] = pack16(c0 == (uint32_t)tb ? sc.match : mis0, c1 == (uint32_t)tb ? sc.match : mis1);
@@ -485,41 +499,20 @@ __device__ __noinline__ void pair_profile(const SeqView q, const int32_t m, cons
   }
 }
 
-// windows of two problems (forward reference bytes, 0..4) staged with 32 sentinel columns in front and sentinels up to column
-// nstage + 32 behind.  All loads of a lane are issued before the first store: one memory latency per pair of windows.
-__device__ __noinline__ void pair_stage(const uint8_t* __restrict__ ga, const int32_t na, const uint8_t* __restrict__ gb, const int32_t nb, const int32_t nstage,
-                                        uint8_t* __restrict__ s_ref) {
+// A window of n columns lies in shared memory at w[0 .. n) (bulk copy of the reference bytes, 0..4): write the sentinel
+// letter (table 5) into the 32 columns before it and from column n up to column nstage + 32.
+__device__ __forceinline__ void pair_sentinels(uint8_t* __restrict__ w, const int32_t n, const int32_t nstage) {
   const int lane = (int)lane_id();
-  constexpr int K = (kRefStage + 64) / 32;
-  uint32_t va[K], vb[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int32_t j = lane + 32 * k - 32;
-    const bool in = lane + 32 * k < nstage + 64;
-    va[k] = (j >= 0 && j < na && in) ? min((uint32_t)__ldg(ga + j), 4u) : 5u;
-    vb[k] = (j >= 0 && j < nb && in) ? min((uint32_t)__ldg(gb + j), 4u) : 5u;
-  }
-#pragma unroll
-  for (int k = 0; k < K; ++k) if (lane + 32 * k < nstage + 64) { s_ref[lane + 32 * k] = (uint8_t)va[k]; s_ref[kRefStage + 64 + lane + 32 * k] = (uint8_t)vb[k]; }
+  w[lane - 32] = 5;
+  for (int32_t j = n + lane; j < nstage + 33; j += 32) w[j] = 5;
 }
-
-struct PairProblem { SeqView q; int32_t m; const uint8_t* t; int32_t n; };   // t: first window column (forward reference bytes)
 
 __device__ __forceinline__ int pair_rows(const int32_t m) { return m <= 32 ? 1 : m <= 64 ? 2 : m <= 96 ? 3 : m <= 128 ? 4 : m <= 160 ? 5 : m <= 192 ? 6 : 8; }
 
-// scores of two problems (B may be empty: m == 0, n == 0) -> score A | score B << 16.  s_ref: 2 x (kRefStage + 64) bytes,
-// s_prof: 2 x kPairProfWords words of this warp.  buildA / buildB: the profile of that half is not the resident one
-// (a batch of one read reuses its query many times).
-__device__ uint32_t sw_pair(const PairProblem A, const PairProblem B, const int R, const bool buildA, const bool buildB, const SwScore sc,
-                            uint8_t* s_ref, uint32_t* s_prof) {
-  const int32_t nmax = max(A.n, B.n);
-  __syncwarp();
-  pair_stage(A.t, A.n, B.t, B.n, nmax, s_ref);
-  if (buildA) pair_profile(A.q, A.m, R, sc, s_prof);
-  if (buildB) pair_profile(B.q, B.m, R, sc, s_prof + kPairProfWords);
-  __syncwarp();
-  const uint32_t* pa = s_prof; const uint32_t* pb = s_prof + kPairProfWords;
-  const uint8_t* ra = s_ref; const uint8_t* rb = s_ref + kRefStage + 64;
+// the packed pass for R rows per lane: profiles and windows (column 0 at wa[0] / wb[0], sentinels in place) are in shared memory
+__device__ __forceinline__ uint32_t sw_pair_dispatch(const int R, const uint32_t* pa, const uint32_t* pb, const uint8_t* wa, const uint8_t* wb, const int32_t nmax,
+                                                     const SwScore sc) {
+  const uint8_t* ra = wa - 32; const uint8_t* rb = wb - 32;
   switch (R) {
     case 1: return sw_pair_warp<1>(pa, pb, ra, rb, nmax, sc);
     case 2: return sw_pair_warp<2>(pa, pb, ra, rb, nmax, sc);
@@ -529,6 +522,26 @@ __device__ uint32_t sw_pair(const PairProblem A, const PairProblem B, const int 
     case 6: return sw_pair_warp<6>(pa, pb, ra, rb, nmax, sc);
     default: return sw_pair_warp<8>(pa, pb, ra, rb, nmax, sc);
   }
+}
+
+// ---- TMA bulk copy + mbarrier (cp.async.bulk; SASS: UBLKCP / SYNCS) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// global -> shared bulk copy (16-byte aligned source, destination and size); completion is counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
