@@ -144,12 +144,21 @@ int smr_index_info(const smr_ctx*, uint64_t out[6]);
  *    traverse() with KVDB-equivalent carry-over (read.cpp:429-539).
  *    seq_cat: reads in 0..4 (4 = ambiguous, as nt_table yields), concatenated; seq_off[nreads+1].
  *    Host buffers; the call copies host->device, runs, and copies the results back.
- *    results[nreads]; alns[nreads * max(1,num_alignments)]; cigar_pool[cigar_cap] u32 words;
+ *    results[nreads]; alns[nreads * smr_aln_slots()] (= num_alignments per read; see smr_set_aln_slots for 0); cigar_pool[cigar_cap] u32 words;
  *    counters[SMR_CNT_FIXED + n_index_files] are ADDED to (caller zeroes them). */
 int smr_align_batch(smr_ctx*, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads,
                     smr_read_result* results, smr_aln* alns,
                     uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used,
                     uint64_t* counters, uint32_t n_counters);
+
+/* "All alignments" (opts.num_alignments == 0, src/sortmerna/alignment.cpp:420-424: every accepted alignment is appended, nothing
+ * stops the candidate loop, scripts/test.jinja t9): the number of alignments of a read is unbounded, so the flat result layout needs
+ * a stride.  smr_set_aln_slots sets it (default 16); alns[] / stats then hold nreads * slots entries, results[r].n_align of them
+ * used.  If a read accepts more, the call fails with SMR_ERR_CAPACITY and smr_aln_slots_needed() names the stride that batch
+ * needs (nothing is truncated silently).  smr_aln_slots() = the stride in effect: num_alignments when > 0, else the value set. */
+int smr_set_aln_slots(smr_ctx*, uint32_t slots);
+uint32_t smr_aln_slots(const smr_ctx*);
+uint32_t smr_aln_slots_needed(const smr_ctx*);
 
 /* Optional: where the next smr_align_batch / smr_download_results stores smr_aln_stats for every stored alignment (same
  * indexing as alns[]; nullptr = do not compute).  Host buffer of nreads * max(1,num_alignments) entries. */

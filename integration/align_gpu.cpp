@@ -7,11 +7,21 @@
 //
 // Differences to the CPU driver, all invisible to the rest of the program:
 //   * every (index, part) is made resident on the GPU once; reads are streamed ONCE (the reference re-reads them per index part);
-//   * reads are handed over in batches; the per-read KVDB blob is produced by smr_pack_kvdb_blobs (byte-identical to
-//     Read::toBinString) and stored under the same key (read.id);
+//   * the feed is drained by several parser threads (one per group of the reference's "processors": each processor id owns
+//     its own split file, processor.cpp:104-160), which encode reads into batches; a bounded queue hands every full batch to
+//     one worker thread per GPU (SMR_GPUS), so parsing, H2D / kernels / D2H and the KVDB stores overlap;
+//   * the per-read KVDB blob is produced by smr_pack_kvdb_blobs (byte-identical to Read::toBinString) and stored under the same
+//     key (read.id);
 //   * Readstats counters come back from the library (num_aligned, reads_matched_per_db, num_short of the last index pass).
+// Resume (-task with a KVDB that already holds results) is not supported by this path: every read is aligned again (the CPU
+// driver consults Read::load_db first, processor.cpp:116-126).
+#include <algorithm>
+#include <condition_variable>
 #include <cstdint>
+#include <deque>
 #include <fstream>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -43,12 +53,34 @@ void die(smr_ctx* ctx, const char* what) {
   exit(EXIT_FAILURE);
 }
 
+struct Batch {
+  std::vector<std::string> ids; std::string seqcat; std::vector<uint64_t> off{0};
+  std::vector<smr_read_result> res; std::vector<smr_aln> alns; std::vector<uint32_t> cigars; uint64_t used = 0; std::vector<uint64_t> cnt;
+  std::string blobs; std::vector<uint64_t> boff;
+  void reset() { ids.clear(); seqcat.clear(); off.assign(1, 0); used = 0; }
+};
+
+// full batches on their way to the GPU workers, empty ones on their way back to the parsers (bounded: host memory stays
+// at a few batches however long the input is)
+class BatchQueue {
+  std::mutex m; std::condition_variable cv; std::deque<std::unique_ptr<Batch>> q; bool closed = false;
+ public:
+  void push(std::unique_ptr<Batch> b) { { std::lock_guard<std::mutex> l(m); q.push_back(std::move(b)); } cv.notify_one(); }
+  std::unique_ptr<Batch> pop() {   // nullptr once closed and drained
+    std::unique_lock<std::mutex> l(m);
+    cv.wait(l, [&] { return !q.empty() || closed; });
+    if (q.empty()) return nullptr;
+    std::unique_ptr<Batch> b = std::move(q.front()); q.pop_front();
+    return b;
+  }
+  void close() { { std::lock_guard<std::mutex> l(m); closed = true; } cv.notify_all(); }
+};
+
 }  // namespace
 
 void align(Readfeed& readfeed, Readstats& readstats, Index& /*index: the library keeps its own resident form*/, KeyValueDatabase& kvdb, Runopts& opts)
 {
   INFO("==== Starting alignment (libsmr_b200) ====");
-  if (opts.num_alignments == 0) { ERR("'-num_alignments 0' is not supported by the GPU path"); exit(EXIT_FAILURE); }
   // one context per GPU (SMR_GPUS, default 1; never more than the devices present): reads shard by record, every GPU holds the
   // whole index, the only cross-GPU state are the Readstats counters (summed below) -- SURVEY 8(e)
   int ngpu = 1;
@@ -76,77 +108,96 @@ void align(Readfeed& readfeed, Readstats& readstats, Index& /*index: the library
       std::string cat; std::vector<uint64_t> off(1, 0);
       for (auto& r : refs.buffer) { cat += r.sequence; off.push_back(cat.size()); }
       const uint32_t skip[3] = {opts.skiplengths[i][0], opts.skiplengths[i][1], opts.skiplengths[i][2]};
+      std::vector<std::thread> loaders;                                // one host thread per GPU: flattening + upload run side by side
       for (smr_ctx* ctx : ctxs)
-        if (smr_load_index_part(ctx, (uint32_t)i, part, kmer.data(), kmer.size(), trie.data(), trie.size(), pos.data(), pos.size(),
-                                (const uint8_t*)cat.data(), off.data(), (uint32_t)refs.buffer.size(), refstats.lnwin[i], refstats.minimal_score[i], skip) != SMR_OK)
-          die(ctx, "smr_load_index_part");
+        loaders.emplace_back([&, ctx] {
+          if (smr_load_index_part(ctx, (uint32_t)i, part, kmer.data(), kmer.size(), trie.data(), trie.size(), pos.data(), pos.size(),
+                                  (const uint8_t*)cat.data(), off.data(), (uint32_t)refs.buffer.size(), refstats.lnwin[i], refstats.minimal_score[i], skip) != SMR_OK)
+            die(ctx, "smr_load_index_part");
+        });
+      for (auto& t : loaders) t.join();
       refs.unload();
     }
 
-  // batches of reads from the unchanged Readfeed; read ids ("<file>_<n>") stay the KVDB keys.  Up to one batch per GPU is in
-  // flight; results are stored in batch order.
-  const uint32_t slots = (uint32_t)std::max<int32_t>(1, (int32_t)opts.num_alignments);
+  // batches of reads from the unchanged Readfeed; read ids ("<file>_<n>") stay the KVDB keys
   const size_t nrefs = opts.indexfiles.size();
-  uint32_t batch_reads = 1u << 20;
+  uint32_t batch_reads = 1u << 19;
   if (const char* e = getenv("SMR_BATCH_READS")) batch_reads = (uint32_t)std::max(1, atoi(e));
-  struct Batch {
-    std::vector<std::string> ids; std::string seqcat; std::vector<uint64_t> off{0};
-    std::vector<smr_read_result> res; std::vector<smr_aln> alns; std::vector<uint32_t> cigars; uint64_t used = 0; std::vector<uint64_t> cnt;
-    std::string blobs; std::vector<uint64_t> boff;
-  };
-  std::vector<Batch> pending;
-  pending.emplace_back();
+  BatchQueue full, empty;
+
   std::vector<uint64_t> total(SMR_CNT_FIXED + nrefs, 0);
+  std::mutex total_m;
+
   auto run_batch = [&](smr_ctx* ctx, Batch& b) {
     const uint32_t n = (uint32_t)b.ids.size();
-    b.res.resize(n); b.alns.resize((size_t)n * slots); b.cigars.resize((size_t)64 * n * slots + 4096); b.cnt.assign(SMR_CNT_FIXED + nrefs, 0);
-    if (smr_align_batch(ctx, (const uint8_t*)b.seqcat.data(), b.off.data(), n, b.res.data(), b.alns.data(), b.cigars.data(), b.cigars.size(), &b.used,
-                        b.cnt.data(), (uint32_t)b.cnt.size()) != SMR_OK) die(ctx, "smr_align_batch");
-    b.boff.resize((size_t)n + 1);
-    smr_pack_kvdb_blobs(b.res.data(), b.alns.data(), b.cigars.data(), n, slots, (int32_t)opts.num_alignments, nullptr, nullptr, 0, b.boff.data());
-    b.blobs.assign(b.boff[n], '\0');
-    if (smr_pack_kvdb_blobs(b.res.data(), b.alns.data(), b.cigars.data(), n, slots, (int32_t)opts.num_alignments, nullptr, (uint8_t*)&b.blobs[0], b.blobs.size(),
-                            b.boff.data()) != SMR_OK) die(ctx, "smr_pack_kvdb_blobs");
-  };
-  auto flush = [&]() {                       // run the pending batches (one per GPU, concurrently), then store their results in order
-    if (pending.back().ids.empty()) pending.pop_back();
-    if (pending.empty()) { pending.emplace_back(); return; }
-    std::vector<std::thread> workers;
-    for (size_t k = 1; k < pending.size(); ++k) workers.emplace_back(run_batch, ctxs[k], std::ref(pending[k]));
-    run_batch(ctxs[0], pending[0]);
-    for (auto& t : workers) t.join();
-    for (Batch& b : pending) {
-      for (uint32_t r = 0; r < (uint32_t)b.ids.size(); ++r)
-        if (b.boff[r + 1] > b.boff[r]) kvdb.put(b.ids[r], b.blobs.substr(b.boff[r], b.boff[r + 1] - b.boff[r]));   // == kvdb.put(read.id, read.toBinString())
-      for (size_t k = 0; k < b.cnt.size(); ++k) total[k] += b.cnt[k];
+    for (;;) {
+      const uint32_t slots = smr_aln_slots(ctx);       // num_alignments, or the stride of the all-alignments mode (-num_alignments 0)
+      b.res.resize(n); b.alns.resize((size_t)n * slots); b.cnt.assign(SMR_CNT_FIXED + nrefs, 0);
+      if (b.cigars.size() < (size_t)16 * n * slots + 4096) b.cigars.resize((size_t)16 * n * slots + 4096);
+      const int rc = smr_align_batch(ctx, (const uint8_t*)b.seqcat.data(), b.off.data(), n, b.res.data(), b.alns.data(), b.cigars.data(), b.cigars.size(), &b.used,
+                                     b.cnt.data(), (uint32_t)b.cnt.size());
+      if (rc == SMR_ERR_CAPACITY && opts.num_alignments == 0 && smr_aln_slots_needed(ctx) > slots) {   // a read stored more alignments than the stride
+        if (smr_set_aln_slots(ctx, smr_aln_slots_needed(ctx)) != SMR_OK) die(ctx, "smr_set_aln_slots");
+        continue;
+      }
+      if (rc == SMR_ERR_CAPACITY && b.cigars.size() < ((size_t)1 << 32)) { b.cigars.resize(b.cigars.size() * 2); continue; }   // CIGAR pool too small: grow, again
+      if (rc != SMR_OK) die(ctx, "smr_align_batch");
+      b.boff.resize((size_t)n + 1);
+      smr_pack_kvdb_blobs(b.res.data(), b.alns.data(), b.cigars.data(), n, slots, (int32_t)opts.num_alignments, nullptr, nullptr, 0, b.boff.data());
+      b.blobs.assign(b.boff[n], '\0');
+      if (smr_pack_kvdb_blobs(b.res.data(), b.alns.data(), b.cigars.data(), n, slots, (int32_t)opts.num_alignments, nullptr, (uint8_t*)&b.blobs[0], b.blobs.size(),
+                              b.boff.data()) != SMR_OK) die(ctx, "smr_pack_kvdb_blobs");
+      break;
     }
-    pending.clear();
-    pending.emplace_back();
+    for (uint32_t r = 0; r < n; ++r)
+      if (b.boff[r + 1] > b.boff[r]) kvdb.put(b.ids[r], b.blobs.substr(b.boff[r], b.boff[r + 1] - b.boff[r]));   // == kvdb.put(read.id, read.toBinString())
+    std::lock_guard<std::mutex> l(total_m);
+    for (size_t k = 0; k < b.cnt.size(); ++k) total[k] += b.cnt[k];
   };
 
+  std::vector<std::thread> workers;
+  for (int g = 0; g < ngpu; ++g)
+    workers.emplace_back([&, g] {
+      while (std::unique_ptr<Batch> b = full.pop()) { run_batch(ctxs[g], *b); b->reset(); empty.push(std::move(b)); }
+    });
+
   readfeed.init_reading();
-  std::string readstr;
-  for (int id = 0; id < (int)opts.num_proc_thread; ++id) {        // the reference's per-processor feed order (processor.cpp:104-160)
-    int idx = id * (int)readfeed.num_sense;
-    for (; readfeed.next(idx, readstr);) {
-      Read read(readstr);
-      read.init(opts);
-      if (!read.isEmpty && read.isValid) {                         // too-short reads go along: the library counts them (num_short) and never aligns them
-        Batch& b = pending.back();
-        b.ids.push_back(read.id);
-        for (char c : read.sequence) b.seqcat.push_back((char)nt_table[(int)((unsigned char)c & 0x7F)]);   // 0..3, 4 = ambiguous (common.hpp:68-77)
-        b.off.push_back(b.seqcat.size());
-        if (b.ids.size() == batch_reads) { if ((int)pending.size() == ngpu) flush(); else pending.emplace_back(); }
+  // parser threads: processor id t, t + T, t + 2T, ... each in the reference's own feed order (processor.cpp:104-160)
+  const int nproc = (int)opts.num_proc_thread;
+  int nparse = std::max(1, std::min(nproc, (int)std::thread::hardware_concurrency()));
+  if (const char* e = getenv("SMR_PARSE_THREADS")) nparse = std::max(1, std::min(nproc, atoi(e)));
+  for (int k = 0; k < nparse + 2 * ngpu; ++k) empty.push(std::make_unique<Batch>());   // one per parser + two per GPU (one running, one queued)
+  std::vector<std::thread> parsers;
+  for (int t = 0; t < nparse; ++t)
+    parsers.emplace_back([&, t] {
+      std::unique_ptr<Batch> cur = empty.pop();
+      std::string readstr;
+      for (int id = t; id < nproc; id += nparse) {
+        int idx = id * (int)readfeed.num_sense;
+        for (; readfeed.next(idx, readstr);) {
+          Read read(readstr);
+          read.init(opts);
+          if (!read.isEmpty && read.isValid) {                       // too-short reads go along: the library counts them (num_short) and never aligns them
+            cur->ids.push_back(read.id);
+            const size_t o = cur->seqcat.size(), len = read.sequence.size();
+            cur->seqcat.resize(o + len);
+            for (size_t k = 0; k < len; ++k) cur->seqcat[o + k] = (char)nt_table[(int)((unsigned char)read.sequence[k] & 0x7F)];   // 0..3, 4 = ambiguous (common.hpp:68-77)
+            cur->off.push_back(o + len);
+            if (cur->ids.size() == batch_reads) { full.push(std::move(cur)); cur = empty.pop(); }
+          }
+          readstr.resize(0);
+          // Known deviation (paired files only): the reference `continue`s past its file switch for a read it does not process in
+          // the current index pass (too short, or already is_done from an earlier index: processor.cpp:116-124 vs :160), so from
+          // then on it draws mates from the wrong file and stops when either file ends -- which reads are searched against which
+          // index then depends on the thread count and on earlier results.  Here every read is searched against every index.
+          if (opts.is_paired) idx ^= 1;
+        }
       }
-      readstr.resize(0);
-      // Known deviation (paired files only): the reference `continue`s past its file switch for a read it does not process in
-      // the current index pass (too short, or already is_done from an earlier index: processor.cpp:116-124 vs :160), so from
-      // then on it draws mates from the wrong file and stops when either file ends -- which reads are searched against which
-      // index then depends on the thread count and on earlier results.  Here every read is searched against every index.
-      if (opts.is_paired) idx ^= 1;
-    }
-  }
-  flush();
+      if (!cur->ids.empty()) full.push(std::move(cur)); else empty.push(std::move(cur));
+    });
+  for (auto& t : parsers) t.join();
+  full.close();
+  for (auto& t : workers) t.join();
   readfeed.rewind_in();
   readfeed.init_vzlib_in();
 

@@ -20,6 +20,7 @@ struct smr_ctx {
   struct Part { ora_index* ix; uint16_t index_num, part; std::vector<uint8_t> refseq; std::vector<uint64_t> refoff; uint32_t nref, ms; uint32_t skip[3]; };
   std::vector<Part> parts;
   uint32_t n_index_files = 0;
+  uint32_t all_slots = 16, need_slots = 0;
 };
 
 extern "C" {
@@ -48,6 +49,10 @@ int smr_set_params(smr_ctx* c, const smr_params* p) {
   memcpy(&c->prm, p, sizeof(ora_params));
   return SMR_OK;
 }
+
+int smr_set_aln_slots(smr_ctx* c, uint32_t slots) { if (!c || !slots) return SMR_ERR_ARG; c->all_slots = slots; return SMR_OK; }
+uint32_t smr_aln_slots(const smr_ctx* c) { return c->prm.num_alignments > 0 ? (uint32_t)c->prm.num_alignments : c->all_slots; }
+uint32_t smr_aln_slots_needed(const smr_ctx* c) { return c->need_slots; }
 
 int smr_load_index_part(smr_ctx* c, uint32_t index_num, uint32_t part, const void* kmer, size_t kb, const void* trie, size_t tb, const void* pos, size_t pb,
                         const uint8_t* refseq, const uint64_t* ref_off, uint32_t nref, uint32_t lnwin, uint32_t minimal_score, const uint32_t skip[3]) {
@@ -84,8 +89,10 @@ int smr_align_batch(smr_ctx* c, const uint8_t* seq_cat, const uint64_t* seq_off,
   std::vector<uint64_t> matched(c->n_index_files, 0);
   ora_counters oc{};
   uint64_t used = 0;
+  ora_set_aln_slots(c->all_slots);
   const int rc = ora_align(ix.data(), inum.data(), ipart.data(), n, c->n_index_files, rs.data(), ro.data(), nref.data(), ms.data(), skip.data(), &c->prm,
                            seq_cat, seq_off, nreads, (ora_read_result*)results, (ora_aln*)alns, cigar_pool, cigar_cap, &used, matched.data(), &oc, 4);
+  if (rc == 2) c->need_slots = ora_aln_slots_needed();
   if (rc != 0) { c->err = "mock: ora_align failed"; return SMR_ERR_CAPACITY; }
   if (cigar_used) *cigar_used = used;
   if (counters) {

@@ -124,15 +124,8 @@ def align(indexes, index_nums, parts, n_index_files, refs, minimal_scores, skipl
     L = lib()
     nidx = len(indexes)
     n = batch.n
-    slots = max(1, params.num_alignments)
-    res = np.zeros(n, RESULT_DTYPE)
-    alns = np.zeros(n * slots, ALN_DTYPE)
-    if cigar_cap is None:
-        cigar_cap = 64 * n * slots + 1024
-    pool = np.zeros(cigar_cap, np.uint32)
-    used = C.c_uint64(0)
-    matched = np.zeros(n_index_files, np.uint64)
-    counters = np.zeros(len(COUNTER_NAMES), np.uint64)
+    cat = np.ascontiguousarray(batch.cat, np.uint8)
+    off = np.ascontiguousarray(batch.off, np.uint64)
     idx_arr = (C.c_void_p * nidx)(*[ix.h for ix in indexes])
     inum = np.asarray(index_nums, np.uint16)
     ipart = np.asarray(parts, np.uint16)
@@ -142,15 +135,29 @@ def align(indexes, index_nums, parts, n_index_files, refs, minimal_scores, skipl
     ms = np.asarray(minimal_scores, np.uint32)
     sk = np.asarray(skiplengths, np.uint32).reshape(-1)
     assert sk.size == 3 * nidx
-    cat = np.ascontiguousarray(batch.cat, np.uint8)
-    off = np.ascontiguousarray(batch.off, np.uint64)
-    rc = L.ora_align(idx_arr, C.c_void_p(inum.ctypes.data), C.c_void_p(ipart.ctypes.data), C.c_uint32(nidx),
-                     C.c_uint32(n_index_files), refseq, refoff, C.c_void_p(nref.ctypes.data),
-                     C.c_void_p(ms.ctypes.data), C.c_void_p(sk.ctypes.data), C.byref(params),
-                     C.c_void_p(cat.ctypes.data), C.c_void_p(off.ctypes.data), C.c_uint32(n),
-                     C.c_void_p(res.ctypes.data), C.c_void_p(alns.ctypes.data), C.c_void_p(pool.ctypes.data),
-                     C.c_uint64(cigar_cap), C.byref(used), C.c_void_p(matched.ctypes.data),
-                     C.c_void_p(counters.ctypes.data), C.c_int(nthreads))
+    slots = params.num_alignments if params.num_alignments > 0 else 16   # 0 = all alignments: stride grown on demand
+    user_cap = cigar_cap
+    L.ora_aln_slots_needed.restype = C.c_uint32
+    while True:
+        L.ora_set_aln_slots(C.c_uint32(slots))
+        res = np.zeros(n, RESULT_DTYPE)
+        alns = np.zeros(n * slots, ALN_DTYPE)
+        cigar_cap = user_cap if user_cap is not None else 64 * n * slots + 1024
+        pool = np.zeros(cigar_cap, np.uint32)
+        used = C.c_uint64(0)
+        matched = np.zeros(n_index_files, np.uint64)
+        counters = np.zeros(len(COUNTER_NAMES), np.uint64)
+        rc = L.ora_align(idx_arr, C.c_void_p(inum.ctypes.data), C.c_void_p(ipart.ctypes.data), C.c_uint32(nidx),
+                         C.c_uint32(n_index_files), refseq, refoff, C.c_void_p(nref.ctypes.data),
+                         C.c_void_p(ms.ctypes.data), C.c_void_p(sk.ctypes.data), C.byref(params),
+                         C.c_void_p(cat.ctypes.data), C.c_void_p(off.ctypes.data), C.c_uint32(n),
+                         C.c_void_p(res.ctypes.data), C.c_void_p(alns.ctypes.data), C.c_void_p(pool.ctypes.data),
+                         C.c_uint64(cigar_cap), C.byref(used), C.c_void_p(matched.ctypes.data),
+                         C.c_void_p(counters.ctypes.data), C.c_int(nthreads))
+        if rc == 2 and params.num_alignments == 0 and int(L.ora_aln_slots_needed()) > slots:
+            slots = int(L.ora_aln_slots_needed())
+            continue
+        break
     if rc != 0:
         raise RuntimeError(f"ora_align rc={rc}")
     return dict(res=res, alns=alns, cigar=pool[: used.value].copy(), matched=matched,

@@ -663,7 +663,12 @@ void align_one(const uint8_t* seq04, uint32_t len, Persist& db, const PassCtx& p
 
 } // namespace
 
+static thread_local uint32_t g_all_slots = 16, g_need_slots = 0;   /* per calling thread (the stand-in of the C ABI runs one context per thread) */
+
 extern "C" {
+
+void ora_set_aln_slots(uint32_t slots) { g_all_slots = slots ? slots : 1; g_need_slots = 0; }
+uint32_t ora_aln_slots_needed(void) { return g_need_slots; }
 
 ora_index* ora_index_load(const char* prefix, uint32_t part, uint32_t lnwin, char* err, size_t errlen) {
   auto fail = [&](const std::string& m) -> ora_index* { if (err && errlen) snprintf(err, errlen, "%s", m.c_str()); return nullptr; };
@@ -771,7 +776,7 @@ int ora_align(const ora_index* const* idx, const uint16_t* index_num, const uint
       for (auto& t : th) t.join();
     }
   }
-  const uint32_t slots = prm->num_alignments > 0 ? (uint32_t)prm->num_alignments : 1;
+  const uint32_t slots = prm->num_alignments > 0 ? (uint32_t)prm->num_alignments : g_all_slots;   /* 0 = all alignments: caller-set stride */
   uint64_t used = 0; int rc = 0;
   for (uint32_t r = 0; r < nreads; ++r) {
     const Persist& p = db[r];
@@ -781,7 +786,7 @@ int ora_align(const ora_index* const* idx, const uint16_t* index_num, const uint
     o.lastIndex = p.lastIndex; o.lastPart = p.lastPart; o.hit_seeds = p.hit_seeds; o.min_index = p.min_index; o.max_index = p.max_index;
     o.max_SW_count = p.max_SW_count; o.is_done = p.is_done; o.is_hit = p.is_hit;
     o.n_align = (uint32_t)p.alignv.size();
-    if (o.n_align > slots) { rc = 2; o.n_align = slots; } /* num_alignments == 0 (unbounded) is not supported by the flat result layout */
+    if (o.n_align > slots) { rc = 2; if (o.n_align > g_need_slots) g_need_slots = o.n_align; o.n_align = slots; } /* all-alignments mode: stride too small, ora_aln_slots_needed() */
     for (uint32_t a = 0; a < o.n_align; ++a) {
       const Aln& s = p.alignv[a]; ora_aln& d = alns[(uint64_t)r * slots + a];
       memset(&d, 0, sizeof(d));

@@ -87,7 +87,8 @@ int ora_ssw_align(const int8_t* read, int32_t readLen, const int8_t* ref, int32_
  *   minimal_score[k]  refstats.minimal_score[index_num[k]]; skiplengths[k*3..] the three pass shifts
  *   is_last_idx: computed as k == nidx-1
  *   reads: 0..4 (4 = ambiguous), concatenated + offsets (nreads+1)
- * Outputs: res[nreads], alns[nreads*max(1,num_alignments)], cigar pool (u32), per-db match counters.
+ * Outputs: res[nreads], alns[nreads*slots] (slots = num_alignments, or the stride set by ora_set_aln_slots when it is 0:
+ * "all alignments", alignment.cpp:420-424; rc 2 + ora_aln_slots_needed() when a read stored more), cigar pool (u32), per-db match counters.
  */
 int ora_align(const ora_index* const* idx, const uint16_t* index_num, const uint16_t* part, uint32_t nidx,
               uint32_t n_index_files,
@@ -98,6 +99,9 @@ int ora_align(const ora_index* const* idx, const uint16_t* index_num, const uint
               ora_read_result* res, ora_aln* alns, uint32_t* cigar_pool, uint64_t cigar_cap,
               uint64_t* cigar_used, uint64_t* reads_matched_per_db /* n_index_files */,
               ora_counters* counters, int nthreads);
+
+void ora_set_aln_slots(uint32_t slots);
+uint32_t ora_aln_slots_needed(void);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,8 @@ STATUS = {0: "SMR_OK", 1: "SMR_ERR_CUDA", 2: "SMR_ERR_ARG", 3: "SMR_ERR_INDEX", 
 SYMBOLS = ["smr_init", "smr_destroy", "smr_last_error", "smr_device_count", "smr_load_index_part",
            "smr_set_minimal_score", "smr_set_params", "smr_index_info", "smr_align_batch", "smr_upload_batch",
            "smr_run_resident", "smr_download_results", "smr_last_timings", "smr_debug_seed_windows", "smr_debug_ssw",
-           "smr_debug_dpx_peak", "smr_set_stats_buffer", "smr_build_index", "smr_upload_fastx", "smr_resident_layout", "smr_pack_kvdb_blobs"]
+           "smr_debug_dpx_peak", "smr_set_stats_buffer", "smr_build_index", "smr_upload_fastx", "smr_resident_layout", "smr_pack_kvdb_blobs",
+           "smr_set_aln_slots", "smr_aln_slots", "smr_aln_slots_needed"]
 
 CNT_NAMES = ("num_aligned", "num_short", "sw_calls", "sw_cells", "windows", "trie_nodes", "buckets",
              "bucket_entries", "pos_entries", "lis_calls", "dbg_max_read_cycles", "dbg_sum_read_cycles", "dbg_lis_kernel_cycles",
@@ -76,6 +77,11 @@ def load_library():
         L.smr_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         L.smr_destroy.argtypes = [C.c_void_p]
         L.smr_destroy.restype = None
+        L.smr_aln_slots.restype = C.c_uint32
+        L.smr_aln_slots.argtypes = [C.c_void_p]
+        L.smr_aln_slots_needed.restype = C.c_uint32
+        L.smr_aln_slots_needed.argtypes = [C.c_void_p]
+        L.smr_set_aln_slots.argtypes = [C.c_void_p, C.c_uint32]
         for name in SYMBOLS:
             getattr(L, name)  # AttributeError if the build is stale
         _lib = L
@@ -160,6 +166,10 @@ class Aligner:
         self.params = params
         self._check(self.L.smr_set_params(self.h, C.byref(params)), "smr_set_params")
 
+    def set_aln_slots(self, slots: int):
+        """smr_set_aln_slots: stride of the result layout in the all-alignments mode (num_alignments == 0)."""
+        self._check(self.L.smr_set_aln_slots(self.h, C.c_uint32(slots)), "smr_set_aln_slots")
+
     def load_index_part(self, index_num: int, part: int, prefix: str, refs: hostio.References, minimal_score: int,
                         skiplengths=(18, 9, 3), lnwin: int = 18):
         sfx = f"_{part}.dat"
@@ -184,7 +194,7 @@ class Aligner:
         return dict(zip(("parts", "hbm_bytes", "nodes", "entries", "ids", "positions"), map(int, out)))
 
     def _outputs(self, n, reuse=False):
-        slots = max(1, self.params.num_alignments)
+        slots = int(self.L.smr_aln_slots(self.h))   # num_alignments, or the stride of the all-alignments mode (0)
         if reuse:   # the same host buffers for every call of this shape (a streaming caller consumes a batch before the next)
             key = (n, slots, self.n_index_files)
             if getattr(self, "_out_key", None) != key:
@@ -212,12 +222,18 @@ class Aligner:
         cat = np.ascontiguousarray(cat, np.uint8)
         off = np.ascontiguousarray(off, np.uint64)
         n = off.size - 1
-        slots, res, alns, pool, cap, counters = self._outputs(n, reuse_outputs)
-        stats = np.zeros(n * slots, STATS_DTYPE) if with_stats else None
-        self._check(self.L.smr_set_stats_buffer(self.h, _ptr(stats) if with_stats else C.c_void_p(0)), "smr_set_stats_buffer")
-        used = C.c_uint64(0)
-        rc = self.L.smr_align_batch(self.h, _ptr(cat), _ptr(off), C.c_uint32(n), _ptr(res), _ptr(alns), _ptr(pool),
-                                    C.c_uint64(cap), C.byref(used), _ptr(counters), C.c_uint32(counters.size))
+        while True:
+            slots, res, alns, pool, cap, counters = self._outputs(n, reuse_outputs)
+            stats = np.zeros(n * slots, STATS_DTYPE) if with_stats else None
+            self._check(self.L.smr_set_stats_buffer(self.h, _ptr(stats) if with_stats else C.c_void_p(0)), "smr_set_stats_buffer")
+            used = C.c_uint64(0)
+            rc = self.L.smr_align_batch(self.h, _ptr(cat), _ptr(off), C.c_uint32(n), _ptr(res), _ptr(alns), _ptr(pool),
+                                        C.c_uint64(cap), C.byref(used), _ptr(counters), C.c_uint32(counters.size))
+            need = int(self.L.smr_aln_slots_needed(self.h)) if rc == 5 and self.params.num_alignments == 0 else 0
+            if need > slots:   # all-alignments mode: the library names the stride this batch needs; allocate and run again
+                self.set_aln_slots(need)
+                continue
+            break
         self._check(rc, "smr_align_batch")
         self.L.smr_set_stats_buffer(self.h, C.c_void_p(0))
         out = self._pack(res, alns, pool, used.value, counters, slots)

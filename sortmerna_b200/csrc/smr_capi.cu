@@ -43,6 +43,8 @@ struct smr_ctx {
   uint32_t n_index_files = 0;
   int sm_count = 148;
   uint32_t chunk_reads = 1u << 20;
+  uint32_t need_slots = 0;       // set with SMR_ERR_CAPACITY in all-alignments mode: the stride the batch needs
+  uint32_t all_slots = 16;       // stride of the result layout when num_alignments == 0 (smr_set_aln_slots)
   uint32_t lis_ctas_per_sm = kLisMinCtas;   // persistent CTAs of the candidate kernel per SM (matches its __launch_bounds__)
 
   // resident batch
@@ -84,6 +86,9 @@ namespace {
       return SMR_ERR_CUDA;                                                                         \
     }                                                                                              \
   } while (0)
+
+// alignment slots per read in every flat result array: num_alignments, or the stride set for "all alignments" (0)
+uint32_t slots_of(const smr_ctx* ctx) { return ctx->prm.num_alignments > 0 ? (uint32_t)ctx->prm.num_alignments : std::max(1u, ctx->all_slots); }
 
 int ensure(smr_ctx* ctx, DevBuf& b, size_t bytes) {
   if (bytes <= b.cap && b.p) return SMR_OK;
@@ -163,7 +168,7 @@ int setup_arenas(smr_ctx* ctx) {
   while (ctx->lis_ctas > 16 && ctx->lis_stride * ctx->lis_warps > budget) { ctx->lis_ctas /= 2; ctx->lis_warps = ctx->lis_ctas * kPlannerWarps; }
   if (int rc = ensure(ctx, ctx->lis_arena, ctx->lis_stride * ctx->lis_warps)) return rc;
   if (int rc = ensure(ctx, ctx->lis_epochs, (size_t)ctx->lis_warps * 4)) return rc;
-  if (int rc = ensure(ctx, ctx->lis_queue, (size_t)kQueueCap * sizeof(QSlot) + 64)) return rc;
+  if (int rc = ensure(ctx, ctx->lis_queue, (size_t)2 * kQueueCap * sizeof(QSlot) + 64)) return rc;
   if (int rc = ensure(ctx, ctx->lis_done, (size_t)ctx->lis_warps * 4 + 64)) return rc;
   if (int rc = ensure(ctx, ctx->lis_rows, (size_t)ctx->lis_ctas * kScorerWarps * 2 * ctx->row_cap * 4)) return rc;
   // histogram epochs start at 0 over a zeroed histogram (every run: the arena layout depends on the scale of the run)
@@ -218,7 +223,7 @@ int upload_batch_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_
     ctx->h_off.resize(nreads + 1);
     for (uint32_t r = 0; r <= nreads; ++r) ctx->h_off[r] = seq_off[r] - seq_off[0];
   }
-  const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
+  const uint32_t slots = slots_of(ctx);
   int rc;
   if ((rc = ensure(ctx, ctx->seq04, total + 64))) return rc;
   if ((rc = ensure(ctx, ctx->seq_off, (size_t)(nreads + 1) * 4))) return rc;
@@ -238,7 +243,7 @@ int upload_batch_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_
 // the part of an upload that does not depend on where the reads came from: seq04 / seq_off / pk_off are on the device,
 // ctx->off32 (host) holds the offsets; sizes the per-batch buffers and 2-bit packs the reads
 int finish_upload(smr_ctx* ctx, uint32_t nreads, uint64_t w) {
-  const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
+  const uint32_t slots = slots_of(ctx);
   const std::vector<uint32_t>& off32 = ctx->off32;
   int rc;
   if ((rc = ensure(ctx, ctx->pk03, (size_t)(w + 4) * 4))) return rc;
@@ -378,12 +383,12 @@ DevBatch make_batch(smr_ctx* ctx, uint32_t c0, uint32_t n) {
 int run_impl(smr_ctx* ctx) {
   if (!ctx->have_params) { ctx->err = "smr_set_params not called"; return SMR_ERR_ARG; }
   if (ctx->parts.empty()) { ctx->err = "no index loaded"; return SMR_ERR_ARG; }
-  if (ctx->prm.num_alignments <= 0) { ctx->err = "num_alignments == 0 (report all alignments) is not supported"; return SMR_ERR_UNSUPPORTED; }
+  if (ctx->prm.num_alignments < 0) { ctx->err = "num_alignments < 0"; return SMR_ERR_ARG; }
   if (ctx->prm.minoccur != 0) { ctx->err = "minoccur != 0 is not supported"; return SMR_ERR_UNSUPPORTED; }
   ctx->t_seed = ctx->t_lis = ctx->t_final = ctx->t_total = 0; ctx->n_launch = 0;
   const uint32_t nreads = ctx->nreads;
   if (nreads == 0) return SMR_OK;
-  const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
+  const uint32_t slots = slots_of(ctx);
   int rc;
   if ((rc = setup_arenas(ctx))) return rc;
   // device copy of the part table (finalize looks parts up by slot)
@@ -493,7 +498,7 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
   const uint32_t n = ctx->nreads;
   flagged.clear();
   if (n == 0) return SMR_OK;
-  const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
+  const uint32_t slots = slots_of(ctx);
   cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1);
   CK(cudaEventRecord(e0, ctx->stream));
   int prc;
@@ -529,9 +534,11 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
   // pass 1 (sequential, cheap): flagged reads, cigar offsets in the caller's pool (running sum in read order), counters
   std::vector<uint64_t>& coff = ctx->h_coff; coff.resize((size_t)n + 1);
   uint64_t run = out.cigar_used;
+  uint32_t need_slots = 0;
   for (uint32_t r = 0; r < n; ++r) {
     coff[r] = run;
     if (fl[r] & kErrTrace) { ctx->err = "trace back error (ssw.c:707 is fatal in the reference too)"; rc = SMR_ERR_INDEX; }
+    if (fl[r] & kOvfSlots) { need_slots = std::max(need_slots, st[r].n_align); continue; }   // not retried: the stride is the caller's
     if (fl[r]) { flagged.push_back(r); for (int bit = 0; bit < 6; ++bit) if (fl[r] & (1u << bit)) ctx->flag_hist[bit]++; continue; }
     const ReadState& s = st[r];
     for (uint32_t k = 0; k < slots && k < s.n_align; ++k) run += oa[(size_t)r * slots + k].cigar_len;
@@ -542,6 +549,12 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
     }
   }
   coff[n] = run;
+  if (need_slots) {
+    ctx->err = "all-alignments mode: a read stored " + std::to_string(need_slots) + " alignments, the result stride is " + std::to_string(slots) +
+               " (smr_set_aln_slots(" + std::to_string(need_slots) + ") or more, then call again)";
+    ctx->need_slots = need_slots;
+    return SMR_ERR_CAPACITY;
+  }
   if (run > out.cigar_cap) { ctx->err = "cigar pool too small"; return SMR_ERR_CAPACITY; }
   out.cigar_used = run;
   // pass 2: results, alignments and cigars of disjoint read ranges, by a few host threads for large batches
@@ -714,6 +727,15 @@ int smr_set_params(smr_ctx* ctx, const smr_params* p) {
   return SMR_OK;
 }
 
+int smr_set_aln_slots(smr_ctx* ctx, uint32_t slots) {
+  if (!ctx || slots == 0 || slots > (1u << 20)) return SMR_ERR_ARG;
+  ctx->all_slots = slots;
+  return SMR_OK;
+}
+
+uint32_t smr_aln_slots(const smr_ctx* ctx) { return ctx ? slots_of(ctx) : 0; }
+uint32_t smr_aln_slots_needed(const smr_ctx* ctx) { return ctx ? ctx->need_slots : 0; }
+
 int smr_index_info(const smr_ctx* ctx, uint64_t out[6]) {
   if (!ctx || !out) return SMR_ERR_ARG;
   memset(out, 0, 6 * sizeof(uint64_t));
@@ -726,7 +748,7 @@ int smr_align_batch(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_of
                     uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used, uint64_t* counters, uint32_t n_counters) {
   if (!ctx || !seq_cat || !seq_off || !results || !alns || (!cigar_pool && cigar_cap)) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
+  const uint32_t slots = slots_of(ctx);
   memset(results, 0, (size_t)nreads * sizeof(smr_read_result));
   memset(alns, 0, (size_t)nreads * slots * sizeof(smr_aln));
   HostOut out{results, alns, cigar_pool, cigar_cap, 0, counters, n_counters};
@@ -782,7 +804,7 @@ int smr_download_results(smr_ctx* ctx, smr_read_result* results, smr_aln* alns, 
                          uint64_t* counters, uint32_t n_counters) {
   if (!ctx || !results || !alns) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
-  const uint32_t slots = (uint32_t)std::max(1, ctx->prm.num_alignments);
+  const uint32_t slots = slots_of(ctx);
   const uint32_t n = ctx->nreads;
   memset(results, 0, (size_t)n * sizeof(smr_read_result));
   memset(alns, 0, (size_t)n * slots * sizeof(smr_aln));

@@ -57,7 +57,7 @@ struct AlnWork {
 
 // hit record produced by the seed kernel: id + (window position | variant << 24)
 constexpr uint32_t kVarFwd = 0, kVarRevT = 1, kVarRevA = 2;  // reverse strand with N->T / N->A
-constexpr uint32_t kWinMask = 0x00FFFFFFu;
+constexpr uint32_t kWinMask = 0x00FFFFFFu;   // hit.y = window position | variant << 24 | pass class << 28 (the first pass whose grid holds the position)
 
 // overflow / status flags per read (cleared by a retry with larger scratch)
 constexpr uint32_t kOvfSeedLane = 1u;   // more hits in one window than the per-lane buffer
@@ -66,6 +66,7 @@ constexpr uint32_t kOvfPairs = 4u;      // candidate with more (refpos,readpos) 
 constexpr uint32_t kOvfTrace = 8u;      // traceback direction matrix larger than the arena
 constexpr uint32_t kOvfCigar = 16u;     // cigar pool exhausted
 constexpr uint32_t kErrTrace = 32u;     // "Trace back error" (ssw.c:707) -- fatal in the reference
+constexpr uint32_t kOvfSlots = 64u;     // num_alignments == 0: more accepted alignments than the caller's stride (not retried: SMR_ERR_CAPACITY)
 
 // instrumentation counters (device side, u64), same order as SMR_CNT_* after the first two
 enum DevCnt { dcNumAligned = 0, dcNumShort, dcSwCalls, dcSwCells, dcWindows, dcNodes, dcBuckets, dcEntries, dcPosEntries,

@@ -73,7 +73,8 @@ constexpr int kScorerSmem = 2 * kPairProfWords * 4 + 2 * (int)sizeof(ScSlot);   
 constexpr int kPlannerSmem = 128 * 16;                                          // kPairsShared pairs + LIS arrays
 constexpr int kLisSmemBytes = kScorerWarps * kScorerSmem + kPlannerWarps * kPlannerSmem;
 constexpr int kPairsShared = 128;  // pairs / LIS arrays kept in shared memory up to this many
-constexpr uint32_t kQueueCap = 1u << 20;         // task-pair ring (slots)
+constexpr uint32_t kQueueCap = 1u << 20;         // task-pair ring (slots), per queue
+constexpr uint32_t kSmallRound = 32;              // rounds of up to this many pairs go to the express queue
 constexpr uint32_t kNoTask = 0xFFFFFFu;
 constexpr uint32_t kPoison = 0xFFFFu;             // planner id of the shutdown entries
 constexpr uint32_t kBatchCandCap = 4096;          // candidates per batch
@@ -119,8 +120,8 @@ struct LisGlobals {
   uint8_t* arena_base; size_t arena_stride;   // per-planner arena
   uint32_t hist_cap, cand_cap, pair_cap, row_cap, pall_cap, task_cap;
   uint32_t* epochs;                            // [planners]
-  QSlot* ring;                                 // [kQueueCap]
-  uint32_t* q_head; uint32_t* q_tail;          // consumer / producer cursors
+  QSlot* ring;                                 // [2][kQueueCap]: queue 0 = small rounds (latency matters), queue 1 = bulk
+  uint32_t* q_head; uint32_t* q_tail;          // consumer / producer cursors; queue q uses [q * 16] (64 bytes apart)
   uint32_t* planners_done;                     // planners that ran out of reads
   uint32_t* done;                              // [planners] tasks scored so far for each planner
   int32_t* score_rows;                         // [scorers][2 * row_cap] scratch of the s32 row-block fallback
@@ -194,14 +195,6 @@ __device__ __noinline__ unsigned long long warp_sort32_u64(unsigned long long ke
 }
 __device__ __forceinline__ uint32_t next_pow2(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
 
-// class of a window position = the first pass whose grid contains it (paralleltraversal.cpp:118-131)
-__device__ __forceinline__ uint32_t pass_class(uint32_t p, uint32_t s0, uint32_t s1, uint32_t s2) {
-  if (p % s0 == 0) return 0;
-  if (p % s1 == 0) return 1;
-  if (p % s2 == 0) return 2;
-  return 3;
-}
-
 struct ReadCtx {           // per-read working state (uniform across the warp)
   uint32_t r, len, seq_base;
   bool reversed, hasn;
@@ -213,12 +206,12 @@ struct ReadCtx {           // per-read working state (uniform across the warp)
   uint32_t max_SW_count;
   bool is_done, is_hit, is_new_hit;
   bool form04;             // read currently in the 0-4 alphabet (read.is04); only meaningful when hasn
+  bool ovf_slots;          // an accepted alignment did not fit the per-read stride (all-alignments mode)
   uint32_t flags;
 };
 
 __device__ __forceinline__ bool hit_selected(const uint2 h, const ReadCtx& rc, uint32_t s0, uint32_t s1, uint32_t s2) {
-  const uint32_t var = h.y >> 24, p = h.y & kWinMask;
-  const uint32_t c = pass_class(p, s0, s1, s2);
+  const uint32_t var = (h.y >> 24) & 15u, c = h.y >> 28;   // class computed once, by the seed kernel (paralleltraversal.cpp:118-131)
   if (c > rc.pass_n) return false;
   return var == rc.vcls[c];
 }
@@ -261,19 +254,23 @@ __device__ __noinline__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
   const LisGlobals& g = *E.g;
   const unsigned lane = lane_id();
   const uint32_t npairs = (nsel + 1) >> 1;
+  // two queues: a planner with a handful of tasks must not wait behind the thousands of pairs of a read from a conserved region
+  // (each scorer keeps one input slot for either queue, so the express queue is served within about one alignment time)
+  const uint32_t qi = npairs <= kSmallRound ? 0u : 1u;
+  QSlot* ring = g.ring + (size_t)qi * kQueueCap;
   uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(g.q_tail, npairs);
+  if (lane == 0) base = atomicAdd(g.q_tail + qi * 16, npairs);
   base = __shfl_sync(kFull, base, 0);
   for (uint32_t i = lane; i < npairs; i += 32) {
     const uint32_t idx = base + i;
-    QSlot* sl = g.ring + (idx & (kQueueCap - 1));
+    QSlot* sl = ring + (idx & (kQueueCap - 1));
     while (ld_volatile_u32(&sl->seq) != idx) __nanosleep(64);        // the consumer of the previous lap has left the slot
     const uint32_t ta = E.ar.sel[2 * i], tb = (2 * i + 1 < nsel) ? E.ar.sel[2 * i + 1] : kNoTask;
     sl->planner = E.planner; sl->ta = ta; sl->tb = tb;
   }
   __threadfence();      // task records + entries before the sequence numbers that publish them
   __syncwarp();
-  for (uint32_t i = lane; i < npairs; i += 32) { const uint32_t idx = base + i; st_volatile_u32(&g.ring[idx & (kQueueCap - 1)].seq, idx + 1); }
+  for (uint32_t i = lane; i < npairs; i += 32) { const uint32_t idx = base + i; st_volatile_u32(&ring[idx & (kQueueCap - 1)].seq, idx + 1); }
   E.submitted += nsel;
   if (lane == 0) { while (ld_volatile_u32(g.done + E.planner) != E.submitted) __nanosleep(128); __threadfence(); }
   __syncwarp();
@@ -839,7 +836,9 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
                   if (lane == 0) B.hit_db[rc.r] = (uint16_t)ix.index_num;
                 }
                 if (N == 0 || !o.is_best || (o.is_best && rc.n_align < N)) {                    // :420-424
-                  if (rc.n_align < E.g->slots) { if (lane == 0) slots[rc.n_align] = a; rc.n_align++; rc.is_new_hit = true; }
+                  // (N == 0, "all alignments": the count runs on past the caller's stride so that the host can name the stride needed)
+                  if (rc.n_align < E.g->slots) { if (lane == 0) slots[rc.n_align] = a; } else rc.ovf_slots = true;
+                  rc.n_align++; rc.is_new_hit = true;
                 } else if (o.is_best && rc.n_align == N && slots[rc.min_index].score1 < score1) {  // :425-459
                   if (N > 1 && rc.max_index == 0 && rc.min_index == 0) {
                     uint32_t mn = 0, mx = 0, mns = slots[0].score1, mxs = slots[0].score1;      // findMinIndex / findMaxIndex (:533-561)
@@ -904,8 +903,7 @@ __device__ void traverse_dev(PassEnv& E, ReadCtx& rc, const bool is_last_strand)
       bool cnt = false;
       if (h < nh) {
         const uint2 hv = hits[h];
-        const uint32_t p = hv.y & kWinMask;
-        if ((hv.y >> 24) == var && pass_class(p, s0, s1, s2) == pass_n) cnt = (h == 0) || (hits[h - 1].y != hv.y);
+        if (((hv.y >> 24) & 15u) == var && (hv.y >> 28) == pass_n) cnt = (h == 0) || (hits[h - 1].y != hv.y);
       }
       newly += __popc(__ballot_sync(kFull, cnt));
     }
@@ -934,12 +932,15 @@ __device__ void fetcher_loop(const DevBatch& b, const DevParams& prm, const LisG
   ScSlot* sl = (ScSlot*)(scorer_smem + (size_t)(lane >> 1) * kScorerSmem + 2 * kPairProfWords * 4) + (lane & 1u);
   uint32_t filled = 0, h = 0;
   bool have = false, done = !mine;
+  const uint32_t qi = lane & 1u;                 // slot 0 of every scorer is fed from the express queue, slot 1 from the bulk queue
+  QSlot* ring = g.ring + (size_t)qi * kQueueCap;
+  uint32_t* q_head = g.q_head + qi * 16;
   for (;;) {
     bool progress = false;
     if (!done) {
-      if (!have && sl->freed == filled) { h = atomicAdd(g.q_head, 1u); have = true; }
+      if (!have && sl->freed == filled) { h = atomicAdd(q_head, 1u); have = true; }
       if (have) {
-        QSlot* qs = g.ring + (h & (kQueueCap - 1));
+        QSlot* qs = ring + (h & (kQueueCap - 1));
         if (ld_volatile_u32(&qs->seq) == h + 1u) {
           __threadfence();
           const uint32_t planner = __ldcg(&qs->planner), ta = __ldcg(&qs->ta), tb = __ldcg(&qs->tb);
@@ -1113,7 +1114,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     const long long t_read0 = clock64();
     ReadCtx rc;
     rc.r = r; rc.seq_base = b.seq_off[r]; rc.len = b.seq_off[r + 1] - rc.seq_base;
-    rc.hasn = b.has_n[r] != 0; rc.flags = 0;
+    rc.hasn = b.has_n[r] != 0; rc.flags = 0; rc.ovf_slots = false;
     for (uint32_t p = 0; p < g.nparts && !rc.flags; ++p) {
       const DevIndex& ix = g.parts[p];
       const ReadState st = b.state[r];
@@ -1142,6 +1143,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
       }
       __syncwarp();
     }
+    if (rc.ovf_slots) rc.flags |= kOvfSlots;
     if (rc.flags && lane == 0) atomicOr(&b.flags[r], rc.flags);
     { const unsigned long long dt = (unsigned long long)(clock64() - t_read0); t_max = dt > t_max ? dt : t_max; t_sum += dt; }
     __syncwarp();
@@ -1155,16 +1157,19 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     atomicMax(&b.counters[dcMaxReadCycles], t_max); atomicAdd(&b.counters[dcSumReadCycles], t_sum);
     atomicMax(&b.counters[dcLisKernelCycles], (unsigned long long)(clock64() - t_k0));
     // the last planner out shuts the scorers down: one entry each
-    const uint32_t nplanners = gridDim.x * kPlannerWarps, nscorers = gridDim.x * kScorerWarps * 2;   // one shutdown entry per fetcher lane
+    const uint32_t nplanners = gridDim.x * kPlannerWarps, nscorers = gridDim.x * kScorerWarps;   // one shutdown entry per fetcher lane of each queue
     if (atomicAdd(g.planners_done, 1u) + 1u == nplanners) {
-      const uint32_t base = atomicAdd(g.q_tail, nscorers);
-      for (uint32_t i = 0; i < nscorers; ++i) {
-        const uint32_t idx = base + i;
-        QSlot* sl = g.ring + (idx & (kQueueCap - 1));
-        while (ld_volatile_u32(&sl->seq) != idx) __nanosleep(64);
-        sl->planner = kPoison; sl->ta = kNoTask; sl->tb = kNoTask;
-        __threadfence();
-        st_volatile_u32(&sl->seq, idx + 1);
+      for (uint32_t qi = 0; qi < 2; ++qi) {
+        QSlot* ring = g.ring + (size_t)qi * kQueueCap;
+        const uint32_t base = atomicAdd(g.q_tail + qi * 16, nscorers);
+        for (uint32_t i = 0; i < nscorers; ++i) {
+          const uint32_t idx = base + i;
+          QSlot* sl = ring + (idx & (kQueueCap - 1));
+          while (ld_volatile_u32(&sl->seq) != idx) __nanosleep(64);
+          sl->planner = kPoison; sl->ta = kNoTask; sl->tb = kNoTask;
+          __threadfence();
+          st_volatile_u32(&sl->seq, idx + 1);
+        }
       }
     }
   }
@@ -1173,9 +1178,9 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
 // queue / counter reset before every lis_kernel launch
 __global__ void lis_reset_kernel(LisGlobals g, uint32_t nplanners) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < kQueueCap) { QSlot s; s.seq = i; s.planner = 0; s.ta = 0; s.tb = 0; g.ring[i] = s; }
+  if (i < kQueueCap) { QSlot s; s.seq = i; s.planner = 0; s.ta = 0; s.tb = 0; g.ring[i] = s; g.ring[kQueueCap + i] = s; }
   if (i < nplanners) g.done[i] = 0;
-  if (i == 0) { *g.q_head = 0; *g.q_tail = 0; *g.planners_done = 0; }
+  if (i == 0) { g.q_head[0] = 0; g.q_head[16] = 0; g.q_tail[0] = 0; g.q_tail[16] = 0; *g.planners_done = 0; }
 }
 
 }  // namespace smr

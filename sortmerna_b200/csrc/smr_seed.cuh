@@ -81,6 +81,14 @@ __device__ __forceinline__ bool apply_entry(uint32_t code, uint32_t id, bool ful
   return false;
 }
 
+// class of a window position = the first pass whose grid contains it (paralleltraversal.cpp:118-131)
+__device__ __forceinline__ uint32_t pass_class(uint32_t p, uint32_t s0, uint32_t s1, uint32_t s2) {
+  if (p % s0 == 0) return 0;
+  if (p % s1 == 0) return 1;
+  if (p % s2 == 0) return 2;
+  return 3;
+}
+
 constexpr int kAccCap = 192;   // matching entries buffered per flush
 
 struct CoopSmem {              // per warp
@@ -261,7 +269,7 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
         const size_t base = region + total + incl - n;
         for (uint32_t k = 0; k < n; ++k) {
           const uint32_t id = lh.buf[k * lh.stride];
-          b.hits[base + k] = make_uint2(id, p | (var << 24));
+          b.hits[base + k] = make_uint2(id, p | (var << 24) | (pass_class(p, s0, s1, s2) << 28));
           cost += __ldg(ix.pos_off + id + 1) - __ldg(ix.pos_off + id);
         }
       }

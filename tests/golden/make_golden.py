@@ -44,6 +44,8 @@ CASES = {
     "scores_exotic": ["-match", "2", "-mismatch", "-7", "-gap_open", "3", "-gap_ext", "1"],
     "edges_pct": ["-edges", "10%"],
     "seeds3": ["-num_seeds", "3"],
+    # "all alignments" (alignment.cpp:420-424; the reference's own t9, scripts/test.jinja:425-476): every accepted alignment is stored
+    "all": ["-num_alignments", "0"],
 }
 # index-build options that change the index LAYOUT (not the alignment parameters): the reference builds its own index for these
 EXTRA_INDEX_CASES = {
@@ -221,7 +223,25 @@ def make_denovo():
     shutil.rmtree(tmp, ignore_errors=True)
 
 
+def make_one_case(case):
+    """python tests/golden/make_golden.py case NAME: (re)generate one option set on the committed inputs."""
+    arc_p, bac_p, reads_p = (os.path.join(HERE, f) for f in ("db_arc.fasta", "db_bac.fasta", "reads_mix.fq"))
+    tmp = tempfile.mkdtemp(prefix="smr_golden_1_")
+    extra = CASES[case]
+    r = ora.run_reference([arc_p, bac_p], reads_p, os.path.join(tmp, case), extra=["-sam", "-blast", "1 cigar qcov qstrand", "-fastx", "-other"] + extra, threads=1)
+    log = ora.parse_log(r["log"])
+    sam = ["\t".join(f[:9] + ["*", "*"] + f[11:]) for f in (ln.split("\t") for ln in ora.read_sam_rows(os.path.join(r["out_dir"], "aligned.sam")))]
+    blast = [ln.rstrip("\n") for ln in open(os.path.join(r["out_dir"], "aligned.blast"))]
+    os.makedirs(os.path.join(HERE, "case_" + case), exist_ok=True)
+    with open(os.path.join(HERE, "case_" + case, "expected.json"), "w") as f:
+        json.dump(dict(args=extra, log=log, sam=sam, blast=blast), f, indent=0)
+    print(case, "passing", log["passing"], "failing", log["failing"], "sam rows", len(sam), "minimal", log["minimal_score"])
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "case":
+        return make_one_case(sys.argv[2])
     if len(sys.argv) > 1 and sys.argv[1] == "denovo":
         return make_denovo()
     if len(sys.argv) > 1 and sys.argv[1] == "extra":

@@ -21,8 +21,9 @@ REPORTS = ["-sam", "-blast", "1 cigar qcov qstrand", "-fastx", "-other"]
 
 @need
 @pytest.mark.parametrize("extra", [[], ["-num_alignments", "3"], ["-no-best", "-num_alignments", "2"], ["-F"], ["-otu_map", "-de_novo_otu", "-id", "0.97", "-coverage", "0.97"],
-                                   ["-m", "0.5"], ["-match", "2", "-mismatch", "-4", "-gap_open", "6", "-gap_ext", "3", "-N", "-2", "-edges", "10%"]],
-                         ids=["default", "best3", "nobest2", "fwd", "denovo", "parts", "scores_edges"])
+                                   ["-m", "0.5"], ["-match", "2", "-mismatch", "-4", "-gap_open", "6", "-gap_ext", "3", "-N", "-2", "-edges", "10%"],
+                                   ["-num_alignments", "0"]],
+                         ids=["default", "best3", "nobest2", "fwd", "denovo", "parts", "scores_edges", "all_alignments"])
 def test_host_program_with_binding_writes_reference_outputs(extra):
     d = tempfile.mkdtemp(prefix="smr_integ_")
     try:
@@ -61,6 +62,45 @@ def test_paired_files(threads):
 
 
 @need
+def test_paired_feed_deviation_is_pinned():
+    """The documented deviation (integration/align_gpu.cpp): for paired files the reference's align2 `continue`s past its file
+    switch for a read it skips in the current index pass (shorter than the seed, or is_done from an earlier index:
+    processor.cpp:116-124 vs :160) and from then on pairs the wrong mates; the binding searches every read against every index.
+    Pinned here: with one too-short read in file 1 the reference aligns FEWER reads than are alignable, the binding aligns
+    exactly the reads the reference aligns when the same reads are given as ONE (unpaired) file -- i.e. the binding's paired
+    result equals the quirk-free feed, and the difference to the reference's paired run is the quirk, nothing else."""
+    d = tempfile.mkdtemp(prefix="smr_integ_")
+    try:
+        h, s, q = hostio.read_fastx(os.path.join(GOLDEN, "reads_mix.fq"))
+        keep = [i for i in range(len(h)) if len(s[i]) >= 18][:400]
+        short = next(i for i in range(len(h)) if len(s[i]) < 18)
+        f1, f2 = keep[:200], keep[200:400]
+        f1[20] = short                                   # one read shorter than the seed early in file 1
+        paths = []
+        for k, ids in enumerate((f1, f2)):
+            p = os.path.join(d, f"r{k + 1}.fq")
+            with open(p, "w") as f:
+                for i in ids:
+                    f.write(f"{h[i]}\n{s[i].decode()}\n+\n{q[i].decode()}\n")
+            paths.append(p)
+        both = os.path.join(d, "both.fq")                # the same reads, interleaved as the paired feed delivers them, one file
+        with open(both, "w") as f:
+            for a, b in zip(f1, f2):
+                for i in (a, b):
+                    f.write(f"{h[i]}\n{s[i].decode()}\n+\n{q[i].decode()}\n")
+        extra = ["-sam", "-num_alignments", "3"]
+        ref_paired, _ = run_host("sortmerna_ref", os.path.join(d, "refp"), paths, extra + ["-paired_in"], threads=1)
+        got_paired, _ = run_host("sortmerna_gpu_mock", os.path.join(d, "gotp"), paths, extra + ["-paired_in"], threads=1)
+        ref_single, _ = run_host("sortmerna_ref", os.path.join(d, "refs"), [both], extra, threads=1)
+        rows = lambda o: sorted(ln for ln in o["aligned.sam"] if ln and not ln.startswith("@"))
+        assert rows(got_paired) == rows(ref_single)      # the binding = the reference on the quirk-free feed of the same reads
+        assert len(rows(ref_paired)) < len(rows(ref_single))   # the reference's own paired run loses reads to the quirk
+        assert set(rows(ref_paired)) <= set(rows(ref_single))  # ... and aligns nothing differently
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+@need
 def test_two_gpus_small_batches(monkeypatch):
     """SMR_GPUS=2: one context per GPU, batches dispatched concurrently, results stored in batch order, counters summed -- with
     100-read batches so that several rounds of two batches each happen (the stand-in reports two devices)."""
@@ -85,15 +125,14 @@ T9_ROWS = [   # scripts/test.jinja:447-476 (t9 "test_output_all_alignments_f_rc"
 
 
 def run_t9(binary):
-    """the reference's t9: one read against a reference file holding a sequence and its reverse complement.  The original asks
-    for `-num_alignments 0` (all alignments), which the GPU path does not implement; `-no-best -num_alignments 2` stores the same
-    two alignments (checked against the reference binary with its original arguments in the build container)."""
+    """the reference's t9 with its original arguments (scripts/test.jinja:425-445): one read against a reference file holding a
+    sequence and its reverse complement, `-num_alignments 0` (all alignments)."""
     import subprocess
     d = tempfile.mkdtemp(prefix="smr_t9_")
     try:
         t9 = os.path.join(GOLDEN, "t9")
         cmd = [os.path.join(REF_DIR, binary), "-ref", os.path.join(t9, "ref_GQ099317_forward_and_rc.fasta"), "-reads", os.path.join(t9, "illumina_GQ099317.fasta"),
-               "-no-best", "-num_alignments", "2", "-mismatch", "-3", "-sam", "-workdir", d, "-threads", "1", "-task", "4"]
+               "-num_alignments", "0", "-mismatch", "-3", "-sam", "-v", "-workdir", d, "-threads", "1", "-task", "4"]
         p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
         assert p.returncode == 0, p.stdout[-2000:]
         return [ln.rstrip("\n").split("\t") for ln in open(os.path.join(d, "out", "aligned.sam")) if not ln.startswith("@")]
