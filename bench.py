@@ -140,11 +140,18 @@ def _gen_reads_numpy(pool, n, seed):
 
 
 def write_fastq(path, reads):
+    """Illumina-like 4-line FASTQ, constant quality 'I', fixed-width ids (records of equal size: written as one array)."""
+    n = reads.shape[0]
     lut = np.frombuffer(b"ACGT", dtype=np.uint8)
-    qual = b"I" * READ_LEN
+    rec = np.empty((n, 10 + 1 + READ_LEN + 3 + READ_LEN + 1), dtype=np.uint8)
+    ids = np.char.zfill(np.arange(n).astype("S9"), 9)
+    rec[:, 0] = ord("@"); rec[:, 1:10] = np.frombuffer(ids.tobytes(), dtype=np.uint8).reshape(n, 9); rec[:, 10] = 10
+    rec[:, 11:11 + READ_LEN] = lut[reads]
+    o = 11 + READ_LEN
+    rec[:, o] = 10; rec[:, o + 1] = ord("+"); rec[:, o + 2] = 10
+    rec[:, o + 3:o + 3 + READ_LEN] = ord("I"); rec[:, o + 3 + READ_LEN] = 10
     with open(path, "wb") as f:
-        for i in range(reads.shape[0]):
-            f.write(b"@s%d\n" % i + lut[reads[i]].tobytes() + b"\n+\n" + qual + b"\n")
+        f.write(rec.tobytes())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -252,6 +259,58 @@ def host_cores():
     return eff, dict(os_cpu_count=ncpu, affinity=aff, cgroup_quota=quota, threads_used=eff, loadavg_1m=load)
 
 
+def cli_e2e(args, cores, core_info):
+    """What a user runs: the reference's host program with the binding (oracle/_ref/sortmerna_gpu -ref x8 -reads file.fq) against
+    the unmodified reference binary on the same file -- 'Done alignment' seconds and total wall, flat FASTQ (and .gz with
+    --cli-gz).  The CPU binary gets a bounded prefix of the same file (its cost is linear in reads)."""
+    import gzip
+    import shutil
+    from oracle import ora
+    fastas, idx_dir, _, refs, _, _ = load_databases()
+    ref_idx = reference_index_dir(fastas)
+    pool = DbPool(refs)
+    n = args.cli_reads
+    gpu_bin = os.path.join(ROOT, "oracle", "_ref", "sortmerna_gpu")
+    out = {"reads": n, "gpus": args.cli_gpus, "host": core_info}
+    with tempfile.TemporaryDirectory(prefix="smr_cli_") as d:
+        reads = gen_reads(pool, n, GEN_SEED + 4242)
+        fq = os.path.join(d, "reads.fq")
+        write_fastq(fq, reads)
+        inputs = [("flat", fq)]
+        if args.cli_gz:
+            gz = fq + ".gz"
+            with open(fq, "rb") as fi, gzip.open(gz, "wb", compresslevel=1) as fo:
+                shutil.copyfileobj(fi, fo, 1 << 24)
+            inputs.append(("gz", gz))
+        env = dict(os.environ, SMR_GPUS=str(args.cli_gpus))
+        for name, path in inputs:
+            cmd = [gpu_bin] + sum((["-ref", f] for f in fastas), []) + ["-reads", path, "-workdir", os.path.join(d, "w_" + name), "-idx-dir", idx_dir,
+                                                                      "-threads", str(cores), "-task", "4", "-fastx", "-sam"]
+            t0 = time.perf_counter()
+            p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=3000)
+            wall = time.perf_counter() - t0
+            if p.returncode != 0:
+                raise SystemExit("sortmerna_gpu failed:\n" + p.stdout[-3000:])
+            m = re.search(r"Done alignment in ([0-9.eE+-]+) sec", p.stdout)
+            m2 = re.search(r"resident on \d+ GPU\(s\) in ([0-9.eE+-]+) sec; reads streamed, aligned and stored in ([0-9.eE+-]+) sec", p.stdout)
+            log = ora.parse_log(open(os.path.join(d, "w_" + name, "out", "aligned.log")).read())
+            out["gpu_" + name] = {"wall_s": wall, "done_alignment_s": float(m.group(1)) if m else None, "index_load_s": float(m2.group(1)) if m2 else None,
+                                  "stream_align_store_s": float(m2.group(2)) if m2 else None, "reads_per_s_alignment": n / float(m2.group(2)) if m2 else None,
+                                  "reads_per_s_wall": n / wall, "passing": log["passing"], "failing": log["failing"]}
+        ncpu = min(n, args.cli_cpu_reads)
+        fq_cpu = os.path.join(d, "reads_cpu.fq")
+        write_fastq(fq_cpu, reads[:ncpu])
+        t0 = time.perf_counter()
+        r = ora.run_reference(fastas, fq_cpu, os.path.join(d, "w_cpu"), extra=["-fastx", "-sam"], threads=cores, idx_dir=ref_idx)
+        wall = time.perf_counter() - t0
+        m = re.search(r"Done alignment in ([0-9.eE+-]+) sec", r["stdout"])
+        log = ora.parse_log(r["log"])
+        out["cpu_flat"] = {"reads": ncpu, "threads": cores, "wall_s": wall, "done_alignment_s": float(m.group(1)) if m else None,
+                           "reads_per_s_alignment": ncpu / float(m.group(1)) if m else None, "reads_per_s_wall": ncpu / wall,
+                           "passing": log["passing"], "failing": log["failing"]}
+    return out
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -269,6 +328,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cli-e2e", action="store_true", help="time the drop-in host program (oracle/_ref/sortmerna_gpu) against the reference binary and exit")
+    ap.add_argument("--cli-reads", type=int, default=2_000_000)
+    ap.add_argument("--cli-cpu-reads", type=int, default=100_000)
+    ap.add_argument("--cli-gpus", type=int, default=1)
+    ap.add_argument("--cli-gz", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library chatter) goes to stderr
     sys.stdout.flush()
@@ -282,6 +346,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores, core_info = host_cores()
+
+    if args.cli_e2e:
+        emit({"cli_e2e": cli_e2e(args, cores, core_info)})
+        return
 
     if args.impl == "reference":
         if rank != 0:

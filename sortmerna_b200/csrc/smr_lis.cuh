@@ -220,14 +220,17 @@ __device__ __forceinline__ bool hit_selected(const uint2 h, const ReadCtx& rc, u
 __device__ uint32_t find_lis_dev(const unsigned long long* __restrict__ P, uint32_t n, uint32_t* b, uint32_t* p, uint32_t& first) {
   if (n == 0) { first = 0; return 0; }
   uint32_t nb = 1; b[0] = 0;
+#pragma unroll 1
   for (uint32_t i = 1; i < n; ++i) {
     const uint32_t ai = (uint32_t)P[i];
     if ((uint32_t)P[b[nb - 1]] < ai) { p[i] = b[nb - 1]; b[nb++] = i; continue; }
     uint32_t u = 0, v = nb - 1;
+#pragma unroll 1
     while (u < v) { const uint32_t c = (u + v) >> 1; if ((uint32_t)P[b[c]] < ai) u = c + 1; else v = c; }
     if (ai < (uint32_t)P[b[u]]) { if (u > 0) p[i] = b[u - 1]; b[u] = i; }
   }
   uint32_t v = b[nb - 1];
+#pragma unroll 1
   for (uint32_t u = nb; u-- > 1;) v = p[v];
   first = v;
   return nb;
@@ -240,7 +243,7 @@ struct PassEnv {
   const uint2* hits; uint32_t nh;                               // hit region of (current part, current read)
   uint32_t planner;                                             // ordinal of this planner warp
   uint32_t submitted;                                           // tasks handed to the scorers so far (g.done[planner] catches up)
-  unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls, n_spec_calls, n_spec_cells /* rounds A */, n_rounds_b;
+  unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls, n_spec_calls, n_spec_cells /* rounds A */, n_rounds_b, w1_cyc, w1_cnt, express_pairs;
   unsigned long long cyc[8];                                    // warp cycles per phase: vote, order, group, plan, wait, replay
 };
 
@@ -261,19 +264,25 @@ __device__ __noinline__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
   uint32_t base = 0;
   if (lane == 0) base = atomicAdd(g.q_tail + qi * 16, npairs);
   base = __shfl_sync(kFull, base, 0);
+#pragma unroll 1
   for (uint32_t i = lane; i < npairs; i += 32) {
     const uint32_t idx = base + i;
     QSlot* sl = ring + (idx & (kQueueCap - 1));
+#pragma unroll 1
     while (ld_volatile_u32(&sl->seq) != idx) __nanosleep(64);        // the consumer of the previous lap has left the slot
     const uint32_t ta = E.ar.sel[2 * i], tb = (2 * i + 1 < nsel) ? E.ar.sel[2 * i + 1] : kNoTask;
     sl->planner = E.planner; sl->ta = ta; sl->tb = tb;
   }
   __threadfence();      // task records + entries before the sequence numbers that publish them
   __syncwarp();
+#pragma unroll 1
   for (uint32_t i = lane; i < npairs; i += 32) { const uint32_t idx = base + i; st_volatile_u32(&ring[idx & (kQueueCap - 1)].seq, idx + 1); }
   E.submitted += nsel;
+  const long long tw0 = clock64();
   if (lane == 0) { while (ld_volatile_u32(g.done + E.planner) != E.submitted) __nanosleep(128); __threadfence(); }
   __syncwarp();
+  if (npairs == 1) { E.w1_cyc += (unsigned long long)(clock64() - tw0); E.w1_cnt++; }
+  if (qi == 0) E.express_pairs += npairs;
 }
 
 __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score, const uint32_t ncand, const bool by_level,
@@ -292,11 +301,13 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
 
   // ---- 1. votes per reference (alignment.cpp:118-138) ----
   if (++E.epoch >= 2048u) {   // epoch tag wrapped (11 bits: bit 31 of a histogram word marks a pair cursor): clear once
+#pragma unroll 1
     for (uint32_t i = lane; i < E.ar.hist_cap; i += 32) E.ar.hist[i] = 0;
     E.epoch = 1; __syncwarp();
   }
   const uint32_t ep = E.epoch;
   uint32_t ncand = 0;
+#pragma unroll 1
   for (uint32_t h0 = 0; h0 < nh; h0 += 32) {
     const uint32_t h = h0 + lane;
     uint32_t o_l = 0, s_l = 0;
@@ -317,6 +328,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
       return e < tot ? __ldg(&ix.pos[o_own + (e - ex_own)]).y : 0xFFFFFFFFu;
     };
     uint32_t seq_next = tot ? fetch_seq(0) : 0xFFFFFFFFu;
+#pragma unroll 1
     for (uint32_t e0 = 0; e0 < tot; e0 += 32) {
       const uint32_t seq = seq_next;
       if (e0 + 32 < tot) seq_next = fetch_seq(e0 + 32);   // in flight while this round's histogram words are read
@@ -364,10 +376,12 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   } else {
     const uint32_t n_sum = (E.ar.hist_cap + 1023u) / 1024u;
     uint32_t out = 0;
+#pragma unroll 1
     for (uint32_t s0w = 0; s0w < n_sum; s0w += 32) {
       uint32_t sw = 0;
       if (s0w + lane < n_sum) { sw = E.ar.summary[s0w + lane]; if (sw) E.ar.summary[s0w + lane] = 0; }
       unsigned lanes = __ballot_sync(kFull, sw != 0);
+#pragma unroll 1
       while (lanes) {
         const int L = __ffs(lanes) - 1; lanes &= lanes - 1;
         const uint32_t w = __shfl_sync(kFull, sw, L), base_word = (s0w + L) * 32u;
@@ -375,6 +389,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
         if ((w >> lane) & 1u) { bw = E.ar.bitmap[base_word + lane]; E.ar.bitmap[base_word + lane] = 0; }
         const uint32_t pc = __popc(bw), incl = warp_incl_scan_u32(pc), tot = __shfl_sync(kFull, incl, 31);
         uint32_t pos = out + incl - pc;
+#pragma unroll 1
         while (bw) {
           const uint32_t bit = __ffs(bw) - 1; bw &= bw - 1;
           const uint32_t seq = (base_word + lane) * 32u + bit, c = E.ar.hist[seq] & 0xFFFFFu;
@@ -400,9 +415,11 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
     uint32_t running = 0;
     const unsigned long long* list = E.ar.cand;
     uint32_t tc = 0;
+#pragma unroll 1
     for (uint32_t i0 = 0; i0 < ncand; i0 += 32) { const uint32_t i = i0 + lane; if (i < ncand) tc += 0xFFFFFu - (uint32_t)(list[i] >> 32); }
     tc = warp_sum_u32(tc);
     if (tc <= E.ar.pall_cap && ncand > 1) {
+#pragma unroll 1
       for (uint32_t i0 = 0; i0 < ncand; i0 += 32) {
         const uint32_t i = i0 + lane;
         uint32_t c = 0, seq = 0;
@@ -412,6 +429,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
         running += tot;
       }
       __syncwarp();
+#pragma unroll 1
       for (uint32_t h0 = 0; h0 < nh; h0 += 32) {
         const uint32_t h = h0 + lane;
         uint32_t o_l = 0, s_l = 0, w_l = 0;
@@ -432,6 +450,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
           return e < tot ? __ldg(&ix.pos[o_own + (e - ex_own)]) : make_uint2(0u, 0xFFFFFFFFu);
         };
         uint2 ps_next = tot ? fetch_pos(0, w_nxt) : make_uint2(0u, 0xFFFFFFFFu);
+#pragma unroll 1
         for (uint32_t e0 = 0; e0 < tot; e0 += 32) {
           const uint2 ps = ps_next; w_cur = w_nxt;
           if (e0 + 32 < tot) ps_next = fetch_pos(e0 + 32, w_nxt);
@@ -452,6 +471,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   __syncwarp();
   if (grouped) {   // the cursors must not survive the call: histogram words are epoch-tagged votes otherwise
     const unsigned long long* list = E.ar.cand;
+#pragma unroll 1
     for (uint32_t i = lane; i < ncand; i += 32) E.ar.hist[(uint32_t)list[i]] = 0;
     __syncwarp();
   }
@@ -474,9 +494,11 @@ __device__ __noinline__ void plan_slide_thread(const PassEnv& E, const ReadCtx& 
   uint32_t begin_ref = (uint32_t)(P[0] >> 32), begin_read = (uint32_t)P[0];
   bool reset = false;            // a push step without a task since the previous task of this candidate
   uint32_t lead = kNoTask;       // the last unconditional task of this candidate
+#pragma unroll 1
   while (it != np) {
     const uint64_t end_ref_max = (uint64_t)begin_ref + rlen - begin_read - lnwin + 1;     // :231
     bool push = false;
+#pragma unroll 1
     while (it != np && (uint64_t)(uint32_t)(P[it] >> 32) <= end_ref_max) { ++it; push = true; }
     bool task = false;
     if ((it - f) >= (uint32_t)o.num_seeds) {
@@ -549,9 +571,11 @@ __device__ __noinline__ bool plan_candidate_warp(PassEnv& E, ReadCtx& rc, const 
   uint32_t filled = 0;
   if (grouped) {   // the pairs of this reference were grouped by the one-pass scatter
     const uint32_t seg_end = E.ar.hist[max_ref] & 0x7FFFFFFFu, seg = seg_end - np;
+#pragma unroll 1
     for (uint32_t i = lane; i < np; i += 32) P[i] = E.ar.pall[seg + i];
     filled = np;
   } else
+#pragma unroll 1
   for (uint32_t h0 = 0; h0 < nh; h0 += 32) {
     const uint32_t h = h0 + lane;
     uint32_t first = 0, cnt = 0, win = 0;
@@ -561,13 +585,16 @@ __device__ __noinline__ bool plan_candidate_warp(PassEnv& E, ReadCtx& rc, const 
         win = hv.y & kWinMask;
         uint32_t lo = __ldg(ix.pos_off + hv.x), hi = __ldg(ix.pos_off + hv.x + 1);
         const uint32_t end = hi;
+#pragma unroll 1
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(&ix.pos[mid]).y < max_ref) lo = mid + 1; else hi = mid; }
         first = lo;
+#pragma unroll 1
         while (first + cnt < end && __ldg(&ix.pos[first + cnt]).y == max_ref) ++cnt;
       }
     }
     const uint32_t incl = warp_incl_scan_u32(cnt), tot = __shfl_sync(kFull, incl, 31);
     uint32_t w = filled + incl - cnt;
+#pragma unroll 1
     for (uint32_t c = 0; c < cnt; ++c, ++w) if (w < np) P[w] = ((unsigned long long)__ldg(&ix.pos[first + c]).x << 32) | win;
     filled += tot;
   }
@@ -581,6 +608,7 @@ __device__ __noinline__ bool plan_candidate_warp(PassEnv& E, ReadCtx& rc, const 
     __syncwarp();
   } else {
     const uint32_t np2 = next_pow2(np);
+#pragma unroll 1
     for (uint32_t i = np + lane; i < np2; i += 32) P[i] = ~0ull;
     __syncwarp();
     warp_sort_u64(P, np2);
@@ -607,12 +635,14 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
   uint32_t cap = 8;   // candidates per batch; doubles per batch (a perfect-score stop wastes at most what was useful)
   uint32_t* cfirst = E.ar.cfirst; uint32_t* ccnt = cfirst + kBatchCandCap; uint32_t* cumask = ccnt + kBatchCandCap;
 
+#pragma unroll 1
   for (;;) {
     // the next group: everything (sorted) for small lists, else the members of the current count level
     uint32_t ngrp = ncand, next_level = 0;
     if (by_level) {
       if (level == 0) break;
       ngrp = 0;
+#pragma unroll 1
       for (uint32_t i0 = 0; i0 < ncand; i0 += 32) {
         const uint32_t i = i0 + lane;
         unsigned long long key = 0; uint32_t c = 0;
@@ -628,6 +658,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
       __syncwarp();
     }
     uint32_t k = 0;
+#pragma unroll 1
     while (k < ngrp && searching) {
       long long tc0 = clock64();
       // ---- entry of the batch's first candidate (:158-169): decided now, with the scores known so far ----
@@ -645,6 +676,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
       uint32_t nb = 0;
       {
         uint32_t drops = 0, tsum = 0, prev = prev_occur; bool ended = false;
+#pragma unroll 1
         for (uint32_t c0 = 0; !ended; c0 += 32) {
           const uint32_t c = c0 + lane;
           const bool in = k + c < ngrp && c < cap_now;
@@ -662,6 +694,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
       if (nb == 0) { rc.flags |= kErrTrace; return; }   // (the first candidate always belongs: its pairs fit, np <= pair_cap is checked below)
       // ---- plan: one candidate per lane (its few pairs in thread-local arrays); candidates with many pairs by the whole warp ----
       uint32_t tbase = 0, nselA = 0, ncond = 0;
+#pragma unroll 1
       for (uint32_t c0 = 0; c0 < nb; c0 += 32) {
         const uint32_t c = c0 + lane;
         const bool valid = c < nb;
@@ -674,15 +707,18 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
           const uint64_t ref_base = __ldg(ix.ref_off + max_ref), ref_next = __ldg(ix.ref_off + max_ref + 1);
           const uint32_t seg = (E.ar.hist[max_ref] & 0x7FFFFFFFu) - np;
           unsigned long long P[kLanePairs]; uint32_t lb[kLanePairs], lp[kLanePairs];
+#pragma unroll 1
           for (uint32_t i = 0; i < np; ++i) {    // insertion sort while loading (refpos asc, readpos asc: alignment.cpp:197-201)
             const unsigned long long v = E.ar.pall[seg + i];
             uint32_t j = i;
+#pragma unroll 1
             while (j > 0 && P[j - 1] > v) { P[j] = P[j - 1]; --j; }
             P[j] = v;
           }
           plan_slide_thread(E, rc, P, np, lb, lp, max_ref, ref_base, ref_next - ref_base, c, toff, cp);
         }
         unsigned big = __ballot_sync(kFull, valid && !small);
+#pragma unroll 1
         while (big) {
           const int L = __ffs(big) - 1; big &= big - 1;
           const unsigned long long ckL = __shfl_sync(kFull, ck, L);
@@ -691,6 +727,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
           if (!plan_candidate_warp(E, rc, ckL, c0 + (uint32_t)L, toffL, grouped, cb)) return;
           if ((int)lane == L) { cp = cb; cp.umask = 0; }
           // its unconditional tasks go to round A now (they may be more than 32: no mask)
+#pragma unroll 1
           for (uint32_t t0 = 0; t0 < cb.cnt; t0 += 32) {
             const uint32_t t = t0 + lane;
             const bool pick = t < cb.cnt && ((E.ar.ptasks[toffL + t].cf >> 24) & kTfUncond);
@@ -705,6 +742,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
           const uint32_t nu = small ? (uint32_t)__popc(cp.umask) : 0u;
           const uint32_t ui = warp_incl_scan_u32(nu);
           uint32_t w = nselA + ui - nu, m = small ? cp.umask : 0u;
+#pragma unroll 1
           while (m) { const uint32_t j = (uint32_t)__ffs(m) - 1u; m &= m - 1u; E.ar.sel[w++] = toff + j; }
           nselA += __shfl_sync(kFull, ui, 31);
         }
@@ -719,6 +757,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
       // ---- round B: tasks heuristic 1 would skip after a successful lead (:243-246) are needed when the lead failed ----
       if (ncond) {
         uint32_t nselB = 0;
+#pragma unroll 1
         for (uint32_t c0 = 0; c0 < nb; c0 += 32) {
           const uint32_t c = c0 + lane;
           const bool valid = c < nb;
@@ -727,6 +766,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
           uint32_t bmask = 0;
           if (valid && !bigc && cnt) {
             uint32_t m = cumask[c];
+#pragma unroll 1
             while (m) {
               const uint32_t j = (uint32_t)__ffs(m) - 1u; m &= m - 1u;
               const uint32_t jn = m ? (uint32_t)__ffs(m) - 1u : cnt;        // next unconditional task (or the end)
@@ -735,12 +775,15 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
           }
           const uint32_t nbm = (uint32_t)__popc(bmask), bi = warp_incl_scan_u32(nbm);
           uint32_t w = nselB + bi - nbm;
+#pragma unroll 1
           while (bmask) { const uint32_t j = (uint32_t)__ffs(bmask) - 1u; bmask &= bmask - 1u; E.ar.sel[w++] = toff + j; }
           nselB += __shfl_sync(kFull, bi, 31);
           unsigned big = __ballot_sync(kFull, valid && bigc && cnt);
+#pragma unroll 1
           while (big) {
             const int L = __ffs(big) - 1; big &= big - 1;
             const uint32_t toffL = __shfl_sync(kFull, toff, L), cntL = __shfl_sync(kFull, cnt, L);
+#pragma unroll 1
             for (uint32_t t0 = 0; t0 < cntL; t0 += 32) {
               const uint32_t t = t0 + lane;
               bool pick = false;
@@ -760,6 +803,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
       }
       { const long long t2 = clock64(); E.cyc[4] += (unsigned long long)(t2 - tc0); tc0 = t2; }
       // ---- replay: the reference's decisions over the scores, in order ----
+#pragma unroll 1
       for (uint32_t c0 = 0; c0 < nb && searching; c0 += 32) {
         // this chunk's candidates: (first task, count, flags, votes), one per lane
         const uint32_t cl = c0 + lane;
@@ -775,6 +819,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
           bool succ = cl < nb && (v_cw & 0x40000000u) != 0 && cntl > 0;   // (many-pair candidates take the sequential path)
           unsigned long long cells = 0;
           if (cl < nb && !(v_cw & 0x40000000u)) {
+#pragma unroll 1
             for (uint32_t j = 0; j < cntl; ++j) {
               const uint4 w0 = __ldcg((const uint4*)&E.ar.tasks[v_toff + j]);
               if ((__ldcg(&E.ar.tasks[v_toff + j].score) & 0xFFFFu) > ix.minimal_score) { succ = true; break; }
@@ -793,6 +838,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
             is_aligned = false; prev_occur = __shfl_sync(kFull, v_occ, ci0 - 1);
           }
         }
+#pragma unroll 1
         for (uint32_t ci = ci0; ci < cend && searching; ++ci) {
           const uint32_t c = c0 + ci;
           const uint32_t toff = __shfl_sync(kFull, v_toff, ci), cw = __shfl_sync(kFull, v_cw, ci), occ = __shfl_sync(kFull, v_occ, ci);
@@ -802,6 +848,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
             prev_occur = occ;
           }
           is_aligned = false;   // the first step of a candidate always pushes: `else is_aligned = false` (:245)
+#pragma unroll 1
           for (uint32_t t0 = 0; t0 < cnt && searching; t0 += 32) {
             // this chunk's tasks: flags, score, cells, one per lane
             const uint32_t tl = toff + t0 + lane;
@@ -812,6 +859,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
               v_alen = w0.z; v_qlen = w0.w; v_sc = __ldcg(&E.ar.tasks[tl].score);
             }
             const uint32_t tend = min(32u, cnt - t0);
+#pragma unroll 1
             for (uint32_t ti = 0; ti < tend && searching; ++ti) {
               const uint32_t fl = __shfl_sync(kFull, v_fl, ti);
               if (fl & kTfReset) is_aligned = false;
@@ -842,6 +890,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
                 } else if (o.is_best && rc.n_align == N && slots[rc.min_index].score1 < score1) {  // :425-459
                   if (N > 1 && rc.max_index == 0 && rc.min_index == 0) {
                     uint32_t mn = 0, mx = 0, mns = slots[0].score1, mxs = slots[0].score1;      // findMinIndex / findMaxIndex (:533-561)
+#pragma unroll 1
                     for (uint32_t i2 = 0; i2 < rc.n_align; ++i2) { const uint32_t s = slots[i2].score1; if (s < mns) { mns = s; mn = i2; } if (s > mxs) { mxs = s; mx = i2; } }
                     rc.min_index = mn; rc.max_index = mx;
                   }
@@ -853,6 +902,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
                   if (score1 > slots[mx].score1 && rc.n_align > 1) {
                     rc.max_index = mn;
                     uint32_t m2 = 0, ms = slots[0].score1;
+#pragma unroll 1
                     for (uint32_t i2 = 0; i2 < rc.n_align; ++i2) { const uint32_t s = slots[i2].score1; if (s < ms) { ms = s; m2 = i2; } }
                     rc.min_index = m2;
                   }
@@ -891,6 +941,7 @@ __device__ void traverse_dev(PassEnv& E, ReadCtx& rc, const bool is_last_strand)
   uint32_t var = rc.reversed ? kVarRevT : kVarFwd;
   uint32_t pass_n = 0;
   bool search = true;
+#pragma unroll 1
   while (search) {
     // first window of the pass: `if (read.is04) read.flip34()` (:126) -> back to 0-3 with N positions = 0 (A)
     if (rc.hasn && rc.form04) { rc.form04 = false; if (rc.reversed) var = kVarRevA; }
@@ -898,6 +949,7 @@ __device__ void traverse_dev(PassEnv& E, ReadCtx& rc, const bool is_last_strand)
     rc.pass_n = pass_n;
     // windows searched for the first time in this pass that produced hits (:242-249)
     uint32_t newly = 0;
+#pragma unroll 1
     for (uint32_t h0 = 0; h0 < nh; h0 += 32) {
       const uint32_t h = h0 + lane;
       bool cnt = false;
@@ -913,6 +965,7 @@ __device__ void traverse_dev(PassEnv& E, ReadCtx& rc, const bool is_last_strand)
     if (search) {                                                                              // :262-277
       if (pass_n == 2) search = false;
       else {
+#pragma unroll 1
         while (pass_n < 2 && ix.skip[pass_n] == ix.skip[pass_n + 1]) { ++pass_n; rc.vcls[pass_n] = var; }
         if (++pass_n > 2) search = false;
       }
@@ -1098,7 +1151,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     uint8_t* sm = lis_smem + (size_t)kScorerWarps * kScorerSmem + (size_t)pw * kPlannerSmem;
     E.s_pairs = (unsigned long long*)sm; E.s_b = (uint32_t*)(sm + kPairsShared * 8); E.s_p = E.s_b + kPairsShared;
   }
-  E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = E.n_spec_calls = E.n_spec_cells = E.n_rounds_b = 0;
+  E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = E.n_spec_calls = E.n_spec_cells = E.n_rounds_b = E.w1_cyc = E.w1_cnt = E.express_pairs = 0;
   for (int i = 0; i < 8; ++i) E.cyc[i] = 0;
   const uint32_t nwork = s_bin_start[kCostBins];
   unsigned long long t_max = 0, t_sum = 0; const long long t_k0 = clock64();
@@ -1153,6 +1206,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     atomicAdd(&b.counters[dcSwCalls], E.n_sw_calls); atomicAdd(&b.counters[dcSwCells], E.n_sw_cells);
     atomicAdd(&b.counters[dcPosEntries], E.n_pos_entries); atomicAdd(&b.counters[dcLisCalls], E.n_lis_calls);
     atomicAdd(&b.counters[dcSpecCalls], E.n_spec_calls); atomicAdd(&b.counters[dcRoundsA], E.n_spec_cells); atomicAdd(&b.counters[dcRoundsB], E.n_rounds_b);
+    atomicAdd(&b.counters[dcW1Cyc], E.w1_cyc); atomicAdd(&b.counters[dcW1Cnt], E.w1_cnt); atomicAdd(&b.counters[dcExpressPairs], E.express_pairs);
     for (int i = 0; i < 6; ++i) atomicAdd(&b.counters[dcCycVote + i], E.cyc[i]);
     atomicMax(&b.counters[dcMaxReadCycles], t_max); atomicAdd(&b.counters[dcSumReadCycles], t_sum);
     atomicMax(&b.counters[dcLisKernelCycles], (unsigned long long)(clock64() - t_k0));

@@ -29,7 +29,8 @@ DBS = ["silva-bac-16s-id90", "silva-bac-23s-id98", "silva-arc-16s-id95", "silva-
        "silva-euk-18s-id95", "silva-euk-28s-id98", "rfam-5s-database-id98", "rfam-5.8s-database-id98"]
 SETS = ["set2_environmental_study_550_amplicon.fasta", "set4_mate_pairs_metatranscriptomics_1.fastq",
         "set4_mate_pairs_metatranscriptomics_2.fastq", "set5_simulated_amplicon_silva_bac_16s.fasta",
-        "silva-bac-16s-database-id85.fasta", "test_read.fasta", "test_ref.fasta"]
+        "silva-bac-16s-database-id85.fasta", "test_read.fasta", "test_ref.fasta",
+        "set4_mate_pairs_metatranscriptomics_1.fastq.gz", "set4_mate_pairs_metatranscriptomics_2.fastq.gz"]   # BASELINE config 4 as written (.gz mates)
 
 
 def db_path(name):
