@@ -495,7 +495,7 @@ def main():
     sw_peak = dpx / 3.5 / 1e3                        # Tcell-updates/s
     tr = {}
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
     except Exception:
         pass
     def _traffic(kernel):   # ncu DRAM bytes of the committed capture, scaled to the reads of one launch of this run

@@ -651,6 +651,7 @@ int smr_init(int device, smr_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SMR_ERR_CUDA; }
   if (const char* e = getenv("SMR_CHUNK_READS")) { const long v = atol(e); if (v >= 32 && v <= (1l << 22)) ctx->chunk_reads = (uint32_t)v; }   // tests: several chunks per batch
+  if (getenv("SMR_NO_INSTR")) ctx->instr = false;   // seed kernel without its window / entry counters (tools/ab_variants.sh: cost of the instrumentation)
   if (const char* e = getenv("SMR_LIS_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 16) ctx->lis_ctas_per_sm = (uint32_t)v; }
   *out = ctx;
   return SMR_OK;

@@ -45,6 +45,10 @@ namespace smr {
 #ifndef SMR_LIS_MIN_CTAS
 #define SMR_LIS_MIN_CTAS 2
 #endif
+#ifndef SMR_LIS_INSTR
+#define SMR_LIS_INSTR 1   // phase accounting with clock64 (bench counters); 0 = compiled out (tools/ab_variants.sh measures its cost)
+#endif
+__device__ __forceinline__ long long lis_clock() { return SMR_LIS_INSTR ? clock64() : 0ll; }
 constexpr int kScorerWarps = SMR_SCORER_WARPS;     // the first warps of a CTA score
 constexpr int kFetcherWarps = 1;                   // then one warp that pops the task queue and stages the scorers' inputs (TMA bulk copies)
 constexpr int kPlannerWarps = SMR_PLANNER_WARPS;   // the others plan
@@ -65,9 +69,8 @@ struct __align__(16) ScSlot {
   uint32_t mB, nB, woffB, qoffB;
   uint32_t metaA, metaB, qabsA, qabsB;
   uint32_t refA, refB, pad0, pad1;
-  unsigned long long bar;             // mbarrier: 1 arrival (the fetcher lane) + the bulk copies' bytes
-  volatile uint32_t freed;            // slots of this buffer the scorer has finished with
-  uint32_t pad2;
+  unsigned long long bar;             // "full" mbarrier: 1 arrival (the fetcher lane) + the bulk copies' bytes
+  unsigned long long ebar;            // "empty" mbarrier: 1 arrival (the scorer, when it has finished with the slot)
 };
 constexpr int kScorerSmem = 2 * kPairProfWords * 4 + 2 * (int)sizeof(ScSlot);   // two query profiles + two input slots
 constexpr int kPlannerSmem = 128 * 16;                                          // kPairsShared pairs + LIS arrays
@@ -217,17 +220,18 @@ __device__ __forceinline__ bool hit_selected(const uint2 h, const ReadCtx& rc, u
 }
 
 // find_lis (alignment.cpp:58-98) over pairs[f .. f+n): returns |LIS| and the index (relative to f) of its first element
-__device__ uint32_t find_lis_dev(const unsigned long long* __restrict__ P, uint32_t n, uint32_t* b, uint32_t* p, uint32_t& first) {
+template <class IdxT>
+__device__ uint32_t find_lis_dev(const unsigned long long* __restrict__ P, uint32_t n, IdxT* b, IdxT* p, uint32_t& first) {
   if (n == 0) { first = 0; return 0; }
   uint32_t nb = 1; b[0] = 0;
 #pragma unroll 1
   for (uint32_t i = 1; i < n; ++i) {
     const uint32_t ai = (uint32_t)P[i];
-    if ((uint32_t)P[b[nb - 1]] < ai) { p[i] = b[nb - 1]; b[nb++] = i; continue; }
+    if ((uint32_t)P[b[nb - 1]] < ai) { p[i] = b[nb - 1]; b[nb++] = (IdxT)i; continue; }
     uint32_t u = 0, v = nb - 1;
 #pragma unroll 1
     while (u < v) { const uint32_t c = (u + v) >> 1; if ((uint32_t)P[b[c]] < ai) u = c + 1; else v = c; }
-    if (ai < (uint32_t)P[b[u]]) { if (u > 0) p[i] = b[u - 1]; b[u] = i; }
+    if (ai < (uint32_t)P[b[u]]) { if (u > 0) p[i] = b[u - 1]; b[u] = (IdxT)i; }
   }
   uint32_t v = b[nb - 1];
 #pragma unroll 1
@@ -278,10 +282,10 @@ __device__ __noinline__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
 #pragma unroll 1
   for (uint32_t i = lane; i < npairs; i += 32) { const uint32_t idx = base + i; st_volatile_u32(&ring[idx & (kQueueCap - 1)].seq, idx + 1); }
   E.submitted += nsel;
-  const long long tw0 = clock64();
-  if (lane == 0) { while (ld_volatile_u32(g.done + E.planner) != E.submitted) __nanosleep(128); __threadfence(); }
+  const long long tw0 = lis_clock();
+  if (lane == 0) { while (ld_volatile_u32(g.done + E.planner) != E.submitted) __nanosleep(256); __threadfence(); }
   __syncwarp();
-  if (npairs == 1) { E.w1_cyc += (unsigned long long)(clock64() - tw0); E.w1_cnt++; }
+  if (npairs == 1) { E.w1_cyc += (unsigned long long)(lis_clock() - tw0); E.w1_cnt++; }
   if (qi == 0) E.express_pairs += npairs;
 }
 
@@ -297,7 +301,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   const uint32_t nh = E.nh;
   const uint32_t ns = (uint32_t)max(o.num_seeds, 1);
   E.n_lis_calls++;
-  long long tph = clock64();
+  long long tph = lis_clock();
 
   // ---- 1. votes per reference (alignment.cpp:118-138) ----
   if (++E.epoch >= 2048u) {   // epoch tag wrapped (11 bits: bit 31 of a histogram word marks a pair cursor): clear once
@@ -353,7 +357,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
       __syncwarp();
     }
   }
-  { const long long t2 = clock64(); E.cyc[0] += (unsigned long long)(t2 - tph); tph = t2; }
+  { const long long t2 = lis_clock(); E.cyc[0] += (unsigned long long)(t2 - tph); tph = t2; }
   if (ncand == 0) return;
   if (ncand > E.ar.cand_cap) { rc.flags |= kOvfPairs; return; }
   __syncwarp();
@@ -405,7 +409,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   }
   __syncwarp();
 
-  { const long long t2 = clock64(); E.cyc[1] += (unsigned long long)(t2 - tph); tph = t2; }
+  { const long long t2 = lis_clock(); E.cyc[1] += (unsigned long long)(t2 - tph); tph = t2; }
   // ---- 2b. group the (refpos, readpos) pairs of ALL candidates in one pass over the position lists ----
   // (the reference rescans every list once per candidate, alignment.cpp:181-194; with thousands of candidates a
   //  per-candidate gather -- even by binary search -- dominates, so the pairs are scattered into per-reference
@@ -466,7 +470,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
       grouped = true;
     }
   }
-  { const long long t2 = clock64(); E.cyc[2] += (unsigned long long)(t2 - tph); tph = t2; }
+  { const long long t2 = lis_clock(); E.cyc[2] += (unsigned long long)(t2 - tph); tph = t2; }
   run_candidates(E, rc, search, max_SW_score, ncand, by_level, level, grouped);
   __syncwarp();
   if (grouped) {   // the cursors must not survive the call: histogram words are epoch-tagged votes otherwise
@@ -477,13 +481,15 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   }
 }
 
-constexpr int kLanePairs = 32;    // candidates with up to this many pairs are planned by ONE lane (32 candidates per warp step)
+constexpr int kLanePairs = 16;    // candidates with up to this many pairs are planned by ONE lane (32 candidates per warp step); thread-local arrays:
+                                  // 16 pairs + two byte-sized LIS arrays = 160 B of local memory per lane (32 pairs with u32 arrays cost 3x the DRAM write-back)
 
 struct CandPlan { uint32_t cnt, umask, nuncond; bool reset; };   // tasks of a candidate; umask: bit j = task j is unconditional (j < 32)
 
 // The sliding window of one candidate over its SORTED pairs (alignment.cpp:205-507 without the ssw_align call), by ONE thread:
 // one task per step that would reach ssw_align, written to tasks[toff ..].  The trajectory of (it, f) does not depend on any score.
-__device__ __noinline__ void plan_slide_thread(const PassEnv& E, const ReadCtx& rc, const unsigned long long* __restrict__ P, const uint32_t np, uint32_t* lb, uint32_t* lp,
+template <class IdxT>
+__device__ __noinline__ void plan_slide_thread(const PassEnv& E, const ReadCtx& rc, const unsigned long long* __restrict__ P, const uint32_t np, IdxT* lb, IdxT* lp,
                                   const uint32_t max_ref, const uint64_t ref_base, const uint64_t reflen, const uint32_t cand_rel, const uint32_t toff,
                                   CandPlan& out) {
   const DevIndex& ix = *E.ix; const DevParams& o = *E.prm;
@@ -660,7 +666,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
     uint32_t k = 0;
 #pragma unroll 1
     while (k < ngrp && searching) {
-      long long tc0 = clock64();
+      long long tc0 = lis_clock();
       // ---- entry of the batch's first candidate (:158-169): decided now, with the scores known so far ----
       {
         const uint32_t occ = 0xFFFFFu - (uint32_t)(E.ar.grp[k] >> 32);
@@ -706,7 +712,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
         if (small) {
           const uint64_t ref_base = __ldg(ix.ref_off + max_ref), ref_next = __ldg(ix.ref_off + max_ref + 1);
           const uint32_t seg = (E.ar.hist[max_ref] & 0x7FFFFFFFu) - np;
-          unsigned long long P[kLanePairs]; uint32_t lb[kLanePairs], lp[kLanePairs];
+          unsigned long long P[kLanePairs]; uint8_t lb[kLanePairs], lp[kLanePairs];
 #pragma unroll 1
           for (uint32_t i = 0; i < np; ++i) {    // insertion sort while loading (refpos asc, readpos asc: alignment.cpp:197-201)
             const unsigned long long v = E.ar.pall[seg + i];
@@ -750,7 +756,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
         tbase += __shfl_sync(kFull, incl, 31);
       }
       __syncwarp();
-      { const long long t2 = clock64(); E.cyc[3] += (unsigned long long)(t2 - tc0); tc0 = t2; }
+      { const long long t2 = lis_clock(); E.cyc[3] += (unsigned long long)(t2 - tc0); tc0 = t2; }
       // ---- score, round A: the unconditional tasks ----
       submit_and_wait(E, nselA);
       E.n_spec_calls += nselA; E.n_spec_cells += nselA ? 1 : 0;
@@ -801,7 +807,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
         submit_and_wait(E, nselB);
         E.n_spec_calls += nselB; E.n_rounds_b += nselB ? 1 : 0;
       }
-      { const long long t2 = clock64(); E.cyc[4] += (unsigned long long)(t2 - tc0); tc0 = t2; }
+      { const long long t2 = lis_clock(); E.cyc[4] += (unsigned long long)(t2 - tc0); tc0 = t2; }
       // ---- replay: the reference's decisions over the scores, in order ----
 #pragma unroll 1
       for (uint32_t c0 = 0; c0 < nb && searching; c0 += 32) {
@@ -919,7 +925,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
           if (searching && (cw & 0x80000000u)) is_aligned = false;
         }
       }
-      { const long long t2 = clock64(); E.cyc[5] += (unsigned long long)(t2 - tc0); }
+      { const long long t2 = lis_clock(); E.cyc[5] += (unsigned long long)(t2 - tc0); }
       k += nb;
       cap = min(cap * 2u, (uint32_t)kBatchCandCap);
       __syncwarp();
@@ -983,7 +989,7 @@ __device__ void fetcher_loop(const DevBatch& b, const DevParams& prm, const LisG
   const SwScore sc{prm.match, prm.mismatch, prm.score_N, prm.gap_open, prm.gap_ext, prm.one};
   const bool mine = lane < 2u * kScorerWarps;
   ScSlot* sl = (ScSlot*)(scorer_smem + (size_t)(lane >> 1) * kScorerSmem + 2 * kPairProfWords * 4) + (lane & 1u);
-  uint32_t filled = 0, h = 0;
+  uint32_t eph = 1, h = 0;                       // parity of the "empty" phase to wait for: a fresh mbarrier counts as released
   bool have = false, done = !mine;
   const uint32_t qi = lane & 1u;                 // slot 0 of every scorer is fed from the express queue, slot 1 from the bulk queue
   QSlot* ring = g.ring + (size_t)qi * kQueueCap;
@@ -991,7 +997,7 @@ __device__ void fetcher_loop(const DevBatch& b, const DevParams& prm, const LisG
   for (;;) {
     bool progress = false;
     if (!done) {
-      if (!have && sl->freed == filled) { h = atomicAdd(q_head, 1u); have = true; }
+      if (!have && mbar_try_wait(&sl->ebar, eph)) { eph ^= 1u; h = atomicAdd(q_head, 1u); have = true; }   // the scorer has released the slot
       if (have) {
         QSlot* qs = ring + (h & (kQueueCap - 1));
         if (ld_volatile_u32(&qs->seq) == h + 1u) {
@@ -1035,13 +1041,12 @@ __device__ void fetcher_loop(const DevBatch& b, const DevParams& prm, const LisG
               bulk_g2s(sl->q[0], b.seq04 + qa0, qab, &sl->bar);
               if (liveb) { bulk_g2s(sl->win[1] + kWinOff, rb + wb0, wbb, &sl->bar); bulk_g2s(sl->q[1], b.seq04 + qb0, qbb, &sl->bar); }
             }
-            ++filled;
           }
         }
       }
     }
     if (__all_sync(kFull, done)) break;
-    if (!__any_sync(kFull, progress)) __nanosleep(64);
+    if (!__any_sync(kFull, progress)) __nanosleep(256);   // polling costs issue slots the scorers want; a quarter of a microsecond is 1 % of one alignment
   }
 }
 
@@ -1054,19 +1059,19 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
   int32_t* rowH = g.score_rows + (size_t)scorer * 2 * g.row_cap; int32_t* rowF = rowH + g.row_cap;
   // identity of the query profile resident in each half: (q_abs, qlen | rev << 31, R)
   uint32_t keyq[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, keym[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}; int keyR = 0;
-  uint32_t par[2] = {0, 0}, nfreed[2] = {0, 0}, exited = 0;
+  uint32_t par[2] = {0, 0}, exited = 0;
   unsigned long long n_pairs = 0, n_cells = 0, n_slow = 0, cy_wait = 0, cy_load = 0, cy_sw = 0, cy_pub = 0;
   for (;;) {
-    long long tq = clock64();
+    long long tq = lis_clock();
     int k = -1;
     for (;;) {
       if (!(exited & 1u) && mbar_try_wait(&slots[0].bar, par[0])) { k = 0; break; }
       if (!(exited & 2u) && mbar_try_wait(&slots[1].bar, par[1])) { k = 1; break; }
-      __nanosleep(32);
+      __nanosleep(128);
     }
     par[k] ^= 1u;
     ScSlot& S = slots[k];
-    { const long long t2 = clock64(); cy_wait += (unsigned long long)(t2 - tq); tq = t2; }
+    { const long long t2 = lis_clock(); cy_wait += (unsigned long long)(t2 - tq); tq = t2; }
     const uint32_t planner = S.planner;
     if (planner == kPoison) { exited |= 1u << k; if (exited == 3u) break; continue; }
     const uint32_t ta = S.ta, tb = S.tb;
@@ -1084,7 +1089,7 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
       if (!(R == keyR && keyq[1] == kqb && keym[1] == kmb)) { const bool rev = (S.metaB & 0x10000u) != 0; pair_profile(S.q[1] + S.qoffB, rev ? -1 : 1, rev, mB, R, sc, s_prof + kPairProfWords); }
       keyR = R; keyq[0] = kqa; keym[0] = kma; keyq[1] = kqb; keym[1] = kmb;
       __syncwarp();
-      { const long long t2 = clock64(); cy_load += (unsigned long long)(t2 - tq); tq = t2; }
+      { const long long t2 = lis_clock(); cy_load += (unsigned long long)(t2 - tq); tq = t2; }
       const uint32_t r2 = sw_pair_dispatch(R, s_prof, s_prof + kPairProfWords, wa, wb, nmax, sc);
       sa = r2 & 0xFFFFu; sb = r2 >> 16;
     } else {
@@ -1098,10 +1103,10 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
       ++n_slow;
     }
     ++n_pairs; n_cells += (unsigned long long)nA * mA + (unsigned long long)nB * mB;
-    { const long long t2 = clock64(); cy_sw += (unsigned long long)(t2 - tq); tq = t2; }
+    { const long long t2 = lis_clock(); cy_sw += (unsigned long long)(t2 - tq); tq = t2; }
     __syncwarp();
     if (lane == 0) {
-      S.freed = ++nfreed[k];                       // the fetcher may refill this slot
+      mbar_arrive(&S.ebar);                        // the fetcher may refill this slot
       SwTask* tasks = carve_arena(g, planner).tasks;
       tasks[ta].score = sa;
       if (two) tasks[tb].score = sb;
@@ -1109,7 +1114,7 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
       atomicAdd(g.done + planner, two ? 2u : 1u);
     }
     __syncwarp();
-    { const long long t2 = clock64(); cy_pub += (unsigned long long)(t2 - tq); }
+    { const long long t2 = lis_clock(); cy_pub += (unsigned long long)(t2 - tq); }
   }
   if (lane == 0) {
     atomicAdd(&b.counters[dcSpecCells], n_cells); atomicAdd(&b.counters[dcSpecPairs], n_pairs); atomicAdd(&b.counters[dcSlowPairs], n_slow);
@@ -1135,7 +1140,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   }
   if (threadIdx.x < 2u * kScorerWarps) {   // the input slots' mbarriers and hand-back counters
     ScSlot* sl = (ScSlot*)(lis_smem + (size_t)(threadIdx.x >> 1) * kScorerSmem + 2 * kPairProfWords * 4) + (threadIdx.x & 1u);
-    mbar_init(&sl->bar, 1); sl->freed = 0;
+    mbar_init(&sl->bar, 1); mbar_init(&sl->ebar, 1);
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -1154,7 +1159,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = E.n_spec_calls = E.n_spec_cells = E.n_rounds_b = E.w1_cyc = E.w1_cnt = E.express_pairs = 0;
   for (int i = 0; i < 8; ++i) E.cyc[i] = 0;
   const uint32_t nwork = s_bin_start[kCostBins];
-  unsigned long long t_max = 0, t_sum = 0; const long long t_k0 = clock64();
+  unsigned long long t_max = 0, t_sum = 0; const long long t_k0 = lis_clock();
   const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);
   for (;;) {
     uint32_t wi = 0;
@@ -1164,7 +1169,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     uint32_t k = 0;
     while (wi >= s_bin_start[k + 1]) ++k;
     const uint32_t r = b.bins[(size_t)(kCostBins - 1 - k) * b.cnt_stride + (wi - s_bin_start[k])];
-    const long long t_read0 = clock64();
+    const long long t_read0 = lis_clock();
     ReadCtx rc;
     rc.r = r; rc.seq_base = b.seq_off[r]; rc.len = b.seq_off[r + 1] - rc.seq_base;
     rc.hasn = b.has_n[r] != 0; rc.flags = 0; rc.ovf_slots = false;
@@ -1198,7 +1203,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     }
     if (rc.ovf_slots) rc.flags |= kOvfSlots;
     if (rc.flags && lane == 0) atomicOr(&b.flags[r], rc.flags);
-    { const unsigned long long dt = (unsigned long long)(clock64() - t_read0); t_max = dt > t_max ? dt : t_max; t_sum += dt; }
+    { const unsigned long long dt = (unsigned long long)(lis_clock() - t_read0); t_max = dt > t_max ? dt : t_max; t_sum += dt; }
     __syncwarp();
   }
   if (lane == 0) {
@@ -1209,7 +1214,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     atomicAdd(&b.counters[dcW1Cyc], E.w1_cyc); atomicAdd(&b.counters[dcW1Cnt], E.w1_cnt); atomicAdd(&b.counters[dcExpressPairs], E.express_pairs);
     for (int i = 0; i < 6; ++i) atomicAdd(&b.counters[dcCycVote + i], E.cyc[i]);
     atomicMax(&b.counters[dcMaxReadCycles], t_max); atomicAdd(&b.counters[dcSumReadCycles], t_sum);
-    atomicMax(&b.counters[dcLisKernelCycles], (unsigned long long)(clock64() - t_k0));
+    atomicMax(&b.counters[dcLisKernelCycles], (unsigned long long)(lis_clock() - t_k0));
     // the last planner out shuts the scorers down: one entry each
     const uint32_t nplanners = gridDim.x * kPlannerWarps, nscorers = gridDim.x * kScorerWarps;   // one shutdown entry per fetcher lane of each queue
     if (atomicAdd(g.planners_done, 1u) + 1u == nplanners) {
