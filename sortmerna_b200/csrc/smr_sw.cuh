@@ -413,7 +413,7 @@ __device__ __noinline__ uint32_t sw_pair_warp(const uint32_t* __restrict__ profA
   const uint32_t* pA = profA + lane;
   const uint32_t* pB = profB + lane;
   const int32_t nsteps = nmax + 31;
-  const uint32_t nge2 = pack16(-sc.ge, -sc.ge), ngo2 = pack16(-sc.go, -sc.go), n2ge2 = pack16(-2 * sc.ge, -2 * sc.ge);
+  const uint32_t nge2 = pack16(-sc.ge, -sc.ge), ngo2 = pack16(-sc.go, -sc.go);
   const uint32_t nz = lane ? (uint32_t)sc.one : 0u;
   // software pipeline, two deep: the column letters are fetched two steps ahead, the substitution scores one step ahead
   uint32_t sc_cur[R];
@@ -450,15 +450,12 @@ __device__ __noinline__ uint32_t sw_pair_warp(const uint32_t* __restrict__ profA
     for (int r = 0; r < R; ++r) X[r] = __viaddmax_s16x2_relu(r == 0 ? diagH : Hp[r - 1], sc_cur[r], E[r]);
     diagH = upH;
     F[0] = upF;
-    // vertical chain F[r+1] = max(F[r] - ge, X[r]) with a look-ahead of two rows: A = max(X[r] - ge, X[r+1]) does not depend on F, so
-    // F[r+2] = max(F[r] - 2 ge, A) and the loop-carried chain is ceil(R/2)+ dependent instructions (8.4 cycles each) instead of R
+    // vertical chain F[r+1] = max(F[r] - ge, X[r]): R dependent instructions (8.4 cycles each).  With four scorer warps per SM
+    // sub-partition the pipe is full anyway (tools/ubench/dp.cu: 2 warps saturate it), so no ALU work is spent on shortening it
+    // (measured: a two-row look-ahead, F[r+2] = max(F[r] - 2 ge, max(X[r] - ge, X[r+1])), 2 more instructions per step: 227 vs 220 ms;
+    //  one-row-per-word profiles merged by IMAD instead of PRMT, 4 more shared loads per step: 238 ms -- the LSU pipe, not the ALU)
 #pragma unroll
-    for (int r = 0; r + 1 < R; r += 2) {
-      const uint32_t A = __viaddmax_s16x2(X[r], nge2, X[r + 1]);
-      F[r + 1] = __viaddmax_s16x2(F[r], nge2, X[r]);
-      F[r + 2] = __viaddmax_s16x2(F[r], n2ge2, A);
-    }
-    if (R & 1) F[R] = __viaddmax_s16x2(F[R - 1], nge2, X[R - 1]);
+    for (int r = 0; r < R; ++r) F[r + 1] = __viaddmax_s16x2(F[r], nge2, X[r]);
     const uint32_t hl = __viaddmax_s16x2(F[R - 1], ngo2, X[R - 1]);
     const uint32_t rawH = __shfl_up_sync(kFull, hl, 1), rawF = __shfl_up_sync(kFull, F[R], 1);
 #pragma unroll
