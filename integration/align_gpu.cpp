@@ -9,7 +9,8 @@
 //   * every (index, part) is made resident on the GPU once; reads are streamed ONCE (the reference re-reads them per index part);
 //   * the feed is drained by several parser threads (one per group of the reference's "processors": each processor id owns
 //     its own split file, processor.cpp:104-160), which encode reads into batches; a bounded queue hands every full batch to
-//     one worker thread per GPU (SMR_GPUS), so parsing, H2D / kernels / D2H and the KVDB stores overlap;
+//     one worker thread per context (SMR_GPUS devices x SMR_CTX_PER_GPU contexts), so parsing, H2D / kernels / D2H and the KVDB
+//     stores overlap;
 //   * the per-read KVDB blob is produced by smr_pack_kvdb_blobs (byte-identical to Read::toBinString) and stored under the same
 //     key (read.id);
 //   * Readstats counters come back from the library (num_aligned, reads_matched_per_db, num_short of the last index pass).
@@ -87,9 +88,14 @@ void align(Readfeed& readfeed, Readstats& readstats, Index& /*index: the library
   // whole index, the only cross-GPU state are the Readstats counters (summed below) -- SURVEY 8(e)
   int ngpu = 1;
   if (const char* e = getenv("SMR_GPUS")) ngpu = std::max(1, std::min(atoi(e), smr_device_count()));
-  std::vector<smr_ctx*> ctxs((size_t)ngpu, nullptr);
-  for (int g = 0; g < ngpu; ++g)
-    if (smr_init(g, &ctxs[g]) != SMR_OK) { ERR("no usable CUDA device ", g, ": the GPU alignment path has no CPU fallback"); exit(EXIT_FAILURE); }
+  // two contexts per GPU (SMR_CTX_PER_GPU): while one batch is in its kernels, the other context copies its batch in / its results
+  // out and packs the KVDB blobs (the library serialises the kernel sections of contexts that share a device)
+  int cpg = 2;
+  if (const char* e = getenv("SMR_CTX_PER_GPU")) cpg = std::max(1, std::min(atoi(e), 4));
+  const int nctx = ngpu * cpg;
+  std::vector<smr_ctx*> ctxs((size_t)nctx, nullptr);
+  for (int c = 0; c < nctx; ++c)
+    if (smr_init(c / cpg, &ctxs[c]) != SMR_OK) { ERR("no usable CUDA device ", c / cpg, ": the GPU alignment path has no CPU fallback"); exit(EXIT_FAILURE); }
 
   Refstats refstats(opts, readstats);            // unchanged: .stats, Gumbel parameters, minimal_score (refstats.cpp:103-276)
   References refs;
@@ -159,7 +165,7 @@ void align(Readfeed& readfeed, Readstats& readstats, Index& /*index: the library
   };
 
   std::vector<std::thread> workers;
-  for (int g = 0; g < ngpu; ++g)
+  for (int g = 0; g < nctx; ++g)
     workers.emplace_back([&, g] {
       while (std::unique_ptr<Batch> b = full.pop()) { run_batch(ctxs[g], *b); b->reset(); empty.push(std::move(b)); }
     });
@@ -169,7 +175,7 @@ void align(Readfeed& readfeed, Readstats& readstats, Index& /*index: the library
   const int nproc = (int)opts.num_proc_thread;
   int nparse = std::max(1, std::min(nproc, (int)std::thread::hardware_concurrency()));
   if (const char* e = getenv("SMR_PARSE_THREADS")) nparse = std::max(1, std::min(nproc, atoi(e)));
-  for (int k = 0; k < nparse + 2 * ngpu; ++k) empty.push(std::make_unique<Batch>());   // one per parser + two per GPU (one running, one queued)
+  for (int k = 0; k < nparse + 2 * nctx; ++k) empty.push(std::make_unique<Batch>());   // one per parser + two per context (one running, one queued)
   std::vector<std::thread> parsers;
   for (int t = 0; t < nparse; ++t)
     parsers.emplace_back([&, t] {

@@ -31,7 +31,7 @@ SYMBOLS = ["smr_init", "smr_destroy", "smr_last_error", "smr_device_count", "smr
 CNT_NAMES = ("num_aligned", "num_short", "sw_calls", "sw_cells", "windows", "trie_nodes", "buckets",
              "bucket_entries", "pos_entries", "lis_calls", "dbg_max_read_cycles", "dbg_sum_read_cycles", "dbg_lis_kernel_cycles",
              "cyc_vote", "cyc_order", "cyc_group", "cyc_plan", "cyc_wait", "cyc_replay", "spec_calls", "spec_cells", "spec_pairs", "slow_pairs",
-             "sc_wait", "sc_load", "sc_sw", "sc_pub", "rounds_a", "rounds_b", "w1_cyc", "w1_cnt", "express_pairs")
+             "sc_wait", "sc_load", "sc_sw", "sc_pub", "rounds_a", "rounds_b", "w1_cyc", "w1_cnt", "dbg_max_read_busy_cycles")
 CNT_FIXED = 32
 
 

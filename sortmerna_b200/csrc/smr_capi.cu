@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -54,7 +55,7 @@ struct smr_ctx {
   DevBuf seq04, seq_off, pk03, pk03alt, pk_off, has_n, hit_cnt, flags, state, hit_db, aln_work, out_aln;
   DevBuf hits, cost, bins, scalars, counters, cigar_pool, parts_dev;
   size_t hits_stride = 0; uint32_t cnt_stride = 0;
-  DevBuf lis_arena, lis_epochs, lis_queue, lis_done, lis_rows, final_arena, lane_hits, tb_arena, tb_jobs, aln_stats;
+  DevBuf lis_arena, lis_epochs, lis_queue, lis_done, lis_rows, lis_dbg, final_arena, lane_hits, tb_arena, tb_jobs, aln_stats;
   smr_aln_stats* host_stats = nullptr;   // optional output of the report arithmetic
   PinBuf h_state, h_flags, h_hitdb, h_outaln, h_stats, h_cigar, h_off32, h_pkoff;
   std::vector<uint64_t> h_coff;
@@ -163,16 +164,18 @@ int setup_arenas(smr_ctx* ctx) {
   ctx->lis_warps = ctx->lis_ctas * kPlannerWarps;   // planner warps (each owns an arena)
   ctx->pall_cap = 32768u * ctx->scale;
   ctx->lis_stride = lis_arena_bytes(ctx->hist_cap, ctx->cand_cap, ctx->pair_cap, ctx->task_cap, ctx->pall_cap);
-  // keep the arena total under ~8 GB: fewer persistent CTAs for huge reference sets
-  const size_t budget = (size_t)8 << 30;
+  // keep the arena total under ~16 GB (of 180): fewer persistent CTAs for huge reference sets
+  const size_t budget = (size_t)16 << 30;
   while (ctx->lis_ctas > 16 && ctx->lis_stride * ctx->lis_warps > budget) { ctx->lis_ctas /= 2; ctx->lis_warps = ctx->lis_ctas * kPlannerWarps; }
   if (int rc = ensure(ctx, ctx->lis_arena, ctx->lis_stride * ctx->lis_warps)) return rc;
   if (int rc = ensure(ctx, ctx->lis_epochs, (size_t)ctx->lis_warps * 4)) return rc;
   if (int rc = ensure(ctx, ctx->lis_queue, (size_t)2 * kQueueCap * sizeof(QSlot) + 64)) return rc;
   if (int rc = ensure(ctx, ctx->lis_done, (size_t)ctx->lis_warps * 4 + 64)) return rc;
+  if (int rc = ensure(ctx, ctx->lis_dbg, 256)) return rc;
+  CK(cudaMemsetAsync(ctx->lis_dbg.p, 0, 256, ctx->stream));
   if (int rc = ensure(ctx, ctx->lis_rows, (size_t)ctx->lis_ctas * kScorerWarps * 2 * ctx->row_cap * 4)) return rc;
   // histogram epochs start at 0 over a zeroed histogram (every run: the arena layout depends on the scale of the run)
-  CK(cudaMemsetAsync(ctx->lis_arena.p, 0, ctx->lis_stride * ctx->lis_warps, ctx->stream));
+  CK(cudaMemset2DAsync(ctx->lis_arena.p, ctx->lis_stride, 0, lis_arena_zero_bytes(ctx->hist_cap), ctx->lis_warps, ctx->stream));   // votes + bitmaps only
   CK(cudaMemsetAsync(ctx->lis_epochs.p, 0, (size_t)ctx->lis_warps * 4, ctx->stream));
   ctx->cap_w = 2 * 256 * ctx->scale + 8;          // band widths up to 256*scale
   ctx->cap_cig = 2 * (ctx->max_len + 64) + 16;
@@ -379,6 +382,14 @@ DevBatch make_batch(smr_ctx* ctx, uint32_t c0, uint32_t n) {
   return b;
 }
 
+// Several contexts may share a device (two per GPU let the copies and the host-side result packing of one batch run under the
+// kernels of the other).  Their KERNEL sections are serialised: the candidate kernel is persistent and needs every one of its CTAs
+// resident at once (planner and scorer warps wait for each other), which two such kernels sharing the SMs could not guarantee.
+std::mutex& device_kernel_mutex(int device) {
+  static std::mutex m[64];
+  return m[device & 63];
+}
+
 // all kernels of one pass over the resident batch
 int run_impl(smr_ctx* ctx) {
   if (!ctx->have_params) { ctx->err = "smr_set_params not called"; return SMR_ERR_ARG; }
@@ -389,6 +400,7 @@ int run_impl(smr_ctx* ctx) {
   const uint32_t nreads = ctx->nreads;
   if (nreads == 0) return SMR_OK;
   const uint32_t slots = slots_of(ctx);
+  std::lock_guard<std::mutex> dev_lock(device_kernel_mutex(ctx->device));   // held until the stream has drained
   int rc;
   if ((rc = setup_arenas(ctx))) return rc;
   // device copy of the part table (finalize looks parts up by slot)
@@ -439,6 +451,7 @@ int run_impl(smr_ctx* ctx) {
       lg.epochs = (uint32_t*)ctx->lis_epochs.p; lg.aln_work = (AlnWork*)ctx->aln_work.p; lg.slots = slots; lg.work_next = sc.lis_next;
       lg.parts = (const DevIndex*)ctx->parts_dev.p; lg.nparts = (uint32_t)hp.size();
       lg.ring = (QSlot*)ctx->lis_queue.p; lg.done = (uint32_t*)ctx->lis_done.p; lg.score_rows = (int32_t*)ctx->lis_rows.p;
+      lg.dbg = (unsigned long long*)ctx->lis_dbg.p;
       lg.q_head = sc.q_head; lg.q_tail = sc.q_tail; lg.planners_done = sc.planners_done;
       lis_reset_kernel<<<kQueueCap / 256, 256, 0, ctx->stream>>>(lg, ctx->lis_warps);
       CK(cudaGetLastError());
@@ -479,6 +492,10 @@ int run_impl(smr_ctx* ctx) {
   CK(cudaStreamSynchronize(ctx->stream));
   float ms = 0;
   cudaEventElapsedTime(&ms, eb, ee); ctx->t_total = ms;
+  if (getenv("SMR_VERBOSE")) {
+    unsigned long long d[16]; cudaMemcpy(d, ctx->lis_dbg.p, 128, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[smr] slowest read %llu: %.2f ms; cycles vote %llu order %llu group %llu plan %llu wait %llu replay %llu; sw calls %llu, tasks scored %llu, rounds %llu\n", d[10], d[0] / 1.965e6, d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9]);
+  }
   for (auto& s : spans) {
     if (s.second == 0) {
       cudaEventElapsedTime(&ms, ctx->ev[s.first], ctx->ev[s.first + 1]); ctx->t_seed += ms;
@@ -593,7 +610,7 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
                                   {SMR_CNT_BUCKET_ENTRIES, dcEntries}, {SMR_CNT_POS_ENTRIES, dcPosEntries}, {SMR_CNT_LIS_CALLS, dcLisCalls},
                                   {10, dcMaxReadCycles}, {11, dcSumReadCycles}, {12, dcLisKernelCycles},
                                   {13, dcCycVote}, {14, dcCycOrder}, {15, dcCycGroup}, {16, dcCycPlan}, {17, dcCycWait}, {18, dcCycReplay}, {19, dcSpecCalls},
-                                  {20, dcSpecCells}, {21, dcSpecPairs}, {22, dcSlowPairs}, {23, dcScWait}, {24, dcScLoad}, {25, dcScSw}, {26, dcScPub}, {27, dcRoundsA}, {28, dcRoundsB}, {29, dcW1Cyc}, {30, dcW1Cnt}, {31, dcExpressPairs}};
+                                  {20, dcSpecCells}, {21, dcSpecPairs}, {22, dcSlowPairs}, {23, dcScWait}, {24, dcScLoad}, {25, dcScSw}, {26, dcScPub}, {27, dcRoundsA}, {28, dcRoundsB}, {29, dcW1Cyc}, {30, dcW1Cnt}, {31, dcMaxReadBusy}};
     for (auto& m : mapc) if ((uint32_t)m[0] < out.n_counters) out.counters[m[0]] += cnt[m[1]];
   }
   return rc;
@@ -663,7 +680,7 @@ void smr_destroy(smr_ctx* ctx) {
   for (auto& pt : ctx->parts) for (void* p : pt.owned) cudaFree(p);
   DevBuf* bufs[] = {&ctx->seq04, &ctx->seq_off, &ctx->pk03, &ctx->pk03alt, &ctx->pk_off, &ctx->has_n, &ctx->hit_cnt, &ctx->flags, &ctx->state,
                     &ctx->hit_db, &ctx->aln_work, &ctx->out_aln, &ctx->hits, &ctx->cost, &ctx->bins, &ctx->scalars, &ctx->counters, &ctx->cigar_pool,
-                    &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->lis_queue, &ctx->lis_done, &ctx->lis_rows, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs, &ctx->aln_stats,
+                    &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->lis_queue, &ctx->lis_done, &ctx->lis_rows, &ctx->lis_dbg, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs, &ctx->aln_stats,
                     &ctx->d_text, &ctx->d_cnt, &ctx->d_scal, &ctx->d_nl, &ctx->d_hdr, &ctx->d_sb, &ctx->d_rec, &ctx->d_spos, &ctx->d_hdroff, &ctx->scan_sums};
   for (DevBuf* b : bufs) release(*b);
   PinBuf* pins[] = {&ctx->h_state, &ctx->h_flags, &ctx->h_hitdb, &ctx->h_outaln, &ctx->h_stats, &ctx->h_cigar, &ctx->h_off32, &ctx->h_pkoff};

@@ -72,7 +72,7 @@ constexpr uint32_t kOvfSlots = 64u;     // num_alignments == 0: more accepted al
 enum DevCnt { dcNumAligned = 0, dcNumShort, dcSwCalls, dcSwCells, dcWindows, dcNodes, dcBuckets, dcEntries, dcPosEntries,
               dcLisCalls, dcMaxReadCycles, dcSumReadCycles, dcLisKernelCycles,
               dcCycVote, dcCycOrder, dcCycGroup, dcCycPlan, dcCycWait, dcCycReplay, dcSpecCalls, dcSpecCells, dcSpecPairs, dcSlowPairs,
-              dcScWait, dcScLoad, dcScSw, dcScPub, dcRoundsA, dcRoundsB, dcW1Cyc, dcW1Cnt, dcExpressPairs, dcCount = 32 };
+              dcScWait, dcScLoad, dcScSw, dcScPub, dcRoundsA, dcRoundsB, dcW1Cyc, dcW1Cnt, dcMaxReadBusy, dcCount = 32 };
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 

@@ -128,6 +128,7 @@ struct LisGlobals {
   uint32_t* planners_done;                     // planners that ran out of reads
   uint32_t* done;                              // [planners] tasks scored so far for each planner
   int32_t* score_rows;                         // [scorers][2 * row_cap] scratch of the s32 row-block fallback
+  unsigned long long* dbg;                     // [16] phase cycles of the read that took longest (SMR_VERBOSE)
   AlnWork* aln_work;                           // [nreads * slots]
   uint32_t slots;
   uint32_t* work_next;                         // [1] persistent-loop cursor
@@ -138,22 +139,25 @@ __device__ __forceinline__ LisArena carve_arena(const LisGlobals& g, uint32_t wa
   LisArena a;
   uint8_t* p = g.arena_base + (size_t)warp * g.arena_stride;
   a.hist_cap = g.hist_cap; a.cand_cap = g.cand_cap; a.pair_cap = g.pair_cap; a.task_cap = g.task_cap;
+  // the part that must start zeroed comes first (lis_arena_zero_bytes): epoch-tagged votes, candidate bitmap and its summary
+  a.hist = (uint32_t*)p; p += (size_t)g.hist_cap * 4;
+  a.bitmap = (uint32_t*)p; p += (size_t)((g.hist_cap + 31) / 32) * 4;
+  a.summary = (uint32_t*)p; p += (size_t)((g.hist_cap + 1023) / 1024) * 4;
+  p = (uint8_t*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
   a.cand = (unsigned long long*)p; p += (size_t)g.cand_cap * 8;
   a.grp = (unsigned long long*)p; p += (size_t)g.cand_cap * 8;
   a.pairs = (unsigned long long*)p; p += (size_t)g.pair_cap * 8;
-  a.hist = (uint32_t*)p; p += (size_t)g.hist_cap * 4;
   a.lis_b = (uint32_t*)p; p += (size_t)g.pair_cap * 4;
   a.lis_p = (uint32_t*)p; p += (size_t)g.pair_cap * 4;
   a.sel = (uint32_t*)p; p += (size_t)g.task_cap * 4;
   a.cfirst = (uint32_t*)p; p += (size_t)kBatchCandCap * 3 * 4;
-  a.bitmap = (uint32_t*)p; p += (size_t)((g.hist_cap + 31) / 32) * 4;
-  a.summary = (uint32_t*)p; p += (size_t)((g.hist_cap + 1023) / 1024) * 4;
   p = (uint8_t*)(((uintptr_t)p + 31) & ~(uintptr_t)31);
   a.pall = (unsigned long long*)p; a.pall_cap = g.pall_cap; p += (size_t)g.pall_cap * 8;
   a.tasks = (SwTask*)p; p += (size_t)g.task_cap * sizeof(SwTask);
   a.ptasks = (PlanTask*)p;
   return a;
 }
+__host__ __device__ inline size_t lis_arena_zero_bytes(uint32_t hist_cap) { return (size_t)hist_cap * 4 + (size_t)((hist_cap + 31) / 32) * 4 + (size_t)((hist_cap + 1023) / 1024) * 4; }
 __host__ __device__ inline size_t lis_arena_bytes(uint32_t hist_cap, uint32_t cand_cap, uint32_t pair_cap, uint32_t task_cap, uint32_t pall_cap) {
   size_t b = (size_t)cand_cap * 16 + (size_t)pair_cap * 8 + (size_t)hist_cap * 4 + (size_t)pair_cap * 8 + (size_t)task_cap * 4 +
              (size_t)kBatchCandCap * 3 * 4 + (size_t)((hist_cap + 31) / 32) * 4 + (size_t)((hist_cap + 1023) / 1024) * 4 + 64 +
@@ -247,7 +251,7 @@ struct PassEnv {
   const uint2* hits; uint32_t nh;                               // hit region of (current part, current read)
   uint32_t planner;                                             // ordinal of this planner warp
   uint32_t submitted;                                           // tasks handed to the scorers so far (g.done[planner] catches up)
-  unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls, n_spec_calls, n_spec_cells /* rounds A */, n_rounds_b, w1_cyc, w1_cnt, express_pairs;
+  unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls, n_spec_calls, n_spec_cells /* rounds A */, n_rounds_b, w1_cyc, w1_cnt;
   unsigned long long cyc[8];                                    // warp cycles per phase: vote, order, group, plan, wait, replay
 };
 
@@ -286,7 +290,7 @@ __device__ __noinline__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
   if (lane == 0) { while (ld_volatile_u32(g.done + E.planner) != E.submitted) __nanosleep(256); __threadfence(); }
   __syncwarp();
   if (npairs == 1) { E.w1_cyc += (unsigned long long)(lis_clock() - tw0); E.w1_cnt++; }
-  if (qi == 0) E.express_pairs += npairs;
+
 }
 
 __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score, const uint32_t ncand, const bool by_level,
@@ -1156,10 +1160,11 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     uint8_t* sm = lis_smem + (size_t)kScorerWarps * kScorerSmem + (size_t)pw * kPlannerSmem;
     E.s_pairs = (unsigned long long*)sm; E.s_b = (uint32_t*)(sm + kPairsShared * 8); E.s_p = E.s_b + kPairsShared;
   }
-  E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = E.n_spec_calls = E.n_spec_cells = E.n_rounds_b = E.w1_cyc = E.w1_cnt = E.express_pairs = 0;
+  E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = E.n_spec_calls = E.n_spec_cells = E.n_rounds_b = E.w1_cyc = E.w1_cnt = 0;
   for (int i = 0; i < 8; ++i) E.cyc[i] = 0;
   const uint32_t nwork = s_bin_start[kCostBins];
   unsigned long long t_max = 0, t_sum = 0; const long long t_k0 = lis_clock();
+  unsigned long long dbg_loc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_busy_max = 0;
   const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);
   for (;;) {
     uint32_t wi = 0;
@@ -1170,6 +1175,8 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     while (wi >= s_bin_start[k + 1]) ++k;
     const uint32_t r = b.bins[(size_t)(kCostBins - 1 - k) * b.cnt_stride + (wi - s_bin_start[k])];
     const long long t_read0 = lis_clock();
+    unsigned long long cyc0[6], calls0 = E.n_sw_calls, spec0 = E.n_spec_calls, ra0 = E.n_spec_cells;
+    for (int i = 0; i < 6; ++i) cyc0[i] = E.cyc[i];
     ReadCtx rc;
     rc.r = r; rc.seq_base = b.seq_off[r]; rc.len = b.seq_off[r + 1] - rc.seq_base;
     rc.hasn = b.has_n[r] != 0; rc.flags = 0; rc.ovf_slots = false;
@@ -1203,7 +1210,11 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     }
     if (rc.ovf_slots) rc.flags |= kOvfSlots;
     if (rc.flags && lane == 0) atomicOr(&b.flags[r], rc.flags);
-    { const unsigned long long dt = (unsigned long long)(lis_clock() - t_read0); t_max = dt > t_max ? dt : t_max; t_sum += dt; }
+    { const unsigned long long dt = (unsigned long long)(lis_clock() - t_read0);
+      if (dt > t_max) { t_max = dt; for (int i = 0; i < 6; ++i) dbg_loc[i] = E.cyc[i] - cyc0[i]; dbg_loc[6] = E.n_sw_calls - calls0; dbg_loc[7] = E.n_spec_calls - spec0; dbg_loc[8] = E.n_spec_cells - ra0; dbg_loc[9] = r; }
+      const unsigned long long busy = dt - (E.cyc[4] - cyc0[4]);   // without the time spent waiting for the scorers
+      t_busy_max = busy > t_busy_max ? busy : t_busy_max;
+      t_sum += dt; }
     __syncwarp();
   }
   if (lane == 0) {
@@ -1211,9 +1222,10 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     atomicAdd(&b.counters[dcSwCalls], E.n_sw_calls); atomicAdd(&b.counters[dcSwCells], E.n_sw_cells);
     atomicAdd(&b.counters[dcPosEntries], E.n_pos_entries); atomicAdd(&b.counters[dcLisCalls], E.n_lis_calls);
     atomicAdd(&b.counters[dcSpecCalls], E.n_spec_calls); atomicAdd(&b.counters[dcRoundsA], E.n_spec_cells); atomicAdd(&b.counters[dcRoundsB], E.n_rounds_b);
-    atomicAdd(&b.counters[dcW1Cyc], E.w1_cyc); atomicAdd(&b.counters[dcW1Cnt], E.w1_cnt); atomicAdd(&b.counters[dcExpressPairs], E.express_pairs);
+    atomicAdd(&b.counters[dcW1Cyc], E.w1_cyc); atomicAdd(&b.counters[dcW1Cnt], E.w1_cnt); atomicMax(&b.counters[dcMaxReadBusy], t_busy_max);
     for (int i = 0; i < 6; ++i) atomicAdd(&b.counters[dcCycVote + i], E.cyc[i]);
-    atomicMax(&b.counters[dcMaxReadCycles], t_max); atomicAdd(&b.counters[dcSumReadCycles], t_sum);
+    if (atomicMax(&b.counters[dcMaxReadCycles], t_max) < t_max && g.dbg) { g.dbg[0] = t_max; for (int i = 0; i < 10; ++i) g.dbg[1 + i] = dbg_loc[i]; }
+    atomicAdd(&b.counters[dcSumReadCycles], t_sum);
     atomicMax(&b.counters[dcLisKernelCycles], (unsigned long long)(lis_clock() - t_k0));
     // the last planner out shuts the scorers down: one entry each
     const uint32_t nplanners = gridDim.x * kPlannerWarps, nscorers = gridDim.x * kScorerWarps;   // one shutdown entry per fetcher lane of each queue

@@ -65,7 +65,7 @@ struct LaneHits {
   uint32_t* buf; uint32_t stride, cap, n; bool overflow;
 };
 
-struct SeedStats { uint32_t entries; };
+struct SeedStats { uint32_t entries, lists; };   // list entries classified; non-empty flat lists scanned (the "buckets" of SURVEY 8(d): one per sub-search)
 
 // the reference's per-entry side effects (traverse_bursttrie.cpp:249-281) applied to a classification code;
 // returns true when the window search ends on a 0-error match
@@ -104,7 +104,7 @@ __device__ void coop_flat(const DevIndex& ix, CoopSmem& sm, const uint32_t off, 
   const unsigned lane = lane_id();
   const uint32_t pw = ix.partialwin;
   const uint32_t incl = warp_incl_scan_u32(cnt), E = __shfl_sync(kFull, incl, 31), excl = incl - cnt;
-  if (INSTR) st.entries += cnt;
+  if (INSTR) { st.entries += cnt; st.lists += cnt ? 1u : 0u; }
   uint32_t nacc = 0;
   for (uint32_t e0 = 0; e0 < E; e0 += 32) {
     const uint32_t e = e0 + lane;
@@ -211,7 +211,7 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
   CoopSmem& sm = s_coop[wic];
   LaneHits lh;
   lh.buf = lane_hits_g + (size_t)warp * cap_g * 32 + lane; lh.stride = 32; lh.cap = cap_g;   // per-window ids live in a per-warp HBM scratch
-  SeedStats st{0};
+  SeedStats st{0, 0};
   uint32_t n_windows = 0, n_short = 0;
   const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);
   const bool do_fwd = !(single && prm.is_reverse), do_rev = !(single && prm.is_forward);
@@ -288,8 +288,8 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
   const uint32_t ns = warp_sum_u32(n_short);
   if (lane == 0 && ns) atomicAdd(&b.counters[dcNumShort], (unsigned long long)ns);
   if (INSTR) {
-    const uint64_t w = warp_sum_u64(n_windows), ne = warp_sum_u64(st.entries);
-    if (lane == 0) { atomicAdd(&b.counters[dcWindows], (unsigned long long)w); atomicAdd(&b.counters[dcEntries], (unsigned long long)ne); }
+    const uint64_t w = warp_sum_u64(n_windows), ne = warp_sum_u64(st.entries), nl = warp_sum_u64(st.lists);
+    if (lane == 0) { atomicAdd(&b.counters[dcWindows], (unsigned long long)w); atomicAdd(&b.counters[dcEntries], (unsigned long long)ne); atomicAdd(&b.counters[dcBuckets], (unsigned long long)nl); }
   }
 }
 
@@ -321,7 +321,7 @@ seed_debug_kernel(DevIndex ix, const uint8_t* seq03, const uint32_t* seq_off, co
     for (uint32_t i = 0; i < ix.lnwin; ++i) V = (V << 2) | (sq[i] & 3u);
   }
   LaneHits lh; lh.buf = ids + (size_t)(active ? k : 0) * cap; lh.stride = 1; lh.cap = active ? cap : 0; lh.n = 0; lh.overflow = false;
-  SeedStats st{0};
+  SeedStats st{0, 0};
   bool z = false;
   const bool full = full_search != 0;
   const uint32_t keyf = (uint32_t)(V >> (2 * pw)), keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
