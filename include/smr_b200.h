@@ -173,6 +173,20 @@ int smr_set_stats_buffer(smr_ctx*, smr_aln_stats* stats);
  * fine; trailing blank lines are ignored.  *nreads = records found. */
 int smr_upload_fastx(smr_ctx*, const char* text, uint64_t nbytes, uint32_t* nreads);
 
+/* The same from a gzip file: `gz` = the bytes of a .fastq.gz / .fasta.gz (one or several gzip members, RFC 1952).  Replaces the
+ * inflate of the reference's read feed (Readfeed::next_gz, src/sortmerna/readfeed.cpp:683-770, izlib.cpp / rapidgzip): the
+ * compressed bytes are copied to the device and inflated there -- block starts found speculatively in every 64 KB of the file, one
+ * decoder thread per span, back-references into not-yet-known history resolved in a second step (sortmerna_b200/csrc/smr_inflate.h)
+ * -- then decoded as in smr_upload_fastx.  A corrupt or truncated file fails with SMR_ERR_ARG (invalid code / header / distance,
+ * ISIZE mismatch); the CRC32 of the members is not checked. */
+int smr_upload_fastx_gz(smr_ctx*, const void* gz, uint64_t nbytes, uint32_t* nreads);
+/* The text behind the resident batch (what smr_upload_fastx was given / what smr_upload_fastx_gz inflated): *nbytes = its size;
+ * copied to `text` when that is not null (cap bytes available).  header_text_off of smr_resident_layout indexes it. */
+int smr_resident_text(smr_ctx*, char* text, uint64_t cap, uint64_t* nbytes);
+/* Test hook: inflate only.  chunk_bytes = distance of the speculative block searches (>= 1024); info = {spans decoded,
+ * candidates found, device time in us, H2D time in us}. */
+int smr_debug_inflate(smr_ctx*, const void* gz, uint64_t nbytes, uint64_t chunk_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_bytes, uint32_t info[4]);
+
 /* Where the resident reads are: header_text_off[r] = offset of record r's header line in the text given to
  * smr_upload_fastx (for Read::getSeqId / report writers; nullptr = skip; only after smr_upload_fastx), read_off[0..nreads] =
  * offsets into the concatenated 0-4 codes, seq04 (optional) = those codes (seq_cap bytes available). */

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "smr_decode.cuh"
+#include "smr_inflate.cuh"
 #include "smr_final.cuh"
 #include "smr_index.h"
 
@@ -60,6 +61,9 @@ struct smr_ctx {
   PinBuf h_state, h_flags, h_hitdb, h_outaln, h_stats, h_cigar, h_off32, h_pkoff;
   std::vector<uint64_t> h_coff;
   DevBuf d_text, d_cnt, d_scal, d_nl, d_hdr, d_sb, d_rec, d_spos, d_hdroff, scan_sums;   // input decode (smr_decode.cuh)
+  DevBuf d_gz, d_cand, d_res, d_sym, d_win, d_ids, d_off, d_cnt64;   // gz inflate (smr_inflate.cuh)
+  uint64_t text_bytes = 0;          // size of the text behind the resident batch (smr_upload_fastx / _gz)
+  uint32_t inf_spans = 0, inf_candidates = 0; double t_inflate = 0;
   bool device_only_reads = false;   // the resident batch was decoded on the device: no host copy of the sequences yet
   double t_decode = 0;
   uint32_t tb_threads = 0, tb_cap_w = 0, tb_cap_cig = 0; size_t tb_cap_dir = 0, tb_stride = 0;
@@ -113,8 +117,9 @@ void release(PinBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; 
 template <class T>
 int upload_vec(smr_ctx* ctx, Part& pt, const std::vector<T>& v, const T** out) {
   void* d = nullptr;
-  size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+  size_t bytes = v.size() * sizeof(T) + 64;   // the seed kernel reads whole aligned groups of four list entries
   CK(cudaMalloc(&d, bytes));
+  CK(cudaMemset(d, 0, bytes));
   if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   pt.owned.push_back(d); pt.bytes += bytes;
   *out = (const T*)d;
@@ -298,18 +303,23 @@ int device_scan(smr_ctx* ctx, const uint32_t* in, uint32_t* out, uint64_t n, uin
 }
 
 // FASTA / FASTQ text -> resident batch (smr_decode.cuh)
-int upload_fastx_impl(smr_ctx* ctx, const char* text, uint64_t nbytes, uint32_t* nreads_out) {
+// text == nullptr: the text is already in ctx->d_text (inflated on the device), first byte given
+int upload_fastx_impl(smr_ctx* ctx, const char* text, uint64_t nbytes, uint32_t* nreads_out, char first_byte = 0) {
   *nreads_out = 0;
   ctx->nreads = 0;
+  ctx->text_bytes = nbytes;
   if (nbytes == 0) return SMR_OK;
   if (nbytes >= ((uint64_t)1 << 36)) { ctx->err = "text batch too large: split it"; return SMR_ERR_ARG; }
-  const uint32_t fmt = text[0] == '@' ? kFmtFastq : kFmtFasta;
-  if (text[0] != '@' && text[0] != '>') { ctx->err = "reads text must start with '@' (FASTQ) or '>' (FASTA)"; return SMR_ERR_ARG; }
+  const char c0 = text ? text[0] : first_byte;
+  const uint32_t fmt = c0 == '@' ? kFmtFastq : kFmtFasta;
+  if (c0 != '@' && c0 != '>') { ctx->err = "reads text must start with '@' (FASTQ) or '>' (FASTA)"; return SMR_ERR_ARG; }
   cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1), e2 = get_event(ctx, 2);
   int rc;
   CK(cudaEventRecord(e0, ctx->stream));
-  if ((rc = ensure(ctx, ctx->d_text, nbytes + 64))) return rc;
-  CK(cudaMemcpyAsync(ctx->d_text.p, text, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (text) {
+    if ((rc = ensure(ctx, ctx->d_text, nbytes + 64))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_text.p, text, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
   CK(cudaEventRecord(e1, ctx->stream));
   const uint8_t* dt = (const uint8_t*)ctx->d_text.p;
   const uint64_t nchunks = nbytes / 32 + 1;
@@ -363,9 +373,109 @@ int upload_fastx_impl(smr_ctx* ctx, const char* text, uint64_t nbytes, uint32_t*
   ctx->h_seq.clear(); ctx->h_off.clear(); ctx->device_only_reads = true;
   if ((rc = finish_upload(ctx, nreads, h[4]))) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
-  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->t_h2d = ms;
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); if (text) ctx->t_h2d = ms;
   cudaEventElapsedTime(&ms, e1, e2); ctx->t_decode = ms;
   *nreads_out = nreads;
+  return SMR_OK;
+}
+
+const char* inf_status_text(uint32_t st) {
+  switch (st) {
+    case kInfErrCode: return "invalid Huffman code";
+    case kInfErrHeader: return "invalid block header";
+    case kInfErrOverrun: return "compressed data ends inside a block (truncated file)";
+    case kInfErrDistance: return "invalid distance too far back";
+    case kInfErrStored: return "invalid stored block lengths";
+    case kInfErrMember: return "not a gzip member, or its size field disagrees with the data";
+    default: return "internal error";
+  }
+}
+
+// gzip file (host bytes) -> inflated bytes in ctx->d_text.  The five steps of smr_inflate.h; the host only walks the list of
+// spans (a few thousand entries) between the COUNT and the WRITE pass.
+int inflate_impl(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint64_t chunk_bytes, uint64_t* out_bytes) {
+  *out_bytes = 0;
+  ctx->inf_spans = ctx->inf_candidates = 0;
+  if (nbytes < 18) { ctx->err = "gz input: shorter than a gzip header and trailer"; return SMR_ERR_ARG; }
+  if (chunk_bytes < 1024) chunk_bytes = 1024;
+  int rc;
+  cudaEvent_t e0 = get_event(ctx, 0), e1 = get_event(ctx, 1), e2 = get_event(ctx, 2);
+  CK(cudaEventRecord(e0, ctx->stream));
+  const size_t padded = (nbytes + 3) / 4 * 4 + 128;
+  if ((rc = ensure(ctx, ctx->d_gz, padded))) return rc;
+  CK(cudaMemsetAsync((uint8_t*)ctx->d_gz.p + nbytes / 4 * 4, 0, padded - nbytes / 4 * 4, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_gz.p, gz, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaEventRecord(e1, ctx->stream));
+  const uint32_t* w = (const uint32_t*)ctx->d_gz.p;
+  // FIND
+  const uint64_t nchunks = (nbytes + chunk_bytes - 1) / chunk_bytes;
+  if (nchunks > (1u << 24)) { ctx->err = "gz input: too many chunks"; return SMR_ERR_ARG; }
+  std::vector<uint64_t> cand;
+  if (nchunks > 1) {
+    if ((rc = ensure(ctx, ctx->d_cand, nchunks * 8))) return rc;
+    inf_find_kernel<<<(unsigned)(nchunks - 1), 256, 0, ctx->stream>>>(w, nbytes, chunk_bytes, (uint64_t*)ctx->d_cand.p);
+    CK(cudaGetLastError());
+    std::vector<uint64_t> raw(nchunks - 1);
+    CK(cudaMemcpyAsync(raw.data(), ctx->d_cand.p, (nchunks - 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t p : raw) if (p != kInfNone) cand.push_back(p);   // chunk order = position order
+    if (!cand.empty()) CK(cudaMemcpyAsync(ctx->d_cand.p, cand.data(), cand.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  } else if ((rc = ensure(ctx, ctx->d_cand, 8))) return rc;
+  const uint32_t ncand = (uint32_t)cand.size(), ns = ncand + 1;
+  // COUNT
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[0]) { CK(cudaFuncSetAttribute(inf_span_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInfSpanSmem)); attr_done[0] = true; }
+  if (!attr_done[1]) { CK(cudaFuncSetAttribute(inf_span_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInfSpanSmem)); attr_done[1] = true; }
+  if ((rc = ensure(ctx, ctx->d_res, (size_t)ns * sizeof(SpanResult)))) return rc;
+  const unsigned ctas = (ns + kInfSpanThreads - 1) / kInfSpanThreads;
+  inf_span_kernel<false><<<ctas, kInfSpanThreads, kInfSpanSmem, ctx->stream>>>(w, nbytes, (const uint64_t*)ctx->d_cand.p, ncand, nullptr, nullptr, nullptr, ns, nullptr,
+                                                                               (SpanResult*)ctx->d_res.p);
+  CK(cudaGetLastError());
+  std::vector<SpanResult> res(ns);
+  CK(cudaMemcpyAsync(res.data(), ctx->d_res.p, (size_t)ns * sizeof(SpanResult), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::vector<uint32_t> real(ns); std::vector<uint64_t> off(ns), cnt(ns);
+  uint32_t nreal = 0, why = 0;
+  const uint64_t total = inf_chain(cand.data(), ncand, res.data(), real.data(), off.data(), nreal, &why);
+  if (total == kInfNone) { ctx->err = std::string("gz input: ") + inf_status_text(why); return SMR_ERR_ARG; }
+  for (uint32_t k = 0; k < nreal; ++k) cnt[k] = res[real[k]].out_n;
+  ctx->inf_spans = nreal; ctx->inf_candidates = ncand;
+  if ((rc = ensure(ctx, ctx->d_text, total + 64))) return rc;
+  if (total) {
+    // WRITE
+    if ((rc = ensure(ctx, ctx->d_ids, (size_t)nreal * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_off, (size_t)nreal * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->d_cnt64, (size_t)nreal * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->d_sym, (total + 8) * 2))) return rc;
+    if ((rc = ensure(ctx, ctx->d_win, (size_t)(nreal + 1) * kInfWindow))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_ids.p, real.data(), (size_t)nreal * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_off.p, off.data(), (size_t)nreal * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_cnt64.p, cnt.data(), (size_t)nreal * 8, cudaMemcpyHostToDevice, ctx->stream));
+    inf_span_kernel<true><<<(nreal + kInfSpanThreads - 1) / kInfSpanThreads, kInfSpanThreads, kInfSpanSmem, ctx->stream>>>(
+        w, nbytes, (const uint64_t*)ctx->d_cand.p, ncand, (const uint32_t*)ctx->d_ids.p, (const uint64_t*)ctx->d_off.p, (const uint64_t*)ctx->d_cnt64.p, nreal,
+        (uint16_t*)ctx->d_sym.p, (SpanResult*)ctx->d_res.p);
+    CK(cudaGetLastError());
+    // WINDOW, RESOLVE
+    inf_window_kernel<<<1, 1024, 0, ctx->stream>>>((const uint16_t*)ctx->d_sym.p, (const uint64_t*)ctx->d_off.p, (const uint64_t*)ctx->d_cnt64.p, nreal, (uint8_t*)ctx->d_win.p);
+    CK(cudaGetLastError());
+    const uint64_t avg = total / nreal + 1;
+    const unsigned pieces = (unsigned)std::min<uint64_t>(64, std::max<uint64_t>(1, avg / 8192));
+    inf_resolve_kernel<<<dim3(pieces, nreal), 256, 0, ctx->stream>>>((const uint16_t*)ctx->d_sym.p, (const uint64_t*)ctx->d_off.p, (const uint64_t*)ctx->d_cnt64.p,
+                                                                     (const uint8_t*)ctx->d_win.p, (uint8_t*)ctx->d_text.p);
+    CK(cudaGetLastError());
+    std::vector<SpanResult> res2(nreal);
+    CK(cudaMemcpyAsync(res2.data(), ctx->d_res.p, (size_t)nreal * sizeof(SpanResult), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(e2, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t k = 0; k < nreal; ++k)
+      if (res2[k].status != res[real[k]].status || res2[k].out_n != cnt[k] || res2[k].end_bit != res[real[k]].end_bit) { ctx->err = "gz inflate: the write pass disagrees with the count pass"; return SMR_ERR_CUDA; }
+  } else {
+    CK(cudaEventRecord(e2, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->t_h2d = ms;
+  cudaEventElapsedTime(&ms, e1, e2); ctx->t_inflate = ms;
+  *out_bytes = total;
   return SMR_OK;
 }
 
@@ -681,7 +791,8 @@ void smr_destroy(smr_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->seq04, &ctx->seq_off, &ctx->pk03, &ctx->pk03alt, &ctx->pk_off, &ctx->has_n, &ctx->hit_cnt, &ctx->flags, &ctx->state,
                     &ctx->hit_db, &ctx->aln_work, &ctx->out_aln, &ctx->hits, &ctx->cost, &ctx->bins, &ctx->scalars, &ctx->counters, &ctx->cigar_pool,
                     &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->lis_queue, &ctx->lis_done, &ctx->lis_rows, &ctx->lis_dbg, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs, &ctx->aln_stats,
-                    &ctx->d_text, &ctx->d_cnt, &ctx->d_scal, &ctx->d_nl, &ctx->d_hdr, &ctx->d_sb, &ctx->d_rec, &ctx->d_spos, &ctx->d_hdroff, &ctx->scan_sums};
+                    &ctx->d_text, &ctx->d_cnt, &ctx->d_scal, &ctx->d_nl, &ctx->d_hdr, &ctx->d_sb, &ctx->d_rec, &ctx->d_spos, &ctx->d_hdroff, &ctx->scan_sums,
+                    &ctx->d_gz, &ctx->d_cand, &ctx->d_res, &ctx->d_sym, &ctx->d_win, &ctx->d_ids, &ctx->d_off, &ctx->d_cnt64};
   for (DevBuf* b : bufs) release(*b);
   PinBuf* pins[] = {&ctx->h_state, &ctx->h_flags, &ctx->h_hitdb, &ctx->h_outaln, &ctx->h_stats, &ctx->h_cigar, &ctx->h_off32, &ctx->h_pkoff};
   for (PinBuf* b : pins) release(*b);
@@ -794,6 +905,45 @@ int smr_upload_fastx(smr_ctx* ctx, const char* text, uint64_t nbytes, uint32_t* 
   CK(cudaSetDevice(ctx->device));
   ctx->scale = 1;
   return upload_fastx_impl(ctx, text, nbytes, nreads);
+}
+
+int smr_upload_fastx_gz(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint32_t* nreads) {
+  if (!ctx || !gz || !nreads) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ctx->scale = 1;
+  *nreads = 0; ctx->nreads = 0; ctx->text_bytes = 0;
+  uint64_t total = 0;
+  const char* e = getenv("SMR_INFLATE_CHUNK");
+  int rc = inflate_impl(ctx, gz, nbytes, e ? strtoull(e, nullptr, 10) : 65536, &total);
+  if (rc) return rc;
+  if (total == 0) return SMR_OK;
+  char c0 = 0;
+  CK(cudaMemcpy(&c0, ctx->d_text.p, 1, cudaMemcpyDeviceToHost));
+  return upload_fastx_impl(ctx, nullptr, total, nreads, c0);
+}
+
+int smr_resident_text(smr_ctx* ctx, char* text, uint64_t cap, uint64_t* nbytes) {
+  if (!ctx || !nbytes) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  *nbytes = ctx->text_bytes;
+  if (!text || ctx->text_bytes == 0) return SMR_OK;
+  if (cap < ctx->text_bytes) { ctx->err = "text buffer too small"; return SMR_ERR_CAPACITY; }
+  CK(cudaMemcpy(text, ctx->d_text.p, ctx->text_bytes, cudaMemcpyDeviceToHost));
+  return SMR_OK;
+}
+
+int smr_debug_inflate(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint64_t chunk_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_bytes, uint32_t info[4]) {
+  if (!ctx || !gz || !out_bytes) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ctx->nreads = 0; ctx->text_bytes = 0;
+  int rc = inflate_impl(ctx, gz, nbytes, chunk_bytes, out_bytes);
+  if (rc) return rc;
+  if (info) { info[0] = ctx->inf_spans; info[1] = ctx->inf_candidates; info[2] = (uint32_t)(ctx->t_inflate * 1000.0); info[3] = (uint32_t)(ctx->t_h2d * 1000.0); }
+  if (out && *out_bytes) {
+    if (out_cap < *out_bytes) { ctx->err = "output buffer too small"; return SMR_ERR_CAPACITY; }
+    CK(cudaMemcpy(out, ctx->d_text.p, *out_bytes, cudaMemcpyDeviceToHost));
+  }
+  return SMR_OK;
 }
 
 int smr_resident_layout(smr_ctx* ctx, uint64_t* header_text_off, uint64_t* read_off, uint8_t* seq04, uint64_t seq_cap) {

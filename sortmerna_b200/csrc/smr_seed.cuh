@@ -60,10 +60,14 @@ __device__ __forceinline__ uint64_t revcomp_bits(uint64_t v, uint32_t L) {
 }
 
 // Per-lane hit buffer (ids of one window, needed for the per-window de-duplication,
-// traverse_bursttrie.cpp:265-279).  Slot k lives at buf[k*stride].
+// traverse_bursttrie.cpp:265-279).  The first kLaneSmemIds slots live in shared memory (slot k at sbuf[k*32]), the rest in
+// an HBM scratch (slot k at buf[k*stride]); a window rarely has more than three ids.
+constexpr uint32_t kLaneSmemIds = 8;
 struct LaneHits {
-  uint32_t* buf; uint32_t stride, cap, n; bool overflow;
+  uint32_t* sbuf; uint32_t* buf; uint32_t stride, cap, n; bool overflow;
 };
+__device__ __forceinline__ uint32_t lh_get(const LaneHits& lh, uint32_t k) { return k < kLaneSmemIds ? lh.sbuf[k * 32] : lh.buf[k * lh.stride]; }
+__device__ __forceinline__ void lh_set(LaneHits& lh, uint32_t k, uint32_t id) { if (k < kLaneSmemIds) lh.sbuf[k * 32] = id; else lh.buf[k * lh.stride] = id; }
 
 struct SeedStats { uint32_t entries, lists; };   // list entries classified; non-empty flat lists scanned (the "buckets" of SURVEY 8(d): one per sub-search)
 
@@ -73,11 +77,11 @@ __device__ __forceinline__ bool apply_entry(uint32_t code, uint32_t id, bool ful
   const uint32_t d1 = code & 3u;
   if (d1 == 0) return false;
   const bool z = (code & 4u) && !full_search;
-  if (d1 == 2 && z) { lh.n = 1; lh.buf[0] = id; lh.overflow = false; return true; }                  // :256-262
-  for (uint32_t f = 0; f < lh.n && f < lh.cap; ++f) if (lh.buf[f * lh.stride] == id) return false;   // duplicate: :265-277
-  if (lh.n < lh.cap) lh.buf[lh.n * lh.stride] = id; else lh.overflow = true;
+  if (d1 == 2 && z) { lh.n = 1; lh_set(lh, 0, id); lh.overflow = false; return true; }                // :256-262
+  for (uint32_t f = 0; f < lh.n && f < lh.cap; ++f) if (lh_get(lh, f) == id) return false;             // duplicate: :265-277
+  if (lh.n < lh.cap) lh_set(lh, lh.n, id); else lh.overflow = true;
   lh.n++;
-  if (d1 == 1 && z) { lh.n = 1; lh.buf[0] = id; lh.overflow = false; return true; }                  // 0-error one step after the push
+  if (d1 == 1 && z) { lh.n = 1; lh_set(lh, 0, id); lh.overflow = false; return true; }                // 0-error one step after the push
   return false;
 }
 
@@ -89,48 +93,110 @@ __device__ __forceinline__ uint32_t pass_class(uint32_t p, uint32_t s0, uint32_t
   return 3;
 }
 
-constexpr int kAccCap = 192;   // matching entries buffered per flush
+constexpr int kAccCap = 256;   // matching entries buffered per flush (a step adds at most 128)
 
 struct CoopSmem {              // per warp
-  uint32_t id[kAccCap];
-  uint8_t meta[kAccCap];       // owner lane | code << 5
+  uint4 tab[64];               // the non-empty lists of a round in stream order: {first group - first chunk, pattern, first entry, end entry}
+  uint32_t id[kAccCap];        // matching entries in stream order: id, text, owner
+  uint32_t text[kAccCap];
+  uint8_t meta[kAccCap];       // owner lane | 32 for a mirror list
+  uint8_t own[64];             // the same for list k
+  uint16_t run[2][2][32];      // [forward / mirror][begin / end][lane]: the lane's matches of the current flush
+  uint32_t ids[kLaneSmemIds][32];   // LaneHits::sbuf
 };
 
-// One sub-search (forward: trie_F list of the first half, pattern = second half; or mirror) for the 32 windows
-// of a round.  off/cnt: the lane's list in ix.flist (cnt == 0: lane idle).  Appends to lh; sets zero.
+// The two sub-searches of the 32 windows of a round as ONE entry stream:
+//   (a) forward: trie_F list of the first half, pattern = second half (paralleltraversal.cpp:161-186);
+//   (b) mirror: trie_R list of the second half, pattern = first half (:188-240) -- the reference runs (b) only without a
+//       0-error hit in (a); here every (a) list precedes every (b) list in the stream and a lane stops replaying its matches
+//       at its 0-error hit, so streaming (b) regardless changes nothing but the entries read (~5 % of the windows).
+// The unit of work is a CHUNK = one aligned group of four 8-byte entries (one 32-byte sector, two 16-byte loads): a lane
+// finds the list of its chunk once (REDUX.OR of the lists that start in this step + popc, one shared-memory row) and tests
+// four entries with within_one_edit().  Matching entries (text, id, owner) are compacted in stream order; at a flush every lane
+// finds the (at most two) runs of its own matches and replays them -- exact classification and the reference's order-dependent
+// rules (0-error exit, per-window de-duplication, traverse_bursttrie.cpp:249-281) -- all lanes in parallel.
+// offF/cntF/PF, offR/cntR/PR: the lane's two lists in ix.flist (cnt == 0: none).  Appends to lh; sets zero.
 template <bool INSTR>
-__device__ void coop_flat(const DevIndex& ix, CoopSmem& sm, const uint32_t off, const uint32_t cnt, const uint32_t P, const bool full_search,
-                          LaneHits& lh, bool& zero, SeedStats& st) {
+__device__ void coop_stream(const DevIndex& ix, CoopSmem& sm, const uint32_t offF, const uint32_t cntF, const uint32_t PF,
+                            const uint32_t offR, const uint32_t cntR, const uint32_t PR, const bool full_search,
+                            LaneHits& lh, bool& zero, SeedStats& st) {
   const unsigned lane = lane_id();
   const uint32_t pw = ix.partialwin;
-  const uint32_t incl = warp_incl_scan_u32(cnt), E = __shfl_sync(kFull, incl, 31), excl = incl - cnt;
-  if (INSTR) { st.entries += cnt; st.lists += cnt ? 1u : 0u; }
-  uint32_t nacc = 0;
+  const LevMasks km = lev_masks(pw);
+  const uint4* __restrict__ fl4 = reinterpret_cast<const uint4*>(ix.flist);   // group g = fl4[2g], fl4[2g+1]
+  const uint32_t gF = offF >> 2, nF = cntF ? ((offF + cntF + 3u) >> 2) - gF : 0u;
+  const uint32_t gR = offR >> 2, nR = cntR ? ((offR + cntR + 3u) >> 2) - gR : 0u;
+  const uint32_t inF = warp_incl_scan_u32(nF), inR = warp_incl_scan_u32(nR);
+  const uint32_t totF = __shfl_sync(kFull, inF, 31), E = totF + __shfl_sync(kFull, inR, 31);
+  const uint32_t exF = inF - nF, exR = totF + inR - nR;
+  if (INSTR) { st.entries += cntF + cntR; st.lists += (cntF ? 1u : 0u) + (cntR ? 1u : 0u); }
+  if (E == 0) return;
+  const uint32_t lt = (1u << lane) - 1u, le = lt | (1u << lane);
+  {
+    const unsigned mF = __ballot_sync(kFull, nF != 0), mR = __ballot_sync(kFull, nR != 0);
+    if (nF) { const uint32_t k = __popc(mF & lt); sm.tab[k] = make_uint4(gF - exF, PF, offF, offF + cntF); sm.own[k] = (uint8_t)lane; }
+    if (nR) { const uint32_t k = __popc(mF) + __popc(mR & lt); sm.tab[k] = make_uint4(gR - exR, PR, offR, offR + cntR); sm.own[k] = (uint8_t)(lane | 32u); }
+  }
+  __syncwarp();
+  uint32_t cum = 0, nacc = 0;
   for (uint32_t e0 = 0; e0 < E; e0 += 32) {
+    const uint32_t dF = exF - e0, dR = exR - e0;   // a list that began in an earlier step wraps to a huge value
+    const uint32_t bit = ((nF && dF < 32u) ? (1u << dF) : 0u) | ((nR && dR < 32u) ? (1u << dR) : 0u);
+    const uint32_t starts = __reduce_or_sync(kFull, bit);
     const uint32_t e = e0 + lane;
-    uint32_t lo = 0;                         // owner = first lane whose inclusive sum exceeds e
-#pragma unroll
-    for (int stp = 16; stp > 0; stp >>= 1) { const uint32_t v = __shfl_sync(kFull, incl, lo + stp - 1); if (v <= e) lo += stp; }
-    lo = min(lo, 31u);
-    const uint32_t ex_own = __shfl_sync(kFull, excl, lo), off_own = __shfl_sync(kFull, off, lo), P_own = __shfl_sync(kFull, P, lo);
-    uint32_t code = 0, id = 0;
-    if (e < E) {
-      const uint2 en = __ldg(ix.flist + off_own + (e - ex_own));
-      code = classify_bits(P_own, en.x, pw); id = en.y;
+    const uint32_t k = cum + __popc(starts & le) - 1u;      // the list of chunk e (step 0 always has a list starting at chunk 0)
+    cum += __popc(starts);
+    const bool in = e < E;
+    const uint4 t = sm.tab[k];
+    const uint32_t g = t.x + e;
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    if (in) { q0 = __ldg(fl4 + 2 * (size_t)g); q1 = __ldg(fl4 + 2 * (size_t)g + 1); }
+    const bool m0 = within_one_edit(t.y, q0.x, km), m1 = within_one_edit(t.y, q0.z, km);
+    const bool m2 = within_one_edit(t.y, q1.x, km), m3 = within_one_edit(t.y, q1.z, km);
+    const bool any = in && (m0 | m1 | m2 | m3);
+    const unsigned am = __ballot_sync(kFull, any);
+    if (am) {   // entries outside [first, end) of the list dropped, matches compacted in stream order (lane-major, then entry)
+      uint32_t mk = 0;
+      if (any) {
+        const uint32_t i0 = 4u * g;
+        const uint32_t lo = t.z > i0 ? min(t.z - i0, 4u) : 0u, hi = min(t.w - i0, 4u);
+        mk = ((m0 ? 1u : 0u) | (m1 ? 2u : 0u) | (m2 ? 4u : 0u) | (m3 ? 8u : 0u)) & ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+      }
+      const uint32_t nm = __popc(mk);
+      const unsigned b0 = __ballot_sync(kFull, nm & 1u), b1 = __ballot_sync(kFull, nm & 2u), b2 = __ballot_sync(kFull, nm & 4u);
+      uint32_t slot = nacc + __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
+      const uint8_t own = sm.own[k];
+      while (mk) {
+        const uint32_t j = (uint32_t)__ffs((int)mk) - 1u;
+        mk &= mk - 1u;
+        sm.text[slot] = j == 0 ? q0.x : (j == 1 ? q0.z : (j == 2 ? q1.x : q1.z));
+        sm.id[slot] = j == 0 ? q0.y : (j == 1 ? q0.w : (j == 2 ? q1.y : q1.w));
+        sm.meta[slot] = own;
+        ++slot;
+      }
+      nacc += __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
     }
-    const unsigned m = __ballot_sync(kFull, (code & 3u) != 0);
-    if ((code & 3u) != 0) { const uint32_t slot = nacc + __popc(m & ((1u << lane) - 1)); sm.id[slot] = id; sm.meta[slot] = (uint8_t)(lo | (code << 5)); }
-    nacc += __popc(m);
-    if (nacc + 32 > (uint32_t)kAccCap || e0 + 32 >= E) {   // flush: every lane replays its own matches, in list order
+    if (nacc && (nacc > (uint32_t)kAccCap - 128u || e0 + 32 >= E)) {   // flush
+      sm.run[0][0][lane] = 0; sm.run[0][1][lane] = 0; sm.run[1][0][lane] = 0; sm.run[1][1][lane] = 0;
       __syncwarp();
-      for (uint32_t i = 0; i < nacc && !zero; ++i) {
-        const uint32_t mt = sm.meta[i];
-        if ((mt & 31u) == lane) zero = apply_entry(mt >> 5, sm.id[i], full_search, lh);
+      for (uint32_t i = lane; i < nacc; i += 32) {   // a list's matches are contiguous: mark where each (owner, direction) run begins and ends
+        const uint32_t m = sm.meta[i];
+        const uint32_t prev = i ? sm.meta[i - 1] : 0xFFu, next = i + 1 < nacc ? sm.meta[i + 1] : 0xFFu;
+        if (m != prev) sm.run[m >> 5][0][m & 31u] = (uint16_t)i;
+        if (m != next) sm.run[m >> 5][1][m & 31u] = (uint16_t)(i + 1);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t end = sm.run[h][1][lane], P = h ? PR : PF;
+        for (uint32_t i = sm.run[h][0][lane]; i < end && !zero; ++i)
+          zero = apply_entry(classify_bits(P, sm.text[i], pw), sm.id[i], full_search, lh);
       }
       nacc = 0;
       __syncwarp();
     }
   }
+  __syncwarp();   // the table is rewritten by the next round
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -194,6 +260,29 @@ __global__ void pack_reads_kernel(DevBatch b, uint32_t* pk03, uint32_t* pk03alt,
   }
 }
 
+// one window of a read: position, strand variant, the two 9-mer keys and their lookup rows
+struct SeedWin { uint4 lf, lr; uint32_t keyf, keyr, p, var; bool active; };
+__device__ __forceinline__ SeedWin seed_window(const DevIndex& ix, const uint32_t* __restrict__ pk, const uint32_t* __restrict__ pka, uint32_t len,
+                                               uint32_t L, uint32_t pw, uint32_t npos, uint32_t step, uint32_t s0, uint32_t s1, uint32_t s2,
+                                               uint32_t v_lo, uint32_t nq, uint32_t qq) {
+  SeedWin w;
+  const uint32_t vr = (qq >= npos ? 1u : 0u) + (qq >= 2 * npos ? 1u : 0u);   // windows are variant-major; at most three variants
+  w.var = v_lo + vr; w.p = (qq - vr * npos) * step;
+  w.active = qq < nq;
+  if (w.active && step == 1) w.active = (w.p % s0 == 0) || (w.p % s1 == 0) || (w.p % s2 == 0);
+  w.keyf = w.keyr = 0;
+  w.lf = w.lr = make_uint4(0, 0, 0, 0);
+  if (w.active) {
+    uint64_t V;
+    if (w.var == kVarFwd) V = window_fwd(pk, w.p, L);
+    else V = revcomp_bits(window_fwd(w.var == kVarRevT ? pk : pka, len - w.p - L, L), L);
+    w.keyf = (uint32_t)(V >> (2 * pw)); w.keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
+    w.lf = __ldg(&ix.flookup[w.keyf]);
+    w.lr = __ldg(&ix.flookup[w.keyr]);
+  }
+  return w;
+}
+
 constexpr int kSeedWarpsPerCta = 4;
 constexpr int kLaneHitCap = 128;  // ids per window in the per-warp HBM scratch (x scale on a retry)
 
@@ -210,7 +299,7 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
   const bool full = prm.is_full_search != 0;
   CoopSmem& sm = s_coop[wic];
   LaneHits lh;
-  lh.buf = lane_hits_g + (size_t)warp * cap_g * 32 + lane; lh.stride = 32; lh.cap = cap_g;   // per-window ids live in a per-warp HBM scratch
+  lh.sbuf = &sm.ids[0][lane]; lh.buf = lane_hits_g + (size_t)warp * cap_g * 32 + lane; lh.stride = 32; lh.cap = cap_g;   // per-window ids live in a per-warp HBM scratch
   SeedStats st{0, 0};
   uint32_t n_windows = 0, n_short = 0;
   const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);
@@ -238,42 +327,33 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
     const uint32_t nvar = hasn ? 3u : 2u;
     const uint32_t v_lo = do_fwd ? 0u : 1u, v_hi = do_rev ? nvar : 1u;      // variants searched: [v_lo, v_hi)
     const uint32_t nq = (v_hi - v_lo) * npos;
+    // the lane's window of round q0: keys + both lookups (paralleltraversal.cpp:161,215), fetched one round ahead
+    SeedWin nx = seed_window(ix, pk, pka, len, L, pw, npos, step, s0, s1, s2, v_lo, nq, lane);
     for (uint32_t q0 = 0; q0 < nq; q0 += 32) {
-      const uint32_t qq = q0 + lane;
-      const uint32_t var = v_lo + qq / npos, p = (qq % npos) * step;
-      bool active = qq < nq;
-      if (active && step == 1) active = (p % s0 == 0) || (p % s1 == 0) || (p % s2 == 0);
+      const SeedWin w = nx;
+      if (q0 + 32 < nq) nx = seed_window(ix, pk, pka, len, L, pw, npos, step, s0, s1, s2, v_lo, nq, q0 + 32 + lane);
       lh.n = 0; lh.overflow = false;
-      uint32_t keyf = 0, keyr = 0;
-      uint4 lk_f = make_uint4(0, 0, 0, 0);
-      if (active) {
-        uint64_t V;
-        if (var == kVarFwd) V = window_fwd(pk, p, L);
-        else V = revcomp_bits(window_fwd(var == kVarRevT ? pk : pka, len - p - L, L), L);
-        keyf = (uint32_t)(V >> (2 * pw)); keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
-        lk_f = __ldg(&ix.flookup[keyf]);                                        // paralleltraversal.cpp:161
-        ++n_windows;
-      }
+      n_windows += w.active ? 1u : 0u;
       bool zero = false;
-      // sub-search (a): exact first half, <= 1 error in the second half (P = w[9..18) ascending)
-      coop_flat<INSTR>(ix, sm, lk_f.x, lk_f.y, rev_chars(keyr, pw), full, lh, zero, st);
-      // sub-search (b), only without a 0-error hit (:188): exact second half, <= 1 error in the reversed first half
-      uint4 lk_r = make_uint4(0, 0, 0, 0);
-      if (active && !zero) lk_r = __ldg(&ix.flookup[keyr]);                      // :215
-      coop_flat<INSTR>(ix, sm, lk_r.z, lk_r.w, keyf, full, lh, zero, st);
+      // (a) exact first half, <= 1 error in the second half (P = w[9..18) ascending); (b) exact second half, <= 1 error in the reversed first half
+      coop_stream<INSTR>(ix, sm, w.lf.x, w.lf.y, rev_chars(w.keyr, pw), w.lr.z, w.lr.w, w.keyf, full, lh, zero, st);
       if (lh.overflow) flags |= kOvfSeedLane;
       const uint32_t n = lh.overflow ? 0u : lh.n;
-      const uint32_t incl = warp_incl_scan_u32(n), tot = __shfl_sync(kFull, incl, 31);
-      if (total + tot > region_cap) { flags |= kOvfSeedRegion; }
-      else {
-        const size_t base = region + total + incl - n;
-        for (uint32_t k = 0; k < n; ++k) {
-          const uint32_t id = lh.buf[k * lh.stride];
-          b.hits[base + k] = make_uint2(id, p | (var << 24) | (pass_class(p, s0, s1, s2) << 28));
-          cost += __ldg(ix.pos_off + id + 1) - __ldg(ix.pos_off + id);
+      const unsigned hm = __ballot_sync(kFull, n != 0);
+      if (hm) {
+        const uint32_t incl = warp_incl_scan_u32(n), tot = __shfl_sync(kFull, incl, 31);
+        if (total + tot > region_cap) { flags |= kOvfSeedRegion; }
+        else if (n) {
+          const size_t base = region + total + incl - n;
+          const uint32_t tag = w.p | (w.var << 24) | (pass_class(w.p, s0, s1, s2) << 28);
+          for (uint32_t k = 0; k < n; ++k) {
+            const uint32_t id = lh_get(lh, k);
+            b.hits[base + k] = make_uint2(id, tag);
+            cost += __ldg(ix.pos_off + id + 1) - __ldg(ix.pos_off + id);
+          }
         }
+        total += tot;
       }
-      total += tot;
       __syncwarp();
     }
     flags = __reduce_or_sync(kFull, flags);
@@ -320,18 +400,17 @@ seed_debug_kernel(DevIndex ix, const uint8_t* seq03, const uint32_t* seq_off, co
     const uint8_t* sq = seq03 + seq_off[win_read[k]] + win_pos[k];
     for (uint32_t i = 0; i < ix.lnwin; ++i) V = (V << 2) | (sq[i] & 3u);
   }
-  LaneHits lh; lh.buf = ids + (size_t)(active ? k : 0) * cap; lh.stride = 1; lh.cap = active ? cap : 0; lh.n = 0; lh.overflow = false;
+  CoopSmem& sm = s_coop[threadIdx.x >> 5];
+  LaneHits lh; lh.sbuf = &sm.ids[0][threadIdx.x & 31]; lh.buf = ids + (size_t)(active ? k : 0) * cap; lh.stride = 1; lh.cap = active ? cap : 0; lh.n = 0; lh.overflow = false;
   SeedStats st{0, 0};
   bool z = false;
   const bool full = full_search != 0;
   const uint32_t keyf = (uint32_t)(V >> (2 * pw)), keyr = (uint32_t)(V & ((1ull << (2 * pw)) - 1));
   const uint32_t Pf = rev_chars(keyr, pw), Pr = keyf;
   if (mode == 0) {
-    CoopSmem& sm = s_coop[threadIdx.x >> 5];
     const uint4 lf = active ? __ldg(&ix.flookup[keyf]) : make_uint4(0, 0, 0, 0);
-    coop_flat<false>(ix, sm, lf.x, lf.y, Pf, full, lh, z, st);
-    const uint4 lr = (active && !z) ? __ldg(&ix.flookup[keyr]) : make_uint4(0, 0, 0, 0);
-    coop_flat<false>(ix, sm, lr.z, lr.w, Pr, full, lh, z, st);
+    const uint4 lr = active ? __ldg(&ix.flookup[keyr]) : make_uint4(0, 0, 0, 0);
+    coop_stream<false>(ix, sm, lf.x, lf.y, Pf, lr.z, lr.w, Pr, full, lh, z, st);
   } else if (active) {
     const uint4 lf = __ldg(&ix.flookup[keyf]);
     for (uint32_t i = 0; i < lf.y && !z; ++i) { const uint2 en = __ldg(ix.flist + lf.x + i); z = apply_entry(classify_bits(Pf, en.x, pw), en.y, full, lh); }
@@ -340,7 +419,10 @@ seed_debug_kernel(DevIndex ix, const uint8_t* seq03, const uint32_t* seq_off, co
       for (uint32_t i = 0; i < lr.w && !z; ++i) { const uint2 en = __ldg(ix.flist + lr.z + i); z = apply_entry(classify_bits(Pr, en.x, pw), en.y, full, lh); }
     }
   }
-  if (active) { counts[k] = lh.n; zero[k] = z ? 1 : 0; }
+  if (active) {
+    counts[k] = lh.n; zero[k] = z ? 1 : 0;
+    for (uint32_t f = 0; f < lh.n && f < lh.cap && f < kLaneSmemIds; ++f) lh.buf[f] = lh.sbuf[f * 32];   // the ids kept in shared memory
+  }
 }
 
 }  // namespace smr

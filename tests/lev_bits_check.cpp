@@ -72,6 +72,7 @@ int main(int argc, char** argv) {
     const uint32_t want = (uint32_t)(e7 ? 1 : (e8 ? 2 : (e9 ? 3 : 0))) | (memcmp(T, p, 9) == 0 ? 4u : 0u);
     if ((uint32_t)(d1 | z) != want) m1++;
     if (smr::classify_bits(Pb, Tb, pw) != want) m2++;
+    if (smr::within_one_edit(Pb, Tb, smr::lev_masks(pw)) != ((want & 3u) != 0)) m2++;   // the seed kernel's streaming test
     for (int k = 1; k <= 8; k++) {
       int v = 0;
       for (int j = 0; j <= 9; j++) if (ed(T, k, p, j) <= 1) v = 1;
