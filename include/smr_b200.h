@@ -133,6 +133,17 @@ int smr_load_index_part(smr_ctx*, uint32_t index_num, uint32_t part,
                         const void* pos_file, size_t pos_bytes,
                         const uint8_t* refseq_cat, const uint64_t* ref_off, uint32_t nref,
                         uint32_t lnwin, uint32_t minimal_score, const uint32_t skiplengths[3]);
+/* Index build on the device: what smr_build_index + smr_load_index_part do for every part of the index of
+ * `fasta_path`, without the files -- the FASTA is parsed on the host (records, alphabet maps, the part split rule of
+ * indexdb.cpp:1381-1431), then windows, unique L-mers, position lists and the burst-trie order of every list are computed on the
+ * device with sorts (sortmerna_b200/csrc/smr_build_dev.cuh) and stay resident.  Replaces build_index (src/sortmerna/indexdb.cpp:
+ * 1119-2095) + Index::load (index.cpp:143-357) + References::load (references.cpp:55-154) for this index.  The arrays equal those
+ * smr_load_index_part makes from the reference builder's files up to the numbering of the L-mer ids.
+ * *nparts = parts made (ordinals continue the context's part list); report6 as for smr_build_index (nodes: 0). */
+int smr_build_index_device(smr_ctx*, uint32_t index_num, const char* fasta_path, uint32_t lnwin, uint32_t interval, uint32_t max_pos, double max_mb,
+                           const uint32_t skiplengths[3], uint32_t minimal_score, uint32_t* nparts, uint64_t report6[6]);
+/* Test hook: resident array `which` of loaded part `slot` (0 flookup, 1 flist, 2 pos_off, 3 pos, 4 refseq, 5 ref_off). */
+int smr_debug_index_array(smr_ctx*, uint32_t slot, uint32_t which, void* out, uint64_t cap_bytes, uint64_t* nbytes);
 /* refstats.minimal_score depends on the read set (refstats.cpp:247-265): update without reloading */
 int smr_set_minimal_score(smr_ctx*, uint32_t index_num, uint32_t minimal_score);
 int smr_set_params(smr_ctx*, const smr_params*);
@@ -177,8 +188,8 @@ int smr_upload_fastx(smr_ctx*, const char* text, uint64_t nbytes, uint32_t* nrea
  * inflate of the reference's read feed (Readfeed::next_gz, src/sortmerna/readfeed.cpp:683-770, izlib.cpp / rapidgzip): the
  * compressed bytes are copied to the device and inflated there -- block starts found speculatively in every 64 KB of the file, one
  * decoder thread per span, back-references into not-yet-known history resolved in a second step (sortmerna_b200/csrc/smr_inflate.h)
- * -- then decoded as in smr_upload_fastx.  A corrupt or truncated file fails with SMR_ERR_ARG (invalid code / header / distance,
- * ISIZE mismatch); the CRC32 of the members is not checked. */
+ * -- then decoded as in smr_upload_fastx.  The CRC-32 and ISIZE of every member are checked on the inflated bytes; a corrupt or
+ * truncated file fails with SMR_ERR_ARG. */
 int smr_upload_fastx_gz(smr_ctx*, const void* gz, uint64_t nbytes, uint32_t* nreads);
 /* The text behind the resident batch (what smr_upload_fastx was given / what smr_upload_fastx_gz inflated): *nbytes = its size;
  * copied to `text` when that is not null (cap bytes available).  header_text_off of smr_resident_layout indexes it. */

@@ -26,7 +26,8 @@ SYMBOLS = ["smr_init", "smr_destroy", "smr_last_error", "smr_device_count", "smr
            "smr_set_minimal_score", "smr_set_params", "smr_index_info", "smr_align_batch", "smr_upload_batch",
            "smr_run_resident", "smr_download_results", "smr_last_timings", "smr_debug_seed_windows", "smr_debug_ssw",
            "smr_debug_dpx_peak", "smr_set_stats_buffer", "smr_build_index", "smr_upload_fastx", "smr_resident_layout", "smr_pack_kvdb_blobs",
-           "smr_set_aln_slots", "smr_aln_slots", "smr_aln_slots_needed"]
+           "smr_set_aln_slots", "smr_aln_slots", "smr_aln_slots_needed", "smr_upload_fastx_gz", "smr_resident_text", "smr_debug_inflate",
+           "smr_build_index_device", "smr_debug_index_array"]
 
 CNT_NAMES = ("num_aligned", "num_short", "sw_calls", "sw_cells", "windows", "trie_nodes", "buckets",
              "bucket_entries", "pos_entries", "lis_calls", "dbg_max_read_cycles", "dbg_sum_read_cycles", "dbg_lis_kernel_cycles",
@@ -185,6 +186,37 @@ class Aligner:
         self.n_index_files = max(self.n_index_files, index_num + 1)
         self.refs_by_index[index_num] = refs
 
+    def build_index_device(self, index_num: int, fasta: str, refs=None, minimal_score: int = 0, skiplengths=(18, 9, 3), lnwin: int = 18,
+                           interval: int = 1, max_pos: int = 10000, max_mb: float = 3072.0) -> int:
+        """smr_build_index_device: the index of `fasta` built on the device and kept resident (every part); returns the number of
+        parts.  refs: what the result formatters use for this index (a References, or the per-part list of hostio.split_by_parts)."""
+        sk = (C.c_uint32 * 3)(*skiplengths)
+        nparts = C.c_uint32(0)
+        rep = (C.c_uint64 * 6)()
+        self.L.smr_build_index_device.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_void_p, C.c_uint32,
+                                                  C.c_void_p, C.c_void_p]
+        rc = self.L.smr_build_index_device(self.h, index_num, os.fsencode(fasta), lnwin, interval, max_pos, float(max_mb), C.cast(sk, C.c_void_p), minimal_score,
+                                           C.cast(C.byref(nparts), C.c_void_p), C.cast(rep, C.c_void_p))
+        self._check(rc, f"smr_build_index_device({fasta})")
+        self.n_index_files = max(self.n_index_files, index_num + 1)
+        if refs is not None:
+            self.refs_by_index[index_num] = refs
+        self.last_build_report = dict(zip(("parts", "numseq", "windows", "unique_lmers", "trie_nodes", "hbm_bytes"), (int(x) for x in rep)))
+        return int(nparts.value)
+
+    def index_array(self, slot: int, which: str) -> np.ndarray:
+        """smr_debug_index_array: a resident array of loaded part `slot` (flookup u32x4 rows, flist {text,id}, pos_off, pos {pos,seq}, refseq, ref_off)."""
+        k = ("flookup", "flist", "pos_off", "pos", "refseq", "ref_off").index(which)
+        nb = C.c_uint64(0)
+        self._check(self.L.smr_debug_index_array(self.h, C.c_uint32(slot), C.c_uint32(k), C.c_void_p(0), C.c_uint64(0), C.byref(nb)), "smr_debug_index_array")
+        out = np.zeros(int(nb.value), np.uint8)
+        if out.size:
+            self._check(self.L.smr_debug_index_array(self.h, C.c_uint32(slot), C.c_uint32(k), _ptr(out), C.c_uint64(out.size), C.byref(nb)), "smr_debug_index_array")
+        if which == "refseq":
+            return out
+        a = out.view(np.uint32)
+        return a.reshape(-1, {"flookup": 4, "flist": 2, "pos": 2}.get(which, 1)) if which in ("flookup", "flist", "pos") else a
+
     def set_minimal_score(self, index_num: int, score: int):
         self._check(self.L.smr_set_minimal_score(self.h, C.c_uint32(index_num), C.c_uint32(score)), "smr_set_minimal_score")
 
@@ -255,6 +287,38 @@ class Aligner:
         self._check(self.L.smr_upload_fastx(self.h, _ptr(buf), C.c_uint64(buf.size), C.byref(n)), "smr_upload_fastx")
         self._n_resident = int(n.value)
         return self._n_resident
+
+    def upload_fastx_gz(self, gz: bytes) -> int:
+        """smr_upload_fastx_gz: the bytes of a .fastq.gz / .fasta.gz; gzip inflate, record split and 0-4 encoding run on the device."""
+        n = C.c_uint32(0)
+        buf = np.frombuffer(gz, dtype=np.uint8)
+        self._check(self.L.smr_upload_fastx_gz(self.h, _ptr(buf), C.c_uint64(buf.size), C.byref(n)), "smr_upload_fastx_gz")
+        self._n_resident = int(n.value)
+        return self._n_resident
+
+    def resident_text(self) -> bytes:
+        """smr_resident_text: the (inflated) text behind the resident batch; header offsets of resident_layout() index it."""
+        nb = C.c_uint64(0)
+        self._check(self.L.smr_resident_text(self.h, C.c_void_p(0), C.c_uint64(0), C.byref(nb)), "smr_resident_text")
+        out = np.zeros(int(nb.value), np.uint8)
+        if out.size:
+            self._check(self.L.smr_resident_text(self.h, _ptr(out), C.c_uint64(out.size), C.byref(nb)), "smr_resident_text")
+        return out.tobytes()
+
+    def debug_inflate(self, gz: bytes, chunk_bytes: int = 65536, cap: int = 0):
+        """smr_debug_inflate: (inflated bytes, {spans, candidates, device_us, h2d_us})."""
+        buf = np.frombuffer(gz, dtype=np.uint8)
+        nb = C.c_uint64(0)
+        info = (C.c_uint32 * 4)()
+        self._check(self.L.smr_debug_inflate(self.h, _ptr(buf), C.c_uint64(buf.size), C.c_uint64(chunk_bytes), C.c_void_p(0), C.c_uint64(0), C.byref(nb), info),
+                    "smr_debug_inflate")
+        out = np.zeros(int(nb.value), np.uint8)
+        if out.size:   # the inflated text is still in the context's buffer
+            nb2 = C.c_uint64(0)
+            self.L.smr_resident_text.restype = C.c_int
+            self._check(self.L.smr_debug_inflate(self.h, _ptr(buf), C.c_uint64(buf.size), C.c_uint64(chunk_bytes), _ptr(out), C.c_uint64(out.size), C.byref(nb2), info),
+                        "smr_debug_inflate")
+        return out.tobytes(), {"spans": info[0], "candidates": info[1], "device_us": info[2], "h2d_us": info[3]}
 
     def resident_layout(self, with_headers: bool = True, with_seq: bool = True):
         """smr_resident_layout: (header offsets in the uploaded text, read offsets, concatenated 0-4 codes) of the resident batch."""

@@ -50,7 +50,6 @@ struct TriePool {
   uint32_t new_bucket() { buckets.emplace_back(); return (uint32_t)buckets.size() - 1; }
 };
 
-struct Record { std::string name; size_t rec_start, rec_end; std::vector<uint8_t> seq; };
 
 // search_burst_trie + insert_prefix (indexdb.cpp:402-451,147-304) in one walk.
 // c(k) = k-th character of the (partialwin+1)-character tail.  Returns the id stored with the entry.
@@ -143,11 +142,11 @@ bool write_file(const std::string& path, const void* p, size_t n, std::string& e
 
 }  // namespace
 
-std::string build_index_files(const std::string& fasta, const std::string& prefix, const BuildOptions& opt, BuildReport* rep) {
-  const uint32_t L = opt.lnwin, pread = L + 1, half = L / 2;
-  if (L < 8 || L > 26 || (L & 1)) return "unsupported seed length";
-  if (opt.interval == 0) return "interval must be >= 1";
-  std::string err;
+// STEP 1 of build_index (indexdb.cpp:1188-1271): records, nucleotide distribution, total length.  seq = the builder's 2-bit codes
+// (map_nt); seq04 (optional) = the same characters in the aligner's 0..4 alphabet (nt_table, common.hpp:68-77).
+std::string parse_reference_fasta(const std::string& fasta, uint32_t pread, bool want04, std::vector<RefRecord>& recs, double freq[4], uint64_t& full_len,
+                                  size_t& file_size) {
+  static const struct Nt04 { uint8_t m[256]; Nt04() { memset(m, 4, sizeof(m)); const char* a = "AaCcGgTtUu"; const uint8_t v[10] = {0, 0, 1, 1, 2, 2, 3, 3, 3, 3}; for (int i = 0; i < 10; ++i) m[(uint8_t)a[i]] = v[i]; } } k04;
   std::vector<char> file;
   {
     std::ifstream in(fasta, std::ios::binary | std::ios::ate);
@@ -156,15 +155,12 @@ std::string build_index_files(const std::string& fasta, const std::string& prefi
     in.seekg(0);
     if (!file.empty()) in.read(file.data(), (std::streamsize)file.size());
   }
-  // STEP 1 (indexdb.cpp:1188-1271): records, nucleotide distribution, total length
-  std::vector<Record> recs;
-  double freq[4] = {0, 0, 0, 0};
-  uint64_t full_len = 0;
   size_t o = 0;
   const size_t n = file.size();
+  file_size = n;
   if (n == 0) return "empty reference file";
   while (o < n) {
-    Record r;
+    RefRecord r;
     r.rec_start = o;
     if (file[o] != '>') return "Each read header of the database fasta file must begin with '>'; check sequence # " + std::to_string(2 * recs.size());
     ++o;
@@ -178,6 +174,7 @@ std::string build_index_files(const std::string& fasta, const std::string& prefi
       const char c = file[o++];
       if (c != '\n' && c != ' ') {
         r.seq.push_back(kMap.m[(uint8_t)c]);
+        if (want04) r.seq04.push_back(k04.m[(uint8_t)c]);
         if (c != 'N') freq[kMap.m[(uint8_t)c]] += 1.0;
       }
     }
@@ -188,6 +185,41 @@ std::string build_index_files(const std::string& fasta, const std::string& prefi
              ", please filter out all sequences shorter than " + std::to_string(pread) + " to continue index construction.";
     recs.push_back(std::move(r));
   }
+  return std::string();
+}
+
+// which sequences go into the part that starts at record `first` (indexdb.cpp:1381-1431): 9.5e-6 MB per window, a sequence that does
+// not fit alone is skipped.  members empty + no error: nothing but oversized sequences was left.
+std::string next_index_part(const std::vector<RefRecord>& recs, size_t first, uint32_t pread, double max_mb, std::vector<size_t>& members, size_t& next,
+                            uint64_t& start_part, uint64_t& seq_part_size) {
+  members.clear();
+  double index_size = 0;
+  next = first;
+  seq_part_size = 0;
+  start_part = recs[first].rec_start;
+  for (; next < recs.size(); ++next) {
+    const double est = (double)(recs[next].seq.size() - pread + 1) * 9.5e-6;
+    if (est > max_mb) continue;
+    if (index_size + est > max_mb) break;
+    index_size += est;
+    seq_part_size = recs[next].rec_end - start_part;
+    members.push_back(next);
+  }
+  if (members.empty() && next < recs.size())
+    return "no index was created, all of your sequences are too large to be indexed with the current memory limit";
+  return std::string();
+}
+
+std::string build_index_files(const std::string& fasta, const std::string& prefix, const BuildOptions& opt, BuildReport* rep) {
+  const uint32_t L = opt.lnwin, pread = L + 1, half = L / 2;
+  if (L < 8 || L > 26 || (L & 1)) return "unsupported seed length";
+  if (opt.interval == 0) return "interval must be >= 1";
+  std::string err;
+  std::vector<RefRecord> recs;
+  double freq[4] = {0, 0, 0, 0};
+  uint64_t full_len = 0;
+  size_t n = 0;
+  if (!(err = parse_reference_fasta(fasta, pread, false, recs, freq, full_len, n)).empty()) return err;
   const uint32_t limit = 1u << L;
   const uint32_t mask32 = limit - 1;
   const uint32_t burst_depth = pread - half - 3;
@@ -200,24 +232,11 @@ std::string build_index_files(const std::string& fasta, const std::string& prefi
   size_t first = 0;
   uint16_t part_num = 0;
   while (first < recs.size()) {
-    // which sequences go into this part (indexdb.cpp:1381-1431): 9.5e-6 MB per window, a sequence that does not fit alone is skipped
     std::vector<size_t> members;
-    double index_size = 0;
     size_t next = first;
-    uint64_t seq_part_size = 0;
-    const uint64_t start_part = recs[first].rec_start;
-    for (; next < recs.size(); ++next) {
-      const double est = (double)(recs[next].seq.size() - pread + 1) * 9.5e-6;
-      if (est > opt.max_mb) continue;
-      if (index_size + est > opt.max_mb) break;
-      index_size += est;
-      seq_part_size = recs[next].rec_end - start_part;
-      members.push_back(next);
-    }
-    if (members.empty()) {
-      if (next >= recs.size()) break;   // only oversized sequences were left
-      return "no index was created, all of your sequences are too large to be indexed with the current memory limit";
-    }
+    uint64_t seq_part_size = 0, start_part = 0;
+    if (!(err = next_index_part(recs, first, pread, opt.max_mb, members, next, start_part, seq_part_size)).empty()) return err;
+    if (members.empty()) break;   // only oversized sequences were left
     // Mini tries are independent per 9-mer, and forward / reverse tries are independent of each other apart from the ids:
     // worker t of T owns the 9-mers k with k % T == t, once for the forward and once for the reverse tries (2T threads).
     // Forward workers number new L-mers locally (made global by a per-worker base afterwards -- still a bijection onto
@@ -395,7 +414,7 @@ std::string build_index_files(const std::string& fasta, const std::string& prefi
   for (const PartStat& p : parts) put(&p, sizeof(PartStat));
   const uint32_t num_sq = (uint32_t)recs.size();
   put(&num_sq, 4);
-  for (const Record& r : recs) {
+  for (const RefRecord& r : recs) {
     const uint32_t len_id = (uint32_t)r.name.size(), slen = (uint32_t)r.seq.size();
     put(&len_id, 4);
     put(r.name.data(), len_id);

@@ -19,6 +19,13 @@ struct BuildReport {
   uint64_t numseq = 0, windows = 0, unique_lmers = 0, trie_nodes = 0, bytes_written = 0;
 };
 
+// One record of the reference FASTA as the builder sees it.
+struct RefRecord { std::string name; size_t rec_start = 0, rec_end = 0; std::vector<uint8_t> seq, seq04; };
+std::string parse_reference_fasta(const std::string& fasta, uint32_t pread, bool want04, std::vector<RefRecord>& recs, double freq[4], uint64_t& full_len,
+                                  size_t& file_size);
+std::string next_index_part(const std::vector<RefRecord>& recs, size_t first, uint32_t pread, double max_mb, std::vector<size_t>& members, size_t& next,
+                            uint64_t& start_part, uint64_t& seq_part_size);
+
 // Writes <prefix>.kmer_P.dat, .bursttrie_P.dat, .pos_P.dat for every part P and <prefix>.stats.
 // Returns the empty string on success, else the error text (the reference prints it and exits).
 std::string build_index_files(const std::string& fasta, const std::string& prefix, const BuildOptions& opt, BuildReport* report);

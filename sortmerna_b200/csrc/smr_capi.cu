@@ -13,6 +13,8 @@
 
 #include "smr_decode.cuh"
 #include "smr_inflate.cuh"
+#include "smr_build.h"
+#include "smr_build_dev.cuh"
 #include "smr_final.cuh"
 #include "smr_index.h"
 
@@ -23,7 +25,7 @@ namespace {
 struct Part {
   DevIndex d{};
   std::vector<void*> owned;   // device allocations
-  size_t bytes = 0, n_nodes = 0, n_entries = 0, n_ids = 0, n_pos = 0;
+  size_t bytes = 0, n_nodes = 0, n_entries = 0, n_ids = 0, n_pos = 0, n_refseq = 0;
 };
 
 struct DevBuf {
@@ -61,7 +63,7 @@ struct smr_ctx {
   PinBuf h_state, h_flags, h_hitdb, h_outaln, h_stats, h_cigar, h_off32, h_pkoff;
   std::vector<uint64_t> h_coff;
   DevBuf d_text, d_cnt, d_scal, d_nl, d_hdr, d_sb, d_rec, d_spos, d_hdroff, scan_sums;   // input decode (smr_decode.cuh)
-  DevBuf d_gz, d_cand, d_res, d_sym, d_win, d_ids, d_off, d_cnt64;   // gz inflate (smr_inflate.cuh)
+  DevBuf d_gz, d_cand, d_res, d_sym, d_win, d_ids, d_off, d_cnt64, d_moff, d_mem, d_poff, d_plen, d_pcrc;   // gz inflate (smr_inflate.cuh)
   uint64_t text_bytes = 0;          // size of the text behind the resident batch (smr_upload_fastx / _gz)
   uint32_t inf_spans = 0, inf_candidates = 0; double t_inflate = 0;
   bool device_only_reads = false;   // the resident batch was decoded on the device: no host copy of the sequences yet
@@ -123,6 +125,129 @@ int upload_vec(smr_ctx* ctx, Part& pt, const std::vector<T>& v, const T** out) {
   if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   pt.owned.push_back(d); pt.bytes += bytes;
   *out = (const T*)d;
+  return SMR_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// index build on the device (smr_build_dev.cuh): orchestration of one part
+// ---------------------------------------------------------------------------------------------------------------------
+struct TempPool {   // device scratch of one build, freed on return
+  std::vector<void*> v;
+  ~TempPool() { for (void* p : v) cudaFree(p); }
+  template <class T> cudaError_t get(T** out, size_t n) { void* p = nullptr; cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); if (e == cudaSuccess) v.push_back(p); *out = (T*)p; return e; }
+};
+
+int build_part_device(smr_ctx* ctx, const std::vector<RefRecord>& recs, const std::vector<size_t>& members, const BuildOptions& opt, Part& pt) {
+  BuildGeom g{};
+  g.L = opt.lnwin; g.half = g.L / 2; g.pread = g.L + 1; g.interval = opt.interval; g.max_pos = opt.max_pos; g.burst_depth = g.pread - g.half - 3;
+  g.nseq = (uint32_t)members.size();
+  const uint32_t list_bits = 2 * g.half + 1, key_bits = list_bits + 2 * g.burst_depth;
+  if (key_bits > 64 || 2 * g.pread > 62 || 2 * (g.half + 1) > 32) { ctx->err = "seed length too large for the device builder"; return SMR_ERR_UNSUPPORTED; }
+  // host: concatenated builder codes + 0..4 codes, offsets, first window of every sequence
+  std::vector<uint64_t> soff(g.nseq + 1, 0);
+  std::vector<uint32_t> wstart(g.nseq + 1, 0);
+  uint64_t total_win = 0;
+  for (uint32_t k = 0; k < g.nseq; ++k) {
+    const size_t len = recs[members[k]].seq.size();
+    soff[k + 1] = soff[k] + len;
+    total_win += (len - g.pread + g.interval) / g.interval;
+    if (total_win >= (1ull << 31)) { ctx->err = "more than 2^31 windows in one index part"; return SMR_ERR_UNSUPPORTED; }
+    wstart[k + 1] = (uint32_t)total_win;
+  }
+  if (soff[g.nseq] >= 0xFFFFFFFFull) { ctx->err = "reference part larger than 4 GB"; return SMR_ERR_UNSUPPORTED; }
+  g.nwin = (uint32_t)total_win;
+  std::vector<uint8_t> codes(soff[g.nseq]), c04(soff[g.nseq] + 64, 4);
+  for (uint32_t k = 0; k < g.nseq; ++k) {
+    const RefRecord& r = recs[members[k]];
+    memcpy(codes.data() + soff[k], r.seq.data(), r.seq.size());
+    memcpy(c04.data() + soff[k], r.seq04.data(), r.seq04.size());
+  }
+  std::vector<uint32_t> roff(g.nseq + 1);
+  for (uint32_t k = 0; k <= g.nseq; ++k) roff[k] = (uint32_t)soff[k];
+  TempPool tp;
+  cudaStream_t st = ctx->stream;
+  const uint32_t n = g.nwin;
+  const unsigned tb = 256, gw = (n + tb - 1) / tb;
+  uint8_t* d_codes; uint64_t* d_soff; uint32_t* d_wstart;
+  CK(tp.get(&d_codes, codes.size() + 64)); CK(tp.get(&d_soff, soff.size())); CK(tp.get(&d_wstart, wstart.size()));
+  CK(cudaMemcpyAsync(d_codes, codes.data(), codes.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_soff, soff.data(), soff.size() * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_wstart, wstart.data(), wstart.size() * 4, cudaMemcpyHostToDevice, st));
+  uint64_t *keyA, *keyB; uint32_t *valA, *valB, *u0, *u1, *u2, *u3, *win_id;
+  CK(tp.get(&keyA, n)); CK(tp.get(&keyB, n)); CK(tp.get(&valA, n)); CK(tp.get(&valB, n));
+  CK(tp.get(&u0, n)); CK(tp.get(&u1, n)); CK(tp.get(&u2, n)); CK(tp.get(&u3, n)); CK(tp.get(&win_id, n));
+  // cub scratch, sized for the largest call (entries: at most 2n)
+  size_t cub_bytes = 0, need = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, 2 * (size_t)n, 0, 64, st); cub_bytes = std::max(cub_bytes, need);
+  cub::DeviceScan::InclusiveSum(nullptr, need, (uint32_t*)nullptr, (uint32_t*)nullptr, 2 * (size_t)n, st); cub_bytes = std::max(cub_bytes, need);
+  cub::DeviceScan::InclusiveScan(nullptr, need, (uint32_t*)nullptr, (uint32_t*)nullptr, cub::Max(), 2 * (size_t)n, st); cub_bytes = std::max(cub_bytes, need);
+  uint8_t* d_cub; CK(tp.get(&d_cub, cub_bytes + 256));
+  // 1. windows sorted by value (stable: equal values keep scan order)
+  bld_windows_kernel<<<gw, tb, 0, st>>>(d_codes, d_soff, d_wstart, g, keyA, valA);
+  CK(cudaGetLastError());
+  need = cub_bytes; CK(cub::DeviceRadixSort::SortPairs(d_cub, need, keyA, keyB, valA, valB, (size_t)n, 0, (int)(2 * g.pread), st));
+  // 2. distinct (L+1)-mers, ids of the L-mers
+  bld_heads_kernel<<<gw, tb, 0, st>>>(keyB, n, u0, u1);
+  CK(cudaGetLastError());
+  need = cub_bytes; CK(cub::DeviceScan::InclusiveSum(d_cub, need, u0, u2, (size_t)n, st));
+  need = cub_bytes; CK(cub::DeviceScan::InclusiveSum(d_cub, need, u1, u3, (size_t)n, st));
+  uint32_t nent = 0, nids = 0;
+  CK(cudaMemcpyAsync(&nent, u2 + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&nids, u3 + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint32_t E = 2 * nent;
+  uint32_t *e_list, *e_pref, *e_text, *e_id, *e_arr, *e_tpar; uint8_t* e_leaf;
+  CK(tp.get(&e_list, E)); CK(tp.get(&e_pref, E)); CK(tp.get(&e_text, E)); CK(tp.get(&e_id, E)); CK(tp.get(&e_arr, E)); CK(tp.get(&e_tpar, E)); CK(tp.get(&e_leaf, E));
+  CK(cudaMemsetAsync(e_tpar, 0, (size_t)E * 4, st)); CK(cudaMemsetAsync(e_leaf, 0, E, st));
+  bld_entries_kernel<<<gw, tb, 0, st>>>(keyB, valB, u0, u2, u3, g, nent, win_id, e_list, e_pref, e_text, e_id, e_arr);
+  CK(cudaGetLastError());
+  // 3. positions (persistent arrays)
+  auto keep_alloc = [&](void** out, size_t bytes) -> cudaError_t { cudaError_t e = cudaMalloc(out, bytes + 64); if (e == cudaSuccess) { pt.owned.push_back(*out); pt.bytes += bytes + 64; e = cudaMemsetAsync(*out, 0, bytes + 64, st); } return e; };
+  bld_poskeys_kernel<<<gw, tb, 0, st>>>(win_id, n, keyA);
+  CK(cudaGetLastError());
+  need = cub_bytes; CK(cub::DeviceRadixSort::SortKeys(d_cub, need, keyA, keyB, (size_t)n, 0, 64, st));
+  bld_posflag_kernel<<<gw, tb, 0, st>>>(keyB, n, u0);
+  CK(cudaGetLastError());
+  need = cub_bytes; CK(cub::DeviceScan::InclusiveScan(d_cub, need, u0, u1, cub::Max(), (size_t)n, st));
+  bld_poskeep_kernel<<<gw, tb, 0, st>>>(u1, n, g.max_pos, u2);
+  CK(cudaGetLastError());
+  need = cub_bytes; CK(cub::DeviceScan::InclusiveSum(d_cub, need, u2, u3, (size_t)n, st));
+  uint32_t npos = 0;
+  CK(cudaMemcpyAsync(&npos, u3 + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  void *p_posoff = nullptr, *p_pos = nullptr, *p_flist = nullptr, *p_flookup = nullptr, *p_ref = nullptr, *p_roff = nullptr;
+  CK(keep_alloc(&p_posoff, ((size_t)nids + 1) * 4)); CK(keep_alloc(&p_pos, (size_t)npos * 8));
+  bld_poswrite_kernel<<<gw, tb, 0, st>>>(keyB, u1, u2, u3, d_wstart, g, nids, (uint32_t*)p_posoff, (uint2*)p_pos);
+  CK(cudaGetLastError());
+  // 4. burst-trie order of the entries: first occurrence order, then one stable sort + one decision pass per level
+  const unsigned ge = (E + tb - 1) / tb;
+  uint64_t *ekA, *ekB; uint32_t *pA, *pB;
+  CK(tp.get(&ekA, E)); CK(tp.get(&ekB, E)); CK(tp.get(&pA, E)); CK(tp.get(&pB, E));
+  bld_arrkey_kernel<<<ge, tb, 0, st>>>(e_arr, E, ekA, pA);
+  CK(cudaGetLastError());
+  need = cub_bytes; CK(cub::DeviceRadixSort::SortPairs(d_cub, need, ekA, ekB, pA, pB, (size_t)E, 0, 32, st));
+  for (uint32_t d = 1; d <= g.burst_depth; ++d) {
+    bld_levelkey_kernel<<<ge, tb, 0, st>>>(pB, e_list, e_pref, e_leaf, E, d, g.burst_depth, ekA, pA);
+    CK(cudaGetLastError());
+    need = cub_bytes; CK(cub::DeviceRadixSort::SortPairs(d_cub, need, ekA, ekB, pA, pB, (size_t)E, 0, (int)key_bits, st));
+    if (d < g.burst_depth) { bld_level_kernel<<<ge, tb, 0, st>>>(ekB, pB, E, d, e_arr, e_tpar, e_leaf); CK(cudaGetLastError()); }
+  }
+  // 5. the lists and their lookup rows
+  const size_t nk = (size_t)1 << (2 * g.half);
+  CK(keep_alloc(&p_flist, (size_t)E * 8)); CK(keep_alloc(&p_flookup, nk * 16));
+  bld_flist_kernel<<<ge, tb, 0, st>>>(pB, e_list, e_text, e_id, E, (uint2*)p_flist, (uint32_t*)p_flookup, 0);
+  bld_flist_kernel<<<ge, tb, 0, st>>>(pB, e_list, e_text, e_id, E, (uint2*)p_flist, (uint32_t*)p_flookup, 1);
+  CK(cudaGetLastError());
+  // 6. references for the Smith-Waterman side
+  CK(keep_alloc(&p_ref, c04.size())); CK(keep_alloc(&p_roff, roff.size() * 4));
+  CK(cudaMemcpyAsync(p_ref, c04.data(), c04.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(p_roff, roff.data(), roff.size() * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  pt.d.lnwin = g.L; pt.d.partialwin = g.half; pt.d.nref = g.nseq; pt.d.nids = nids;
+  pt.d.flookup = (const uint4*)p_flookup; pt.d.flist = (const uint2*)p_flist; pt.d.pos_off = (const uint32_t*)p_posoff; pt.d.pos = (const uint2*)p_pos;
+  pt.d.refseq = (const uint8_t*)p_ref; pt.d.ref_off = (const uint32_t*)p_roff;
+  pt.n_entries = E; pt.n_ids = nids; pt.n_pos = npos; pt.n_refseq = c04.size();
   return SMR_OK;
 }
 
@@ -386,7 +511,9 @@ const char* inf_status_text(uint32_t st) {
     case kInfErrOverrun: return "compressed data ends inside a block (truncated file)";
     case kInfErrDistance: return "invalid distance too far back";
     case kInfErrStored: return "invalid stored block lengths";
-    case kInfErrMember: return "not a gzip member, or its size field disagrees with the data";
+    case kInfErrMember: return "not a gzip member";
+    case kInfErrCrc: return "CRC-32 of a member disagrees with its data";
+    case kInfErrSize: return "size field (ISIZE) of a member disagrees with its data";
     default: return "internal error";
   }
 }
@@ -423,13 +550,12 @@ int inflate_impl(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint64_t chunk_b
   } else if ((rc = ensure(ctx, ctx->d_cand, 8))) return rc;
   const uint32_t ncand = (uint32_t)cand.size(), ns = ncand + 1;
   // COUNT
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[0]) { CK(cudaFuncSetAttribute(inf_span_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInfSpanSmem)); attr_done[0] = true; }
-  if (!attr_done[1]) { CK(cudaFuncSetAttribute(inf_span_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInfSpanSmem)); attr_done[1] = true; }
+  CK(cudaFuncSetAttribute(inf_span_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInfSpanSmem));   // per device
+  CK(cudaFuncSetAttribute(inf_span_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInfSpanSmem));
   if ((rc = ensure(ctx, ctx->d_res, (size_t)ns * sizeof(SpanResult)))) return rc;
   const unsigned ctas = (ns + kInfSpanThreads - 1) / kInfSpanThreads;
-  inf_span_kernel<false><<<ctas, kInfSpanThreads, kInfSpanSmem, ctx->stream>>>(w, nbytes, (const uint64_t*)ctx->d_cand.p, ncand, nullptr, nullptr, nullptr, ns, nullptr,
-                                                                               (SpanResult*)ctx->d_res.p);
+  inf_span_kernel<false><<<ctas, kInfSpanThreads, kInfSpanSmem, ctx->stream>>>(w, nbytes, (const uint64_t*)ctx->d_cand.p, ncand, nullptr, nullptr, nullptr, nullptr, nullptr, ns,
+                                                                               nullptr, (SpanResult*)ctx->d_res.p);
   CK(cudaGetLastError());
   std::vector<SpanResult> res(ns);
   CK(cudaMemcpyAsync(res.data(), ctx->d_res.p, (size_t)ns * sizeof(SpanResult), cudaMemcpyDeviceToHost, ctx->stream));
@@ -438,7 +564,9 @@ int inflate_impl(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint64_t chunk_b
   uint32_t nreal = 0, why = 0;
   const uint64_t total = inf_chain(cand.data(), ncand, res.data(), real.data(), off.data(), nreal, &why);
   if (total == kInfNone) { ctx->err = std::string("gz input: ") + inf_status_text(why); return SMR_ERR_ARG; }
-  for (uint32_t k = 0; k < nreal; ++k) cnt[k] = res[real[k]].out_n;
+  std::vector<uint32_t> moff(nreal + 1, 0);
+  for (uint32_t k = 0; k < nreal; ++k) { cnt[k] = res[real[k]].out_n; moff[k + 1] = moff[k] + res[real[k]].members; }
+  const uint32_t nmembers = moff[nreal];
   ctx->inf_spans = nreal; ctx->inf_candidates = ncand;
   if ((rc = ensure(ctx, ctx->d_text, total + 64))) return rc;
   if (total) {
@@ -451,9 +579,12 @@ int inflate_impl(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint64_t chunk_b
     CK(cudaMemcpyAsync(ctx->d_ids.p, real.data(), (size_t)nreal * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_off.p, off.data(), (size_t)nreal * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_cnt64.p, cnt.data(), (size_t)nreal * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ensure(ctx, ctx->d_moff, (size_t)(nreal + 1) * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_mem, (size_t)(nmembers + 1) * sizeof(MemberEnd)))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_moff.p, moff.data(), (size_t)(nreal + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     inf_span_kernel<true><<<(nreal + kInfSpanThreads - 1) / kInfSpanThreads, kInfSpanThreads, kInfSpanSmem, ctx->stream>>>(
-        w, nbytes, (const uint64_t*)ctx->d_cand.p, ncand, (const uint32_t*)ctx->d_ids.p, (const uint64_t*)ctx->d_off.p, (const uint64_t*)ctx->d_cnt64.p, nreal,
-        (uint16_t*)ctx->d_sym.p, (SpanResult*)ctx->d_res.p);
+        w, nbytes, (const uint64_t*)ctx->d_cand.p, ncand, (const uint32_t*)ctx->d_ids.p, (const uint64_t*)ctx->d_off.p, (const uint64_t*)ctx->d_cnt64.p,
+        (const uint32_t*)ctx->d_moff.p, (MemberEnd*)ctx->d_mem.p, nreal, (uint16_t*)ctx->d_sym.p, (SpanResult*)ctx->d_res.p);
     CK(cudaGetLastError());
     // WINDOW, RESOLVE
     inf_window_kernel<<<1, 1024, 0, ctx->stream>>>((const uint16_t*)ctx->d_sym.p, (const uint64_t*)ctx->d_off.p, (const uint64_t*)ctx->d_cnt64.p, nreal, (uint8_t*)ctx->d_win.p);
@@ -464,11 +595,35 @@ int inflate_impl(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint64_t chunk_b
                                                                      (const uint8_t*)ctx->d_win.p, (uint8_t*)ctx->d_text.p);
     CK(cudaGetLastError());
     std::vector<SpanResult> res2(nreal);
+    std::vector<MemberEnd> ends(nmembers);
     CK(cudaMemcpyAsync(res2.data(), ctx->d_res.p, (size_t)nreal * sizeof(SpanResult), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nmembers) CK(cudaMemcpyAsync(ends.data(), ctx->d_mem.p, (size_t)nmembers * sizeof(MemberEnd), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t k = 0; k < nreal; ++k) {
+      if (res2[k].status != res[real[k]].status || res2[k].out_n != cnt[k] || res2[k].end_bit != res[real[k]].end_bit || res2[k].members != res[real[k]].members) {
+        ctx->err = "gz inflate: the write pass disagrees with the count pass"; return SMR_ERR_CUDA;
+      }
+      for (uint32_t m = moff[k]; m < moff[k + 1]; ++m) ends[m].out_end += off[k];
+    }
+    // CRC-32 + ISIZE of every member (RFC 1952 2.3.1): pieces on the device, joined here
+    std::vector<uint64_t> poff; std::vector<uint32_t> plen, first;
+    inf_crc_plan(ends, 32768, poff, plen, first);
+    const uint32_t npieces = (uint32_t)poff.size();
+    std::vector<uint32_t> crcs(npieces);
+    if (npieces) {
+      if ((rc = ensure(ctx, ctx->d_poff, (size_t)npieces * 8))) return rc;
+      if ((rc = ensure(ctx, ctx->d_plen, (size_t)npieces * 4))) return rc;
+      if ((rc = ensure(ctx, ctx->d_pcrc, (size_t)npieces * 4))) return rc;
+      CK(cudaMemcpyAsync(ctx->d_poff.p, poff.data(), (size_t)npieces * 8, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->d_plen.p, plen.data(), (size_t)npieces * 4, cudaMemcpyHostToDevice, ctx->stream));
+      inf_crc_kernel<<<(npieces + 127) / 128, 128, 0, ctx->stream>>>((const uint8_t*)ctx->d_text.p, (const uint64_t*)ctx->d_poff.p, (const uint32_t*)ctx->d_plen.p, npieces,
+                                                                       (uint32_t*)ctx->d_pcrc.p);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(crcs.data(), ctx->d_pcrc.p, (size_t)npieces * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaEventRecord(e2, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t k = 0; k < nreal; ++k)
-      if (res2[k].status != res[real[k]].status || res2[k].out_n != cnt[k] || res2[k].end_bit != res[real[k]].end_bit) { ctx->err = "gz inflate: the write pass disagrees with the count pass"; return SMR_ERR_CUDA; }
+    if (const uint32_t bad = inf_crc_verify(ends, plen, first, crcs.data())) { ctx->err = std::string("gz input: ") + inf_status_text(bad); return SMR_ERR_ARG; }
   } else {
     CK(cudaEventRecord(e2, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -792,7 +947,8 @@ void smr_destroy(smr_ctx* ctx) {
                     &ctx->hit_db, &ctx->aln_work, &ctx->out_aln, &ctx->hits, &ctx->cost, &ctx->bins, &ctx->scalars, &ctx->counters, &ctx->cigar_pool,
                     &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->lis_queue, &ctx->lis_done, &ctx->lis_rows, &ctx->lis_dbg, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs, &ctx->aln_stats,
                     &ctx->d_text, &ctx->d_cnt, &ctx->d_scal, &ctx->d_nl, &ctx->d_hdr, &ctx->d_sb, &ctx->d_rec, &ctx->d_spos, &ctx->d_hdroff, &ctx->scan_sums,
-                    &ctx->d_gz, &ctx->d_cand, &ctx->d_res, &ctx->d_sym, &ctx->d_win, &ctx->d_ids, &ctx->d_off, &ctx->d_cnt64};
+                    &ctx->d_gz, &ctx->d_cand, &ctx->d_res, &ctx->d_sym, &ctx->d_win, &ctx->d_ids, &ctx->d_off, &ctx->d_cnt64,
+                    &ctx->d_moff, &ctx->d_mem, &ctx->d_poff, &ctx->d_plen, &ctx->d_pcrc};
   for (DevBuf* b : bufs) release(*b);
   PinBuf* pins[] = {&ctx->h_state, &ctx->h_flags, &ctx->h_hitdb, &ctx->h_outaln, &ctx->h_stats, &ctx->h_cigar, &ctx->h_off32, &ctx->h_pkoff};
   for (PinBuf* b : pins) release(*b);
@@ -835,9 +991,72 @@ int smr_load_index_part(smr_ctx* ctx, uint32_t index_num, uint32_t part, const v
   if ((rc = upload_vec(ctx, pt, roff, &ro))) return rc;
   pt.d.flookup = (const uint4*)lk; pt.d.flist = (const uint2*)en; pt.d.pos_off = po; pt.d.pos = (const uint2*)ps;
   pt.d.refseq = rs; pt.d.ref_off = ro;
+  pt.n_refseq = rseq.size();
   pt.n_nodes = fx.nodes.size(); pt.n_entries = fx.entries.size(); pt.n_ids = pt.d.nids; pt.n_pos = fx.pos.size();
   ctx->parts.push_back(std::move(pt));
   ctx->n_index_files = std::max(ctx->n_index_files, index_num + 1);
+  return SMR_OK;
+}
+
+int smr_build_index_device(smr_ctx* ctx, uint32_t index_num, const char* fasta_path, uint32_t lnwin, uint32_t interval, uint32_t max_pos, double max_mb,
+                           const uint32_t skiplengths[3], uint32_t minimal_score, uint32_t* nparts, uint64_t report6[6]) {
+  if (!ctx || !fasta_path || !skiplengths) return SMR_ERR_ARG;
+  if (skiplengths[0] == 0 || skiplengths[1] == 0 || skiplengths[2] == 0) { ctx->err = "skiplengths must be positive"; return SMR_ERR_ARG; }
+  if (lnwin < 8 || lnwin > 26 || (lnwin & 1)) { ctx->err = "unsupported seed length"; return SMR_ERR_ARG; }
+  if (interval == 0) { ctx->err = "interval must be >= 1"; return SMR_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  BuildOptions opt; opt.lnwin = lnwin; opt.interval = interval; opt.max_pos = max_pos; opt.max_mb = max_mb;
+  std::vector<RefRecord> recs;
+  double freq[4] = {0, 0, 0, 0};
+  uint64_t full_len = 0; size_t fsize = 0;
+  std::string e;
+  try {
+    e = parse_reference_fasta(fasta_path, lnwin + 1, true, recs, freq, full_len, fsize);
+  } catch (const std::exception& ex) { e = std::string("index build failed: ") + ex.what(); }
+  if (!e.empty()) { ctx->err = e; return SMR_ERR_INDEX; }
+  uint32_t part = 0;
+  uint64_t rep[6] = {0, recs.size(), 0, 0, 0, 0};
+  size_t first = 0;
+  while (first < recs.size()) {
+    std::vector<size_t> members; size_t next = first; uint64_t start_part = 0, seq_part_size = 0;
+    e = next_index_part(recs, first, lnwin + 1, max_mb, members, next, start_part, seq_part_size);
+    if (!e.empty()) { ctx->err = e; return SMR_ERR_INDEX; }
+    if (members.empty()) break;
+    Part pt;
+    int rc = build_part_device(ctx, recs, members, opt, pt);
+    if (rc) { for (void* p : pt.owned) cudaFree(p); return rc; }
+    pt.d.index_num = index_num; pt.d.part = part; pt.d.minimal_score = minimal_score;
+    for (int i = 0; i < 3; ++i) pt.d.skip[i] = skiplengths[i];
+    rep[3] += pt.n_ids; rep[5] += pt.bytes;
+    ctx->parts.push_back(std::move(pt));
+    ctx->n_index_files = std::max(ctx->n_index_files, index_num + 1);
+    ++part; first = next;
+  }
+  if (part == 0) { ctx->err = "no index was created"; return SMR_ERR_INDEX; }
+  rep[0] = part;
+  if (nparts) *nparts = part;
+  if (report6) memcpy(report6, rep, sizeof(rep));
+  return SMR_OK;
+}
+
+int smr_debug_index_array(smr_ctx* ctx, uint32_t slot, uint32_t which, void* out, uint64_t cap_bytes, uint64_t* nbytes) {
+  if (!ctx || !nbytes || slot >= ctx->parts.size()) return SMR_ERR_ARG;
+  CK(cudaSetDevice(ctx->device));
+  const Part& pt = ctx->parts[slot];
+  const void* src = nullptr; uint64_t n = 0;
+  switch (which) {
+    case 0: src = pt.d.flookup; n = ((uint64_t)16) << (2 * pt.d.partialwin); break;
+    case 1: src = pt.d.flist; n = (uint64_t)pt.n_entries * 8; break;
+    case 2: src = pt.d.pos_off; n = ((uint64_t)pt.n_ids + 1) * 4; break;
+    case 3: src = pt.d.pos; n = (uint64_t)pt.n_pos * 8; break;
+    case 4: src = pt.d.refseq; n = pt.n_refseq; break;
+    case 5: src = pt.d.ref_off; n = ((uint64_t)pt.d.nref + 1) * 4; break;
+    default: ctx->err = "no such array"; return SMR_ERR_ARG;
+  }
+  *nbytes = n;
+  if (!out) return SMR_OK;
+  if (cap_bytes < n) { ctx->err = "buffer too small"; return SMR_ERR_CAPACITY; }
+  if (n) CK(cudaMemcpy(out, src, n, cudaMemcpyDeviceToHost));
   return SMR_OK;
 }
 

@@ -36,14 +36,15 @@ __global__ void __launch_bounds__(256) inf_find_kernel(const uint32_t* __restric
 template <bool WRITE>
 __global__ void __launch_bounds__(kInfSpanThreads) inf_span_kernel(const uint32_t* __restrict__ w, uint64_t nbytes, const uint64_t* __restrict__ cand, uint32_t ncand,
                                                                     const uint32_t* __restrict__ ids, const uint64_t* __restrict__ off, const uint64_t* __restrict__ cap,
-                                                                    uint32_t nspans, uint16_t* sym, SpanResult* res) {
+                                                                    const uint32_t* __restrict__ mem_off, MemberEnd* mem, uint32_t nspans, uint16_t* sym, SpanResult* res) {
   extern __shared__ __align__(16) unsigned char inf_smem[];
   InfTabsPadded* tabs = reinterpret_cast<InfTabsPadded*>(inf_smem);
   const uint32_t t = blockIdx.x * kInfSpanThreads + threadIdx.x;
   if (t >= nspans) return;
   const uint32_t i = WRITE ? ids[t] : t;
   SpanResult r;
-  inflate_span<WRITE>(w, nbytes, i ? cand[i - 1] : 0ull, i == 0, cand, ncand, i, tabs[threadIdx.x].t, WRITE ? sym + off[t] : nullptr, WRITE ? cap[t] : 0ull, r);
+  inflate_span<WRITE>(w, nbytes, i ? cand[i - 1] : 0ull, i == 0, cand, ncand, i, tabs[threadIdx.x].t, WRITE ? sym + off[t] : nullptr, WRITE ? cap[t] : 0ull,
+                      WRITE ? mem + mem_off[t] : nullptr, r);
   res[t] = r;
 }
 
@@ -74,6 +75,16 @@ __global__ void __launch_bounds__(256) inf_resolve_kernel(const uint16_t* __rest
   const uint64_t o = off[k], n = cnt[k];
   const uint8_t* pw = win + (size_t)k * kInfWindow;
   for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) out[o + j] = inf_resolve(sym[o + j], pw);
+}
+
+// CRC: one thread per piece of the inflated text (the host cuts the members into pieces of <= 32 KB and joins the values).
+__global__ void __launch_bounds__(128) inf_crc_kernel(const uint8_t* __restrict__ text, const uint64_t* __restrict__ piece_off, const uint32_t* __restrict__ piece_len,
+                                                       uint32_t npieces, uint32_t* crc) {
+  __shared__ uint32_t tab[256];
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = crc_table_entry(i);
+  __syncthreads();
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < npieces) crc[t] = crc_piece(text + piece_off[t], piece_len[t], tab);
 }
 
 }  // namespace smr

@@ -21,6 +21,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <vector>
 #include "smr_levbits.h"   // SMR_HD
 
 namespace smr {
@@ -31,7 +32,7 @@ constexpr uint64_t kInfNone = ~0ull;
 
 // status of a decoded span
 enum InfStatus : uint32_t { kInfLanded = 0, kInfEos = 1, kInfErrCode = 2, kInfErrHeader = 3, kInfErrOverrun = 4, kInfErrDistance = 5,
-                            kInfErrStored = 6, kInfErrMember = 7, kInfErrCapacity = 8 };
+                            kInfErrStored = 6, kInfErrMember = 7, kInfErrCapacity = 8, kInfErrCrc = 9, kInfErrSize = 10 };
 
 // ---------------------------------------------------------------------------------------------------------------------
 // bit reader over the stream as 32-bit little-endian words (the buffer is padded with >= 64 zero bytes)
@@ -221,19 +222,22 @@ struct SpanResult {
   uint32_t status;      // InfStatus
   uint32_t isize_sum;   // sum of the ISIZE fields of the members that ended in this span (mod 2^32)
   uint64_t member_out;  // bytes produced since the last member start seen in this span (kInfNone: no member start seen)
+  uint32_t members;     // gzip members that ended in this span
+  uint32_t pad;
 };
+struct MemberEnd { uint64_t out_end; uint32_t crc, isize; };   // trailer of a member (RFC 1952 2.3.1); out_end counts from the span's first byte
 
 // One span: decode from `start_bit` (a block start; or a member header when `at_member` is set) until a block boundary that is one of
 // the sorted candidate positions cand[first_cand ..ncand) or the end of the gzip stream.  WRITE: 16-bit symbols to out[0 .. out_cap).
 template <bool WRITE>
 SMR_HD void inflate_span(const uint32_t* w, uint64_t nbytes, uint64_t start_bit, bool at_member, const uint64_t* cand, uint32_t ncand,
-                         uint32_t first_cand, HuffTabs& T, uint16_t* out, uint64_t out_cap, SpanResult& res) {
+                         uint32_t first_cand, HuffTabs& T, uint16_t* out, uint64_t out_cap, MemberEnd* mem, SpanResult& res) {
   const uint8_t* bytes = reinterpret_cast<const uint8_t*>(w);
-  const uint64_t nbits = nbytes * 8;
+  const uint64_t nbits = nbytes * 8, wlimit = (nbits >> 5) + 2;   // a decoder that has loaded this many words ran past the end
   uint64_t n = 0, member_base = kInfNone;
-  uint32_t nextc = first_cand, isize_sum = 0;
+  uint32_t nextc = first_cand, isize_sum = 0, members = 0;
   BitIn b; b.w = w;
-  auto finish = [&](uint32_t st, uint64_t endb) { res.end_bit = endb; res.out_n = n; res.status = st; res.isize_sum = isize_sum; res.member_out = member_base == kInfNone ? kInfNone : n - member_base; };
+  auto finish = [&](uint32_t st, uint64_t endb) { res.end_bit = endb; res.out_n = n; res.status = st; res.isize_sum = isize_sum; res.members = members; res.pad = 0; res.member_out = member_base == kInfNone ? kInfNone : n - member_base; };
   uint64_t pos = start_bit;
   if (at_member) {
     const uint64_t q = gz_member_header(bytes, nbytes, pos >> 3);
@@ -282,6 +286,7 @@ SMR_HD void inflate_span(const uint32_t* w, uint64_t nbytes, uint64_t start_bit,
       for (;;) {   // symbols of the block (3.2.3)
         bi_fill(b);
         uint32_t s = huff_decode(b, T.llut, kInfLutBitsL, T.lcount, T.lsym);
+        if (b.next > wlimit) { finish(kInfErrOverrun, pos); return; }
         if (s < 256) {
           if (WRITE) { if (n >= out_cap) { finish(kInfErrCapacity, pos); return; } out[n] = (uint16_t)s; }
           ++n;
@@ -313,7 +318,10 @@ SMR_HD void inflate_span(const uint32_t* w, uint64_t nbytes, uint64_t start_bit,
     if (bfinal) {   // member trailer (RFC 1952: CRC32, ISIZE), then another member or the end
       uint64_t q = (bi_pos(b) + 7) >> 3;
       if (q + 8 > nbytes) { finish(kInfErrOverrun, pos); return; }
-      isize_sum += (uint32_t)bytes[q + 4] | ((uint32_t)bytes[q + 5] << 8) | ((uint32_t)bytes[q + 6] << 16) | ((uint32_t)bytes[q + 7] << 24);
+      const uint32_t crc = (uint32_t)bytes[q] | ((uint32_t)bytes[q + 1] << 8) | ((uint32_t)bytes[q + 2] << 16) | ((uint32_t)bytes[q + 3] << 24);
+      const uint32_t isz = (uint32_t)bytes[q + 4] | ((uint32_t)bytes[q + 5] << 8) | ((uint32_t)bytes[q + 6] << 16) | ((uint32_t)bytes[q + 7] << 24);
+      if (WRITE && mem) { mem[members].out_end = n; mem[members].crc = crc; mem[members].isize = isz; }
+      ++members; isize_sum += isz;
       q += 8;
       const uint64_t h = gz_member_header(bytes, nbytes, q);
       if (h == kInfNone) { finish(kInfEos, q * 8); return; }   // gzip: trailing bytes that are no member are ignored
@@ -321,6 +329,59 @@ SMR_HD void inflate_span(const uint32_t* w, uint64_t nbytes, uint64_t start_bit,
       bi_seek(b, h * 8);
     }
   }
+}
+
+// CRC-32 (RFC 1952 8): per piece on the device, pieces joined on the host.  Polynomials are kept reflected (bit 31 = x^0).
+constexpr uint32_t kCrcPoly = 0xEDB88320u;
+SMR_HD uint32_t crc_table_entry(uint32_t i) {
+  uint32_t c = i;
+  for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ kCrcPoly : c >> 1;
+  return c;
+}
+SMR_HD uint32_t crc_piece(const uint8_t* p, uint64_t n, const uint32_t* tab) {
+  uint32_t c = 0xFFFFFFFFu;
+  for (uint64_t i = 0; i < n; ++i) c = tab[(c ^ p[i]) & 255u] ^ (c >> 8);
+  return ~c;
+}
+inline uint32_t crc_mulmod(uint32_t a, uint32_t b) {   // a * b mod P
+  uint32_t prod = 0;
+  for (int i = 0; i < 32; ++i) {
+    if (a & (0x80000000u >> i)) prod ^= b;
+    b = (b & 1u) ? (b >> 1) ^ kCrcPoly : b >> 1;
+  }
+  return prod;
+}
+inline uint32_t crc_concat(uint32_t crc_a, uint32_t crc_b, uint64_t len_b) {   // CRC of A||B from the CRCs of A and B
+  uint32_t r = 0x80000000u, base = 0x00800000u;   // 1, x^8
+  for (uint64_t n = len_b; n; n >>= 1) { if (n & 1u) r = crc_mulmod(r, base); base = crc_mulmod(base, base); }
+  return crc_mulmod(r, crc_a) ^ crc_b;
+}
+
+// Host side of the CRC / ISIZE check: the members (trailers in stream order, out_end = offset in the whole output) are cut into
+// pieces that end at multiples of `piece` bytes; `first[m]` = first piece of member m.
+inline void inf_crc_plan(const std::vector<MemberEnd>& ends, uint32_t piece, std::vector<uint64_t>& poff, std::vector<uint32_t>& plen, std::vector<uint32_t>& first) {
+  poff.clear(); plen.clear(); first.clear();
+  uint64_t a = 0;
+  for (const MemberEnd& m : ends) {
+    first.push_back((uint32_t)poff.size());
+    while (a < m.out_end) {
+      const uint64_t stop = std::min<uint64_t>(m.out_end, (a / piece + 1) * piece);
+      poff.push_back(a); plen.push_back((uint32_t)(stop - a));
+      a = stop;
+    }
+  }
+  first.push_back((uint32_t)poff.size());
+}
+inline uint32_t inf_crc_verify(const std::vector<MemberEnd>& ends, const std::vector<uint32_t>& plen, const std::vector<uint32_t>& first, const uint32_t* crcs) {
+  uint64_t a = 0;
+  for (size_t m = 0; m < ends.size(); ++m) {
+    if ((uint32_t)(ends[m].out_end - a) != ends[m].isize) return kInfErrSize;
+    uint32_t c = 0;   // CRC of the empty string
+    for (uint32_t k = first[m]; k < first[m + 1]; ++k) c = crc_concat(c, crcs[k], plen[k]);
+    if (c != ends[m].crc) return kInfErrCrc;
+    a = ends[m].out_end;
+  }
+  return 0;
 }
 
 // a resolved byte: the symbol itself, or the byte of the previous span's window a marker names
@@ -331,7 +392,6 @@ SMR_HD uint8_t inf_window_byte(const uint16_t* syms, uint64_t n, const uint8_t* 
   return v >= 0 ? inf_resolve(syms[v], prev_window) : prev_window[kInfWindow + v];
 }
 
-#if !defined(__CUDA_ARCH__)
 // The walk over the COUNT results (host side): span 0 is the start of the stream, span i >= 1 starts at cand[i - 1].  Fills
 // `real` with the spans that are reached and `off` with their output offsets; returns the total size or kInfNone with *why set.
 inline uint64_t inf_chain(const uint64_t* cand, uint32_t ncand, const SpanResult* res, uint32_t* real, uint64_t* off, uint32_t& nreal, uint32_t* why) {
@@ -349,9 +409,8 @@ inline uint64_t inf_chain(const uint64_t* cand, uint32_t ncand, const SpanResult
     if (lo >= ncand || cand[lo] != res[i].end_bit) { *why = kInfErrMember; return kInfNone; }
     i = lo + 1;
   }
-  if ((uint32_t)total != isize) { *why = kInfErrMember; return kInfNone; }   // RFC 1952 ISIZE: sizes mod 2^32
+  if ((uint32_t)total != isize) { *why = kInfErrSize; return kInfNone; }   // RFC 1952 ISIZE: sizes mod 2^32 (per member again after the write pass)
   return total;
 }
-#endif
 
 }  // namespace smr

@@ -29,18 +29,21 @@ int main(int argc, char** argv) {
   std::vector<SpanResult> res(ns);
   HuffTabs T;
   for (uint32_t i = 0; i < ns; ++i)
-    inflate_span<false>(w.data(), nbytes, i ? cand[i - 1] : 0, i == 0, cand.data(), (uint32_t)cand.size(), i, T, nullptr, 0, res[i]);
+    inflate_span<false>(w.data(), nbytes, i ? cand[i - 1] : 0, i == 0, cand.data(), (uint32_t)cand.size(), i, T, nullptr, 0, nullptr, res[i]);
   std::vector<uint32_t> real(ns); std::vector<uint64_t> off(ns);
   uint32_t nreal = 0, why = 0;
   const uint64_t total = inf_chain(cand.data(), (uint32_t)cand.size(), res.data(), real.data(), off.data(), nreal, &why);
   if (total == kInfNone) { printf("error %u\n", why); return 1; }
   // WRITE
   std::vector<uint16_t> sym(total + 1);
+  std::vector<MemberEnd> ends;
   for (uint32_t k = 0; k < nreal; ++k) {
     const uint32_t i = real[k];
     SpanResult r;
-    inflate_span<true>(w.data(), nbytes, i ? cand[i - 1] : 0, i == 0, cand.data(), (uint32_t)cand.size(), i, T, sym.data() + off[k], res[i].out_n, r);
-    if (r.status != res[i].status || r.out_n != res[i].out_n || r.end_bit != res[i].end_bit) { printf("error write pass differs\n"); return 1; }
+    std::vector<MemberEnd> mine(res[i].members + 1);
+    inflate_span<true>(w.data(), nbytes, i ? cand[i - 1] : 0, i == 0, cand.data(), (uint32_t)cand.size(), i, T, sym.data() + off[k], res[i].out_n, mine.data(), r);
+    if (r.status != res[i].status || r.out_n != res[i].out_n || r.end_bit != res[i].end_bit || r.members != res[i].members) { printf("error write pass differs\n"); return 1; }
+    for (uint32_t m = 0; m < r.members; ++m) { mine[m].out_end += off[k]; ends.push_back(mine[m]); }
   }
   // WINDOW (front to back) + RESOLVE
   std::vector<uint8_t> win((size_t)(nreal + 1) * kInfWindow, 0), out(total);
@@ -54,6 +57,16 @@ int main(int argc, char** argv) {
     const uint8_t* prev = win.data() + (size_t)k * kInfWindow;
     const uint64_t n = res[real[k]].out_n;
     for (uint64_t j = 0; j < n; ++j) out[off[k] + j] = inf_resolve(sym[off[k] + j], prev);
+  }
+  // CRC-32 and ISIZE of every member, in pieces as on the device
+  {
+    std::vector<uint64_t> poff; std::vector<uint32_t> plen, first, crcs, tab(256);
+    for (uint32_t i = 0; i < 256; ++i) tab[i] = crc_table_entry(i);
+    inf_crc_plan(ends, 32768, poff, plen, first);
+    crcs.resize(poff.size());
+    for (size_t k = 0; k < poff.size(); ++k) crcs[k] = crc_piece(out.data() + poff[k], plen[k], tab.data());
+    const uint32_t bad = inf_crc_verify(ends, plen, first, crcs.data());
+    if (bad) { printf("error %u\n", bad); return 1; }
   }
   f = fopen(argv[2], "wb");
   fwrite(out.data(), 1, out.size(), f); fclose(f);
