@@ -170,6 +170,16 @@ def load_databases(native_index=True):
     return fastas, idx_dir, [pre[os.path.basename(f)] for f in fastas], refs, stats, built
 
 
+def load_resident_index(al, source, fastas, prefixes, refs, ms, stats):
+    """The 8 databases resident in HBM: built on the device from the FASTA files, or flattened from the on-disk index."""
+    for k in range(len(fastas)):
+        if source == "device":
+            if al.build_index_device(k, fastas[k], refs[k], ms[k], (18, 9, 3), stats[k].lnwin) != 1:
+                raise SystemExit("the benchmark databases are single-part indexes")
+        else:
+            al.load_index_part(k, 0, prefixes[k], refs[k], ms[k], (18, 9, 3), stats[k].lnwin)
+
+
 def reference_index_dir(fastas):
     """The reference legs (cpu_baseline, --impl reference) run the unmodified binary on the index ITS OWN builder makes
     (data_cache/idx_ref; one process per database, outside every timed region) -- never on files our builder wrote."""
@@ -326,6 +336,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU in the whole job; one step = reads/steps of them")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--index-source", default="device", choices=["device", "files"],
+                    help="device: every database indexed on the GPU straight from its FASTA (smr_build_index_device); files: the on-disk index "
+                         "(smr_build_index) flattened by smr_load_index_part.  Same resident arrays up to the id numbering; untimed either way")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cli-e2e", action="store_true", help="time the drop-in host program (oracle/_ref/sortmerna_gpu) against the reference binary and exit")
@@ -401,8 +414,9 @@ def main():
     al = api.Aligner(local_rank)
     prm = api.default_params()
     al.set_params(prm)
-    for k in range(len(fastas)):
-        al.load_index_part(k, 0, prefixes[k], refs[k], ms[k], (18, 9, 3), stats[k].lnwin)
+    t_idx = time.time()
+    load_resident_index(al, args.index_source, fastas, prefixes, refs, ms, stats)
+    index_resident_s = time.time() - t_idx
     info = al.index_info()
     pool = DbPool(refs)
     # reads are sharded by record: each rank owns its own reads; one distinct batch per step, in pinned host memory
@@ -454,8 +468,7 @@ def main():
     from concurrent.futures import ThreadPoolExecutor
     al2 = api.Aligner(local_rank)
     al2.set_params(prm)
-    for k in range(len(fastas)):
-        al2.load_index_part(k, 0, prefixes[k], refs[k], ms[k], (18, 9, 3), stats[k].lnwin)
+    load_resident_index(al2, args.index_source, fastas, prefixes, refs, ms, stats)
     als = [al, al2]
     for a in als:
         a.align(cats[0][: min(n, 1 << 16) * READ_LEN], off[: min(n, 1 << 16) + 1])  # warm the host path
@@ -543,7 +556,7 @@ def main():
         "kernel_ms_per_step": {"seed": float(np.mean(seed_ms)), "candidates_sw": float(np.mean(lis_ms)), "finalize": float(np.mean(fin_ms))},
         "clocks": sampler.summary(),
         "counters": counters,
-        "setup_s": setup_s, "index_build_s": built,
+        "setup_s": setup_s, "index_build_s": built, "index_source": args.index_source, "index_resident_s": round(index_resident_s, 2),
     }
     if not args.no_cpu_baseline and world == 1:   # reported baseline: rank 0 at N = 1 only
         sample = min(n, args.cpu_sample or int(min(400_000, max(20_000, 2_300 * cores))))

@@ -194,7 +194,7 @@ int smr_upload_fastx_gz(smr_ctx*, const void* gz, uint64_t nbytes, uint32_t* nre
 /* The text behind the resident batch (what smr_upload_fastx was given / what smr_upload_fastx_gz inflated): *nbytes = its size;
  * copied to `text` when that is not null (cap bytes available).  header_text_off of smr_resident_layout indexes it. */
 int smr_resident_text(smr_ctx*, char* text, uint64_t cap, uint64_t* nbytes);
-/* Test hook: inflate only.  chunk_bytes = distance of the speculative block searches (>= 1024); info = {spans decoded,
+/* Test hook: inflate only.  chunk_bytes = distance of the speculative block searches (>= 1024; 0 = the default of smr_upload_fastx_gz); info = {spans decoded,
  * candidates found, device time in us, H2D time in us}. */
 int smr_debug_inflate(smr_ctx*, const void* gz, uint64_t nbytes, uint64_t chunk_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_bytes, uint32_t info[4]);
 

@@ -1133,7 +1133,9 @@ int smr_upload_fastx_gz(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint32_t*
   *nreads = 0; ctx->nreads = 0; ctx->text_bytes = 0;
   uint64_t total = 0;
   const char* e = getenv("SMR_INFLATE_CHUNK");
-  int rc = inflate_impl(ctx, gz, nbytes, e ? strtoull(e, nullptr, 10) : 65536, &total);
+  // distance of the speculative block searches: 64 KB for large files, down to 8 KB so that a small file still makes thousands of spans
+  const uint64_t chunk = e ? strtoull(e, nullptr, 10) : std::min<uint64_t>(65536, std::max<uint64_t>(8192, nbytes / 8192));
+  int rc = inflate_impl(ctx, gz, nbytes, chunk, &total);
   if (rc) return rc;
   if (total == 0) return SMR_OK;
   char c0 = 0;
@@ -1155,6 +1157,7 @@ int smr_debug_inflate(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint64_t ch
   if (!ctx || !gz || !out_bytes) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   ctx->nreads = 0; ctx->text_bytes = 0;
+  if (chunk_bytes == 0) chunk_bytes = std::min<uint64_t>(65536, std::max<uint64_t>(8192, nbytes / 8192));   // as smr_upload_fastx_gz
   int rc = inflate_impl(ctx, gz, nbytes, chunk_bytes, out_bytes);
   if (rc) return rc;
   if (info) { info[0] = ctx->inf_spans; info[1] = ctx->inf_candidates; info[2] = (uint32_t)(ctx->t_inflate * 1000.0); info[3] = (uint32_t)(ctx->t_h2d * 1000.0); }

@@ -40,19 +40,21 @@ enum InfStatus : uint32_t { kInfLanded = 0, kInfEos = 1, kInfErrCode = 2, kInfEr
 struct BitIn {
   const uint32_t* w;
   uint64_t buf;
-  uint64_t next;   // next word to load
+  uint64_t next;   // next word to load into `ahead`
   uint32_t cnt;    // valid bits in buf
+  uint32_t ahead;  // w[next - 1], loaded one refill early so that its latency is off the decode chain
 };
 SMR_HD void bi_seek(BitIn& b, uint64_t bitpos) {
   b.next = bitpos >> 5;
   const uint32_t s = (uint32_t)(bitpos & 31);
   b.buf = (uint64_t)b.w[b.next++] >> s;
   b.cnt = 32 - s;
+  b.ahead = b.w[b.next++];
 }
 SMR_HD void bi_fill(BitIn& b) {   // afterwards cnt >= 33
-  if (b.cnt <= 32) { b.buf |= (uint64_t)b.w[b.next++] << b.cnt; b.cnt += 32; }
+  if (b.cnt <= 32) { b.buf |= (uint64_t)b.ahead << b.cnt; b.cnt += 32; b.ahead = b.w[b.next++]; }
 }
-SMR_HD uint64_t bi_pos(const BitIn& b) { return b.next * 32 - b.cnt; }
+SMR_HD uint64_t bi_pos(const BitIn& b) { return (b.next - 1) * 32 - b.cnt; }
 SMR_HD uint32_t bi_peek(const BitIn& b, uint32_t n) { return (uint32_t)(b.buf & ((1ull << n) - 1)); }   // n <= 32 <= cnt
 SMR_HD void bi_skip(BitIn& b, uint32_t n) { b.buf >>= n; b.cnt -= n; }
 SMR_HD uint32_t bi_get(BitIn& b, uint32_t n) { const uint32_t v = bi_peek(b, n); bi_skip(b, n); return v; }
@@ -233,7 +235,7 @@ template <bool WRITE>
 SMR_HD void inflate_span(const uint32_t* w, uint64_t nbytes, uint64_t start_bit, bool at_member, const uint64_t* cand, uint32_t ncand,
                          uint32_t first_cand, HuffTabs& T, uint16_t* out, uint64_t out_cap, MemberEnd* mem, SpanResult& res) {
   const uint8_t* bytes = reinterpret_cast<const uint8_t*>(w);
-  const uint64_t nbits = nbytes * 8, wlimit = (nbits >> 5) + 2;   // a decoder that has loaded this many words ran past the end
+  const uint64_t nbits = nbytes * 8, wlimit = (nbits >> 5) + 3;   // a decoder that has loaded this many words ran past the end
   uint64_t n = 0, member_base = kInfNone;
   uint32_t nextc = first_cand, isize_sum = 0, members = 0;
   BitIn b; b.w = w;
@@ -305,9 +307,23 @@ SMR_HD void inflate_span(const uint32_t* w, uint64_t nbytes, uint64_t start_bit,
         if (member_base != kInfNone && dist > n - member_base) { finish(kInfErrDistance, bi_pos(b)); return; }   // zlib: "invalid distance too far back"
         if (WRITE) {
           if (n + len > out_cap) { finish(kInfErrCapacity, pos); return; }
-          for (uint32_t i = 0; i < len; ++i) {
-            const int64_t v = (int64_t)(n + i) - (int64_t)dist;
-            out[n + i] = v >= 0 ? out[v] : (uint16_t)(256 + kInfWindow + v);
+          // the copy (3.2.3): up to `dist` symbols never overlap what they produce, so they are loaded together before they are
+          // stored -- one memory latency per group instead of one per symbol
+          const uint32_t grp = dist < 8u ? dist : 8u;
+          for (uint32_t i = 0; i < len; i += grp) {
+            uint16_t tmp[8];
+            const uint32_t m = len - i < grp ? len - i : grp;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (uint32_t j = 0; j < 8; ++j) if (j < m) {
+              const int64_t v = (int64_t)(n + i + j) - (int64_t)dist;
+              tmp[j] = v >= 0 ? out[v] : (uint16_t)(256 + kInfWindow + v);
+            }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (uint32_t j = 0; j < 8; ++j) if (j < m) out[n + i + j] = tmp[j];
           }
         }
         n += len;

@@ -72,8 +72,8 @@ def test_bundled_gz_mates_and_throughput(aligner):
     # rate on a large file: ~100 MB of FASTQ text, gzip -6 (one member, a few thousand spans)
     txt = inflate_cases.fastq_text(40000, seed=5) * 8
     gz = gzip.compress(txt, 6)
-    aligner.debug_inflate(gz)      # first call sizes the buffers
-    got, info = aligner.debug_inflate(gz)
+    aligner.debug_inflate(gz, 0)      # first call sizes the buffers
+    got, info = aligner.debug_inflate(gz, 0)
     assert got == txt
     print(f"inflate {len(gz) / 1e6:.1f} MB gz -> {len(txt) / 1e6:.1f} MB: {info['spans']} spans, device {info['device_us'] / 1e3:.1f} ms "
           f"= {len(txt) / max(1, info['device_us']) / 1e3:.2f} GB/s out, H2D {info['h2d_us'] / 1e3:.1f} ms")
