@@ -63,7 +63,7 @@ struct smr_ctx {
   PinBuf h_state, h_flags, h_hitdb, h_outaln, h_stats, h_cigar, h_off32, h_pkoff;
   std::vector<uint64_t> h_coff;
   DevBuf d_text, d_cnt, d_scal, d_nl, d_hdr, d_sb, d_rec, d_spos, d_hdroff, scan_sums;   // input decode (smr_decode.cuh)
-  DevBuf d_gz, d_cand, d_res, d_sym, d_win, d_ids, d_off, d_cnt64, d_moff, d_mem, d_poff, d_plen, d_pcrc;   // gz inflate (smr_inflate.cuh)
+  DevBuf seed_ctr, d_gz, d_cand, d_res, d_sym, d_win, d_ids, d_off, d_cnt64, d_moff, d_mem, d_poff, d_plen, d_pcrc;   // gz inflate (smr_inflate.cuh)
   uint64_t text_bytes = 0;          // size of the text behind the resident batch (smr_upload_fastx / _gz)
   uint32_t inf_spans = 0, inf_candidates = 0; double t_inflate = 0;
   bool device_only_reads = false;   // the resident batch was decoded on the device: no host copy of the sequences yet
@@ -323,7 +323,7 @@ int setup_arenas(smr_ctx* ctx) {
   while (ctx->tb_threads > 4096 && ctx->tb_stride * ctx->tb_threads > budget) ctx->tb_threads /= 2;
   if (int rc = ensure(ctx, ctx->tb_arena, ctx->tb_stride * ctx->tb_threads)) return rc;
   ctx->lane_hits_cap = kLaneHitCap * ctx->scale;
-  ctx->lane_hits_warps = ctx->scale == 1 ? (uint32_t)ctx->sm_count * 8 * kSeedWarpsPerCta : 1024u;
+  ctx->lane_hits_warps = ctx->scale == 1 ? (uint32_t)ctx->sm_count * kSeedCtasPerSm * kSeedWarpsPerCta : 1024u;
   if (int rc = ensure(ctx, ctx->lane_hits, (size_t)ctx->lane_hits_warps * ctx->lane_hits_cap * 32 * 4)) return rc;
   return SMR_OK;
 }
@@ -698,10 +698,13 @@ int run_impl(smr_ctx* ctx) {
     CK(cudaMemsetAsync(b.bin_count, 0, (size_t)kCostBins * 4, ctx->stream));
     cudaEvent_t s0 = get_event(ctx, evi), s1 = get_event(ctx, evi + 1), s2 = get_event(ctx, evi + 2); evi += 3;
     CK(cudaEventRecord(s0, ctx->stream));
+    if ((rc = ensure(ctx, ctx->seed_ctr, hp.size() * 4))) return rc;
+    CK(cudaMemsetAsync(ctx->seed_ctr.p, 0, hp.size() * 4, ctx->stream));   // one work counter per seed launch
     for (size_t pi = 0; pi < hp.size(); ++pi) {
       const int ctas = (int)(ctx->lane_hits_warps / kSeedWarpsPerCta);
-      if (ctx->instr) seed_kernel<true><<<ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, (uint32_t*)ctx->lane_hits.p, ctx->lane_hits_cap);
-      else seed_kernel<false><<<ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, (uint32_t*)ctx->lane_hits.p, ctx->lane_hits_cap);
+      uint32_t* next_read = (uint32_t*)ctx->seed_ctr.p + pi;
+      if (ctx->instr) seed_kernel<true><<<ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, (uint32_t*)ctx->lane_hits.p, ctx->lane_hits_cap, next_read);
+      else seed_kernel<false><<<ctas, kSeedWarpsPerCta * 32, 0, ctx->stream>>>(hp[pi], b, dp, (uint32_t*)ctx->lane_hits.p, ctx->lane_hits_cap, next_read);
       CK(cudaGetLastError());
       ctx->n_launch += 1;
     }
@@ -948,7 +951,7 @@ void smr_destroy(smr_ctx* ctx) {
                     &ctx->parts_dev, &ctx->lis_arena, &ctx->lis_epochs, &ctx->lis_queue, &ctx->lis_done, &ctx->lis_rows, &ctx->lis_dbg, &ctx->final_arena, &ctx->lane_hits, &ctx->tb_arena, &ctx->tb_jobs, &ctx->aln_stats,
                     &ctx->d_text, &ctx->d_cnt, &ctx->d_scal, &ctx->d_nl, &ctx->d_hdr, &ctx->d_sb, &ctx->d_rec, &ctx->d_spos, &ctx->d_hdroff, &ctx->scan_sums,
                     &ctx->d_gz, &ctx->d_cand, &ctx->d_res, &ctx->d_sym, &ctx->d_win, &ctx->d_ids, &ctx->d_off, &ctx->d_cnt64,
-                    &ctx->d_moff, &ctx->d_mem, &ctx->d_poff, &ctx->d_plen, &ctx->d_pcrc};
+                    &ctx->d_moff, &ctx->d_mem, &ctx->d_poff, &ctx->d_plen, &ctx->d_pcrc, &ctx->seed_ctr};
   for (DevBuf* b : bufs) release(*b);
   PinBuf* pins[] = {&ctx->h_state, &ctx->h_flags, &ctx->h_hitdb, &ctx->h_outaln, &ctx->h_stats, &ctx->h_cigar, &ctx->h_off32, &ctx->h_pkoff};
   for (PinBuf* b : pins) release(*b);

@@ -139,18 +139,27 @@ __device__ void coop_stream(const DevIndex& ix, CoopSmem& sm, const uint32_t off
   }
   __syncwarp();
   uint32_t cum = 0, nacc = 0;
-  for (uint32_t e0 = 0; e0 < E; e0 += 32) {
+  // the chunk of a lane in step e0: its list (row k of the table) and its two 16-byte loads -- issued one step ahead of their use
+  uint32_t kn; uint4 tn, q0n, q1n; bool inn;
+  auto fetch = [&](const uint32_t e0) {
     const uint32_t dF = exF - e0, dR = exR - e0;   // a list that began in an earlier step wraps to a huge value
     const uint32_t bit = ((nF && dF < 32u) ? (1u << dF) : 0u) | ((nR && dR < 32u) ? (1u << dR) : 0u);
     const uint32_t starts = __reduce_or_sync(kFull, bit);
     const uint32_t e = e0 + lane;
-    const uint32_t k = cum + __popc(starts & le) - 1u;      // the list of chunk e (step 0 always has a list starting at chunk 0)
+    kn = cum + __popc(starts & le) - 1u;      // the list of chunk e (step 0 always has a list starting at chunk 0)
     cum += __popc(starts);
-    const bool in = e < E;
-    const uint4 t = sm.tab[k];
-    const uint32_t g = t.x + e;
-    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
-    if (in) { q0 = __ldg(fl4 + 2 * (size_t)g); q1 = __ldg(fl4 + 2 * (size_t)g + 1); }
+    inn = e < E;
+    tn = sm.tab[kn];
+    const uint32_t g = tn.x + e;
+    q0n = make_uint4(0, 0, 0, 0); q1n = q0n;
+    if (inn) { q0n = __ldg(fl4 + 2 * (size_t)g); q1n = __ldg(fl4 + 2 * (size_t)g + 1); }
+    tn.x = g;
+  };
+  fetch(0);
+  for (uint32_t e0 = 0; e0 < E; e0 += 32) {
+    const uint32_t k = kn; const uint4 t = tn, q0 = q0n, q1 = q1n; const bool in = inn;
+    const uint32_t g = t.x;
+    if (e0 + 32 < E) fetch(e0 + 32);
     const bool m0 = within_one_edit(t.y, q0.x, km), m1 = within_one_edit(t.y, q0.z, km);
     const bool m2 = within_one_edit(t.y, q1.x, km), m3 = within_one_edit(t.y, q1.z, km);
     const bool any = in && (m0 | m1 | m2 | m3);
@@ -284,17 +293,22 @@ __device__ __forceinline__ SeedWin seed_window(const DevIndex& ix, const uint32_
 }
 
 constexpr int kSeedWarpsPerCta = 4;
+#ifndef SMR_SEED_MIN_CTAS
+#define SMR_SEED_MIN_CTAS 8
+#endif
+constexpr int kSeedCtasPerSm = SMR_SEED_MIN_CTAS;   // resident CTAs per SM the register budget is set for (8: 64 registers)
+constexpr int kSeedGrab = 4;      // reads a warp draws from the work counter at a time
 constexpr int kLaneHitCap = 128;  // ids per window in the per-warp HBM scratch (x scale on a retry)
 
 // The seed kernel.  grid-stride over reads, one warp per read.
 //   lane_hits_g: per-lane id buffers [total warps][cap_g][32]
 template <bool INSTR>
-__global__ void __launch_bounds__(kSeedWarpsPerCta * 32, 8)
-seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint32_t cap_g) {
+__global__ void __launch_bounds__(kSeedWarpsPerCta * 32, kSeedCtasPerSm)
+seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint32_t cap_g, uint32_t* next_read) {
   __shared__ CoopSmem s_coop[kSeedWarpsPerCta];
   const unsigned lane = lane_id();
   const uint32_t wic = threadIdx.x >> 5;
-  const uint32_t warp = blockIdx.x * kSeedWarpsPerCta + wic, nwarps = gridDim.x * kSeedWarpsPerCta;
+  const uint32_t warp = blockIdx.x * kSeedWarpsPerCta + wic;
   const uint32_t L = ix.lnwin, pw = ix.partialwin;
   const bool full = prm.is_full_search != 0;
   CoopSmem& sm = s_coop[wic];
@@ -309,7 +323,12 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
   const uint32_t s0 = ix.skip[0], s1 = ix.skip[1], s2 = ix.skip[2];
   const uint32_t step = (s0 % s2 == 0 && s1 % s2 == 0) ? s2 : 1u;
 
-  for (uint32_t r = b.r0 + warp; r < b.r0 + b.nreads; r += nwarps) {
+  // reads are handed out kSeedGrab at a time from a counter: a warp that drew cheap reads (no hit in this database) takes more
+  for (uint32_t g0 = 0;;) {
+    if (lane == 0) g0 = atomicAdd(next_read, (uint32_t)kSeedGrab);
+    g0 = __shfl_sync(kFull, g0, 0);
+    if (g0 >= b.nreads) break;
+  for (uint32_t r = b.r0 + g0; r < b.r0 + min(g0 + (uint32_t)kSeedGrab, b.nreads); ++r) {
     const uint32_t len = b.seq_off[r + 1] - b.seq_off[r];
     const uint32_t cnt_idx = ix.slot * b.cnt_stride + (r - b.r0);
     if (lane == 0) b.hit_cnt[cnt_idx] = 0;
@@ -363,6 +382,7 @@ seed_kernel(DevIndex ix, DevBatch b, DevParams prm, uint32_t* lane_hits_g, uint3
       if (flags) atomicOr(&b.flags[r], flags);
       if (total) atomicAdd(&b.cost[r - b.r0], max(cost, 1u));
     }
+  }
   }
   // instrumentation + num_short (processor.cpp:113)
   const uint32_t ns = warp_sum_u32(n_short);
