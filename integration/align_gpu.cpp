@@ -108,14 +108,30 @@ void align(Readfeed& readfeed, Readstats& readstats, Index& /*index: the library
   for (smr_ctx* ctx : ctxs) if (smr_set_params(ctx, &p) != SMR_OK) die(ctx, "smr_set_params");
 
   // every (index, part) becomes resident once per GPU (the reference loads / unloads them one at a time, processor.cpp:216-262)
-  for (size_t i = 0; i < opts.indexfiles.size(); ++i)
+  // SMR_INDEX_DEVICE=1: the library indexes the reference FASTA itself on the GPU (smr_build_index_device) with the options of this
+  // run instead of reading the index files -- same resident arrays when the files were built with the same options.
+  const bool index_on_device = getenv("SMR_INDEX_DEVICE") && atoi(getenv("SMR_INDEX_DEVICE")) != 0;
+  for (size_t i = 0; i < opts.indexfiles.size(); ++i) {
+    const uint32_t skip[3] = {opts.skiplengths[i][0], opts.skiplengths[i][1], opts.skiplengths[i][2]};
+    if (index_on_device) {
+      std::vector<std::thread> loaders;
+      for (smr_ctx* ctx : ctxs)
+        loaders.emplace_back([&, ctx] {
+          uint32_t nparts = 0;
+          if (smr_build_index_device(ctx, (uint32_t)i, opts.indexfiles[i].first.c_str(), refstats.lnwin[i], opts.interval, opts.max_pos, opts.max_file_size, skip,
+                                     refstats.minimal_score[i], &nparts, nullptr) != SMR_OK)
+            die(ctx, "smr_build_index_device");
+          if (nparts != refstats.num_index_parts[i]) { ERR("index ", i, ": ", nparts, " parts built on the device, ", refstats.num_index_parts[i], " in the .stats file (different -m ?)"); exit(EXIT_FAILURE); }
+        });
+      for (auto& t : loaders) t.join();
+      continue;
+    }
     for (uint16_t part = 0; part < refstats.num_index_parts[i]; ++part) {
       const std::string pfx = opts.indexfiles[i].second, sfx = "_" + std::to_string(part) + ".dat";
       const std::vector<char> kmer = slurp(pfx + ".kmer" + sfx), trie = slurp(pfx + ".bursttrie" + sfx), pos = slurp(pfx + ".pos" + sfx);
       refs.load((uint32_t)i, part, opts, refstats);                    // unchanged References::load: sequences in the 0-4 alphabet
       std::string cat; std::vector<uint64_t> off(1, 0);
       for (auto& r : refs.buffer) { cat += r.sequence; off.push_back(cat.size()); }
-      const uint32_t skip[3] = {opts.skiplengths[i][0], opts.skiplengths[i][1], opts.skiplengths[i][2]};
       std::vector<std::thread> loaders;                                // one host thread per GPU: flattening + upload run side by side
       for (smr_ctx* ctx : ctxs)
         loaders.emplace_back([&, ctx] {
@@ -126,6 +142,7 @@ void align(Readfeed& readfeed, Readstats& readstats, Index& /*index: the library
       for (auto& t : loaders) t.join();
       refs.unload();
     }
+  }
 
   const auto t_loaded = std::chrono::high_resolution_clock::now();
   // batches of reads from the unchanged Readfeed; read ids ("<file>_<n>") stay the KVDB keys

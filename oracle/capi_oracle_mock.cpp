@@ -75,6 +75,12 @@ int smr_load_index_part(smr_ctx* c, uint32_t index_num, uint32_t part, const voi
   return SMR_OK;
 }
 
+// the stand-in has no device: the binding's SMR_INDEX_DEVICE=1 path is a GPU test (tests/test_gpu_integration.py)
+int smr_build_index_device(smr_ctx* c, uint32_t, const char*, uint32_t, uint32_t, uint32_t, double, const uint32_t*, uint32_t, uint32_t*, uint64_t*) {
+  if (c) c->err = "mock: no device index builder";
+  return SMR_ERR_UNSUPPORTED;
+}
+
 int smr_align_batch(smr_ctx* c, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads, smr_read_result* results, smr_aln* alns,
                     uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used, uint64_t* counters, uint32_t n_counters) {
   static_assert(sizeof(smr_read_result) == sizeof(ora_read_result) && sizeof(smr_aln) == sizeof(ora_aln), "result layouts differ");

@@ -434,7 +434,7 @@ int upload_fastx_impl(smr_ctx* ctx, const char* text, uint64_t nbytes, uint32_t*
   ctx->nreads = 0;
   ctx->text_bytes = nbytes;
   if (nbytes == 0) return SMR_OK;
-  if (nbytes >= ((uint64_t)1 << 36)) { ctx->err = "text batch too large: split it"; return SMR_ERR_ARG; }
+  if (nbytes >= 0xF0000000ull) { ctx->err = "text batch of 2^32 bytes or more: split it (line counts and sequence offsets are 32-bit on the device)"; return SMR_ERR_ARG; }
   const char c0 = text ? text[0] : first_byte;
   const uint32_t fmt = c0 == '@' ? kFmtFastq : kFmtFasta;
   if (c0 != '@' && c0 != '>') { ctx->err = "reads text must start with '@' (FASTQ) or '>' (FASTA)"; return SMR_ERR_ARG; }
@@ -678,6 +678,7 @@ int run_impl(smr_ctx* ctx) {
   CK(cudaMemcpyAsync(ctx->parts_dev.p, hp.data(), hp.size() * sizeof(DevIndex), cudaMemcpyHostToDevice, ctx->stream));
   // cigar pool on the device: generous fixed share per alignment slot
   ctx->cigar_cap_dev = (uint64_t)nreads * slots * 24 * ctx->scale + 4096;
+  if (ctx->cigar_cap_dev >= 0xFFFFFFFFull) { ctx->err = "CIGAR pool of this batch would pass 2^32 words (smr_aln.cigar_off is 32-bit): use smaller batches"; return SMR_ERR_CAPACITY; }
   if ((rc = ensure(ctx, ctx->cigar_pool, ctx->cigar_cap_dev * 4))) return rc;
   const Scalars sc = scalars_of(ctx);
   CK(cudaMemsetAsync(ctx->scalars.p, 0, 512, ctx->stream));
@@ -858,6 +859,7 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
         if (k >= s.n_align) continue;
         const OutAln& d = oa[(size_t)r * slots + k];
         memcpy(out.cigar_pool + at, cig + d.cigar_off, (size_t)d.cigar_len * 4);
+        if (at + d.cigar_len >= 0xFFFFFFFFull) { ctx->err = "CIGAR pool offset passes 2^32 words: use smaller batches"; return SMR_ERR_CAPACITY; }
         a.cigar_off = (uint32_t)at; a.cigar_len = d.cigar_len; at += d.cigar_len;
         a.ref_num = d.ref_num; a.ref_begin1 = d.ref_begin1; a.ref_end1 = d.ref_end1; a.read_begin1 = d.read_begin1; a.read_end1 = d.read_end1;
         a.readlen = d.readlen; a.score1 = d.score1; a.part = d.part; a.index_num = d.index_num; a.strand = d.strand;
@@ -970,7 +972,10 @@ int smr_load_index_part(smr_ctx* ctx, uint32_t index_num, uint32_t part, const v
   if (skiplengths[0] == 0 || skiplengths[1] == 0 || skiplengths[2] == 0) { ctx->err = "skiplengths must be positive"; return SMR_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   FlatIndex fx;
-  std::string e = flatten_index(kmer_file, kmer_bytes, bursttrie_file, bursttrie_bytes, pos_file, pos_bytes, lnwin, fx);
+  std::string e;
+  try {
+    e = flatten_index(kmer_file, kmer_bytes, bursttrie_file, bursttrie_bytes, pos_file, pos_bytes, lnwin, fx);
+  } catch (const std::exception& ex) { e = std::string("index files could not be read: ") + ex.what(); }   // bad_alloc / length_error on a malformed file
   if (!e.empty()) { ctx->err = e; return SMR_ERR_INDEX; }
   const uint64_t ref_total = ref_off[nref] - ref_off[0];
   if (ref_total >= 0xFFFFFFFFull) { ctx->err = "reference part larger than 4 GB"; return SMR_ERR_UNSUPPORTED; }

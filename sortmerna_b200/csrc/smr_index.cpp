@@ -68,16 +68,18 @@ uint32_t parse_mini_trie(Reader& rd, FlatIndex& fx) {
 }
 
 // appends the entries of the mini trie rooted at `node` to fx.flist in the reference's DFS order
-void dfs_flatten(const FlatIndex& fx, std::vector<Entry>& out, uint32_t node, uint32_t depth, uint32_t path) {
+bool dfs_flatten(const FlatIndex& fx, std::vector<Entry>& out, uint32_t node, uint32_t depth, uint32_t path) {
+  if (depth > fx.partialwin) return false;   // a mini trie is at most partialwin + 1 characters deep (malformed file otherwise)
   for (uint32_t c = 0; c < 4; ++c) {
     const uint32_t w0 = fx.nodes[node].w[2 * c], w1 = fx.nodes[node].w[2 * c + 1];
     const uint32_t flag = w0 & 3u, tp = path | (c << (2 * depth));
-    if (flag == 1) dfs_flatten(fx, out, w1, depth + 1, tp);
+    if (flag == 1) { if (!dfs_flatten(fx, out, w1, depth + 1, tp)) return false; }
     else if (flag == 2) {
       const uint32_t cnt = w0 >> 2;
       for (uint32_t k = 0; k < cnt; ++k) out.push_back(Entry{tp | (fx.entries[w1 + k].tail << (2 * (depth + 1))), fx.entries[w1 + k].id});
     }
   }
+  return true;
 }
 
 }  // namespace
@@ -113,7 +115,7 @@ std::string flatten_index(const void* kmer_file, size_t kmer_bytes, const void* 
     for (int j = 0; j < 2; ++j) {
       const uint32_t root = fx.lookup[(size_t)i * 2 + j];
       const size_t o = fx.flist.size();
-      if (root != kNone) dfs_flatten(fx, fx.flist, root, 0, 0);
+      if (root != kNone && !dfs_flatten(fx, fx.flist, root, 0, 0)) return "bursttrie stream corrupt: trie deeper than the seed half at 9-mer " + std::to_string(i);
       fx.flookup[(size_t)i * 4 + 2 * j] = (uint32_t)o;
       fx.flookup[(size_t)i * 4 + 2 * j + 1] = (uint32_t)(fx.flist.size() - o);
       fx.max_list = std::max(fx.max_list, (uint32_t)(fx.flist.size() - o));
@@ -123,6 +125,7 @@ std::string flatten_index(const void* kmer_file, size_t kmer_bytes, const void* 
   Reader pr{(const uint8_t*)pos_file, pos_bytes};
   uint32_t n = pr.u32();
   if (pr.bad) return "pos file truncated";
+  if (4 + (uint64_t)n * 4 > pos_bytes) return "pos file: id count larger than the file";
   fx.pos_off.assign((size_t)n + 1, 0);
   fx.pos.reserve((pos_bytes - 4 - (size_t)n * 4) / 8);
   for (uint32_t i = 0; i < n; ++i) {

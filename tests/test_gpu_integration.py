@@ -118,6 +118,11 @@ def test_baseline_config4_through_the_binary():
         assert sorted(got) == sorted(ref)
         for fn in got:
             assert got[fn] == ref[fn], fn
+        # the same with the 8 indexes built on the GPU from the FASTA files (smr_build_index_device) instead of read from the index files
+        dev, log = _run_binary("sortmerna_gpu", fastas, reads, idx, os.path.join(d, "dev"), extra, env=dict(os.environ, SMR_INDEX_DEVICE="1"))
+        assert "Starting alignment (libsmr_b200)" in log
+        for fn in ref:
+            assert dev[fn] == ref[fn], "device-built index: " + fn
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
