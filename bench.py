@@ -180,6 +180,25 @@ def load_resident_index(al, source, fastas, prefixes, refs, ms, stats):
             al.load_index_part(k, 0, prefixes[k], refs[k], ms[k], (18, 9, 3), stats[k].lnwin)
 
 
+def survey_8d_seed(fastas, prefixes, refs, ms, stats, reads03, threads, reads_per_step, seed_ms, peak_gbs):
+    """Bytes per read of SURVEY 8(d)'s seed figure: windows x 8 B (two k-mer counts) + visited trie nodes x 4 B + visited buckets x
+    (4 B + 8 B x entries) + read bases 1 B/nt per (strand, index part), counted by the oracle's walk (oracle/smr_oracle.cpp: the
+    reference's pass schedule and pruned DFS) -- and the rate / fraction of the HBM peak the seed kernels reach measured against it."""
+    from oracle import ora
+    n = reads03.shape[0]
+    batch = hostio.ReadBatch([f"@r{i}" for i in range(n)], [b""] * n, [b""] * n, np.ascontiguousarray(reads03.reshape(-1)),
+                             (np.arange(n + 1, dtype=np.uint64) * READ_LEN))
+    oix = [ora.OracleIndex(p, 0, st.lnwin) for p, st in zip(prefixes, stats)]
+    k = len(oix)
+    got = ora.align(oix, list(range(k)), [0] * k, k, refs, ms, [18, 9, 3] * k, ora.default_params(), batch, nthreads=max(1, min(threads, 16)))
+    c = got["counters"]
+    per_read = (c["windows"] * 8 + c["trie_nodes"] * 4 + c["buckets"] * 4 + c["bucket_entries"] * 8) / n + READ_LEN * 2 * k
+    ach = per_read * reads_per_step / (seed_ms / 1e3) / 1e9
+    return {"bytes_per_read": round(per_read, 1), "achieved": ach, "unit": "GB/s", "frac": ach / peak_gbs,
+            "per_read": {kk: round(c[kk] / n, 1) for kk in ("windows", "trie_nodes", "buckets", "bucket_entries")},
+            "sample": f"oracle walk (reference pass schedule + pruned DFS) on the first {n} reads of the workload, 8 databases"}
+
+
 def reference_index_dir(fastas):
     """The reference legs (cpu_baseline, --impl reference) run the unmodified binary on the index ITS OWN builder makes
     (data_cache/idx_ref; one process per database, outside every timed region) -- never on files our builder wrote."""
@@ -565,6 +584,13 @@ def main():
                                "sample": f"first {sample} reads of the same synthetic workload vs the 8 databases, reference CPU build "
                                          f"(oracle/_ref/sortmerna_ref -threads {cores}), alignment loops {t:.1f} s (index loading excluded; "
                                          f"'Done alignment' incl. loading {total:.1f} s)"}
+        # SURVEY 8(d)'s own numerator for the seed search -- what the reference's pruned trie walk touches, "on-disk-minimal, each
+        # datum once per (read, strand, index part)" -- from the oracle's instrumented walk (the checker, CPU) on a small sample
+        try:
+            out["roofline_seed"]["survey_8d"] = survey_8d_seed(fastas, prefixes, refs, ms, stats, first_reads[:2000], cores, n,
+                                                                float(np.mean(seed_ms)), peak)
+        except Exception as e:     # the oracle library is test infrastructure: its absence must not cost the bench line
+            out["roofline_seed"]["survey_8d"] = {"unavailable": str(e)[:200]}
     emit(out)
     if world > 1:
         dist.destroy_process_group()

@@ -20,6 +20,7 @@
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cuda/functional>
 #include "smr_dev.cuh"
 
 namespace smr {

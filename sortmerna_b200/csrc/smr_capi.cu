@@ -181,7 +181,7 @@ int build_part_device(smr_ctx* ctx, const std::vector<RefRecord>& recs, const st
   size_t cub_bytes = 0, need = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, need, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, 2 * (size_t)n, 0, 64, st); cub_bytes = std::max(cub_bytes, need);
   cub::DeviceScan::InclusiveSum(nullptr, need, (uint32_t*)nullptr, (uint32_t*)nullptr, 2 * (size_t)n, st); cub_bytes = std::max(cub_bytes, need);
-  cub::DeviceScan::InclusiveScan(nullptr, need, (uint32_t*)nullptr, (uint32_t*)nullptr, cub::Max(), 2 * (size_t)n, st); cub_bytes = std::max(cub_bytes, need);
+  cub::DeviceScan::InclusiveScan(nullptr, need, (uint32_t*)nullptr, (uint32_t*)nullptr, cuda::maximum<uint32_t>{}, 2 * (size_t)n, st); cub_bytes = std::max(cub_bytes, need);
   uint8_t* d_cub; CK(tp.get(&d_cub, cub_bytes + 256));
   // 1. windows sorted by value (stable: equal values keep scan order)
   bld_windows_kernel<<<gw, tb, 0, st>>>(d_codes, d_soff, d_wstart, g, keyA, valA);
@@ -209,7 +209,7 @@ int build_part_device(smr_ctx* ctx, const std::vector<RefRecord>& recs, const st
   need = cub_bytes; CK(cub::DeviceRadixSort::SortKeys(d_cub, need, keyA, keyB, (size_t)n, 0, 64, st));
   bld_posflag_kernel<<<gw, tb, 0, st>>>(keyB, n, u0);
   CK(cudaGetLastError());
-  need = cub_bytes; CK(cub::DeviceScan::InclusiveScan(d_cub, need, u0, u1, cub::Max(), (size_t)n, st));
+  need = cub_bytes; CK(cub::DeviceScan::InclusiveScan(d_cub, need, u0, u1, cuda::maximum<uint32_t>{}, (size_t)n, st));
   bld_poskeep_kernel<<<gw, tb, 0, st>>>(u1, n, g.max_pos, u2);
   CK(cudaGetLastError());
   need = cub_bytes; CK(cub::DeviceScan::InclusiveSum(d_cub, need, u2, u3, (size_t)n, st));
@@ -842,6 +842,7 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
     return SMR_ERR_CAPACITY;
   }
   if (run > out.cigar_cap) { ctx->err = "cigar pool too small"; return SMR_ERR_CAPACITY; }
+  if (run >= 0xFFFFFFFFull) { ctx->err = "CIGAR pool offset passes 2^32 words (smr_aln.cigar_off is 32-bit): use smaller batches"; return SMR_ERR_CAPACITY; }
   out.cigar_used = run;
   // pass 2: results, alignments and cigars of disjoint read ranges, by a few host threads for large batches
   auto pack = [&](uint32_t lo, uint32_t hi) {
@@ -859,7 +860,6 @@ int download_impl(smr_ctx* ctx, HostOut& out, std::vector<uint32_t>& flagged, co
         if (k >= s.n_align) continue;
         const OutAln& d = oa[(size_t)r * slots + k];
         memcpy(out.cigar_pool + at, cig + d.cigar_off, (size_t)d.cigar_len * 4);
-        if (at + d.cigar_len >= 0xFFFFFFFFull) { ctx->err = "CIGAR pool offset passes 2^32 words: use smaller batches"; return SMR_ERR_CAPACITY; }
         a.cigar_off = (uint32_t)at; a.cigar_len = d.cigar_len; at += d.cigar_len;
         a.ref_num = d.ref_num; a.ref_begin1 = d.ref_begin1; a.ref_end1 = d.ref_end1; a.read_begin1 = d.read_begin1; a.read_end1 = d.read_end1;
         a.readlen = d.readlen; a.score1 = d.score1; a.part = d.part; a.index_num = d.index_num; a.strand = d.strand;
