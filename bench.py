@@ -540,7 +540,8 @@ def main():
     sw_peak = dpx / 3.5 / 1e3                        # Tcell-updates/s
     tr = {}
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        cands = [os.path.join(ROOT, "profiles", f) for f in ("r2b_traffic.json", "r2_traffic.json")]   # the newest committed capture
+        tr = json.load(open(next(f for f in cands if os.path.exists(f))))
     except Exception:
         pass
     def _traffic(kernel):   # ncu DRAM bytes of the committed capture, scaled to the reads of one launch of this run

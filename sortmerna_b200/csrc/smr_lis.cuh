@@ -81,6 +81,9 @@ constexpr uint32_t kSmallRound = 32;              // rounds of up to this many p
 constexpr uint32_t kNoTask = 0xFFFFFFu;
 constexpr uint32_t kPoison = 0xFFFFu;             // planner id of the shutdown entries
 constexpr uint32_t kBatchCandCap = 4096;          // candidates per batch
+#ifndef SMR_BATCH_CAP0
+#define SMR_BATCH_CAP0 32                         // candidates in the first batch of a call (8: 219.5 ms, 32: 216.8, 128: 216.8 per 500 k reads)
+#endif
 
 // one Smith-Waterman call the reference would make (alignment.cpp:365-381), as the scorers see it
 struct SwTask {
@@ -642,7 +645,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
   uint32_t prev_occur = 0;
   const uint32_t N = (uint32_t)o.num_alignments;
   AlnWork* slots = E.g->aln_work + (size_t)rc.r * E.g->slots;
-  uint32_t cap = 8;   // candidates per batch; doubles per batch (a perfect-score stop wastes at most what was useful)
+  uint32_t cap = SMR_BATCH_CAP0;   // candidates per batch; doubles per batch (a perfect-score stop wastes at most what was useful)
   uint32_t* cfirst = E.ar.cfirst; uint32_t* ccnt = cfirst + kBatchCandCap; uint32_t* cumask = ccnt + kBatchCandCap;
 
 #pragma unroll 1

@@ -2,7 +2,7 @@
 # The ncu passes behind profiles/ (run on the GPU box through gpurun; see /opt/skills/guides/B200_PROFILING.md).
 # Index cache first: building it under ncu crashes the profiler's child process.
 set -e
-R=${ROUND:-r2}
+R=${ROUND:-r2b}
 python -c "import bench; bench.load_databases()" > /dev/null 2>&1
 K="regex:seed_kernel|lis_kernel|lis_reset_kernel|finalize_kernel|traceback_kernel|pack_reads_kernel|bin_kernel"
 mkdir -p gpurun_out
