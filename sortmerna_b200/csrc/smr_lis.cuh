@@ -81,6 +81,9 @@ constexpr uint32_t kSmallRound = 32;              // rounds of up to this many p
 constexpr uint32_t kNoTask = 0xFFFFFFu;
 constexpr uint32_t kPoison = 0xFFFFu;             // planner id of the shutdown entries
 constexpr uint32_t kBatchCandCap = 4096;          // candidates per batch
+#ifndef SMR_PLANNER_POLL_NS
+#define SMR_PLANNER_POLL_NS 256                     // sleep between two looks of a planner at its score counter
+#endif
 #ifndef SMR_BATCH_CAP0
 #define SMR_BATCH_CAP0 32                         // candidates in the first batch of a call (8: 219.5 ms, 32: 216.8, 128: 216.8 per 500 k reads)
 #endif
@@ -290,7 +293,13 @@ __device__ __noinline__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
   for (uint32_t i = lane; i < npairs; i += 32) { const uint32_t idx = base + i; st_volatile_u32(&ring[idx & (kQueueCap - 1)].seq, idx + 1); }
   E.submitted += nsel;
   const long long tw0 = lis_clock();
-  if (lane == 0) { while (ld_volatile_u32(g.done + E.planner) != E.submitted) __nanosleep(256); __threadfence(); }
+  if (lane == 0) {
+    // (pointer and target in registers: the poll is four instructions -- the waiting planners share their schedulers with the scorers)
+    const uint32_t* const dp = g.done + E.planner;
+    const uint32_t want = E.submitted;
+    while (ld_volatile_u32(dp) != want) __nanosleep(SMR_PLANNER_POLL_NS);
+    __threadfence();
+  }
   __syncwarp();
   if (npairs == 1) { E.w1_cyc += (unsigned long long)(lis_clock() - tw0); E.w1_cnt++; }
 
