@@ -82,7 +82,7 @@ constexpr uint32_t kNoTask = 0xFFFFFFu;
 constexpr uint32_t kPoison = 0xFFFFu;             // planner id of the shutdown entries
 constexpr uint32_t kBatchCandCap = 4096;          // candidates per batch
 #ifndef SMR_PLANNER_POLL_NS
-#define SMR_PLANNER_POLL_NS 256                     // sleep between two looks of a planner at its score counter
+#define SMR_PLANNER_POLL_NS 1024                    // sleep between two looks of a planner at its score counter (256: 215.1 ms, 512: 214.2, 1024: 213.4)
 #endif
 #ifndef SMR_BATCH_CAP0
 #define SMR_BATCH_CAP0 32                         // candidates in the first batch of a call (8: 219.5 ms, 32: 216.8, 128: 216.8 per 500 k reads)
