@@ -171,6 +171,12 @@ int smr_set_aln_slots(smr_ctx*, uint32_t slots);
 uint32_t smr_aln_slots(const smr_ctx*);
 uint32_t smr_aln_slots_needed(const smr_ctx*);
 
+/* Instrumentation (default OFF; the environment variable SMR_INSTR=1 turns it on at smr_init).  With it, the seed kernel counts
+ * SMR_CNT_WINDOWS / BUCKETS / BUCKET_ENTRIES and the candidate kernel accounts its phases with the cycle counter (the SMR_CNT_*
+ * entries from DBG_MAX_READ_CYCLES on): separate instantiations of both kernels, 2-3 % slower.  Everything a caller of the
+ * reference would see -- results, Readstats counters, SW_CALLS / SW_CELLS / POS_ENTRIES / LIS_CALLS -- is identical either way. */
+int smr_set_instrumentation(smr_ctx*, int on);
+
 /* Optional: where the next smr_align_batch / smr_download_results stores smr_aln_stats for every stored alignment (same
  * indexing as alns[]; nullptr = do not compute).  Host buffer of nreads * max(1,num_alignments) entries. */
 int smr_set_stats_buffer(smr_ctx*, smr_aln_stats* stats);

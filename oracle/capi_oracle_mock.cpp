@@ -50,6 +50,7 @@ int smr_set_params(smr_ctx* c, const smr_params* p) {
   return SMR_OK;
 }
 
+int smr_set_instrumentation(smr_ctx* c, int) { return c ? SMR_OK : SMR_ERR_ARG; }
 int smr_set_aln_slots(smr_ctx* c, uint32_t slots) { if (!c || !slots) return SMR_ERR_ARG; c->all_slots = slots; return SMR_OK; }
 uint32_t smr_aln_slots(const smr_ctx* c) { return c->prm.num_alignments > 0 ? (uint32_t)c->prm.num_alignments : c->all_slots; }
 uint32_t smr_aln_slots_needed(const smr_ctx* c) { return c->need_slots; }

@@ -27,7 +27,7 @@ SYMBOLS = ["smr_init", "smr_destroy", "smr_last_error", "smr_device_count", "smr
            "smr_run_resident", "smr_download_results", "smr_last_timings", "smr_debug_seed_windows", "smr_debug_ssw",
            "smr_debug_dpx_peak", "smr_set_stats_buffer", "smr_build_index", "smr_upload_fastx", "smr_resident_layout", "smr_pack_kvdb_blobs",
            "smr_set_aln_slots", "smr_aln_slots", "smr_aln_slots_needed", "smr_upload_fastx_gz", "smr_resident_text", "smr_debug_inflate",
-           "smr_build_index_device", "smr_debug_index_array"]
+           "smr_build_index_device", "smr_debug_index_array", "smr_set_instrumentation"]
 
 CNT_NAMES = ("num_aligned", "num_short", "sw_calls", "sw_cells", "windows", "trie_nodes", "buckets",
              "bucket_entries", "pos_entries", "lis_calls", "dbg_max_read_cycles", "dbg_sum_read_cycles", "dbg_lis_kernel_cycles",
@@ -83,6 +83,7 @@ def load_library():
         L.smr_aln_slots_needed.restype = C.c_uint32
         L.smr_aln_slots_needed.argtypes = [C.c_void_p]
         L.smr_set_aln_slots.argtypes = [C.c_void_p, C.c_uint32]
+        L.smr_set_instrumentation.argtypes = [C.c_void_p, C.c_int]
         for name in SYMBOLS:
             getattr(L, name)  # AttributeError if the build is stale
         _lib = L
@@ -166,6 +167,11 @@ class Aligner:
     def set_params(self, params: Params):
         self.params = params
         self._check(self.L.smr_set_params(self.h, C.byref(params)), "smr_set_params")
+
+    def set_instrumentation(self, on: bool):
+        """smr_set_instrumentation: the instrumented instantiations of the seed and candidate kernels (seed-side counters and the
+        cycle shares in `counters`); default off."""
+        self._check(self.L.smr_set_instrumentation(self.h, C.c_int(1 if on else 0)), "smr_set_instrumentation")
 
     def set_aln_slots(self, slots: int):
         """smr_set_aln_slots: stride of the result layout in the all-alignments mode (num_alignments == 0)."""

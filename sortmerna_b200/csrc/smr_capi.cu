@@ -76,7 +76,7 @@ struct smr_ctx {
   uint32_t lane_hits_cap = 0, lane_hits_warps = 0;
   uint64_t cigar_cap_dev = 0;
   uint32_t scale = 1;         // scratch scale of the current run (1 = fast path)
-  bool instr = true;          // count windows/nodes/entries in the seed kernel
+  bool instr = false;         // smr_set_instrumentation: seed kernel counts windows / lists / entries, candidate kernel accounts its phases (clock64)
   uint64_t flag_hist[6] = {0, 0, 0, 0, 0, 0};  // overflow causes seen so far (seed lane / seed region / pairs / trace / cigar / error)
   // timings
   std::vector<cudaEvent_t> ev;
@@ -287,8 +287,9 @@ int setup_arenas(smr_ctx* ctx) {
   ctx->row_cap = ctx->max_len + 2 * edges + 2 * 64 + 64;
   // planner and scorer warps wait for each other: EVERY CTA of the grid must be resident at once
   int occ = 0;
-  CK(cudaFuncSetAttribute(lis_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLisSmemBytes));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lis_kernel, kLisWarpsPerCta * 32, kLisSmemBytes));
+  CK(cudaFuncSetAttribute(lis_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLisSmemBytes));
+  CK(cudaFuncSetAttribute(lis_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLisSmemBytes));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lis_kernel<true>, kLisWarpsPerCta * 32, kLisSmemBytes));   // (same launch bounds and shared memory for both)
   if (occ < 1) { ctx->err = "lis_kernel does not fit on an SM"; return SMR_ERR_CUDA; }
   ctx->lis_ctas = (uint32_t)ctx->sm_count * std::min<uint32_t>(ctx->lis_ctas_per_sm, (uint32_t)occ);
   ctx->lis_warps = ctx->lis_ctas * kPlannerWarps;   // planner warps (each owns an arena)
@@ -724,7 +725,8 @@ int run_impl(smr_ctx* ctx) {
       lg.q_head = sc.q_head; lg.q_tail = sc.q_tail; lg.planners_done = sc.planners_done;
       lis_reset_kernel<<<kQueueCap / 256, 256, 0, ctx->stream>>>(lg, ctx->lis_warps);
       CK(cudaGetLastError());
-      lis_kernel<<<ctx->lis_ctas, kLisWarpsPerCta * 32, kLisSmemBytes, ctx->stream>>>(b, dp, lg);
+      if (ctx->instr) lis_kernel<true><<<ctx->lis_ctas, kLisWarpsPerCta * 32, kLisSmemBytes, ctx->stream>>>(b, dp, lg);
+      else lis_kernel<false><<<ctx->lis_ctas, kLisWarpsPerCta * 32, kLisSmemBytes, ctx->stream>>>(b, dp, lg);
       CK(cudaGetLastError());
       CK(cudaEventRecord(s2, ctx->stream));
       spans.push_back({evi - 3, 0});
@@ -938,7 +940,7 @@ int smr_init(int device, smr_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SMR_ERR_CUDA; }
   if (const char* e = getenv("SMR_CHUNK_READS")) { const long v = atol(e); if (v >= 32 && v <= (1l << 22)) ctx->chunk_reads = (uint32_t)v; }   // tests: several chunks per batch
-  if (getenv("SMR_NO_INSTR")) ctx->instr = false;   // seed kernel without its window / entry counters (tools/ab_variants.sh: cost of the instrumentation)
+  if (const char* e = getenv("SMR_INSTR")) ctx->instr = atoi(e) != 0;   // instrumented instantiations of the seed and candidate kernels (smr_set_instrumentation)
   if (const char* e = getenv("SMR_LIS_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 16) ctx->lis_ctas_per_sm = (uint32_t)v; }
   *out = ctx;
   return SMR_OK;
@@ -1112,6 +1114,12 @@ int smr_align_batch(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_of
   int rc = align_impl(ctx, seq_cat, seq_off, nreads, out, nullptr, 0);
   if (cigar_used) *cigar_used = out.cigar_used;
   return rc;
+}
+
+int smr_set_instrumentation(smr_ctx* ctx, int on) {
+  if (!ctx) return SMR_ERR_ARG;
+  ctx->instr = on != 0;
+  return SMR_OK;
 }
 
 int smr_set_stats_buffer(smr_ctx* ctx, smr_aln_stats* stats) {

@@ -36,19 +36,20 @@
 
 namespace smr {
 
+// One CTA of 32 warps per SM: 16 scorers + 1 fetcher (one lane per scorer slot) + 15 planners.  (Two CTAs of 8 + 1 + 7 need two
+// fetcher warps per SM: one planner fewer -- 213.1 vs 207.1 ms per 500 k reads; 14 + 1 + 17: 209.6.)
 #ifndef SMR_SCORER_WARPS
-#define SMR_SCORER_WARPS 8
+#define SMR_SCORER_WARPS 16
 #endif
 #ifndef SMR_PLANNER_WARPS
-#define SMR_PLANNER_WARPS 7
+#define SMR_PLANNER_WARPS 15
 #endif
 #ifndef SMR_LIS_MIN_CTAS
-#define SMR_LIS_MIN_CTAS 2
+#define SMR_LIS_MIN_CTAS 1
 #endif
-#ifndef SMR_LIS_INSTR
-#define SMR_LIS_INSTR 1   // phase accounting with clock64 (bench counters); 0 = compiled out (tools/ab_variants.sh measures its cost)
-#endif
-__device__ __forceinline__ long long lis_clock() { return SMR_LIS_INSTR ? clock64() : 0ll; }
+// Phase accounting with clock64 (the cycle shares bench.py reports) is a template parameter of the kernel: the product runs the
+// instantiation without it (smr_set_instrumentation; 199.6 vs 204.9 ms per 500 k reads with it).
+template <bool kInstr> __device__ __forceinline__ long long lis_clock() { return kInstr ? clock64() : 0ll; }
 constexpr int kScorerWarps = SMR_SCORER_WARPS;     // the first warps of a CTA score
 constexpr int kFetcherWarps = 1;                   // then one warp that pops the task queue and stages the scorers' inputs (TMA bulk copies)
 constexpr int kPlannerWarps = SMR_PLANNER_WARPS;   // the others plan
@@ -84,6 +85,19 @@ constexpr uint32_t kBatchCandCap = 4096;          // candidates per batch
 #ifndef SMR_PLANNER_POLL_NS
 #define SMR_PLANNER_POLL_NS 1024                    // sleep between two looks of a planner at its score counter (256: 215.1 ms, 512: 214.2, 1024: 213.4)
 #endif
+constexpr uint32_t kScorePending = 0xFFFFFFFFu;     // score word of a task that has been handed to the scorers and not been scored yet
+// Sensitivity experiments (tools/ab_round.sh; never set in the shipped build): stretch a role's own work by N per cent with sleeps
+// (no issue slots taken) -- how much the kernel slows tells which role bounds it.
+#ifndef SMR_EXP_PLANNER_DELAY
+#define SMR_EXP_PLANNER_DELAY 0
+#endif
+#ifndef SMR_EXP_SCORER_DELAY
+#define SMR_EXP_SCORER_DELAY 0
+#endif
+__device__ __forceinline__ void exp_delay(const long long t0, const int pct) {
+  const long long now = clock64(), until = now + (now - t0) * pct / 100;
+  while (clock64() < until) __nanosleep(256);
+}
 #ifndef SMR_BATCH_CAP0
 #define SMR_BATCH_CAP0 32                         // candidates in the first batch of a call (8: 219.5 ms, 32: 216.8, 128: 216.8 per 500 k reads)
 #endif
@@ -264,8 +278,10 @@ struct PassEnv {
 // ---- the task queue (bounded MPMC ring, per-slot sequence numbers) ----
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return *(const volatile uint32_t*)p; }
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) { *(volatile uint32_t*)p = v; }
+__device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // hands the tasks sel[0 .. nsel) of this planner to the scorers, two per queue entry, and waits for their scores
+template <bool kInstr>
 __device__ __noinline__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
   if (nsel == 0) return;
   const LisGlobals& g = *E.g;
@@ -278,6 +294,10 @@ __device__ __noinline__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
   uint32_t base = 0;
   if (lane == 0) base = atomicAdd(g.q_tail + qi * 16, npairs);
   base = __shfl_sync(kFull, base, 0);
+  // One pass: entry, then its sequence number with a RELEASE store (MEMBAR.ALL.GPU + ST: the task records -- written by any lane
+  // before the __syncwarp -- and the entry are visible before the number that publishes them).  __threadfence() would also
+  // invalidate the SM's whole L1 (CCTL.IVALL: its acquire half), every time, for every warp of the SM.
+  __syncwarp();
 #pragma unroll 1
   for (uint32_t i = lane; i < npairs; i += 32) {
     const uint32_t idx = base + i;
@@ -285,30 +305,38 @@ __device__ __noinline__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
 #pragma unroll 1
     while (ld_volatile_u32(&sl->seq) != idx) __nanosleep(64);        // the consumer of the previous lap has left the slot
     const uint32_t ta = E.ar.sel[2 * i], tb = (2 * i + 1 < nsel) ? E.ar.sel[2 * i + 1] : kNoTask;
+    E.ar.tasks[ta].score = kScorePending; if (tb != kNoTask) E.ar.tasks[tb].score = kScorePending;
     sl->planner = E.planner; sl->ta = ta; sl->tb = tb;
+    st_release_gpu_u32(&sl->seq, idx + 1);
   }
-  __threadfence();      // task records + entries before the sequence numbers that publish them
-  __syncwarp();
-#pragma unroll 1
-  for (uint32_t i = lane; i < npairs; i += 32) { const uint32_t idx = base + i; st_volatile_u32(&ring[idx & (kQueueCap - 1)].seq, idx + 1); }
   E.submitted += nsel;
-  const long long tw0 = lis_clock();
+  const long long tw0 = lis_clock<kInstr>();
   if (lane == 0) {
     // (pointer and target in registers: the poll is four instructions -- the waiting planners share their schedulers with the scorers)
     const uint32_t* const dp = g.done + E.planner;
     const uint32_t want = E.submitted;
     while (ld_volatile_u32(dp) != want) __nanosleep(SMR_PLANNER_POLL_NS);
-    __threadfence();
   }
   __syncwarp();
-  if (npairs == 1) { E.w1_cyc += (unsigned long long)(lis_clock() - tw0); E.w1_cnt++; }
+  // The counter is only a hint: a scorer adds to it after a plain store of the score, with no fence in between (a MEMBAR per pair
+  // cost the scorers 5 % of their time).  What is relied on is each score word itself: it held kScorePending at submission.
+#pragma unroll 1
+  for (uint32_t i = lane; i < nsel; i += 32) {
+    const uint32_t* const sp = &E.ar.tasks[E.ar.sel[i]].score;
+#pragma unroll 1
+    while (ld_volatile_u32(sp) == kScorePending) __nanosleep(64);
+  }
+  __syncwarp();
+  if (npairs == 1) { E.w1_cyc += (unsigned long long)(lis_clock<kInstr>() - tw0); E.w1_cnt++; }
 
 }
 
+template <bool kInstr>
 __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score, const uint32_t ncand, const bool by_level,
                                uint32_t level, const bool grouped);
 
 // compute_lis_alignment (alignment.cpp:100-509).  Uniform control flow; warp-parallel inner scans.
+template <bool kInstr>
 __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score) {
   const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
   const unsigned lane = lane_id();
@@ -317,7 +345,8 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   const uint32_t nh = E.nh;
   const uint32_t ns = (uint32_t)max(o.num_seeds, 1);
   E.n_lis_calls++;
-  long long tph = lis_clock();
+  long long tph = lis_clock<kInstr>();
+  const long long t_call0 = SMR_EXP_PLANNER_DELAY ? clock64() : 0ll;
 
   // ---- 1. votes per reference (alignment.cpp:118-138) ----
   if (++E.epoch >= 2048u) {   // epoch tag wrapped (11 bits: bit 31 of a histogram word marks a pair cursor): clear once
@@ -348,6 +377,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
       return e < tot ? __ldg(&ix.pos[o_own + (e - ex_own)]).y : 0xFFFFFFFFu;
     };
     uint32_t seq_next = tot ? fetch_seq(0) : 0xFFFFFFFFu;
+    // one leader lane per distinct reference of the step reads the epoch-tagged word and writes it back
 #pragma unroll 1
     for (uint32_t e0 = 0; e0 < tot; e0 += 32) {
       const uint32_t seq = seq_next;
@@ -373,7 +403,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
       __syncwarp();
     }
   }
-  { const long long t2 = lis_clock(); E.cyc[0] += (unsigned long long)(t2 - tph); tph = t2; }
+  { const long long t2 = lis_clock<kInstr>(); E.cyc[0] += (unsigned long long)(t2 - tph); tph = t2; }
   if (ncand == 0) return;
   if (ncand > E.ar.cand_cap) { rc.flags |= kOvfPairs; return; }
   __syncwarp();
@@ -386,7 +416,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   if (!by_level) {
     unsigned long long key = ~0ull;
     if (lane < ncand) {
-      const uint32_t seq = (uint32_t)E.ar.cand[lane]; const uint32_t c = E.ar.hist[seq] & 0xFFFFFu;
+      const uint32_t seq = (uint32_t)E.ar.cand[lane]; const uint32_t c = __ldcg(&E.ar.hist[seq]) & 0xFFFFFu;   // (L2: the votes are atomics)
       key = ((unsigned long long)(0xFFFFFu - c) << 32) | seq;
       E.ar.bitmap[seq >> 5] = 0; E.ar.summary[seq >> 10] = 0;
     }
@@ -412,7 +442,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
 #pragma unroll 1
         while (bw) {
           const uint32_t bit = __ffs(bw) - 1; bw &= bw - 1;
-          const uint32_t seq = (base_word + lane) * 32u + bit, c = E.ar.hist[seq] & 0xFFFFFu;
+          const uint32_t seq = (base_word + lane) * 32u + bit, c = __ldcg(&E.ar.hist[seq]) & 0xFFFFFu;
           if (pos < E.ar.cand_cap) E.ar.cand[pos] = ((unsigned long long)(0xFFFFFu - c) << 32) | seq;
           ++pos; level = max(level, c);
         }
@@ -425,7 +455,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   }
   __syncwarp();
 
-  { const long long t2 = lis_clock(); E.cyc[1] += (unsigned long long)(t2 - tph); tph = t2; }
+  { const long long t2 = lis_clock<kInstr>(); E.cyc[1] += (unsigned long long)(t2 - tph); tph = t2; }
   // ---- 2b. group the (refpos, readpos) pairs of ALL candidates in one pass over the position lists ----
   // (the reference rescans every list once per candidate, alignment.cpp:181-194; with thousands of candidates a
   //  per-candidate gather -- even by binary search -- dominates, so the pairs are scattered into per-reference
@@ -470,13 +500,13 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
           return e < tot ? __ldg(&ix.pos[o_own + (e - ex_own)]) : make_uint2(0u, 0xFFFFFFFFu);
         };
         uint2 ps_next = tot ? fetch_pos(0, w_nxt) : make_uint2(0u, 0xFFFFFFFFu);
+        // ONE round trip per entry: the add returns the cursor when bit 31 is set; on the word of a non-candidate (an epoch-tagged
+        // count below num_seeds that nothing reads again in this epoch) the extra count is harmless.
 #pragma unroll 1
         for (uint32_t e0 = 0; e0 < tot; e0 += 32) {
           const uint2 ps = ps_next; w_cur = w_nxt;
           if (e0 + 32 < tot) ps_next = fetch_pos(e0 + 32, w_nxt);
           if (ps.y < E.ar.hist_cap) {
-            // ONE round trip: the add returns the cursor when bit 31 is set; on the word of a non-candidate (an epoch-tagged
-            // count below num_seeds that nothing reads again in this epoch) the extra count is harmless
             const uint32_t old = atomicAdd(&E.ar.hist[ps.y], 1u);
             if (old & 0x80000000u) E.ar.pall[old & 0x7FFFFFFFu] = ((unsigned long long)ps.x << 32) | w_cur;
           }
@@ -486,8 +516,9 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
       grouped = true;
     }
   }
-  { const long long t2 = lis_clock(); E.cyc[2] += (unsigned long long)(t2 - tph); tph = t2; }
-  run_candidates(E, rc, search, max_SW_score, ncand, by_level, level, grouped);
+  { const long long t2 = lis_clock<kInstr>(); E.cyc[2] += (unsigned long long)(t2 - tph); tph = t2; }
+  if (SMR_EXP_PLANNER_DELAY) exp_delay(t_call0, SMR_EXP_PLANNER_DELAY);
+  run_candidates<kInstr>(E, rc, search, max_SW_score, ncand, by_level, level, grouped);
   __syncwarp();
   if (grouped) {   // the cursors must not survive the call: histogram words are epoch-tagged votes otherwise
     const unsigned long long* list = E.ar.cand;
@@ -592,7 +623,7 @@ __device__ __noinline__ bool plan_candidate_warp(PassEnv& E, ReadCtx& rc, const 
   else { rc.flags |= kOvfPairs; return false; }
   uint32_t filled = 0;
   if (grouped) {   // the pairs of this reference were grouped by the one-pass scatter
-    const uint32_t seg_end = E.ar.hist[max_ref] & 0x7FFFFFFFu, seg = seg_end - np;
+    const uint32_t seg_end = __ldcg(&E.ar.hist[max_ref]) & 0x7FFFFFFFu, seg = seg_end - np;
 #pragma unroll 1
     for (uint32_t i = lane; i < np; i += 32) P[i] = E.ar.pall[seg + i];
     filled = np;
@@ -645,6 +676,7 @@ __device__ __noinline__ bool plan_candidate_warp(PassEnv& E, ReadCtx& rc, const 
 
 // candidates in order (alignment.cpp:150-508), in batches: plan -> score (by the scorer warps) -> replay.
 // Returns through rc.flags on scratch overflow.
+template <bool kInstr>
 __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score, const uint32_t ncand, const bool by_level,
                                uint32_t level, const bool grouped) {
   const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
@@ -682,7 +714,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
     uint32_t k = 0;
 #pragma unroll 1
     while (k < ngrp && searching) {
-      long long tc0 = lis_clock();
+      long long tc0 = lis_clock<kInstr>();
       // ---- entry of the batch's first candidate (:158-169): decided now, with the scores known so far ----
       {
         const uint32_t occ = 0xFFFFFu - (uint32_t)(E.ar.grp[k] >> 32);
@@ -727,7 +759,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
         CandPlan cp{0, 0, 0, false};
         if (small) {
           const uint64_t ref_base = __ldg(ix.ref_off + max_ref), ref_next = __ldg(ix.ref_off + max_ref + 1);
-          const uint32_t seg = (E.ar.hist[max_ref] & 0x7FFFFFFFu) - np;
+          const uint32_t seg = (__ldcg(&E.ar.hist[max_ref]) & 0x7FFFFFFFu) - np;
           unsigned long long P[kLanePairs]; uint8_t lb[kLanePairs], lp[kLanePairs];
 #pragma unroll 1
           for (uint32_t i = 0; i < np; ++i) {    // insertion sort while loading (refpos asc, readpos asc: alignment.cpp:197-201)
@@ -772,9 +804,9 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
         tbase += __shfl_sync(kFull, incl, 31);
       }
       __syncwarp();
-      { const long long t2 = lis_clock(); E.cyc[3] += (unsigned long long)(t2 - tc0); tc0 = t2; }
+      { const long long t2 = lis_clock<kInstr>(); E.cyc[3] += (unsigned long long)(t2 - tc0); tc0 = t2; }
       // ---- score, round A: the unconditional tasks ----
-      submit_and_wait(E, nselA);
+      submit_and_wait<kInstr>(E, nselA);
       E.n_spec_calls += nselA; E.n_spec_cells += nselA ? 1 : 0;
       // ---- round B: tasks heuristic 1 would skip after a successful lead (:243-246) are needed when the lead failed ----
       if (ncond) {
@@ -820,10 +852,10 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
           }
         }
         __syncwarp();
-        submit_and_wait(E, nselB);
+        submit_and_wait<kInstr>(E, nselB);
         E.n_spec_calls += nselB; E.n_rounds_b += nselB ? 1 : 0;
       }
-      { const long long t2 = lis_clock(); E.cyc[4] += (unsigned long long)(t2 - tc0); tc0 = t2; }
+      { const long long t2 = lis_clock<kInstr>(); E.cyc[4] += (unsigned long long)(t2 - tc0); tc0 = t2; }
       // ---- replay: the reference's decisions over the scores, in order ----
 #pragma unroll 1
       for (uint32_t c0 = 0; c0 < nb && searching; c0 += 32) {
@@ -941,7 +973,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
           if (searching && (cw & 0x80000000u)) is_aligned = false;
         }
       }
-      { const long long t2 = lis_clock(); E.cyc[5] += (unsigned long long)(t2 - tc0); }
+      { const long long t2 = lis_clock<kInstr>(); E.cyc[5] += (unsigned long long)(t2 - tc0); }
       k += nb;
       cap = min(cap * 2u, (uint32_t)kBatchCandCap);
       __syncwarp();
@@ -952,6 +984,7 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
 }
 
 // traverse() pass loop for one strand (paralleltraversal.cpp:92-297)
+template <bool kInstr>
 __device__ void traverse_dev(PassEnv& E, ReadCtx& rc, const bool is_last_strand) {
   const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
   const unsigned lane = lane_id();
@@ -982,7 +1015,7 @@ __device__ void traverse_dev(PassEnv& E, ReadCtx& rc, const bool is_last_strand)
       newly += __popc(__ballot_sync(kFull, cnt));
     }
     rc.hit_seeds += newly;
-    if (rc.hit_seeds >= (uint32_t)o.num_seeds) compute_lis_dev(E, rc, search, max_SW_score);  // :256-258
+    if (rc.hit_seeds >= (uint32_t)o.num_seeds) compute_lis_dev<kInstr>(E, rc, search, max_SW_score);  // :256-258
     if (rc.flags) return;
     if (search) {                                                                              // :262-277
       if (pass_n == 2) search = false;
@@ -1017,7 +1050,7 @@ __device__ void fetcher_loop(const DevBatch& b, const DevParams& prm, const LisG
       if (have) {
         QSlot* qs = ring + (h & (kQueueCap - 1));
         if (ld_volatile_u32(&qs->seq) == h + 1u) {
-          __threadfence();
+          // (the entry and the task records are read past L1 -- ld.cg -- after the number has been seen: no L1 invalidation needed)
           const uint32_t planner = __ldcg(&qs->planner), ta = __ldcg(&qs->ta), tb = __ldcg(&qs->tb);
           st_volatile_u32(&qs->seq, h + kQueueCap);   // slot free for the next lap (after the payload was read)
           have = false; progress = true;
@@ -1067,6 +1100,7 @@ __device__ void fetcher_loop(const DevBatch& b, const DevParams& prm, const LisG
 }
 
 // ---- scorer role: take a staged task pair, score it with the packed kernel, report ----
+template <bool kInstr>
 __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGlobals& g, uint8_t* sm, const uint32_t scorer) {
   const unsigned lane = lane_id();
   const SwScore sc{prm.match, prm.mismatch, prm.score_N, prm.gap_open, prm.gap_ext, prm.one};
@@ -1078,7 +1112,7 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
   uint32_t par[2] = {0, 0}, exited = 0;
   unsigned long long n_pairs = 0, n_cells = 0, n_slow = 0, cy_wait = 0, cy_load = 0, cy_sw = 0, cy_pub = 0;
   for (;;) {
-    long long tq = lis_clock();
+    long long tq = lis_clock<kInstr>();
     int k = -1;
     for (;;) {
       if (!(exited & 1u) && mbar_try_wait(&slots[0].bar, par[0])) { k = 0; break; }
@@ -1087,7 +1121,7 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
     }
     par[k] ^= 1u;
     ScSlot& S = slots[k];
-    { const long long t2 = lis_clock(); cy_wait += (unsigned long long)(t2 - tq); tq = t2; }
+    { const long long t2 = lis_clock<kInstr>(); cy_wait += (unsigned long long)(t2 - tq); tq = t2; }
     const uint32_t planner = S.planner;
     if (planner == kPoison) { exited |= 1u << k; if (exited == 3u) break; continue; }
     const uint32_t ta = S.ta, tb = S.tb;
@@ -1101,12 +1135,17 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
       pair_sentinels(wa, nA, nmax);
       pair_sentinels(wb, nB, nmax);
       const uint32_t kqa = S.qabsA, kma = (uint32_t)mA | ((S.metaA & 0x10000u) << 15), kqb = mB ? S.qabsB : 0xFFFFFFFEu, kmb = mB ? ((uint32_t)mB | ((S.metaB & 0x10000u) << 15)) : 0u;
-      if (!(R == keyR && keyq[0] == kqa && keym[0] == kma)) { const bool rev = (S.metaA & 0x10000u) != 0; pair_profile(S.q[0] + S.qoffA, rev ? -1 : 1, rev, mA, R, sc, s_prof); }
-      if (!(R == keyR && keyq[1] == kqb && keym[1] == kmb)) { const bool rev = (S.metaB & 0x10000u) != 0; pair_profile(S.q[1] + S.qoffB, rev ? -1 : 1, rev, mB, R, sc, s_prof + kPairProfWords); }
-      keyR = R; keyq[0] = kqa; keym[0] = kma; keyq[1] = kqb; keym[1] = kmb;
+      // the two tasks of a pair are usually steps of one read on one strand with the same query segment: one profile serves both
+      if (R != keyR) { keyq[0] = keyq[1] = 0xFFFFFFFFu; keyR = R; }
+      if (!(keyq[0] == kqa && keym[0] == kma)) { const bool rev = (S.metaA & 0x10000u) != 0; pair_profile(S.q[0] + S.qoffA, rev ? -1 : 1, rev, mA, R, sc, s_prof); keyq[0] = kqa; keym[0] = kma; }
+      const uint32_t* profB = s_prof;
+      if (!(kqb == kqa && kmb == kma)) {
+        if (!(keyq[1] == kqb && keym[1] == kmb)) { const bool rev = (S.metaB & 0x10000u) != 0; pair_profile(S.q[1] + S.qoffB, rev ? -1 : 1, rev, mB, R, sc, s_prof + kPairProfWords); keyq[1] = kqb; keym[1] = kmb; }
+        profB = s_prof + kPairProfWords;
+      }
       __syncwarp();
-      { const long long t2 = lis_clock(); cy_load += (unsigned long long)(t2 - tq); tq = t2; }
-      const uint32_t r2 = sw_pair_dispatch(R, s_prof, s_prof + kPairProfWords, wa, wb, nmax, sc);
+      { const long long t2 = lis_clock<kInstr>(); cy_load += (unsigned long long)(t2 - tq); tq = t2; }
+      const uint32_t r2 = sw_pair_dispatch(R, s_prof, profB, wa, wb, nmax, sc);
       sa = r2 & 0xFFFFu; sb = r2 >> 16;
     } else {
       // shapes or scoring schemes outside the 16-bit kernel: the s32 wavefront (row blocks for long queries), from global memory
@@ -1119,18 +1158,18 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
       ++n_slow;
     }
     ++n_pairs; n_cells += (unsigned long long)nA * mA + (unsigned long long)nB * mB;
-    { const long long t2 = lis_clock(); cy_sw += (unsigned long long)(t2 - tq); tq = t2; }
+    if (SMR_EXP_SCORER_DELAY) exp_delay(tq, SMR_EXP_SCORER_DELAY);
+    { const long long t2 = lis_clock<kInstr>(); cy_sw += (unsigned long long)(t2 - tq); tq = t2; }
     __syncwarp();
     if (lane == 0) {
       mbar_arrive(&S.ebar);                        // the fetcher may refill this slot
       SwTask* tasks = carve_arena(g, planner).tasks;
-      tasks[ta].score = sa;
-      if (two) tasks[tb].score = sb;
-      __threadfence();
+      st_volatile_u32(&tasks[ta].score, sa);
+      if (two) st_volatile_u32(&tasks[tb].score, sb);
       atomicAdd(g.done + planner, two ? 2u : 1u);
     }
     __syncwarp();
-    { const long long t2 = lis_clock(); cy_pub += (unsigned long long)(t2 - tq); }
+    { const long long t2 = lis_clock<kInstr>(); cy_pub += (unsigned long long)(t2 - tq); }
   }
   if (lane == 0) {
     atomicAdd(&b.counters[dcSpecCells], n_cells); atomicAdd(&b.counters[dcSpecPairs], n_pairs); atomicAdd(&b.counters[dcSlowPairs], n_slow);
@@ -1143,6 +1182,7 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
 // (processor.cpp:219-277) run read-major, with the KVDB carry-over of read.cpp:429-539 kept in
 // DevBatch::state between parts (equivalent because reads are independent).  Scorer warps
 // run scorer_loop until the last planner has published the shutdown entries.
+template <bool kInstr>
 __global__ void __launch_bounds__(kLisWarpsPerCta * 32, kLisMinCtas)
 lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   extern __shared__ __align__(16) uint8_t lis_smem[];     // kLisSmemBytes: scorer warps first, then planner warps
@@ -1160,7 +1200,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  if (wic < (uint32_t)kScorerWarps) { scorer_loop(b, prm, g, lis_smem + (size_t)wic * kScorerSmem, blockIdx.x * kScorerWarps + wic); return; }
+  if (wic < (uint32_t)kScorerWarps) { scorer_loop<kInstr>(b, prm, g, lis_smem + (size_t)wic * kScorerSmem, blockIdx.x * kScorerWarps + wic); return; }
   if (wic == (uint32_t)kScorerWarps) { fetcher_loop(b, prm, g, lis_smem); return; }
   const uint32_t pw = wic - kScorerWarps - kFetcherWarps, planner = blockIdx.x * kPlannerWarps + pw;
   PassEnv E;
@@ -1175,7 +1215,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   E.n_sw_calls = E.n_sw_cells = E.n_pos_entries = E.n_lis_calls = E.n_spec_calls = E.n_spec_cells = E.n_rounds_b = E.w1_cyc = E.w1_cnt = 0;
   for (int i = 0; i < 8; ++i) E.cyc[i] = 0;
   const uint32_t nwork = s_bin_start[kCostBins];
-  unsigned long long t_max = 0, t_sum = 0; const long long t_k0 = lis_clock();
+  unsigned long long t_max = 0, t_sum = 0; const long long t_k0 = lis_clock<kInstr>();
   unsigned long long dbg_loc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_busy_max = 0;
   const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);
   for (;;) {
@@ -1186,7 +1226,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     uint32_t k = 0;
     while (wi >= s_bin_start[k + 1]) ++k;
     const uint32_t r = b.bins[(size_t)(kCostBins - 1 - k) * b.cnt_stride + (wi - s_bin_start[k])];
-    const long long t_read0 = lis_clock();
+    const long long t_read0 = lis_clock<kInstr>();
     unsigned long long cyc0[6], calls0 = E.n_sw_calls, spec0 = E.n_spec_calls, ra0 = E.n_spec_cells;
     for (int i = 0; i < 6; ++i) cyc0[i] = E.cyc[i];
     ReadCtx rc;
@@ -1209,7 +1249,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
       const int num_strands = single ? 1 : 2;                                                 // processor.cpp:130-146
       for (int count = 0; count < num_strands && !rc.is_done && !rc.flags; ++count) {
         if ((single && prm.is_reverse) || count == 1) rc.reversed = true;
-        traverse_dev(E, rc, single || count == 1);
+        traverse_dev<kInstr>(E, rc, single || count == 1);
       }
       if (rc.flags) break;
       if (rc.is_new_hit && rc.n_align > 0 && lane == 0) {                                     // kvdb.put (processor.cpp:150-155)
@@ -1222,7 +1262,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     }
     if (rc.ovf_slots) rc.flags |= kOvfSlots;
     if (rc.flags && lane == 0) atomicOr(&b.flags[r], rc.flags);
-    { const unsigned long long dt = (unsigned long long)(lis_clock() - t_read0);
+    { const unsigned long long dt = (unsigned long long)(lis_clock<kInstr>() - t_read0);
       if (dt > t_max) { t_max = dt; for (int i = 0; i < 6; ++i) dbg_loc[i] = E.cyc[i] - cyc0[i]; dbg_loc[6] = E.n_sw_calls - calls0; dbg_loc[7] = E.n_spec_calls - spec0; dbg_loc[8] = E.n_spec_cells - ra0; dbg_loc[9] = r; }
       const unsigned long long busy = dt - (E.cyc[4] - cyc0[4]);   // without the time spent waiting for the scorers
       t_busy_max = busy > t_busy_max ? busy : t_busy_max;
@@ -1238,7 +1278,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
     for (int i = 0; i < 6; ++i) atomicAdd(&b.counters[dcCycVote + i], E.cyc[i]);
     if (atomicMax(&b.counters[dcMaxReadCycles], t_max) < t_max && g.dbg) { g.dbg[0] = t_max; for (int i = 0; i < 10; ++i) g.dbg[1 + i] = dbg_loc[i]; }
     atomicAdd(&b.counters[dcSumReadCycles], t_sum);
-    atomicMax(&b.counters[dcLisKernelCycles], (unsigned long long)(lis_clock() - t_k0));
+    atomicMax(&b.counters[dcLisKernelCycles], (unsigned long long)(lis_clock<kInstr>() - t_k0));
     // the last planner out shuts the scorers down: one entry each
     const uint32_t nplanners = gridDim.x * kPlannerWarps, nscorers = gridDim.x * kScorerWarps;   // one shutdown entry per fetcher lane of each queue
     if (atomicAdd(g.planners_done, 1u) + 1u == nplanners) {

@@ -5,7 +5,7 @@ for v in ${VARIANTS:-default}; do
   python - <<PY
 import json
 j=json.load(open("gpurun_out/ab_$v.json"))
-c=j["counters"]; s=c["dbg_sum_read_cycles"]
+c=j["counters"]; s=c["dbg_sum_read_cycles"] or 1
 print("$v", "value",round(j["value"]), "e2e", round(j["e2e"]["value"]), "ms", {k: round(x,1) for k,x in j["kernel_ms_per_step"].items()}, "frac", round(j["roofline"]["frac"],3))
 print("   planner shares", {k: round(c[k]/s,3) for k in ("cyc_vote","cyc_order","cyc_group","cyc_plan","cyc_wait","cyc_replay")}, "maxread_ms", round(c["dbg_max_read_cycles"]/j["steps"]/1.965e6,1), "spec", round(j["roofline"]["speculation_overhead"],4))
 ss=sum(c[k] for k in ("sc_wait","sc_load","sc_sw","sc_pub"))
