@@ -302,8 +302,9 @@ int setup_arenas(smr_ctx* ctx) {
   if (int rc = ensure(ctx, ctx->lis_epochs, (size_t)ctx->lis_warps * 4)) return rc;
   if (int rc = ensure(ctx, ctx->lis_queue, (size_t)2 * kQueueCap * sizeof(QSlot) + 64)) return rc;
   if (int rc = ensure(ctx, ctx->lis_done, (size_t)ctx->lis_warps * 4 + 64)) return rc;
-  if (int rc = ensure(ctx, ctx->lis_dbg, 256)) return rc;
-  CK(cudaMemsetAsync(ctx->lis_dbg.p, 0, 256, ctx->stream));
+  const size_t dbg_bytes = (size_t)(kTlBase + kTlRows * kTlBuckets) * 8;
+  if (int rc = ensure(ctx, ctx->lis_dbg, dbg_bytes)) return rc;
+  CK(cudaMemsetAsync(ctx->lis_dbg.p, 0, dbg_bytes, ctx->stream));
   if (int rc = ensure(ctx, ctx->lis_rows, (size_t)ctx->lis_ctas * kScorerWarps * 2 * ctx->row_cap * 4)) return rc;
   // histogram epochs start at 0 over a zeroed histogram (every run: the arena layout depends on the scale of the run)
   CK(cudaMemset2DAsync(ctx->lis_arena.p, ctx->lis_stride, 0, lis_arena_zero_bytes(ctx->hist_cap), ctx->lis_warps, ctx->stream));   // votes + bitmaps only
@@ -311,7 +312,7 @@ int setup_arenas(smr_ctx* ctx) {
   ctx->cap_w = 2 * 256 * ctx->scale + 8;          // band widths up to 256*scale
   ctx->cap_cig = 2 * (ctx->max_len + 64) + 16;
   ctx->cap_dir = (size_t)65536 * ctx->scale + (size_t)ctx->max_len * 9 * 3 + 64;
-  ctx->final_warps = (uint32_t)ctx->sm_count * 4 * kFinalWarpsPerCta;
+  ctx->final_warps = (uint32_t)ctx->sm_count * kFinalCtasPerSm * kFinalWarpsPerCta;
   ctx->final_stride = final_arena_bytes(ctx->cap_w, ctx->cap_cig, ctx->row_cap, ctx->cap_dir);
   while (ctx->final_warps > 64 && ctx->final_stride * ctx->final_warps > budget) ctx->final_warps /= 2;
   if (int rc = ensure(ctx, ctx->final_arena, ctx->final_stride * ctx->final_warps)) return rc;
@@ -695,7 +696,7 @@ int run_impl(smr_ctx* ctx) {
     const uint32_t n = std::min(ctx->chunk_reads, nreads - c0);
     DevBatch b = make_batch(ctx, c0, n);
     b.seq_base0 = ctx->off32[c0];
-    CK(cudaMemsetAsync(sc.work_n, 0, 8, ctx->stream));   // (unused word) + lis_next
+    CK(cudaMemsetAsync(sc.work_n, 0, 12, ctx->stream));  // (unused word) + the two cursors of the candidate kernel's schedule (lis_next and the word behind it; finalize re-zeroes that one for itself)
     CK(cudaMemsetAsync(b.cost, 0, (size_t)n * 4, ctx->stream));
     CK(cudaMemsetAsync(b.bin_count, 0, (size_t)kCostBins * 4, ctx->stream));
     cudaEvent_t s0 = get_event(ctx, evi), s1 = get_event(ctx, evi + 1), s2 = get_event(ctx, evi + 2); evi += 3;
@@ -766,6 +767,17 @@ int run_impl(smr_ctx* ctx) {
   if (getenv("SMR_VERBOSE")) {
     unsigned long long d[16]; cudaMemcpy(d, ctx->lis_dbg.p, 128, cudaMemcpyDeviceToHost);
     fprintf(stderr, "[smr] slowest read %llu: %.2f ms; cycles vote %llu order %llu group %llu plan %llu wait %llu replay %llu; sw calls %llu, tasks scored %llu, rounds %llu\n", d[10], d[0] / 1.965e6, d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9]);
+  }
+  if (ctx->instr && getenv("SMR_TIMELINE")) {   // ns per role and state in 1 ms buckets since the kernel's start (this run's candidate launches summed)
+    std::vector<unsigned long long> tl((size_t)kTlRows * kTlBuckets);
+    cudaMemcpy(tl.data(), (const unsigned long long*)ctx->lis_dbg.p + kTlBase, tl.size() * 8, cudaMemcpyDeviceToHost);
+    static const char* names[kTlRows] = {"scorer_wait_ns", "scorer_busy_ns", "planner_wait_ns", "planner_vote_group_ns", "reads_done", "planner_alive_ns"};
+    for (int r = 0; r < kTlRows; ++r) {
+      int last = 0; for (int k = 0; k < kTlBuckets; ++k) if (tl[(size_t)r * kTlBuckets + k]) last = k + 1;
+      fprintf(stderr, "[smr timeline] %s", names[r]);
+      for (int k = 0; k < last; ++k) fprintf(stderr, " %llu", tl[(size_t)r * kTlBuckets + k]);
+      fprintf(stderr, "\n");
+    }
   }
   for (auto& s : spans) {
     if (s.second == 0) {

@@ -46,8 +46,12 @@ __host__ __device__ inline size_t final_arena_bytes(uint32_t cap_w, uint32_t cap
 }
 
 constexpr int kFinalWarpsPerCta = 4;
+#ifndef SMR_FINAL_MIN_CTAS
+#define SMR_FINAL_MIN_CTAS 6     // resident CTAs per SM the register budget is set for (3: 167 registers, 15.3 ms finalize + traceback per 500 k reads; 4: 128, 14.4; 5: 96, 14.3; 6: 80, 13.8)
+#endif
+constexpr int kFinalCtasPerSm = SMR_FINAL_MIN_CTAS;
 
-__global__ void __launch_bounds__(kFinalWarpsPerCta * 32)
+__global__ void __launch_bounds__(kFinalWarpsPerCta * 32, kFinalCtasPerSm)
 finalize_kernel(DevBatch b, DevParams prm, FinalGlobals g) {
   __shared__ __align__(16) uint8_t s_ref[kFinalWarpsPerCta][kRefStage + 64];
   __shared__ int32_t s_prof[kFinalWarpsPerCta][kProfWords];

@@ -50,6 +50,21 @@ namespace smr {
 // Phase accounting with clock64 (the cycle shares bench.py reports) is a template parameter of the kernel: the product runs the
 // instantiation without it (smr_set_instrumentation; 199.6 vs 204.9 ms per 500 k reads with it).
 template <bool kInstr> __device__ __forceinline__ long long lis_clock() { return kInstr ? clock64() : 0ll; }
+// Timeline of the instrumented instantiation (SMR_TIMELINE=1 prints it): nanoseconds per role and state in 1 ms buckets since the
+// start of the kernel -- g.dbg + kTlBase + row * kTlBuckets; rows: 0 scorers waiting for a staged pair, 1 scorers busy, 2 planners
+// waiting for scores, 3 planners voting / ordering / grouping, 4 reads finished (count), 5 planner warps alive (ns).
+constexpr int kTlBuckets = 512, kTlRows = 6, kTlBase = 16;
+constexpr unsigned long long kTlBucketNs = 1000000ull;
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __noinline__ void tl_add(unsigned long long* row, const unsigned long long t_start, unsigned long long a, const unsigned long long b) {
+  if (lane_id() != 0 || b <= a) return;
+#pragma unroll 1
+  while (a < b) {
+    const unsigned long long k = (a - t_start) / kTlBucketNs, edge = t_start + (k + 1) * kTlBucketNs, e = b < edge ? b : edge;
+    if (k < (unsigned long long)kTlBuckets) atomicAdd(row + k, e - a);
+    a = e;
+  }
+}
 constexpr int kScorerWarps = SMR_SCORER_WARPS;     // the first warps of a CTA score
 constexpr int kFetcherWarps = 1;                   // then one warp that pops the task queue and stages the scorers' inputs (TMA bulk copies)
 constexpr int kPlannerWarps = SMR_PLANNER_WARPS;   // the others plan
@@ -88,6 +103,21 @@ constexpr uint32_t kBatchCandCap = 4096;          // candidates per batch
 constexpr uint32_t kScorePending = 0xFFFFFFFFu;     // score word of a task that has been handed to the scorers and not been scored yet
 // Sensitivity experiments (tools/ab_round.sh; never set in the shipped build): stretch a role's own work by N per cent with sleeps
 // (no issue slots taken) -- how much the kernel slows tells which role bounds it.
+// Schedule of the reads over the planner warps.  The seed kernel bins the reads of a chunk by log2 of their voting work; index 0 of the
+// schedule is the heaviest read.  With ONE heaviest-first cursor (round 2a) every planner starts on a read whose votes take
+// milliseconds: the scorers wait for 20 ms of 205 (the kernel's role timeline, SMR_TIMELINE / tools/timeline_summary.py).  So two
+// cursors: SMR_SCHED_A planners in 8 take the heaviest nwork >> SMR_SPLIT_SHIFT reads in order, the others start right behind them,
+// on reads whose few candidates reach the scorers within microseconds -- the scorers are busy 12 ms after the launch -- and go on
+// towards the light end; a planner whose region is exhausted helps in the other.  SMR_SCHED_A = 0: the single cursor.
+// Measured (ms per 500 k reads, candidate kernel): single cursor 201.8; 4 in 8 planners on the heaviest 1/64: 198.1, 1/16: 195.3,
+// 1/8: 191.5 - 194.8; 2 in 8 on 1/32: 195.5; variants that also start planners at the light end (the reads without Smith-Waterman
+// work, which otherwise end the kernel with idle scorers) lost what they gained there at the start: 197 - 206.
+#ifndef SMR_SCHED_A
+#define SMR_SCHED_A 4
+#endif
+#ifndef SMR_SPLIT_SHIFT
+#define SMR_SPLIT_SHIFT 3
+#endif
 #ifndef SMR_EXP_PLANNER_DELAY
 #define SMR_EXP_PLANNER_DELAY 0
 #endif
@@ -148,7 +178,7 @@ struct LisGlobals {
   uint32_t* planners_done;                     // planners that ran out of reads
   uint32_t* done;                              // [planners] tasks scored so far for each planner
   int32_t* score_rows;                         // [scorers][2 * row_cap] scratch of the s32 row-block fallback
-  unsigned long long* dbg;                     // [16] phase cycles of the read that took longest (SMR_VERBOSE)
+  unsigned long long* dbg;                     // [16] phase cycles of the read that took longest (SMR_VERBOSE); [kTlBase ..) the timeline rows
   AlnWork* aln_work;                           // [nreads * slots]
   uint32_t slots;
   uint32_t* work_next;                         // [1] persistent-loop cursor
@@ -270,6 +300,7 @@ struct PassEnv {
   unsigned long long* s_pairs; uint32_t* s_b; uint32_t* s_p;   // shared-memory fast buffers (kPairsShared)
   const uint2* hits; uint32_t nh;                               // hit region of (current part, current read)
   uint32_t planner;                                             // ordinal of this planner warp
+  unsigned long long tl0;                                       // %globaltimer at the start of the kernel (instrumented instantiation)
   uint32_t submitted;                                           // tasks handed to the scorers so far (g.done[planner] catches up)
   unsigned long long n_sw_calls, n_sw_cells, n_pos_entries, n_lis_calls, n_spec_calls, n_spec_cells /* rounds A */, n_rounds_b, w1_cyc, w1_cnt;
   unsigned long long cyc[8];                                    // warp cycles per phase: vote, order, group, plan, wait, replay
@@ -311,6 +342,7 @@ __device__ __noinline__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
   }
   E.submitted += nsel;
   const long long tw0 = lis_clock<kInstr>();
+  const unsigned long long tlw = kInstr ? tl_now() : 0ull;
   if (lane == 0) {
     // (pointer and target in registers: the poll is four instructions -- the waiting planners share their schedulers with the scorers)
     const uint32_t* const dp = g.done + E.planner;
@@ -328,6 +360,7 @@ __device__ __noinline__ void submit_and_wait(PassEnv& E, const uint32_t nsel) {
   }
   __syncwarp();
   if (npairs == 1) { E.w1_cyc += (unsigned long long)(lis_clock<kInstr>() - tw0); E.w1_cnt++; }
+  if (kInstr && g.dbg) tl_add(g.dbg + kTlBase + 2 * kTlBuckets, E.tl0, tlw, tl_now());
 
 }
 
@@ -346,6 +379,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
   const uint32_t ns = (uint32_t)max(o.num_seeds, 1);
   E.n_lis_calls++;
   long long tph = lis_clock<kInstr>();
+  const unsigned long long tlv = kInstr ? tl_now() : 0ull;
   const long long t_call0 = SMR_EXP_PLANNER_DELAY ? clock64() : 0ll;
 
   // ---- 1. votes per reference (alignment.cpp:118-138) ----
@@ -517,6 +551,7 @@ __device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uin
     }
   }
   { const long long t2 = lis_clock<kInstr>(); E.cyc[2] += (unsigned long long)(t2 - tph); tph = t2; }
+  if (kInstr && E.g->dbg) tl_add(E.g->dbg + kTlBase + 3 * kTlBuckets, E.tl0, tlv, tl_now());
   if (SMR_EXP_PLANNER_DELAY) exp_delay(t_call0, SMR_EXP_PLANNER_DELAY);
   run_candidates<kInstr>(E, rc, search, max_SW_score, ncand, by_level, level, grouped);
   __syncwarp();
@@ -1111,8 +1146,10 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
   uint32_t keyq[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}, keym[2] = {0xFFFFFFFFu, 0xFFFFFFFFu}; int keyR = 0;
   uint32_t par[2] = {0, 0}, exited = 0;
   unsigned long long n_pairs = 0, n_cells = 0, n_slow = 0, cy_wait = 0, cy_load = 0, cy_sw = 0, cy_pub = 0;
+  const unsigned long long tl0 = kInstr ? tl_now() : 0ull;
   for (;;) {
     long long tq = lis_clock<kInstr>();
+    const unsigned long long tla = kInstr ? tl_now() : 0ull;
     int k = -1;
     for (;;) {
       if (!(exited & 1u) && mbar_try_wait(&slots[0].bar, par[0])) { k = 0; break; }
@@ -1122,6 +1159,8 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
     par[k] ^= 1u;
     ScSlot& S = slots[k];
     { const long long t2 = lis_clock<kInstr>(); cy_wait += (unsigned long long)(t2 - tq); tq = t2; }
+    const unsigned long long tlb = kInstr ? tl_now() : 0ull;
+    if (kInstr && g.dbg) tl_add(g.dbg + kTlBase + 0 * kTlBuckets, tl0, tla, tlb);
     const uint32_t planner = S.planner;
     if (planner == kPoison) { exited |= 1u << k; if (exited == 3u) break; continue; }
     const uint32_t ta = S.ta, tb = S.tb;
@@ -1170,6 +1209,7 @@ __device__ void scorer_loop(const DevBatch& b, const DevParams& prm, const LisGl
     }
     __syncwarp();
     { const long long t2 = lis_clock<kInstr>(); cy_pub += (unsigned long long)(t2 - tq); }
+    if (kInstr && g.dbg) tl_add(g.dbg + kTlBase + 1 * kTlBuckets, tl0, tlb, tl_now());
   }
   if (lane == 0) {
     atomicAdd(&b.counters[dcSpecCells], n_cells); atomicAdd(&b.counters[dcSpecPairs], n_pairs); atomicAdd(&b.counters[dcSlowPairs], n_slow);
@@ -1206,7 +1246,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   PassEnv E;
   E.b = &b; E.prm = &prm; E.g = &g;
   E.ar = carve_arena(g, planner);
-  E.planner = planner; E.submitted = 0;
+  E.planner = planner; E.submitted = 0; E.tl0 = kInstr ? tl_now() : 0ull;
   E.epoch_ptr = g.epochs + planner; E.epoch = *E.epoch_ptr;
   {
     uint8_t* sm = lis_smem + (size_t)kScorerWarps * kScorerSmem + (size_t)pw * kPlannerSmem;
@@ -1218,11 +1258,28 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
   unsigned long long t_max = 0, t_sum = 0; const long long t_k0 = lis_clock<kInstr>();
   unsigned long long dbg_loc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_busy_max = 0;
   const bool single = (prm.is_forward != 0) != (prm.is_reverse != 0);
+  bool in_a = (int)(planner % 8u) < SMR_SCHED_A; (void)in_a;   // which region this planner draws from
   for (;;) {
     uint32_t wi = 0;
+#if SMR_SCHED_A
+    {   // two cursors over the heaviest-first schedule (see the comment at SMR_SCHED_A); a planner whose region is exhausted helps in the other
+      const uint32_t m = nwork >> SMR_SPLIT_SHIFT;
+      bool got = false;
+#pragma unroll 1
+      for (int tries = 0; tries < 2 && !got; ++tries) {
+        uint32_t a = 0;
+        if (lane == 0) a = atomicAdd(g.work_next + (in_a ? 0 : 1), 1u);
+        a = __shfl_sync(kFull, a, 0);
+        if (in_a) { if (a < m) { wi = a; got = true; } else in_a = false; }
+        else { if (a < nwork - m) { wi = m + a; got = true; } else in_a = true; }
+      }
+      if (!got) break;
+    }
+#else
     if (lane == 0) wi = atomicAdd(g.work_next, 1u);
     wi = __shfl_sync(kFull, wi, 0);
     if (wi >= nwork) break;
+#endif
     uint32_t k = 0;
     while (wi >= s_bin_start[k + 1]) ++k;
     const uint32_t r = b.bins[(size_t)(kCostBins - 1 - k) * b.cnt_stride + (wi - s_bin_start[k])];
@@ -1267,8 +1324,10 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
       const unsigned long long busy = dt - (E.cyc[4] - cyc0[4]);   // without the time spent waiting for the scorers
       t_busy_max = busy > t_busy_max ? busy : t_busy_max;
       t_sum += dt; }
+    if (kInstr && g.dbg && lane == 0) { const unsigned long long k = (tl_now() - E.tl0) / kTlBucketNs; if (k < (unsigned long long)kTlBuckets) atomicAdd(g.dbg + kTlBase + 4 * kTlBuckets + k, 1ull); }
     __syncwarp();
   }
+  if (kInstr && g.dbg) tl_add(g.dbg + kTlBase + 5 * kTlBuckets, E.tl0, E.tl0, tl_now());
   if (lane == 0) {
     *E.epoch_ptr = E.epoch;
     atomicAdd(&b.counters[dcSwCalls], E.n_sw_calls); atomicAdd(&b.counters[dcSwCells], E.n_sw_cells);
