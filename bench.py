@@ -566,7 +566,7 @@ def main():
     sw_peak = dpx / 3.5 / 1e3                        # Tcell-updates/s
     tr = {}
     try:
-        cands = [os.path.join(ROOT, "profiles", f) for f in ("r2b_traffic.json", "r2_traffic.json")]   # the newest committed capture
+        cands = [os.path.join(ROOT, "profiles", f) for f in ("r2c_traffic.json", "r2b_traffic.json", "r2_traffic.json")]   # the newest committed capture
         tr = json.load(open(next(f for f in cands if os.path.exists(f))))
     except Exception:
         pass

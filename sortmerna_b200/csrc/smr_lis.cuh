@@ -369,8 +369,11 @@ __device__ void run_candidates(PassEnv& E, ReadCtx& rc, bool& search, const uint
                                uint32_t level, const bool grouped);
 
 // compute_lis_alignment (alignment.cpp:100-509).  Uniform control flow; warp-parallel inner scans.
+// (not inlined: the compiler otherwise clones this function -- and run_candidates inside it -- for both strands and both sides of the
+//  pass loop, four copies = 150 KB of kernel text that the planner warps walk through: a fifth of the kernel's stall samples were
+//  instruction fetches)
 template <bool kInstr>
-__device__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score) {
+__device__ __noinline__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& search, const uint32_t max_SW_score) {
   const DevIndex& ix = *E.ix; const DevBatch& B = *E.b; const DevParams& o = *E.prm;
   const unsigned lane = lane_id();
   const uint32_t s0 = ix.skip[0], s1 = ix.skip[1], s2 = ix.skip[2];

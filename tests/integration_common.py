@@ -29,7 +29,20 @@ def run_host(binary, workdir, reads, extra, threads=2):
     return out, p.stdout
 
 
-def assert_same_outputs(a, b):
+_PER_DB = re.compile(r"^(\s+\S+\.fasta\t+)([0-9.]+)\s*$")
+
+
+def assert_same_outputs(a, b, ref_threads=2):
+    """a: our run, b: the reference binary's.  With several threads the reference's "Coverage by database" figures come from
+    ++readstats.reads_matched_per_db[...] without synchronisation (src/sortmerna/alignment.cpp:415,454-457): now and
+    then a run loses an update (66.33 % instead of 66.67 % of 300 reads).  Those lines are compared with a tolerance of one
+    percentage point then, and exactly when the reference ran single-threaded (ref_threads=1); everything else is always exact."""
     assert sorted(a) == sorted(b), (sorted(a), sorted(b))
     for fn in a:
-        assert a[fn] == b[fn], f"{fn} differs: first difference {next((x, y) for x, y in zip(a[fn], b[fn]) if x != y)}"
+        x, y = list(a[fn]), list(b[fn])
+        if ref_threads > 1 and fn.endswith(".log") and len(x) == len(y):
+            for i, (p, q) in enumerate(zip(x, y)):
+                mp, mq = _PER_DB.match(p), _PER_DB.match(q)
+                if mp and mq and mp.group(1) == mq.group(1) and abs(float(mp.group(2)) - float(mq.group(2))) <= 1.0:
+                    y[i] = p
+        assert x == y, f"{fn} differs: first difference {next((p, q) for p, q in zip(x, y) if p != q)}"

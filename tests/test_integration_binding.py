@@ -56,7 +56,7 @@ def test_paired_files(threads):
         extra = REPORTS + ["-paired_in", "-num_alignments", "3"]
         ref, _ = run_host("sortmerna_ref", os.path.join(d, "ref"), paths, extra, threads=threads)
         got, _ = run_host("sortmerna_gpu_mock", os.path.join(d, "got"), paths, extra, threads=threads)
-        assert_same_outputs(got, ref)
+        assert_same_outputs(got, ref, ref_threads=threads)
     finally:
         shutil.rmtree(d, ignore_errors=True)
 
