@@ -268,11 +268,11 @@ cudaEvent_t get_event(smr_ctx* ctx, size_t i) {
   return ctx->ev[i];
 }
 
-// scalars block layout (u32): [0]=work_n [1]=lis work_next [2]=final work_next ; cigar_used (u64) at byte 16 ; task queue cursors at 32..
-struct Scalars { uint32_t* work_n; uint32_t* lis_next; uint32_t* fin_next; unsigned long long* cigar_used; uint32_t* q_head; uint32_t* q_tail; uint32_t* planners_done; };
+// scalars block layout (u32): [0]=work_n [1]=lis work_next [2]=final work_next [3]=lis work_next of the second cursor ; cigar_used (u64) at byte 16 ; task queue cursors at 128..
+struct Scalars { uint32_t* work_n; uint32_t* lis_next; uint32_t* fin_next; uint32_t* lis_next_b; unsigned long long* cigar_used; uint32_t* q_head; uint32_t* q_tail; uint32_t* planners_done; };
 Scalars scalars_of(smr_ctx* ctx) {
   uint8_t* p = (uint8_t*)ctx->scalars.p;
-  return Scalars{(uint32_t*)p, (uint32_t*)(p + 4), (uint32_t*)(p + 8), (unsigned long long*)(p + 16), (uint32_t*)(p + 128), (uint32_t*)(p + 256), (uint32_t*)(p + 384)};
+  return Scalars{(uint32_t*)p, (uint32_t*)(p + 4), (uint32_t*)(p + 8), (uint32_t*)(p + 12), (unsigned long long*)(p + 16), (uint32_t*)(p + 128), (uint32_t*)(p + 256), (uint32_t*)(p + 384)};
 }
 
 int setup_arenas(smr_ctx* ctx) {
@@ -696,7 +696,7 @@ int run_impl(smr_ctx* ctx) {
     const uint32_t n = std::min(ctx->chunk_reads, nreads - c0);
     DevBatch b = make_batch(ctx, c0, n);
     b.seq_base0 = ctx->off32[c0];
-    CK(cudaMemsetAsync(sc.work_n, 0, 12, ctx->stream));  // (unused word) + the two cursors of the candidate kernel's schedule (lis_next and the word behind it; finalize re-zeroes that one for itself)
+    CK(cudaMemsetAsync(sc.work_n, 0, 16, ctx->stream));  // (unused word), the two cursors of the candidate kernel's read schedule, finalize's cursor (zeroed again before it runs)
     CK(cudaMemsetAsync(b.cost, 0, (size_t)n * 4, ctx->stream));
     CK(cudaMemsetAsync(b.bin_count, 0, (size_t)kCostBins * 4, ctx->stream));
     cudaEvent_t s0 = get_event(ctx, evi), s1 = get_event(ctx, evi + 1), s2 = get_event(ctx, evi + 2); evi += 3;
@@ -719,7 +719,7 @@ int run_impl(smr_ctx* ctx) {
       lg.arena_base = (uint8_t*)ctx->lis_arena.p; lg.arena_stride = ctx->lis_stride;
       lg.hist_cap = ctx->hist_cap; lg.cand_cap = ctx->cand_cap; lg.pair_cap = ctx->pair_cap; lg.row_cap = ctx->row_cap; lg.pall_cap = ctx->pall_cap;
       lg.task_cap = ctx->task_cap;
-      lg.epochs = (uint32_t*)ctx->lis_epochs.p; lg.aln_work = (AlnWork*)ctx->aln_work.p; lg.slots = slots; lg.work_next = sc.lis_next;
+      lg.epochs = (uint32_t*)ctx->lis_epochs.p; lg.aln_work = (AlnWork*)ctx->aln_work.p; lg.slots = slots; lg.work_next = sc.lis_next; lg.work_next_b = sc.lis_next_b;
       lg.parts = (const DevIndex*)ctx->parts_dev.p; lg.nparts = (uint32_t)hp.size();
       lg.ring = (QSlot*)ctx->lis_queue.p; lg.done = (uint32_t*)ctx->lis_done.p; lg.score_rows = (int32_t*)ctx->lis_rows.p;
       lg.dbg = (unsigned long long*)ctx->lis_dbg.p;

@@ -16,7 +16,7 @@
 //   * ssw_align's reverse pass and CIGAR are deferred to the finalize kernel: accept / replace / stop
 //     decisions only need score1 (:388-469).
 //
-// Warp specialisation.  The kernel's warps have two roles:
+// Warp specialisation.  One persistent CTA of 32 warps per SM; its warps have three roles (16 scorers, 1 fetcher, 15 planners):
 //   * PLANNER warps own reads.  For each compute_lis_alignment call they vote, order and group as above, then walk the
 //     candidates in the reference's order WITHOUT scoring: every (candidate, sliding-window step) that would reach
 //     ssw_align becomes a task record (window, query segment).  Which steps reach it is score-independent -- the
@@ -30,6 +30,12 @@
 //     the packed 16-bit DPX kernel (smr_sw.cuh), whoever the read belongs to: a read with thousands of candidates is
 //     scored by the whole GPU instead of by its one warp (round 1: the heaviest read occupied one warp for 310 of the
 //     376 ms), and the integer-pipe loop never waits on the memory-latency phases of voting and grouping.
+//   * The FETCHER warp (one lane per scorer input slot) pops the queue and stages the scorers' inputs -- reference window and query
+//     segment -- with TMA bulk copies (cp.async.bulk + mbarrier), two slots per scorer: one fills while the other is scored.
+// Hand-over without fences: __threadfence() is MEMBAR.SC.GPU + CCTL.IVALL on sm_100a -- it also invalidates the SM's whole L1.  A
+// planner publishes a queue entry with a release store (MEMBAR.ALL.GPU + ST) after marking the score words of its tasks pending;
+// the fetcher reads entry and task records past L1; a scorer stores its scores and adds to the planner's counter with no fence in
+// between; the planner takes the counter as a hint and then looks at every score word itself.
 #pragma once
 #include "smr_seed.cuh"
 #include "smr_sw.cuh"
@@ -181,7 +187,8 @@ struct LisGlobals {
   unsigned long long* dbg;                     // [16] phase cycles of the read that took longest (SMR_VERBOSE); [kTlBase ..) the timeline rows
   AlnWork* aln_work;                           // [nreads * slots]
   uint32_t slots;
-  uint32_t* work_next;                         // [1] persistent-loop cursor
+  uint32_t* work_next;                         // [1] persistent-loop cursor (SMR_SCHED_A: over the heaviest reads)
+  uint32_t* work_next_b;                       // [1] second cursor (SMR_SCHED_A: over the rest of the schedule)
   const DevIndex* parts; uint32_t nparts;      // every loaded (index,part) in --ref order
 };
 
@@ -1271,7 +1278,7 @@ lis_kernel(DevBatch b, DevParams prm, LisGlobals g) {
 #pragma unroll 1
       for (int tries = 0; tries < 2 && !got; ++tries) {
         uint32_t a = 0;
-        if (lane == 0) a = atomicAdd(g.work_next + (in_a ? 0 : 1), 1u);
+        if (lane == 0) a = atomicAdd(in_a ? g.work_next : g.work_next_b, 1u);
         a = __shfl_sync(kFull, a, 0);
         if (in_a) { if (a < m) { wi = a; got = true; } else in_a = false; }
         else { if (a < nwork - m) { wi = m + a; got = true; } else in_a = true; }

@@ -232,6 +232,25 @@ def test_resident_path_equals_host_path(aligner, golden):
     assert t["launches"] > 0 and t["total_ms"] > 0
 
 
+def test_instrumented_kernels_give_the_same_results(aligner, golden):
+    """smr_set_instrumentation: the instrumented instantiations of the seed and candidate kernels (what bench.py's counter pass runs)
+    return what the product kernels return; only they fill the seed-side counters."""
+    exp = load_case("default")
+    for k in range(2):
+        aligner.set_minimal_score(k, exp["log"]["minimal_score"][k])
+    b = golden["batch"]
+    a = aligner.align(b.cat, b.off)
+    aligner.set_instrumentation(True)
+    try:
+        c = aligner.align(b.cat, b.off)
+    finally:
+        aligner.set_instrumentation(False)
+    assert_same_results(a, c, "instrumented")
+    for k in ("num_aligned", "num_short", "sw_calls", "sw_cells", "pos_entries", "lis_calls"):
+        assert a["counters"][k] == c["counters"][k], k
+    assert a["counters"]["windows"] == 0 and c["counters"]["windows"] > 0
+
+
 def test_edge_batches(aligner, golden, oracle_indexes):
     """empty read, reads shorter than the seed, single read, all-N read, duplicate reads"""
     ora = _ora()
