@@ -460,7 +460,7 @@ __device__ __noinline__ void compute_lis_dev(PassEnv& E, ReadCtx& rc, bool& sear
   if (!by_level) {
     unsigned long long key = ~0ull;
     if (lane < ncand) {
-      const uint32_t seq = (uint32_t)E.ar.cand[lane]; const uint32_t c = __ldcg(&E.ar.hist[seq]) & 0xFFFFFu;   // (L2: the votes are atomics)
+      const uint32_t seq = (uint32_t)E.ar.cand[lane]; const uint32_t c = __ldcg(&E.ar.hist[seq]) & 0xFFFFFu;   // (read at L2, where the pair cursors of the grouping pass -- atomics -- live as well)
       key = ((unsigned long long)(0xFFFFFu - c) << 32) | seq;
       E.ar.bitmap[seq >> 5] = 0; E.ar.summary[seq >> 10] = 0;
     }
