@@ -722,7 +722,7 @@ int run_impl(smr_ctx* ctx) {
       lg.epochs = (uint32_t*)ctx->lis_epochs.p; lg.aln_work = (AlnWork*)ctx->aln_work.p; lg.slots = slots; lg.work_next = sc.lis_next; lg.work_next_b = sc.lis_next_b;
       lg.parts = (const DevIndex*)ctx->parts_dev.p; lg.nparts = (uint32_t)hp.size();
       lg.ring = (QSlot*)ctx->lis_queue.p; lg.done = (uint32_t*)ctx->lis_done.p; lg.score_rows = (int32_t*)ctx->lis_rows.p;
-      lg.dbg = (unsigned long long*)ctx->lis_dbg.p;
+      lg.dbg = (getenv("SMR_TIMELINE") || getenv("SMR_VERBOSE")) ? (unsigned long long*)ctx->lis_dbg.p : nullptr;   // (the timeline costs the instrumented kernel an atomic per scored pair)
       lg.q_head = sc.q_head; lg.q_tail = sc.q_tail; lg.planners_done = sc.planners_done;
       lis_reset_kernel<<<kQueueCap / 256, 256, 0, ctx->stream>>>(lg, ctx->lis_warps);
       CK(cudaGetLastError());
