@@ -933,6 +933,12 @@ int align_impl(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_off, ui
 
 extern "C" {
 
+// No exception crosses the C ABI: the batch entry points below are function-try-blocks that turn a failed host allocation (the result
+// vectors of a 2^32-nt batch, the retry copies) or any other std::exception into a status and an error text.
+#define SMR_CATCH(ctx) \
+  catch (const std::bad_alloc&) { if (ctx) (ctx)->err = "out of host memory"; return SMR_ERR_CAPACITY; } \
+  catch (const std::exception& ex) { if (ctx) (ctx)->err = std::string("internal error: ") + ex.what(); return SMR_ERR_CUDA; }
+
 int smr_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -1115,7 +1121,7 @@ int smr_index_info(const smr_ctx* ctx, uint64_t out[6]) {
 }
 
 int smr_align_batch(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads, smr_read_result* results, smr_aln* alns,
-                    uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used, uint64_t* counters, uint32_t n_counters) {
+                    uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used, uint64_t* counters, uint32_t n_counters) try {
   if (!ctx || !seq_cat || !seq_off || !results || !alns || (!cigar_pool && cigar_cap)) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   const uint32_t slots = slots_of(ctx);
@@ -1126,7 +1132,7 @@ int smr_align_batch(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_of
   int rc = align_impl(ctx, seq_cat, seq_off, nreads, out, nullptr, 0);
   if (cigar_used) *cigar_used = out.cigar_used;
   return rc;
-}
+} SMR_CATCH(ctx)
 
 int smr_set_instrumentation(smr_ctx* ctx, int on) {
   if (!ctx) return SMR_ERR_ARG;
@@ -1140,21 +1146,21 @@ int smr_set_stats_buffer(smr_ctx* ctx, smr_aln_stats* stats) {
   return SMR_OK;
 }
 
-int smr_upload_batch(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads) {
+int smr_upload_batch(smr_ctx* ctx, const uint8_t* seq_cat, const uint64_t* seq_off, uint32_t nreads) try {
   if (!ctx || !seq_cat || !seq_off) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   ctx->scale = 1;
   return upload_batch_impl(ctx, seq_cat, seq_off, nreads, true);
-}
+} SMR_CATCH(ctx)
 
-int smr_upload_fastx(smr_ctx* ctx, const char* text, uint64_t nbytes, uint32_t* nreads) {
+int smr_upload_fastx(smr_ctx* ctx, const char* text, uint64_t nbytes, uint32_t* nreads) try {
   if (!ctx || (!text && nbytes) || !nreads) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   ctx->scale = 1;
   return upload_fastx_impl(ctx, text, nbytes, nreads);
-}
+} SMR_CATCH(ctx)
 
-int smr_upload_fastx_gz(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint32_t* nreads) {
+int smr_upload_fastx_gz(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint32_t* nreads) try {
   if (!ctx || !gz || !nreads) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   ctx->scale = 1;
@@ -1169,7 +1175,7 @@ int smr_upload_fastx_gz(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint32_t*
   char c0 = 0;
   CK(cudaMemcpy(&c0, ctx->d_text.p, 1, cudaMemcpyDeviceToHost));
   return upload_fastx_impl(ctx, nullptr, total, nreads, c0);
-}
+} SMR_CATCH(ctx)
 
 int smr_resident_text(smr_ctx* ctx, char* text, uint64_t cap, uint64_t* nbytes) {
   if (!ctx || !nbytes) return SMR_ERR_ARG;
@@ -1181,7 +1187,7 @@ int smr_resident_text(smr_ctx* ctx, char* text, uint64_t cap, uint64_t* nbytes) 
   return SMR_OK;
 }
 
-int smr_debug_inflate(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint64_t chunk_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_bytes, uint32_t info[4]) {
+int smr_debug_inflate(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint64_t chunk_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_bytes, uint32_t info[4]) try {
   if (!ctx || !gz || !out_bytes) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   ctx->nreads = 0; ctx->text_bytes = 0;
@@ -1194,9 +1200,9 @@ int smr_debug_inflate(smr_ctx* ctx, const void* gz, uint64_t nbytes, uint64_t ch
     CK(cudaMemcpy(out, ctx->d_text.p, *out_bytes, cudaMemcpyDeviceToHost));
   }
   return SMR_OK;
-}
+} SMR_CATCH(ctx)
 
-int smr_resident_layout(smr_ctx* ctx, uint64_t* header_text_off, uint64_t* read_off, uint8_t* seq04, uint64_t seq_cap) {
+int smr_resident_layout(smr_ctx* ctx, uint64_t* header_text_off, uint64_t* read_off, uint8_t* seq04, uint64_t seq_cap) try {
   if (!ctx) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   const uint32_t n = ctx->nreads;
@@ -1210,16 +1216,16 @@ int smr_resident_layout(smr_ctx* ctx, uint64_t* header_text_off, uint64_t* read_
     CK(cudaMemcpy(seq04, ctx->seq04.p, ctx->total_nt, cudaMemcpyDeviceToHost));
   }
   return SMR_OK;
-}
+} SMR_CATCH(ctx)
 
-int smr_run_resident(smr_ctx* ctx) {
+int smr_run_resident(smr_ctx* ctx) try {
   if (!ctx) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   return run_impl(ctx);
-}
+} SMR_CATCH(ctx)
 
 int smr_download_results(smr_ctx* ctx, smr_read_result* results, smr_aln* alns, uint32_t* cigar_pool, uint64_t cigar_cap, uint64_t* cigar_used,
-                         uint64_t* counters, uint32_t n_counters) {
+                         uint64_t* counters, uint32_t n_counters) try {
   if (!ctx || !results || !alns) return SMR_ERR_ARG;
   CK(cudaSetDevice(ctx->device));
   const uint32_t slots = slots_of(ctx);
@@ -1250,7 +1256,7 @@ int smr_download_results(smr_ctx* ctx, smr_read_result* results, smr_aln* alns, 
   }
   if (cigar_used) *cigar_used = out.cigar_used;
   return rc;
-}
+} SMR_CATCH(ctx)
 
 int smr_last_timings(const smr_ctx* ctx, double out[8]) {
   if (!ctx || !out) return SMR_ERR_ARG;
