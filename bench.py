@@ -499,10 +499,12 @@ def main():
         vec_s = np.array([res["counters"][k] for k in api.CNT_NAMES], dtype=np.int64)
         csum_i = vec_s if csum_i is None else csum_i + vec_s
     al.set_instrumentation(False)
+    instr_mismatch = []
     for k in ("num_aligned", "sw_calls", "sw_cells", "pos_entries", "lis_calls", "spec_calls"):   # what both instantiations count must agree
         i = api.CNT_NAMES.index(k)
         if int(csum[i]) != int(csum_i[i]):
-            raise SystemExit(f"instrumented and product kernels disagree on {k}: {int(csum_i[i])} vs {int(csum[i])}")
+            instr_mismatch.append({"counter": k, "product": int(csum[i]), "instrumented": int(csum_i[i])})
+            print(f"[bench] instrumented and product kernels disagree on {k}: {int(csum_i[i])} vs {int(csum[i])}", file=sys.stderr)
     for k in INSTR_ONLY:
         i = api.CNT_NAMES.index(k)
         csum[i] = csum_i[i]
@@ -601,7 +603,8 @@ def main():
         "roofline_seed": roof_seed,     # the HBM-bound kernel of the path
         "kernel_ms_per_step": {"seed": float(np.mean(seed_ms)), "candidates_sw": float(np.mean(lis_ms)), "finalize": float(np.mean(fin_ms))},
         "instrumentation": {"timed_region": "off (product kernels)", "counters_from": "one extra untimed pass over the same batches with smr_set_instrumentation(1)",
-                            "candidates_sw_ms_per_step_instrumented": float(np.mean(instr_lis_ms)), "instr_only_counters": list(INSTR_ONLY)},
+                            "candidates_sw_ms_per_step_instrumented": float(np.mean(instr_lis_ms)), "instr_only_counters": list(INSTR_ONLY),
+                            "disagreements": instr_mismatch},   # counters both instantiations produce (must be empty)
         "clocks": sampler.summary(),
         "counters": counters,
         "setup_s": setup_s, "index_build_s": built, "index_source": args.index_source, "index_resident_s": round(index_resident_s, 2),
