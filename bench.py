@@ -489,25 +489,32 @@ def main():
     # ---- the same K batches once more, UNTIMED, through the instrumented instantiations of the kernels (smr_set_instrumentation):
     #      the seed-side counters (windows, lists, entries) and the cycle shares of the candidate kernel's roles come from this pass;
     #      the timed passes above run the product's kernels, which carry neither ----
-    al.set_instrumentation(True)
-    csum_i, instr_lis_ms = None, []
-    for s_i in range(args.steps):
-        al.upload(cats[s_i], off)
-        al.run_resident()
-        instr_lis_ms.append(al.timings()["lis_ms"])
-        res = al.download()
-        vec_s = np.array([res["counters"][k] for k in api.CNT_NAMES], dtype=np.int64)
-        csum_i = vec_s if csum_i is None else csum_i + vec_s
-    al.set_instrumentation(False)
-    instr_mismatch = []
-    for k in ("num_aligned", "sw_calls", "sw_cells", "pos_entries", "lis_calls", "spec_calls"):   # what both instantiations count must agree
-        i = api.CNT_NAMES.index(k)
-        if int(csum[i]) != int(csum_i[i]):
-            instr_mismatch.append({"counter": k, "product": int(csum[i]), "instrumented": int(csum_i[i])})
-            print(f"[bench] instrumented and product kernels disagree on {k}: {int(csum_i[i])} vs {int(csum[i])}", file=sys.stderr)
-    for k in INSTR_ONLY:
-        i = api.CNT_NAMES.index(k)
-        csum[i] = csum_i[i]
+    csum_i, instr_lis_ms, instr_mismatch, instr_error = None, [], [], None
+    try:
+        al.set_instrumentation(True)
+        for s_i in range(args.steps):
+            al.upload(cats[s_i], off)
+            al.run_resident()
+            instr_lis_ms.append(al.timings()["lis_ms"])
+            res = al.download()
+            vec_s = np.array([res["counters"][k] for k in api.CNT_NAMES], dtype=np.int64)
+            csum_i = vec_s if csum_i is None else csum_i + vec_s
+        for k in ("num_aligned", "sw_calls", "sw_cells", "pos_entries", "lis_calls", "spec_calls"):   # what both instantiations count must agree
+            i = api.CNT_NAMES.index(k)
+            if int(csum[i]) != int(csum_i[i]):
+                instr_mismatch.append({"counter": k, "product": int(csum[i]), "instrumented": int(csum_i[i])})
+                print(f"[bench] instrumented and product kernels disagree on {k}: {int(csum_i[i])} vs {int(csum[i])}", file=sys.stderr)
+        for k in INSTR_ONLY:
+            i = api.CNT_NAMES.index(k)
+            csum[i] = csum_i[i]
+    except Exception as e:     # the bench line must not depend on the counter pass: the timed numbers above stand without it
+        instr_error = str(e)[:300]
+        print(f"[bench] instrumented pass failed: {instr_error}", file=sys.stderr)
+    finally:
+        try:
+            al.set_instrumentation(False)
+        except Exception:
+            pass
     # ---- end to end through the public call: pinned host buffers in, host results out, every step ----
     # Two contexts on the GPU, one host thread each, batches alternate: the H2D copy of one batch and the D2H copy + host-side
     # result packing of another run under the kernels of a third (the library serialises the kernel sections of contexts that
@@ -603,8 +610,9 @@ def main():
         "roofline_seed": roof_seed,     # the HBM-bound kernel of the path
         "kernel_ms_per_step": {"seed": float(np.mean(seed_ms)), "candidates_sw": float(np.mean(lis_ms)), "finalize": float(np.mean(fin_ms))},
         "instrumentation": {"timed_region": "off (product kernels)", "counters_from": "one extra untimed pass over the same batches with smr_set_instrumentation(1)",
-                            "candidates_sw_ms_per_step_instrumented": float(np.mean(instr_lis_ms)), "instr_only_counters": list(INSTR_ONLY),
-                            "disagreements": instr_mismatch},   # counters both instantiations produce (must be empty)
+                            "candidates_sw_ms_per_step_instrumented": float(np.mean(instr_lis_ms)) if instr_lis_ms else None,
+                            "instr_only_counters": list(INSTR_ONLY), "disagreements": instr_mismatch,   # counters both instantiations produce (must be empty)
+                            "error": instr_error},
         "clocks": sampler.summary(),
         "counters": counters,
         "setup_s": setup_s, "index_build_s": built, "index_source": args.index_source, "index_resident_s": round(index_resident_s, 2),
